@@ -1,0 +1,140 @@
+/*
+ * seedx.h — C ABI of libseedx.so, the B200 (sm_100a) kernel library behind the SEED-X inference hot path.
+ *
+ * The reference (AILab-CVC/SEED-X) has no FFI/plugin layer: every FLOP is reached through
+ * torch.nn.functional / xformers / diffusers library calls made from its nn.Module.forward methods.
+ * Each entry point below therefore names the reference call site(s) (file:line under /root/reference)
+ * whose arithmetic it replaces.  The Python host (seed-x_b200/*.py) mirrors the reference modules and
+ * calls these functions through ctypes with raw device pointers; see INTEGRATION.md for the binding.
+ *
+ * Conventions
+ *  - the caller owns every buffer; pointers are raw CUDA device pointers unless noted otherwise
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream)
+ *  - every function returns 0 on success, non-zero on failure; seedx_last_error() describes the failure
+ *  - nothing here allocates device memory, spawns threads or synchronises the device
+ *  - fp16 = IEEE binary16 (the reference runs `torch.float16`, src/inference/eval_*.py `dtype`)
+ */
+#ifndef SEEDX_H_
+#define SEEDX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEEDX_ABI_VERSION 1
+
+/* dtype tags */
+enum { SEEDX_F16 = 1, SEEDX_F32 = 2 };
+/* activations */
+enum { SEEDX_ACT_NONE = 0, SEEDX_ACT_GELU_ERF = 1, SEEDX_ACT_SILU = 2 };
+
+const char* seedx_last_error(void);
+int seedx_abi_version(void);
+/* number of kernels launched by this process through the library since load (bench.py's gpu_launches) */
+int64_t seedx_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM / implicit-GEMM convolution (tcgen05 + TMEM accumulators + TMA operand staging)
+ *
+ *   D[b][m][n] = epilogue( alpha * sum_k A[b][m][k] * B[b][n][k] )         A, B fp16, fp32 accumulate
+ *
+ * replaces F.linear / nn.Linear / nn.Conv2d / torch.bmm at:
+ *   src/models/tokenizer/qwen_visual.py:186,228,253-255,136-146,393,415      (ViT linears, patch-embed conv, proj)
+ *   src/models/mllm/modeling_llama_xformer.py:166-167,204-206,239,707        (LLaMA q/k/v/o, SwiGLU MLP, lm_head; prefill)
+ *   src/models/detokenizer/resampler.py:9-16,46-75,89-116,266-286            (perceiver resampler linears)
+ *   diffusers==0.25.0 UNet2DConditionModel / AutoencoderKL convs + linears, called from
+ *   src/models/detokenizer/pipeline_stable_diffusion_xl_t2i_edit.py:915-922,973 and adapter_modules.py:156-167
+ *
+ * epilogue order: x = alpha*acc; x += bias_n[n]; x += bias_m[m]; x += bias_g[(m / bias_g_rows)*N + n];
+ *                 if gated:  y[n/2] = x[2j] * act(x[2j+1])   (N_out = N/2)   else  y = act(x);
+ *                 y += residual[(res_row_mod ? m % res_row_mod : m)][n];  store as out_dtype.
+ * conv mode (conv_taps_h > 0): A is an NHWC image [conv_n, conv_h, conv_w, conv_c]; M = conv_n*conv_h*conv_w;
+ *   stride-1 "same" convolution; B is [N, taps*roundup(conv_c,64)] with k = (kh*KW + kw)*Cpad + c.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct seedx_gemm_args {
+  const void* A;       /* fp16 [batch][M][K] (row stride lda) — or NHWC image in conv mode            */
+  const void* B;       /* fp16 [batch or 1][N][K] (row stride ldb), nn.Linear weight layout            */
+  void* D;             /* fp16/fp32 [batch][M][N_out] (row stride ldd)                                 */
+  int64_t M, N, K;
+  int64_t batch;
+  int64_t lda, ldb, ldd;             /* elements */
+  int64_t strideA, strideB, strideD; /* batch strides, elements; strideB == 0 → B shared by all batches */
+  float alpha;
+  const float* bias_n; /* fp32 [N] or NULL */
+  const float* bias_m; /* fp32 [M] or NULL */
+  const float* bias_g; /* fp32 [M / bias_g_rows][N] or NULL (e.g. time-embedding add of a ResnetBlock2D) */
+  int64_t bias_g_rows;
+  const void* residual; /* [batch][M or res_row_mod][N_out] or NULL */
+  int32_t residual_dtype; /* SEEDX_F16 / SEEDX_F32 */
+  int64_t ldr, strideR, res_row_mod;
+  int32_t act;       /* SEEDX_ACT_* */
+  int32_t gated;     /* 0/1 */
+  int32_t out_dtype; /* SEEDX_F16 / SEEDX_F32 */
+  /* conv mode */
+  int32_t conv_taps_h, conv_taps_w; /* 0,0 = plain GEMM; 3,3 or 1,1 */
+  int64_t conv_n, conv_h, conv_w, conv_c;
+  int32_t tile_n;    /* 0 = auto; else 64/128/256 */
+} seedx_gemm_args;
+
+int seedx_gemm_f16(const seedx_gemm_args* args, void* stream);
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused softmax attention (flash-style; scores never reach HBM).  fp16 q/k/v/o, fp32 softmax.
+ *   O[b,h,i,:] = softmax_j(scale * Q[b,h,i,:].K[b,h,j,:] (+causal: j <= i + sk - sq)) V[b,h,j,:]
+ * Strides are in elements; a batch stride of 0 shares the tensor across the batch (learned queries).
+ * replaces: src/models/tokenizer/qwen_visual.py:204-215 (ViT MHSA d=104) and :146 (nn.MultiheadAttention in Resampler,
+ *   d=128/160); src/models/mllm/modeling_llama_xformer.py:225-237 (xformers memory_efficient_attention, causal prefill);
+ *   src/models/detokenizer/resampler.py:62-73,104-116; diffusers AttnProcessor2_0 (F.scaled_dot_product_attention).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct seedx_attn_args {
+  const void* q; const void* k; const void* v; void* o;
+  int64_t q_stride_b, q_stride_h, q_stride_s;
+  int64_t k_stride_b, k_stride_h, k_stride_s;
+  int64_t v_stride_b, v_stride_h, v_stride_s;
+  int64_t o_stride_b, o_stride_h, o_stride_s;
+  int32_t batch, heads, sq, sk, d;
+  float scale;
+  int32_t causal;
+} seedx_attn_args;
+
+int seedx_attention_f16(const seedx_attn_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm (rms=0) / RMSNorm (rms=1) over the last dimension, fp32 statistics.
+ *   y = (x - mean) * rsqrt(var + eps) * gamma + beta ;  out2 (optional) = y + add[row % add_rows][:]
+ * replaces nn.LayerNorm at qwen_visual.py:400,280-281,139-141,414; resampler.py:55-56,279; diffusers
+ *   BasicTransformerBlock.norm{1,2,3}; transformers LlamaRMSNorm used at modeling_llama_xformer.py:95,258-259,443.
+ * ---------------------------------------------------------------------------------------------- */
+int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,
+                    int64_t ldo, void* out2, const float* add, int64_t add_rows, int64_t rows, int64_t cols, float eps,
+                    int rms, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm (+ optional SiLU) on NHWC fp16 images; the input may be the channel-concatenation [x1 | x2] (UNet skip
+ * connections); raw_out (optional) receives the un-normalised concatenation.  stats_ws: n*groups*2 doubles.
+ * replaces diffusers ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm, UNet conv_norm_out, VAE norms
+ *   (SURVEY.md Appendix B.2), reached from pipeline_stable_diffusion_xl_t2i_edit.py:915-922,973.
+ * ---------------------------------------------------------------------------------------------- */
+int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, int64_t c2, int64_t n, int64_t hw, int groups,
+                         const float* gamma, const float* beta, float eps, int silu_act, void* out, void* raw_out,
+                         void* stats_ws, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small HBM-bound data-movement kernels
+ * ---------------------------------------------------------------------------------------------- */
+/* NCHW image -> patch rows [n*gh*gw, kpad] fp16, k = c*p*p + i*p + j, zero padded to kpad
+ * (im2col of the stride-14 patch-embed conv, qwen_visual.py:352,393-396) */
+int seedx_patchify(const void* x, int x_dtype, int64_t n, int64_t c, int64_t h, int64_t w, int64_t patch, void* out,
+                   int64_t kpad, void* stream);
+/* elementwise dtype conversion (fp16 <-> fp32), count elements */
+int seedx_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t count, void* stream);
+/* mean over groups of `k` consecutive tokens: [n, t, c] -> [n, t/k, c]  (F.avg_pool1d at adapter_modules.py:112-115) */
+int seedx_avgpool_tokens(const void* x, int dtype, int64_t n, int64_t t, int64_t c, int64_t k, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEEDX_H_ */

@@ -1,0 +1,435 @@
+// seedx-b200: tcgen05 tensor-core GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   D[b][m][n] = epi( alpha * sum_k A[b][m][k] * B[b][n][k] )      fp16 operands, fp32 accumulate in TMEM
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2..5 = epilogue.
+// Operands are staged by TMA into 128B-swizzled K-major tiles (BM=128 x BK=64, BN x BK=64) through a
+// STAGES-deep mbarrier ring; the accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of
+// tile i overlaps the main loop of tile i+1.  In conv mode the A tile of k-step (tap, channel-chunk) is a
+// shifted [th x tw] pixel window of the NHWC image fetched by a 4-D tensor map, out-of-bounds = zero padding
+// (im2col-free implicit GEMM).
+//
+// Reference call sites replaced: see include/seedx.h (seedx_gemm_f16).
+#include "common.cuh"
+#include "../../include/seedx.h"
+
+namespace seedx {
+
+struct GemmParams {
+  void* D;
+  const float* bias_n;
+  const float* bias_m;
+  const float* bias_g;
+  const void* residual;
+  int M, N, K;
+  int batch;
+  int m_blocks, n_blocks, k_blocks;
+  long long ldd, strideD, ldr, strideR;
+  int res_row_mod, bias_g_rows;
+  float alpha;
+  int act, gated, out_f32, res_f32, vec_ok, b_batched;
+  // conv
+  int conv, taps_w, c_chunks, conv_w, conv_h, tile_w, tile_h, tiles_per_img, tiles_w, pad;
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+template <int BN>
+struct TileCfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two: 128 / 256 / 512
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+SEEDX_DEVINL float apply_act(float x, int act) {
+  if (act == SEEDX_ACT_GELU_ERF) return gelu_erf(x);
+  if (act == SEEDX_ACT_SILU) return silu(x);
+  return x;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tiles_per_batch = p.m_blocks * p.n_blocks;
+  const int num_tiles = tiles_per_batch * p.batch;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int b = t / tiles_per_batch;
+        const int r = t - b * tiles_per_batch;
+        const int n_blk = r / p.m_blocks;
+        const int m_blk = r - n_blk * p.m_blocks;
+        int img = 0, h0 = 0, w0 = 0;
+        if (p.conv) {
+          img = m_blk / p.tiles_per_img;
+          const int rem = m_blk - img * p.tiles_per_img;
+          const int th_i = rem / p.tiles_w;
+          h0 = th_i * p.tile_h;
+          w0 = (rem - th_i * p.tiles_w) * p.tile_w;
+        }
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + A_STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          if (p.conv) {
+            const int tap = kb / p.c_chunks;
+            const int cc = kb - tap * p.c_chunks;
+            const int kh = tap / p.taps_w;
+            const int kw = tap - kh * p.taps_w;
+            tma_load_4d(sa, &tmA, full_bar(stage), cc * BK, w0 + kw - p.pad, h0 + kh - p.pad, img);
+          } else {
+            tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM, b);
+          }
+          tma_load_3d(sb, &tmB, full_bar(stage), kb * BK, n_blk * BN, p.b_batched ? b : 0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (single thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 fp16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps (TMEM -> regs -> global)
+    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int n_out = p.gated ? (p.N >> 1) : p.N;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int b = t / tiles_per_batch;
+      const int r = t - b * tiles_per_batch;
+      const int n_blk = r / p.m_blocks;
+      const int m_blk = r - n_blk * p.m_blocks;
+      const int row = m_blk * BM + lane_grp * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int n0 = n_blk * BN;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
+
+      const float bm = (p.bias_m != nullptr && row_ok) ? p.bias_m[row] : 0.f;
+      const float* bg = (p.bias_g != nullptr && row_ok) ? p.bias_g + (long long)(row / p.bias_g_rows) * p.N : nullptr;
+      const int rrow = p.res_row_mod ? (row % p.res_row_mod) : row;
+
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= p.N) break;  // warp-uniform
+        __syncwarp();              // tcgen05.ld is warp-collective: reconverge after the predicated stores
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        tmem_ld_wait();
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) * p.alpha + bm;
+        const int col0 = n0 + c;
+        if (p.bias_n != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) x[i] += __ldg(p.bias_n + col0 + i);
+        }
+        if (bg != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (col0 + i < p.N) x[i] += __ldg(bg + col0 + i);
+        }
+        int nvals = 32;
+        int ocol0 = col0;
+        if (p.gated) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = x[2 * i] * apply_act(x[2 * i + 1], p.act);
+          nvals = 16;
+          ocol0 = col0 >> 1;
+        } else if (p.act != SEEDX_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = apply_act(x[i], p.act);
+        }
+        if (!row_ok) continue;
+        const bool full = (ocol0 + nvals <= n_out) && p.vec_ok;
+        if (p.residual != nullptr) {
+          if (p.res_f32) {
+            const float* rp = (const float*)p.residual + (long long)b * p.strideR + (long long)rrow * p.ldr + ocol0;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                if (i < nvals) {
+                  const float4 q = *(const float4*)(rp + i);
+                  x[i] += q.x, x[i + 1] += q.y, x[i + 2] += q.z, x[i + 3] += q.w;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nvals && ocol0 + i < n_out) x[i] += rp[i];
+            }
+          } else {
+            const __half* rp = (const __half*)p.residual + (long long)b * p.strideR + (long long)rrow * p.ldr + ocol0;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                if (i < nvals) {
+                  const uint4 q = *(const uint4*)(rp + i);
+                  const __half2* h = (const __half2*)&q;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(h[j]);
+                    x[i + 2 * j] += f.x, x[i + 2 * j + 1] += f.y;
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (i < nvals && ocol0 + i < n_out) x[i] += __half2float(rp[i]);
+            }
+          }
+        }
+        if (p.out_f32) {
+          float* dp = (float*)p.D + (long long)b * p.strideD + (long long)row * p.ldd + ocol0;
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              if (i < nvals) *(float4*)(dp + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvals && ocol0 + i < n_out) dp[i] = x[i];
+          }
+        } else {
+          __half* dp = (__half*)p.D + (long long)b * p.strideD + (long long)row * p.ldd + ocol0;
+          if (full) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              if (i < nvals) {
+                uint4 q;
+                __half2* h = (__half2*)&q;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(x[i + 2 * j], x[i + 2 * j + 1]);
+                *(uint4*)(dp + i) = q;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < nvals && ocol0 + i < n_out) dp[i] = __float2half_rn(x[i]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+void count_launch();
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using Cfg = TileCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SEEDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles = p.m_blocks * p.n_blocks * p.batch;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
+}
+
+}  // namespace seedx
+
+using namespace seedx;
+
+extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
+  SEEDX_REQUIRE(a != nullptr, "seedx_gemm_f16: null args");
+  SEEDX_REQUIRE(a->A && a->B && a->D, "seedx_gemm_f16: null operand pointer");
+  SEEDX_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0 && a->batch > 0, "seedx_gemm_f16: empty problem M=%lld N=%lld K=%lld",
+                (long long)a->M, (long long)a->N, (long long)a->K);
+  SEEDX_REQUIRE(a->K % 8 == 0, "seedx_gemm_f16: K=%lld must be a multiple of 8 (16-byte TMA rows)", (long long)a->K);
+  SEEDX_REQUIRE(((uintptr_t)a->A % 16 == 0) && ((uintptr_t)a->B % 16 == 0), "seedx_gemm_f16: operands must be 16B aligned");
+  SEEDX_REQUIRE(a->out_dtype == SEEDX_F16 || a->out_dtype == SEEDX_F32, "seedx_gemm_f16: bad out_dtype");
+  const bool conv = a->conv_taps_h > 0;
+  GemmParams p{};
+  int bn = a->tile_n;
+  if (bn == 0) bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  SEEDX_REQUIRE(bn == 64 || bn == 128 || bn == 256, "seedx_gemm_f16: tile_n must be 64/128/256");
+  if (a->gated) SEEDX_REQUIRE(a->N % 2 == 0, "seedx_gemm_f16: gated epilogue needs even N");
+
+  CUtensorMap ta, tb;
+  if (!conv) {
+    SEEDX_REQUIRE(a->lda % 8 == 0 && a->lda >= a->K, "seedx_gemm_f16: lda must be >= K and a multiple of 8");
+    uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->batch};
+    uint64_t bstride = a->batch > 1 ? (uint64_t)a->strideA * 2 : (uint64_t)a->lda * 2 * (uint64_t)a->M;
+    SEEDX_REQUIRE(bstride % 16 == 0, "seedx_gemm_f16: strideA must be a multiple of 8 elements");
+    uint64_t strides[2] = {(uint64_t)a->lda * 2, bstride};
+    uint32_t box[3] = {BK, BM, 1};
+    if (int e = encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a->A, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return e;
+    p.k_blocks = (int)((a->K + BK - 1) / BK);
+    p.m_blocks = (int)((a->M + BM - 1) / BM);
+  } else {
+    const int64_t C = a->conv_c, W = a->conv_w, H = a->conv_h, NI = a->conv_n;
+    SEEDX_REQUIRE(C % 8 == 0 && C > 0, "seedx_gemm_f16(conv): channels must be a multiple of 8");
+    SEEDX_REQUIRE(a->conv_taps_h == a->conv_taps_w && (a->conv_taps_h == 1 || a->conv_taps_h == 3),
+                  "seedx_gemm_f16(conv): only 1x1 and 3x3 kernels");
+    int tw, th;
+    if (W <= 128) {
+      SEEDX_REQUIRE(128 % W == 0, "seedx_gemm_f16(conv): width %lld must divide 128", (long long)W);
+      tw = (int)W, th = (int)(128 / W);
+      SEEDX_REQUIRE(H % th == 0, "seedx_gemm_f16(conv): height %lld not a multiple of tile height %d", (long long)H, th);
+    } else {
+      SEEDX_REQUIRE(W % 128 == 0, "seedx_gemm_f16(conv): width %lld must be a multiple of 128", (long long)W);
+      tw = 128, th = 1;
+    }
+    SEEDX_REQUIRE(a->M == NI * H * W, "seedx_gemm_f16(conv): M != n*h*w");
+    const int cchunks = (int)((C + BK - 1) / BK);
+    SEEDX_REQUIRE(a->K == (int64_t)a->conv_taps_h * a->conv_taps_w * cchunks * BK,
+                  "seedx_gemm_f16(conv): K=%lld must equal taps*roundup(C,64)=%lld", (long long)a->K,
+                  (long long)a->conv_taps_h * a->conv_taps_w * cchunks * BK);
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
+    uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)th, 1};
+    if (int e = encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a->A, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return e;
+    p.conv = 1;
+    p.taps_w = a->conv_taps_w;
+    p.c_chunks = cchunks;
+    p.conv_w = (int)W, p.conv_h = (int)H;
+    p.tile_w = tw, p.tile_h = th;
+    p.tiles_w = (int)(W / tw);
+    p.tiles_per_img = (int)((H / th) * (W / tw));
+    p.pad = a->conv_taps_h / 2;
+    p.k_blocks = a->conv_taps_h * a->conv_taps_w * cchunks;
+    p.m_blocks = (int)(a->M / BM);
+  }
+  {
+    SEEDX_REQUIRE(a->ldb % 8 == 0 && a->ldb >= a->K, "seedx_gemm_f16: ldb must be >= K and a multiple of 8");
+    const bool bb = a->batch > 1 && a->strideB != 0;
+    uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->N, (uint64_t)(bb ? a->batch : 1)};
+    uint64_t bstride = bb ? (uint64_t)a->strideB * 2 : (uint64_t)a->ldb * 2 * (uint64_t)a->N;
+    SEEDX_REQUIRE(bstride % 16 == 0, "seedx_gemm_f16: strideB must be a multiple of 8 elements");
+    uint64_t strides[2] = {(uint64_t)a->ldb * 2, bstride};
+    uint32_t box[3] = {BK, (uint32_t)bn, 1};
+    if (int e = encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a->B, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+      return e;
+    p.b_batched = bb ? 1 : 0;
+  }
+  p.D = a->D;
+  p.bias_n = a->bias_n, p.bias_m = a->bias_m, p.bias_g = a->bias_g;
+  p.bias_g_rows = a->bias_g ? (int)a->bias_g_rows : 1;
+  SEEDX_REQUIRE(p.bias_g_rows > 0, "seedx_gemm_f16: bias_g_rows must be > 0");
+  p.residual = a->residual;
+  p.M = (int)a->M, p.N = (int)a->N, p.K = (int)a->K, p.batch = (int)a->batch;
+  p.n_blocks = (int)((a->N + bn - 1) / bn);
+  p.ldd = a->ldd, p.strideD = a->strideD, p.ldr = a->ldr, p.strideR = a->strideR;
+  p.res_row_mod = (int)a->res_row_mod;
+  p.alpha = a->alpha;
+  p.act = a->act, p.gated = a->gated;
+  p.out_f32 = a->out_dtype == SEEDX_F32;
+  p.res_f32 = a->residual_dtype == SEEDX_F32;
+  if (a->residual) SEEDX_REQUIRE(a->residual_dtype == SEEDX_F16 || a->residual_dtype == SEEDX_F32, "seedx_gemm_f16: bad residual_dtype");
+  // vector epilogue needs 16-byte aligned rows on D (and residual)
+  const int oe = p.out_f32 ? 4 : 8;
+  bool vec = ((uintptr_t)a->D % 16 == 0) && (a->ldd % oe == 0) && (a->strideD % oe == 0);
+  if (a->residual) {
+    const int re = p.res_f32 ? 4 : 8;
+    vec = vec && ((uintptr_t)a->residual % 16 == 0) && (a->ldr % re == 0) && (a->strideR % re == 0);
+  }
+  p.vec_ok = vec ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bn == 256) return launch_gemm<256>(ta, tb, p, st);
+  if (bn == 128) return launch_gemm<128>(ta, tb, p, st);
+  return launch_gemm<64>(ta, tb, p, st);
+}

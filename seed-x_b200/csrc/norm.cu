@@ -1,0 +1,230 @@
+// seedx-b200: normalisation kernels (HBM-bound, fp32 statistics).
+//
+//  * seedx_layernorm  : LayerNorm / RMSNorm over the last dim, fp16|fp32 in -> fp16|fp32 out, optional second output
+//                       out2 = y + add[row % add_rows]  (positional embedding add of the Resampler key path)
+//      replaces nn.LayerNorm at src/models/tokenizer/qwen_visual.py:400,280-281,139-141,414,
+//               src/models/detokenizer/resampler.py:55-56,279, diffusers BasicTransformerBlock norms,
+//               LlamaRMSNorm (transformers) used at src/models/mllm/modeling_llama_xformer.py:95,258-259,443
+//  * seedx_groupnorm_nhwc : GroupNorm(32) (+SiLU) on NHWC fp16 images, optional channel-concat of two sources
+//      replaces diffusers ResnetBlock2D/Transformer2DModel/VAE GroupNorm+SiLU.
+#include "common.cuh"
+#include "../../include/seedx.h"
+
+namespace seedx {
+
+void count_launch();
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm / RMSNorm : one CTA (256 threads) per row, row cached in registers (cols <= 8192)
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_THREADS = 256;
+constexpr int LN_MAXPT = 32;
+
+SEEDX_DEVINL float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float t = (l < (int)(blockDim.x >> 5)) ? sh[l] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(LN_THREADS)
+layernorm_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 TO* __restrict__ out, long long ldo, TO* __restrict__ out2, const float* __restrict__ add, int add_rows,
+                 int cols, float eps, int rms) {
+  __shared__ float sh[8];
+  const long long row = blockIdx.x;
+  const TI* xr = x + row * ldx;
+  float v[LN_MAXPT];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXPT; ++i) {
+    const int c = threadIdx.x + i * LN_THREADS;
+    v[i] = (c < cols) ? (float)xr[c] : 0.f;
+    s += v[i];
+  }
+  float mean = 0.f;
+  if (!rms) mean = block_sum(s, sh) / (float)cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXPT; ++i) {
+    const int c = threadIdx.x + i * LN_THREADS;
+    const float d = (c < cols) ? (v[i] - mean) : 0.f;
+    q += d * d;
+  }
+  const float var = block_sum(q, sh) / (float)cols;
+  const float rstd = rsqrtf(var + eps);
+  TO* orow = out + row * ldo;
+  TO* orow2 = out2 ? out2 + row * ldo : nullptr;
+  const float* arow = add ? add + (long long)(row % add_rows) * cols : nullptr;
+#pragma unroll
+  for (int i = 0; i < LN_MAXPT; ++i) {
+    const int c = threadIdx.x + i * LN_THREADS;
+    if (c < cols) {
+      float y = (v[i] - mean) * rstd;
+      if (gamma) y *= gamma[c];
+      if (beta) y += beta[c];
+      orow[c] = (TO)y;
+      if (orow2) orow2[c] = (TO)(y + arow[c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm on NHWC fp16, 2 passes: (1) per-(image, group) sum / sum-of-squares (fp32 partials, fp64 atomics),
+// (2) apply per-channel scale/shift (+SiLU).  Input may be the channel concatenation of two tensors.
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_PIX_PER_BLOCK = 64;
+
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int hw, int groups,
+                double* __restrict__ stats /*[n][groups][2]*/) {
+  extern __shared__ float gsm[];  // [groups][2]
+  const int n = blockIdx.y;
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) gsm[i] = 0.f;
+  __syncthreads();
+  const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
+  const int p1 = min(p0 + GN_PIX_PER_BLOCK, hw);
+  const int vec_per_pix = C >> 3;  // 8 halves per 16-byte vector; c1, c2 multiples of 8
+  const int total = (p1 - p0) * vec_per_pix;
+  // each thread owns a fixed channel-vector when blockDim % vec_per_pix == 0 is not guaranteed -> accumulate per element
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int pix = p0 + idx / vec_per_pix;
+    const int cv = (idx % vec_per_pix) * 8;
+    const __half* src = (cv < c1) ? x1 + ((long long)n * hw + pix) * c1 + cv : x2 + ((long long)n * hw + pix) * c2 + (cv - c1);
+    const uint4 q = *(const uint4*)src;
+    const __half2* h = (const __half2*)&q;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __half22float2(h[j]);
+      f[2 * j] = t.x, f[2 * j + 1] = t.y;
+    }
+    // the 8 channels span at most two groups when cpg >= 8, more when cpg < 8: handle generally
+    int g_prev = cv / cpg;
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (cv + j) / cpg;
+      if (g != g_prev) {
+        atomicAdd(&gsm[2 * g_prev], s);
+        atomicAdd(&gsm[2 * g_prev + 1], ss);
+        s = 0.f, ss = 0.f, g_prev = g;
+      }
+      s += f[j], ss += f[j] * f[j];
+    }
+    atomicAdd(&gsm[2 * g_prev], s);
+    atomicAdd(&gsm[2 * g_prev + 1], ss);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&stats[(long long)n * groups * 2 + i], (double)gsm[i]);
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int hw, int groups,
+                const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float eps, int silu_act, __half* __restrict__ out, __half* __restrict__ raw_out, int pix_per_block) {
+  extern __shared__ float ssm[];  // scale[C], shift[C]
+  const int n = blockIdx.y;
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  float* scale = ssm;
+  float* shift = ssm + C;
+  const double cnt = (double)hw * (double)cpg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double m = stats[((long long)n * groups + g) * 2] / cnt;
+    double var = stats[((long long)n * groups + g) * 2 + 1] / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    scale[c] = rstd * ga;
+    shift[c] = be - (float)m * rstd * ga;
+  }
+  __syncthreads();
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, hw);
+  const int vec_per_pix = C >> 3;
+  const int total = (p1 - p0) * vec_per_pix;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int pix = p0 + idx / vec_per_pix;
+    const int cv = (idx % vec_per_pix) * 8;
+    const __half* src = (cv < c1) ? x1 + ((long long)n * hw + pix) * c1 + cv : x2 + ((long long)n * hw + pix) * c2 + (cv - c1);
+    const uint4 q = *(const uint4*)src;
+    const long long ooff = ((long long)n * hw + pix) * C + cv;
+    if (raw_out) *(uint4*)(raw_out + ooff) = q;
+    const __half2* h = (const __half2*)&q;
+    uint4 o;
+    __half2* oh = (__half2*)&o;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 t = __half22float2(h[j]);
+      float a = t.x * scale[cv + 2 * j] + shift[cv + 2 * j];
+      float b = t.y * scale[cv + 2 * j + 1] + shift[cv + 2 * j + 1];
+      if (silu_act) a = silu(a), b = silu(b);
+      oh[j] = __floats2half2_rn(a, b);
+    }
+    *(uint4*)(out + ooff) = o;
+  }
+}
+
+}  // namespace seedx
+
+using namespace seedx;
+
+extern "C" int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out,
+                               int out_dtype, int64_t ldo, void* out2, const float* add, int64_t add_rows, int64_t rows,
+                               int64_t cols, float eps, int rms, void* stream) {
+  SEEDX_REQUIRE(x && out, "seedx_layernorm: null pointer");
+  SEEDX_REQUIRE(rows > 0 && cols > 0 && cols <= LN_THREADS * LN_MAXPT, "seedx_layernorm: cols=%lld out of range (1..%d)", (long long)cols,
+                LN_THREADS * LN_MAXPT);
+  SEEDX_REQUIRE((out2 == nullptr) == (add == nullptr), "seedx_layernorm: out2 and add go together");
+  if (add) SEEDX_REQUIRE(add_rows > 0, "seedx_layernorm: add_rows must be > 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((unsigned)rows);
+#define LN_LAUNCH(TI, TO)                                                                                                  \
+  layernorm_kernel<TI, TO><<<grid, LN_THREADS, 0, st>>>((const TI*)x, ldx, gamma, beta, (TO*)out, ldo, (TO*)out2, add, \
+                                                        (int)(add ? add_rows : 1), (int)cols, eps, rms)
+  if (x_dtype == SEEDX_F32 && out_dtype == SEEDX_F16) LN_LAUNCH(float, __half);
+  else if (x_dtype == SEEDX_F32 && out_dtype == SEEDX_F32) LN_LAUNCH(float, float);
+  else if (x_dtype == SEEDX_F16 && out_dtype == SEEDX_F16) LN_LAUNCH(__half, __half);
+  else if (x_dtype == SEEDX_F16 && out_dtype == SEEDX_F32) LN_LAUNCH(__half, float);
+  else SEEDX_REQUIRE(false, "seedx_layernorm: bad dtype combination");
+#undef LN_LAUNCH
+  count_launch();
+  return check_cuda(cudaGetLastError(), "layernorm_kernel launch");
+}
+
+extern "C" int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, int64_t c2, int64_t n, int64_t hw, int groups,
+                                    const float* gamma, const float* beta, float eps, int silu_act, void* out, void* raw_out,
+                                    void* stats_ws, void* stream) {
+  SEEDX_REQUIRE(x1 && out && stats_ws, "seedx_groupnorm_nhwc: null pointer");
+  const int64_t C = c1 + (x2 ? c2 : 0);
+  if (!x2) c2 = 0;
+  SEEDX_REQUIRE(c1 % 8 == 0 && c2 % 8 == 0 && groups > 0 && C % groups == 0, "seedx_groupnorm_nhwc: bad channel counts c1=%lld c2=%lld",
+                (long long)c1, (long long)c2);
+  SEEDX_REQUIRE(n > 0 && n <= 65535 && hw > 0, "seedx_groupnorm_nhwc: bad n/hw");
+  cudaStream_t st = (cudaStream_t)stream;
+  SEEDX_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * groups * n, st));
+  dim3 g1((unsigned)((hw + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK), (unsigned)n);
+  gn_stats_kernel<<<g1, 256, groups * 2 * sizeof(float), st>>>((const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw, groups,
+                                                               (double*)stats_ws);
+  count_launch();
+  SEEDX_CUDA(cudaGetLastError());
+  // apply: aim for ~4 waves of 148 SMs, at least 16 pixels per block
+  int64_t ppb = (hw * n + 148 * 8 - 1) / (148 * 8);
+  if (ppb < 16) ppb = 16;
+  if (ppb > hw) ppb = hw;
+  dim3 g2((unsigned)((hw + ppb - 1) / ppb), (unsigned)n);
+  const size_t smem = (size_t)C * 2 * sizeof(float);
+  gn_apply_kernel<<<g2, 256, smem, st>>>((const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw, groups, (const double*)stats_ws,
+                                         gamma, beta, eps, silu_act, (__half*)out, (__half*)raw_out, (int)ppb);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "groupnorm kernels launch");
+}

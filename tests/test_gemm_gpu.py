@@ -1,0 +1,103 @@
+"""Parity of the tcgen05 GEMM / implicit-GEMM conv (seedx_gemm_f16) against a torch fp32 reference of the same op.
+
+Tolerance: operands are fp16 (exactly representable in fp32), accumulation fp32 -> the only differences are the
+summation order and the final rounding to the output dtype: rel-Frobenius <= 2e-3 for fp16 out, 1e-5 for fp32 out.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+def mk(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (1024, 1664, 1664), (200, 328, 72),
+                                   (2048, 4992, 1664), (174, 5120, 5120), (77, 40, 8), (1, 32330, 256)])
+@pytest.mark.parametrize("tile_n", [0, 64, 128])
+def test_gemm_plain(M, N, K, tile_n):
+    from seedx_b200 import ops
+    a = mk((M, K), 1).half()
+    w = mk((N, K), 2, K ** -0.5).half()
+    ref = a.float() @ w.float().t()
+    out32 = ops.gemm(a, w, out_dtype=torch.float32, tile_n=tile_n)
+    assert rel(out32, ref) < 1e-5
+    out16 = ops.gemm(a, w, out_dtype=torch.float16, tile_n=tile_n)
+    assert rel(out16, ref) < 2e-3
+
+
+def test_gemm_epilogues():
+    from seedx_b200 import ops
+    M, N, K = 384, 768, 320
+    a = mk((M, K), 3).half()
+    w = mk((N, K), 4, K ** -0.5).half()
+    bias = mk((N,), 5)
+    bias_m = mk((M,), 6)
+    res32 = mk((M, N), 7)
+    res16 = mk((M, N), 8).half()
+    acc = a.float() @ w.float().t()
+    # bias + gelu
+    o = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, out_dtype=torch.float32)
+    assert rel(o, F.gelu(acc + bias)) < 1e-5
+    # bias + fp32 residual in place
+    r = res32.clone()
+    ops.gemm(a, w, out=r, bias=bias, residual=r)
+    assert rel(r, acc + bias + res32) < 1e-5
+    # fp16 residual, fp16 out, alpha, bias_m
+    o = ops.gemm(a, w, bias_m=bias_m, residual=res16, alpha=0.5, out_dtype=torch.float16)
+    assert rel(o, 0.5 * acc + bias_m[:, None] + res16.float()) < 2e-3
+    # gated (GEGLU with interleaved columns): y[j] = x[2j] * gelu(x[2j+1])
+    o = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, gated=True, out_dtype=torch.float32)
+    x = acc + bias
+    assert rel(o, x[:, 0::2] * F.gelu(x[:, 1::2])) < 1e-5
+    o = ops.gemm(a, w, act=ops.ACT_SILU, gated=True, out_dtype=torch.float16)
+    assert rel(o, acc[:, 0::2] * F.silu(acc[:, 1::2])) < 2e-3
+    # row-modulo residual (positional-embedding broadcast) + per-row-group bias
+    pos = mk((128, N), 9)
+    bg = mk((3, N), 10)
+    o = ops.gemm(a, w, residual=pos, res_row_mod=128, bias_g=bg, bias_g_rows=128, out_dtype=torch.float32)
+    assert rel(o, acc + pos.repeat(3, 1) + bg.repeat_interleave(128, 0)) < 1e-5
+
+
+def test_gemm_batched_strided():
+    from seedx_b200 import ops
+    B, M, N, K = 5, 200, 136, 104
+    a_full = mk((B, M, 3 * K + 8), 11).half()
+    a = a_full[:, :, K:2 * K]           # strided view (lda = 3K+8), offset 16B aligned (K*2 = 208 B)
+    w = mk((B, N, K), 12, K ** -0.5).half()
+    ref = torch.einsum("bmk,bnk->bmn", a.float(), w.float())
+    o = ops.gemm(a, w, out_dtype=torch.float32)
+    assert rel(o, ref) < 1e-5
+    w1 = w[0].contiguous()
+    o = ops.gemm(a, w1, out_dtype=torch.float32)  # shared B
+    assert rel(o, torch.einsum("bmk,nk->bmn", a.float(), w1.float())) < 1e-5
+
+
+@pytest.mark.parametrize("n,h,w,c,cout,taps", [(2, 32, 32, 128, 192, 3), (1, 64, 64, 320, 320, 3), (2, 128, 128, 64, 64, 3),
+                                               (1, 256, 256, 128, 24, 3), (3, 16, 16, 8, 320, 3), (2, 32, 32, 960, 640, 1),
+                                               (1, 128, 128, 8, 320, 3)])
+def test_conv_nhwc(n, h, w, c, cout, taps):
+    from seedx_b200 import ops
+    x = mk((n, c, h, w), 21).half()
+    wt = mk((cout, c, taps, taps), 22, (c * taps * taps) ** -0.5).half()
+    bias = mk((cout,), 23)
+    temb = mk((n, cout), 24)
+    ref = F.conv2d(x.float(), wt.float(), bias=bias, padding=taps // 2) + temb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    cpad = (c + 63) // 64 * 64
+    wp = torch.zeros((cout, taps, taps, cpad), dtype=torch.float16, device="cuda")
+    wp[..., :c] = wt.permute(0, 2, 3, 1)
+    wp = wp.reshape(cout, taps * taps * cpad).contiguous()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    o = ops.conv2d_nhwc(xn, wp, taps=taps, bias=bias, bias_g=temb, out_dtype=torch.float32)
+    assert rel(o, ref) < 1e-5
+    res = mk((n, h, w, cout), 25).half()
+    o = ops.conv2d_nhwc(xn, wp, taps=taps, bias=bias, bias_g=temb, residual=res, out_dtype=torch.float16)
+    assert rel(o, ref + res.float()) < 2e-3
