@@ -112,3 +112,106 @@ def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None
     g.tile_n = tile_n
     check(lib().seedx_gemm_f16(C.byref(g), _stream()), "seedx_gemm_f16(conv)")
     return out
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+        ("q_sb", C.c_int64), ("q_sh", C.c_int64), ("q_ss", C.c_int64),
+        ("k_sb", C.c_int64), ("k_sh", C.c_int64), ("k_ss", C.c_int64),
+        ("v_sb", C.c_int64), ("v_sh", C.c_int64), ("v_ss", C.c_int64),
+        ("o_sb", C.c_int64), ("o_sh", C.c_int64), ("o_ss", C.c_int64),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("sq", C.c_int32), ("sk", C.c_int32), ("d", C.c_int32),
+        ("scale", C.c_float), ("causal", C.c_int32),
+    ]
+
+
+def attention(q, k, v, out, *, scale, causal=False):
+    """q/k/v/out: fp16 4-D views indexed [batch, head, seq, d] (any strides with d contiguous; q batch stride may be 0)."""
+    _require_cuda(q, k, v, out)
+    for t in (q, k, v, out):
+        assert t.dtype == torch.float16 and t.dim() == 4 and t.stride(3) == 1
+    B, H, Sq, D = out.shape
+    Sk = k.shape[2]
+    a = AttnArgs()
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.q_sb, a.q_sh, a.q_ss = (q.stride(0) if q.shape[0] > 1 or B == 1 else 0), q.stride(1), q.stride(2)
+    if q.shape[0] == 1 and B > 1:
+        a.q_sb = 0
+    a.k_sb, a.k_sh, a.k_ss = k.stride(0), k.stride(1), k.stride(2)
+    a.v_sb, a.v_sh, a.v_ss = v.stride(0), v.stride(1), v.stride(2)
+    a.o_sb, a.o_sh, a.o_ss = out.stride(0), out.stride(1), out.stride(2)
+    a.batch, a.heads, a.sq, a.sk, a.d = B, H, Sq, Sk, D
+    a.scale, a.causal = float(scale), int(causal)
+    check(lib().seedx_attention_f16(C.byref(a), _stream()), "seedx_attention_f16")
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out=None, *, out_dtype=torch.float16, rms=False, add=None, out2=None):
+    """LayerNorm / RMSNorm over the last dim of a 2-D (rows, cols) view; optional out2 = y + add[row % add_rows]."""
+    _require_cuda(x, out)
+    x2 = x.reshape(-1, x.shape[-1])
+    assert x2.stride(1) == 1
+    rows, cols = x2.shape
+    if out is None:
+        out = torch.empty((rows, cols), device=x.device, dtype=out_dtype)
+    o2 = out.reshape(-1, cols)
+    assert o2.stride(1) == 1
+    if add is not None:
+        assert add.dtype == torch.float32 and add.is_contiguous() and add.shape[-1] == cols
+        if out2 is None:
+            out2 = torch.empty_like(o2)
+        assert out2.stride(-2) == o2.stride(0) and out2.dtype == out.dtype
+    fn = lib().seedx_layernorm
+    check(fn(_ptr(x2), _dt(x2), C.c_int64(x2.stride(0)), _ptr(gamma), _ptr(beta), _ptr(o2), _dt(o2), C.c_int64(o2.stride(0)),
+             _ptr(out2), _ptr(add), C.c_int64(add.shape[0] if add is not None else 0), C.c_int64(rows), C.c_int64(cols),
+             C.c_float(eps), C.c_int(int(rms)), _stream()), "seedx_layernorm")
+    return (out, out2) if add is not None else out
+
+
+def groupnorm_nhwc(x1, gamma, beta, eps, *, x2=None, silu=False, groups=32, out=None, raw_out=None, stats_ws=None):
+    """GroupNorm(+SiLU) over NHWC fp16 [N,H,W,C1] (optionally channel-concatenated with x2 [N,H,W,C2])."""
+    _require_cuda(x1, x2, out)
+    assert x1.dtype == torch.float16 and x1.is_contiguous()
+    n, h, w, c1 = x1.shape
+    c2 = 0
+    if x2 is not None:
+        assert x2.dtype == torch.float16 and x2.is_contiguous() and x2.shape[:3] == x1.shape[:3]
+        c2 = x2.shape[3]
+    if out is None:
+        out = torch.empty((n, h, w, c1 + c2), device=x1.device, dtype=torch.float16)
+    if stats_ws is None:
+        stats_ws = torch.empty((n * groups * 2,), device=x1.device, dtype=torch.float64)
+    check(lib().seedx_groupnorm_nhwc(_ptr(x1), C.c_int64(c1), _ptr(x2), C.c_int64(c2), C.c_int64(n), C.c_int64(h * w), C.c_int(groups),
+                                     _ptr(gamma), _ptr(beta), C.c_float(eps), C.c_int(int(silu)), _ptr(out), _ptr(raw_out), _ptr(stats_ws),
+                                     _stream()), "seedx_groupnorm_nhwc")
+    return out
+
+
+def patchify(x, patch, kpad):
+    _require_cuda(x)
+    assert x.is_contiguous() and x.dim() == 4
+    n, c, h, w = x.shape
+    out = torch.empty((n * (h // patch) * (w // patch), kpad), device=x.device, dtype=torch.float16)
+    check(lib().seedx_patchify(_ptr(x), _dt(x), C.c_int64(n), C.c_int64(c), C.c_int64(h), C.c_int64(w), C.c_int64(patch), _ptr(out),
+                               C.c_int64(kpad), _stream()), "seedx_patchify")
+    return out
+
+
+def cast(x, dtype, out=None):
+    _require_cuda(x)
+    assert x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    check(lib().seedx_cast(_ptr(x), _dt(x), _ptr(out), _dt(out), C.c_int64(x.numel()), _stream()), "seedx_cast")
+    return out
+
+
+def avgpool_tokens(x, k):
+    _require_cuda(x)
+    assert x.is_contiguous() and x.dim() == 3
+    n, t, c = x.shape
+    out = torch.empty((n, t // k, c), device=x.device, dtype=x.dtype)
+    check(lib().seedx_avgpool_tokens(_ptr(x), _dt(x), C.c_int64(n), C.c_int64(t), C.c_int64(c), C.c_int64(k), _ptr(out), _stream()),
+          "seedx_avgpool_tokens")
+    return out

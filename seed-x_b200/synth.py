@@ -1,0 +1,236 @@
+"""Deterministic synthetic weights / inputs (no checkpoints or tokenizer files exist offline).
+
+Every tensor is a pure function of (seed, name, shape): values come from a torch CPU generator seeded by a hash of the
+name, so the CPU oracle, the golden-vector script and the CUDA path all see identical parameters.  Tensor names and
+shapes follow the reference modules' state dicts.  Linear/conv weights use std = fan_in^-0.5
+so branch outputs are O(1) and softmaxes are non-uniform.
+"""
+import hashlib
+import math
+from collections import OrderedDict
+
+import torch
+
+SEED = 1234
+
+
+def _gen(name, seed):
+    h = hashlib.sha256(f"{seed}:{name}".encode()).digest()
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int.from_bytes(h[:8], "little") & ((1 << 62) - 1))
+    return g
+
+
+def randn(name, shape, std=1.0, mean=0.0, seed=SEED):
+    t = torch.randn(tuple(shape), generator=_gen(name, seed), dtype=torch.float32)
+    # fp16-representable values: the reference checkpoints are fp16 tensors, so the oracle (fp32 math) and the CUDA path
+    # (fp16 operands) start from bit-identical parameters and inputs
+    return (t * std + mean).half().float()
+
+
+def sincos_2d(embed_dim, grid):
+    """Fixed 2-D sin/cos table of the Resampler (restates qwen_visual.py:44-91): first half encodes the x (width)
+    coordinate, second half y; each half = [sin(p*w_i) | cos(p*w_i)], w_i = 10000^(-i/(D/4))."""
+    q = embed_dim // 4
+    omega = 1.0 / (10000.0 ** (torch.arange(q, dtype=torch.float32) / float(q)))
+    ys, xs = torch.meshgrid(torch.arange(grid, dtype=torch.float32), torch.arange(grid, dtype=torch.float32), indexing="ij")
+
+    def enc(p):
+        o = p.reshape(-1, 1) * omega.reshape(1, -1)
+        return torch.cat([torch.sin(o), torch.cos(o)], dim=1)
+
+    return torch.cat([enc(xs), enc(ys)], dim=1)  # kept fp32: a buffer the reference rebuilds at construction
+
+
+def _norm(sd, prefix, dim, bias=True):
+    sd[prefix + ".weight"] = randn(prefix + ".weight", (dim,), 0.1, 1.0)
+    if bias:
+        sd[prefix + ".bias"] = randn(prefix + ".bias", (dim,), 0.1)
+
+
+def _linear(sd, prefix, out_f, in_f, bias=True, wname="weight"):
+    sd[f"{prefix}.{wname}"] = randn(f"{prefix}.{wname}", (out_f, in_f), in_f ** -0.5)
+    if bias:
+        sd[prefix + ".bias"] = randn(prefix + ".bias", (out_f,), 0.1)
+
+
+def resampler_state_dict(prefix, grid, embed_dim, kv_dim, sd=None):
+    """qwen_visual.Resampler parameters (attn_pool / input_resampler / output_resampler)."""
+    sd = OrderedDict() if sd is None else sd
+    p = prefix
+    sd[p + "pos_embed"] = sincos_2d(embed_dim, grid)
+    sd[p + "query"] = randn(p + "query", (grid * grid, embed_dim), 1.0)
+    if kv_dim != embed_dim:
+        sd[p + "kv_proj.weight"] = randn(p + "kv_proj.weight", (embed_dim, kv_dim), kv_dim ** -0.5)
+    sd[p + "attn.in_proj_weight"] = randn(p + "attn.in_proj_weight", (3 * embed_dim, embed_dim), embed_dim ** -0.5)
+    sd[p + "attn.in_proj_bias"] = randn(p + "attn.in_proj_bias", (3 * embed_dim,), 0.1)
+    _linear(sd, p + "attn.out_proj", embed_dim, embed_dim)
+    _norm(sd, p + "ln_q", embed_dim)
+    _norm(sd, p + "ln_kv", embed_dim)
+    return sd
+
+
+def vit_state_dict(width=1664, layers=48, heads=16, mlp_width=8192, output_dim=4096, n_queries=256, patch=14):
+    """VisionTransformerWithAttnPool parameters (qwen_visual.py:325-385)."""
+    sd = OrderedDict()
+    sd["positional_embedding"] = randn("positional_embedding", (256, width), width ** -0.5)
+    sd["proj"] = randn("proj", (output_dim, output_dim), output_dim ** -0.5)
+    sd["conv1.weight"] = randn("conv1.weight", (width, 3, patch, patch), (3 * patch * patch) ** -0.5)
+    _norm(sd, "ln_pre", width)
+    for i in range(layers):
+        p = f"transformer.resblocks.{i}."
+        _norm(sd, p + "ln_1", width)
+        _norm(sd, p + "ln_2", width)
+        _linear(sd, p + "attn.in_proj", 3 * width, width)
+        _linear(sd, p + "attn.out_proj", width, width)
+        _linear(sd, p + "mlp.c_fc", mlp_width, width)
+        _linear(sd, p + "mlp.c_proj", width, mlp_width)
+    resampler_state_dict("attn_pool.", int(math.isqrt(n_queries)), output_dim, width, sd)
+    _norm(sd, "ln_post", output_dim)
+    return sd
+
+
+def image(name, n, size, seed=SEED):
+    """CLIP-normalised-looking image batch [n,3,size,size] fp32."""
+    return randn(name, (n, 3, size, size), 1.0, seed=seed)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# SDXL UNet / VAE parameters (diffusers state-dict names)
+# ----------------------------------------------------------------------------------------------------------------------
+SDXL_UNET = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280), layers_per_block=2,
+                 down_attn=(False, True, True), transformer_layers=(1, 2, 10), heads=(5, 10, 20), cross_attention_dim=2048,
+                 time_embed_dim=1280, addition_time_embed_dim=256, text_embed_dim=1280, groups=32)
+SDXL_VAE = dict(block_out_channels=(128, 256, 512, 512), layers_per_block=2, latent_channels=4, groups=32, scaling_factor=0.13025)
+# scaled-down configs with the same topology for oracle-sized parity tests
+TINY_UNET = dict(in_channels=4, out_channels=4, block_out_channels=(64, 128, 256), layers_per_block=2,
+                 down_attn=(False, True, True), transformer_layers=(1, 1, 2), heads=(1, 2, 4), cross_attention_dim=128,
+                 time_embed_dim=256, addition_time_embed_dim=32, text_embed_dim=64, groups=32)
+TINY_VAE = dict(block_out_channels=(32, 64, 64, 64), layers_per_block=1, latent_channels=4, groups=32, scaling_factor=0.13025)
+
+
+def _conv(sd, p, cout, cin, k, gain=1.0):
+    sd[p + ".weight"] = randn(p + ".weight", (cout, cin, k, k), gain * (cin * k * k) ** -0.5)
+    sd[p + ".bias"] = randn(p + ".bias", (cout,), 0.05)
+
+
+def _lin(sd, p, out_f, in_f, bias=True, gain=1.0):
+    sd[p + ".weight"] = randn(p + ".weight", (out_f, in_f), gain * in_f ** -0.5)
+    if bias:
+        sd[p + ".bias"] = randn(p + ".bias", (out_f,), 0.05)
+
+
+def _resnet(sd, p, cin, cout, temb):
+    _norm(sd, p + ".norm1", cin)
+    _conv(sd, p + ".conv1", cout, cin, 3)
+    if temb:
+        _lin(sd, p + ".time_emb_proj", cout, temb)
+    _norm(sd, p + ".norm2", cout)
+    _conv(sd, p + ".conv2", cout, cout, 3, gain=0.5)
+    if cin != cout:
+        _conv(sd, p + ".conv_shortcut", cout, cin, 1)
+
+
+def _transformer(sd, p, c, depth, ctx_dim):
+    _norm(sd, p + ".norm", c)
+    _lin(sd, p + ".proj_in", c, c)
+    for k in range(depth):
+        b = f"{p}.transformer_blocks.{k}"
+        for n in ("norm1", "norm2", "norm3"):
+            _norm(sd, f"{b}.{n}", c)
+        for a, kd in (("attn1", c), ("attn2", ctx_dim)):
+            _lin(sd, f"{b}.{a}.to_q", c, c, bias=False)
+            _lin(sd, f"{b}.{a}.to_k", c, kd, bias=False)
+            _lin(sd, f"{b}.{a}.to_v", c, kd, bias=False)
+            _lin(sd, f"{b}.{a}.to_out.0", c, c, gain=0.5)
+        _lin(sd, f"{b}.ff.net.0.proj", 8 * c, c)
+        _lin(sd, f"{b}.ff.net.2", c, 4 * c, gain=0.5)
+    _lin(sd, p + ".proj_out", c, c, gain=0.5)
+
+
+def unet_state_dict(cfg, prefix=""):
+    sd = OrderedDict()
+    boc = cfg["block_out_channels"]
+    te = cfg["time_embed_dim"]
+    nb = len(boc)
+    _conv(sd, "conv_in", boc[0], cfg["in_channels"], 3)
+    _lin(sd, "time_embedding.linear_1", te, boc[0])
+    _lin(sd, "time_embedding.linear_2", te, te)
+    _lin(sd, "add_embedding.linear_1", te, cfg["text_embed_dim"] + 6 * cfg["addition_time_embed_dim"])
+    _lin(sd, "add_embedding.linear_2", te, te)
+    ch = boc[0]
+    for i in range(nb):
+        for j in range(cfg["layers_per_block"]):
+            _resnet(sd, f"down_blocks.{i}.resnets.{j}", ch, boc[i], te)
+            ch = boc[i]
+            if cfg["down_attn"][i]:
+                _transformer(sd, f"down_blocks.{i}.attentions.{j}", ch, cfg["transformer_layers"][i], cfg["cross_attention_dim"])
+        if i < nb - 1:
+            _conv(sd, f"down_blocks.{i}.downsamplers.0.conv", ch, ch, 3)
+    _resnet(sd, "mid_block.resnets.0", ch, ch, te)
+    _transformer(sd, "mid_block.attentions.0", ch, cfg["transformer_layers"][-1], cfg["cross_attention_dim"])
+    _resnet(sd, "mid_block.resnets.1", ch, ch, te)
+    rev = list(reversed(boc))
+    for i in range(nb):
+        r = nb - 1 - i
+        out_c = rev[i]
+        prev = rev[i - 1] if i > 0 else rev[0]
+        inp = rev[min(i + 1, nb - 1)]
+        for j in range(cfg["layers_per_block"] + 1):
+            skip = inp if j == cfg["layers_per_block"] else out_c
+            rin = prev if j == 0 else out_c
+            _resnet(sd, f"up_blocks.{i}.resnets.{j}", rin + skip, out_c, te)
+            if cfg["down_attn"][r]:
+                _transformer(sd, f"up_blocks.{i}.attentions.{j}", out_c, cfg["transformer_layers"][r], cfg["cross_attention_dim"])
+        if i < nb - 1:
+            _conv(sd, f"up_blocks.{i}.upsamplers.0.conv", out_c, out_c, 3)
+    _norm(sd, "conv_norm_out", boc[0])
+    _conv(sd, "conv_out", cfg["out_channels"], boc[0], 3)
+    if prefix:
+        sd = OrderedDict((prefix + k, v) for k, v in sd.items())
+    return sd
+
+
+def _vae_attn(sd, p, c):
+    _norm(sd, p + ".group_norm", c)
+    for n in ("to_q", "to_k", "to_v"):
+        _lin(sd, f"{p}.{n}", c, c)
+    _lin(sd, p + ".to_out.0", c, c, gain=0.5)
+
+
+def vae_state_dict(cfg):
+    sd = OrderedDict()
+    boc = cfg["block_out_channels"]
+    L = cfg["latent_channels"]
+    # encoder
+    _conv(sd, "encoder.conv_in", boc[0], 3, 3)
+    ch = boc[0]
+    for i, c in enumerate(boc):
+        for j in range(cfg["layers_per_block"]):
+            _resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", ch, c, 0)
+            ch = c
+        if i < len(boc) - 1:
+            _conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", ch, ch, 3)
+    _resnet(sd, "encoder.mid_block.resnets.0", ch, ch, 0)
+    _vae_attn(sd, "encoder.mid_block.attentions.0", ch)
+    _resnet(sd, "encoder.mid_block.resnets.1", ch, ch, 0)
+    _norm(sd, "encoder.conv_norm_out", ch)
+    _conv(sd, "encoder.conv_out", 2 * L, ch, 3)
+    _conv(sd, "quant_conv", 2 * L, 2 * L, 1)
+    # decoder
+    _conv(sd, "post_quant_conv", L, L, 1)
+    rev = list(reversed(boc))
+    _conv(sd, "decoder.conv_in", rev[0], L, 3)
+    ch = rev[0]
+    _resnet(sd, "decoder.mid_block.resnets.0", ch, ch, 0)
+    _vae_attn(sd, "decoder.mid_block.attentions.0", ch)
+    _resnet(sd, "decoder.mid_block.resnets.1", ch, ch, 0)
+    for i, c in enumerate(rev):
+        for j in range(cfg["layers_per_block"] + 1):
+            _resnet(sd, f"decoder.up_blocks.{i}.resnets.{j}", ch, c, 0)
+            ch = c
+        if i < len(rev) - 1:
+            _conv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", ch, ch, 3)
+    _norm(sd, "decoder.conv_norm_out", ch)
+    _conv(sd, "decoder.conv_out", 3, ch, 3)
+    return sd

@@ -1,0 +1,46 @@
+"""Import the UNMODIFIED reference modules from /root/reference on CPU (only in the build container; the GPU box has no
+/root/reference).  Three import stubs are needed: deepspeed, transformers.deepspeed, xformers.ops."""
+import importlib
+import sys
+import types
+
+import torch
+import torch.nn.functional as F
+
+REF = "/root/reference"
+
+
+def install_stubs():
+    if "deepspeed" not in sys.modules:
+        ds = types.ModuleType("deepspeed")
+        ds.zero = types.SimpleNamespace(GatheredParameters=None)
+        sys.modules["deepspeed"] = ds
+    if "transformers.deepspeed" not in sys.modules:
+        td = types.ModuleType("transformers.deepspeed")
+        td.is_deepspeed_zero3_enabled = lambda: False
+        sys.modules["transformers.deepspeed"] = td
+    if "xformers" not in sys.modules:
+        xf = types.ModuleType("xformers")
+        xo = types.ModuleType("xformers.ops")
+
+        class LowerTriangularMask:  # marker type, as in xformers
+            pass
+
+        def memory_efficient_attention(q, k, v, attn_bias=None, p=0.0, scale=None):
+            # q,k,v: [B,S,H,D] -> exact softmax attention (xformers semantics)
+            causal = isinstance(attn_bias, LowerTriangularMask)
+            o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=causal, scale=scale)
+            return o.transpose(1, 2)
+
+        xo.memory_efficient_attention = memory_efficient_attention
+        xo.LowerTriangularMask = LowerTriangularMask
+        xf.ops = xo
+        sys.modules["xformers"] = xf
+        sys.modules["xformers.ops"] = xo
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+
+
+def ref_module(dotted):
+    install_stubs()
+    return importlib.import_module(dotted)

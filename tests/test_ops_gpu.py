@@ -1,0 +1,104 @@
+"""Parity of the non-GEMM kernels against torch fp32 references of the same op (CUDA path through the C ABI)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+def mk(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,D,causal", [
+    (2, 16, 1024, 1024, 104, False),   # ViT MHSA
+    (2, 2, 256, 256, 104, False),
+    (3, 32, 256, 1024, 128, False),    # attn_pool (shared queries)
+    (2, 32, 64, 256, 160, False),      # input resampler
+    (1, 40, 174, 174, 128, True),      # LLaMA prefill (causal, ragged)
+    (1, 4, 370, 370, 128, True),
+    (2, 10, 4096, 4096, 64, False),    # UNet self-attention 64x64
+    (2, 20, 1024, 64, 64, False),      # UNet cross-attention
+    (2, 16, 64, 128, 64, False),       # perceiver
+    (2, 16, 1, 65, 64, False),         # AttentionPool2d (single query)
+    (1, 3, 77, 33, 72, False),
+])
+def test_attention(B, H, Sq, Sk, D, causal):
+    from seedx_b200 import ops
+    shared_q = (Sq == 256 and Sk == 1024)
+    q = mk((1 if shared_q else B, Sq, H, D), 1).half()
+    k = mk((B, Sk, H, D), 2).half()
+    v = mk((B, Sk, H, D), 3).half()
+    o = torch.empty((B, Sq, H, D), device="cuda", dtype=torch.float16)
+    scale = D ** -0.5
+    ops.attention(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), o.permute(0, 2, 1, 3), scale=scale, causal=causal)
+    qf = q.float().expand(B, -1, -1, -1).permute(0, 2, 1, 3)
+    ref = F.scaled_dot_product_attention(qf, k.float().permute(0, 2, 1, 3), v.float().permute(0, 2, 1, 3), is_causal=causal, scale=scale)
+    assert rel(o.permute(0, 2, 1, 3), ref) < 2e-3
+
+
+def test_attention_strided_qkv():
+    """ViT layout: packed [N,S,heads,3,d] projection output read in place."""
+    from seedx_b200 import ops
+    N, S, Hh, d = 2, 320, 4, 104
+    qkv = mk((N, S, Hh, 3, d), 5).half()
+    o = torch.empty((N, S, Hh, d), device="cuda", dtype=torch.float16)
+    q, k, v = (qkv[:, :, :, i].permute(0, 2, 1, 3) for i in range(3))
+    ops.attention(q, k, v, o.permute(0, 2, 1, 3), scale=d ** -0.5)
+    ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float(), scale=d ** -0.5)
+    assert rel(o.permute(0, 2, 1, 3), ref) < 2e-3
+
+
+@pytest.mark.parametrize("rows,cols", [(2048, 1664), (5, 208), (300, 4096), (174, 5120), (64, 1024), (7, 8192)])
+def test_layernorm_rmsnorm(rows, cols):
+    from seedx_b200 import ops
+    x = mk((rows, cols), 1, 3.0) + 0.5
+    g, b = mk((cols,), 2) + 1.0, mk((cols,), 3)
+    ref = F.layer_norm(x, (cols,), g, b, 1e-6)
+    assert rel(ops.layernorm(x, g, b, 1e-6, out_dtype=torch.float32), ref) < 1e-5
+    assert rel(ops.layernorm(x.half(), g, b, 1e-6, out_dtype=torch.float16), F.layer_norm(x.half().float(), (cols,), g, b, 1e-6)) < 1e-3
+    add = mk((rows if rows < 64 else 64, cols), 4) if rows % 64 == 0 or rows < 64 else None
+    if add is not None:
+        y, y2 = ops.layernorm(x, g, b, 1e-6, out_dtype=torch.float32, add=add)
+        assert rel(y, ref) < 1e-5
+        assert rel(y2, ref + add.repeat(rows // add.shape[0], 1)) < 1e-5
+    rms = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * g
+    assert rel(ops.layernorm(x, g, None, 1e-5, out_dtype=torch.float32, rms=True), rms) < 1e-5
+
+
+@pytest.mark.parametrize("n,h,w,c1,c2,silu", [(2, 32, 32, 320, 0, True), (2, 16, 16, 1280, 640, True), (1, 64, 64, 640, 320, False),
+                                              (3, 8, 8, 128, 0, True), (1, 128, 128, 320, 0, True)])
+def test_groupnorm(n, h, w, c1, c2, silu):
+    from seedx_b200 import ops
+    x1 = (mk((n, h, w, c1), 1, 2.0) + 0.3).half()
+    x2 = (mk((n, h, w, c2), 2, 0.5) - 1.0).half() if c2 else None
+    C = c1 + c2
+    g, b = mk((C,), 3) + 1.0, mk((C,), 4)
+    xc = torch.cat([x1, x2], dim=3) if c2 else x1
+    ref = F.group_norm(xc.float().permute(0, 3, 1, 2), 32, g, b, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    raw = torch.empty_like(xc) if c2 else None
+    out = ops.groupnorm_nhwc(x1, g, b, 1e-5, x2=x2, silu=silu, raw_out=raw)
+    assert rel(out, ref) < 2e-3
+    if c2:
+        assert torch.equal(raw, xc)
+
+
+def test_patchify_cast_pool():
+    from seedx_b200 import ops
+    x = mk((2, 3, 56, 42), 1)
+    p = ops.patchify(x, 14, 592)
+    ref = F.unfold(x, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert torch.equal(p[:, :588], ref.half()) and (p[:, 588:] == 0).all()
+    assert torch.equal(ops.cast(x, torch.float16), x.half())
+    t = mk((3, 256, 128), 2).half()
+    assert rel(ops.avgpool_tokens(t, 4), F.avg_pool1d(t.float().transpose(1, 2), 4, 4).transpose(1, 2)) < 1e-3
