@@ -134,6 +134,30 @@ int seedx_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t
 /* mean over groups of `k` consecutive tokens: [n, t, c] -> [n, t/k, c]  (F.avg_pool1d at adapter_modules.py:112-115) */
 int seedx_avgpool_tokens(const void* x, int dtype, int64_t n, int64_t t, int64_t c, int64_t k, void* out, void* stream);
 
+/* k x k / stride-s patch gather on NHWC fp16 -> [n*ho*wo, k*k*c] (feeds seedx_gemm_f16 for the stride-2 downsample convs of
+ * the UNet (pad 1) and of the VAE encoder (asymmetric pad (0,1): pad_before = 0); c % 8 == 0) */
+int seedx_im2col_nhwc(const void* x, int64_t n, int64_t h, int64_t w, int64_t c, int k, int stride, int pad_before, int64_t ho,
+                      int64_t wo, void* out, void* stream);
+/* nearest-neighbour 2x upsample on NHWC fp16 (diffusers Upsample2D before its 3x3 conv) */
+int seedx_upsample2x_nhwc(const void* x, int64_t n, int64_t h, int64_t w, int64_t c, void* out, void* stream);
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, shift=0): out[i, 0:dim] = [cos | sin](t[i] * 10000^(-j/(dim/2))), fp16, row stride ldo */
+int seedx_timestep_embedding(const float* t, int64_t count, int dim, void* out, int64_t ldo, void* stream);
+/* out[r, c] = act(x[r, c]) as fp16 (strided rows; act = SEEDX_ACT_*; NONE = plain cast/copy) */
+int seedx_unary_f16(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx, void* out, int64_t ldo, int act, void* stream);
+/* out = softmax(scale * x) along rows, fp32 math, fp16 out (VAE mid-block single-head attention, d=512) */
+int seedx_softmax_rows(const void* x, int x_dtype, int64_t ldx, int64_t rows, int64_t cols, float scale, void* out, int64_t ldo, void* stream);
+/* layout converters at the pipeline boundary (latents / images are NCHW fp32 in the reference API) */
+int seedx_nchw_to_nhwc_f16(const float* x, int64_t n, int64_t c, int64_t hw, int64_t cpad, float scale, void* out, void* stream);
+int seedx_nhwc_to_nchw_f32(const void* x, int x_dtype, int64_t n, int64_t c, int64_t hw, int64_t ldc, float scale, float* out, void* stream);
+/* VaeImageProcessor.postprocess: (x/2+0.5).clamp(0,1)*255 -> uint8 HWC (first 3 channels of an NHWC tensor with row stride ldc) */
+int seedx_image_to_u8(const void* x, int x_dtype, int64_t pixels, int64_t ldc, uint8_t* out, void* stream);
+/* one denoising step on the fp32 sampler state: CFG combine + EulerDiscreteScheduler.step + scale_model_input for the next step.
+ * branches = 2: t2i, eps batch order [uncond, text] (diffusers StableDiffusionXLPipeline via adapter_modules.py:156-167)
+ * branches = 3: edit, order [text, image, uncond], sigma-space combine (pipeline_stable_diffusion_xl_t2i_edit.py:905-953)
+ * eps == NULL: initialisation, x *= init_sigma (prepare_latents, pipeline...edit.py:474-488) */
+int seedx_cfg_euler_step(const float* eps, float* x, void* unet_in, int64_t batch, int64_t hw, int branches, float guidance,
+                         float image_guidance, float sigma, float sigma_next, float init_sigma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

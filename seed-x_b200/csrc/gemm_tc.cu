@@ -29,7 +29,7 @@ struct GemmParams {
   float alpha;
   int act, gated, out_f32, res_f32, vec_ok, b_batched;
   // conv
-  int conv, taps_w, c_chunks, conv_w, conv_h, tile_w, tile_h, tiles_per_img, tiles_w, pad;
+  int conv, taps_w, c_chunks, conv_w, conv_h, tile_w, tile_h, tiles_per_img, tiles_w, pad, imgs_per_tile;
 };
 
 constexpr int BM = 128;
@@ -104,11 +104,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m_blk = r - n_blk * p.m_blocks;
         int img = 0, h0 = 0, w0 = 0;
         if (p.conv) {
-          img = m_blk / p.tiles_per_img;
-          const int rem = m_blk - img * p.tiles_per_img;
-          const int th_i = rem / p.tiles_w;
-          h0 = th_i * p.tile_h;
-          w0 = (rem - th_i * p.tiles_w) * p.tile_w;
+          if (p.imgs_per_tile > 1) {
+            img = m_blk * p.imgs_per_tile;  // whole images per tile; images past the end are TMA zero fill
+          } else {
+            img = m_blk / p.tiles_per_img;
+            const int rem = m_blk - img * p.tiles_per_img;
+            const int th_i = rem / p.tiles_w;
+            h0 = th_i * p.tile_h;
+            w0 = (rem - th_i * p.tiles_w) * p.tile_w;
+          }
         }
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -364,10 +368,14 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
     SEEDX_REQUIRE(C % 8 == 0 && C > 0, "seedx_gemm_f16(conv): channels must be a multiple of 8");
     SEEDX_REQUIRE(a->conv_taps_h == a->conv_taps_w && (a->conv_taps_h == 1 || a->conv_taps_h == 3),
                   "seedx_gemm_f16(conv): only 1x1 and 3x3 kernels");
-    int tw, th;
+    int tw, th, tn = 1;
     if (W <= 128) {
       SEEDX_REQUIRE(128 % W == 0, "seedx_gemm_f16(conv): width %lld must divide 128", (long long)W);
       tw = (int)W, th = (int)(128 / W);
+      if (th > H) {  // small images: one 128-row tile spans several whole images
+        SEEDX_REQUIRE(th % H == 0, "seedx_gemm_f16(conv): %lldx%lld image does not tile 128 rows", (long long)H, (long long)W);
+        tn = (int)(th / H), th = (int)H;
+      }
       SEEDX_REQUIRE(H % th == 0, "seedx_gemm_f16(conv): height %lld not a multiple of tile height %d", (long long)H, th);
     } else {
       SEEDX_REQUIRE(W % 128 == 0, "seedx_gemm_f16(conv): width %lld must be a multiple of 128", (long long)W);
@@ -380,7 +388,7 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
                   (long long)a->conv_taps_h * a->conv_taps_w * cchunks * BK);
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
     uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)th, 1};
+    uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
     if (int e = encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a->A, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
     p.conv = 1;
@@ -390,9 +398,10 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
     p.tile_w = tw, p.tile_h = th;
     p.tiles_w = (int)(W / tw);
     p.tiles_per_img = (int)((H / th) * (W / tw));
+    p.imgs_per_tile = tn;
     p.pad = a->conv_taps_h / 2;
     p.k_blocks = a->conv_taps_h * a->conv_taps_w * cchunks;
-    p.m_blocks = (int)(a->M / BM);
+    p.m_blocks = (int)((a->M + BM - 1) / BM);
   }
   {
     SEEDX_REQUIRE(a->ldb % 8 == 0 && a->ldb >= a->K, "seedx_gemm_f16: ldb must be >= K and a multiple of 8");

@@ -215,3 +215,101 @@ def avgpool_tokens(x, k):
     check(lib().seedx_avgpool_tokens(_ptr(x), _dt(x), C.c_int64(n), C.c_int64(t), C.c_int64(c), C.c_int64(k), _ptr(out), _stream()),
           "seedx_avgpool_tokens")
     return out
+
+
+def _i64(v):
+    return C.c_int64(int(v))
+
+
+def im2col_nhwc(x, k, stride, pad_before, ho, wo):
+    _require_cuda(x)
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    n, h, w, c = x.shape
+    out = torch.empty((n * ho * wo, k * k * c), device=x.device, dtype=torch.float16)
+    check(lib().seedx_im2col_nhwc(_ptr(x), _i64(n), _i64(h), _i64(w), _i64(c), C.c_int(k), C.c_int(stride), C.c_int(pad_before), _i64(ho),
+                                  _i64(wo), _ptr(out), _stream()), "seedx_im2col_nhwc")
+    return out
+
+
+def upsample2x_nhwc(x):
+    _require_cuda(x)
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=torch.float16)
+    check(lib().seedx_upsample2x_nhwc(_ptr(x), _i64(n), _i64(h), _i64(w), _i64(c), _ptr(out), _stream()), "seedx_upsample2x_nhwc")
+    return out
+
+
+def timestep_embedding(t, dim, out):
+    """t: fp32 [count]; out: fp16 2-D view [count, >=dim] (row stride arbitrary) receiving [cos|sin]."""
+    _require_cuda(t, out)
+    assert t.dtype == torch.float32 and t.is_contiguous() and out.dtype == torch.float16 and out.stride(-1) == 1
+    check(lib().seedx_timestep_embedding(_ptr(t), _i64(t.numel()), C.c_int(dim), _ptr(out), _i64(out.stride(0)), _stream()),
+          "seedx_timestep_embedding")
+    return out
+
+
+def unary_f16(x, out=None, act=ACT_NONE):
+    """fp16 out[r,c] = act(x[r,c]) over 2-D (possibly row-strided) views."""
+    _require_cuda(x, out)
+    assert x.dim() == 2 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    assert out.dtype == torch.float16 and out.stride(1) == 1 and out.shape == x.shape
+    check(lib().seedx_unary_f16(_ptr(x), _dt(x), _i64(x.shape[0]), _i64(x.shape[1]), _i64(x.stride(0)), _ptr(out), _i64(out.stride(0)),
+                                C.c_int(act), _stream()), "seedx_unary_f16")
+    return out
+
+
+def softmax_rows(x, scale, out=None):
+    _require_cuda(x, out)
+    assert x.dim() == 2 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    check(lib().seedx_softmax_rows(_ptr(x), _dt(x), _i64(x.stride(0)), _i64(x.shape[0]), _i64(x.shape[1]), C.c_float(scale), _ptr(out),
+                                   _i64(out.stride(0)), _stream()), "seedx_softmax_rows")
+    return out
+
+
+def nchw_to_nhwc_f16(x, cpad, scale=1.0, out=None):
+    _require_cuda(x, out)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    n, c, h, w = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, cpad), device=x.device, dtype=torch.float16)
+    check(lib().seedx_nchw_to_nhwc_f16(_ptr(x), _i64(n), _i64(c), _i64(h * w), _i64(cpad), C.c_float(scale), _ptr(out), _stream()),
+          "seedx_nchw_to_nhwc_f16")
+    return out
+
+
+def nhwc_to_nchw_f32(x, c, scale=1.0):
+    _require_cuda(x)
+    assert x.is_contiguous() and x.dim() == 4
+    n, h, w, ldc = x.shape
+    out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+    check(lib().seedx_nhwc_to_nchw_f32(_ptr(x), _dt(x), _i64(n), _i64(c), _i64(h * w), _i64(ldc), C.c_float(scale), _ptr(out), _stream()),
+          "seedx_nhwc_to_nchw_f32")
+    return out
+
+
+def image_to_u8(x):
+    """x: NHWC [n,h,w,>=3] fp16/fp32 in [-1,1] -> uint8 [n,h,w,3]."""
+    _require_cuda(x)
+    assert x.is_contiguous() and x.dim() == 4
+    n, h, w, ldc = x.shape
+    out = torch.empty((n, h, w, 3), device=x.device, dtype=torch.uint8)
+    check(lib().seedx_image_to_u8(_ptr(x), _dt(x), _i64(n * h * w), _i64(ldc), _ptr(out), _stream()), "seedx_image_to_u8")
+    return out
+
+
+def cfg_euler_step(eps, x, unet_in, branches, guidance, image_guidance, sigma, sigma_next, init_sigma=1.0):
+    _require_cuda(eps, x, unet_in)
+    assert x.dtype == torch.float32 and x.is_contiguous() and unet_in.dtype == torch.float16 and unet_in.is_contiguous()
+    B, c, h, w = x.shape
+    assert c == 4 and unet_in.shape == (branches * B, h, w, 8)
+    if eps is not None:
+        assert eps.dtype == torch.float32 and eps.is_contiguous() and eps.numel() == branches * B * h * w * 4
+    check(lib().seedx_cfg_euler_step(_ptr(eps), _ptr(x), _ptr(unet_in), _i64(B), _i64(h * w), C.c_int(branches), C.c_float(guidance),
+                                     C.c_float(image_guidance), C.c_float(sigma), C.c_float(sigma_next), C.c_float(init_sigma), _stream()),
+          "seedx_cfg_euler_step")
+    return x

@@ -1,0 +1,77 @@
+"""De-tokenizer sampling loops on the GPU: 50-step Euler with classifier-free guidance, then VAE decode.
+
+Restates the control flow of
+  * diffusers StableDiffusionXLPipeline.__call__ as reached from src/models/detokenizer/adapter_modules.py:156-167 (t2i, 2-way CFG)
+  * StableDiffusionXLText2ImageAndEditPipeline.__call__, src/models/detokenizer/pipeline_stable_diffusion_xl_t2i_edit.py:822-994
+    (edit, 3-way CFG in sigma space)
+with the per-step host work reduced to: one timestep write, one CUDA-graph replay of the UNet, one fused CFG+Euler kernel.
+"""
+import torch
+
+from . import ops
+from ._lib import SeedxError
+
+
+class DenoiseLoop:
+    """Owns the static buffers of one (batch, mode) sampling configuration and an optional CUDA graph of the UNet forward."""
+
+    def __init__(self, unet, scheduler, batch, latent_hw, branches, use_graph=True):
+        if branches not in (2, 3):
+            raise SeedxError("branches must be 2 (t2i) or 3 (edit)")
+        self.unet, self.sch, self.B, self.branches = unet, scheduler, batch, branches
+        dev = unet.device
+        h, w = latent_hw
+        self.x = torch.zeros((batch, 4, h, w), device=dev, dtype=torch.float32)
+        self.unet_in = torch.zeros((branches * batch, h, w, 8), device=dev, dtype=torch.float16)
+        self.t_dev = torch.zeros((branches * batch,), device=dev, dtype=torch.float32)
+        self.use_graph = use_graph
+        self.graph = None
+        self.eps = None
+        self.cond = None
+
+    def set_condition(self, ctx, text_embeds, time_ids, image_latents=None):
+        """ctx [branches*B, T, ctx_dim], text_embeds [branches*B, 1280], time_ids [branches*B, 6] in the pipeline's branch order;
+        image_latents: fp32 NCHW [B,4,h,w] for the edit mode (branches [img, img, 0], pipeline...edit.py:544-546)."""
+        self.cond = self.unet.prepare_cond(ctx, text_embeds, time_ids)
+        if image_latents is not None:
+            if self.branches != 3:
+                raise SeedxError("image latents only apply to the 3-branch edit loop")
+            il = ops.nchw_to_nhwc_f16(image_latents.float().contiguous(), 4)        # [B,h,w,4] fp16
+            B = self.B
+            for br in range(2):
+                ops.unary_f16(il.view(-1, 4), out=self.unet_in[br * B:(br + 1) * B].view(-1, 8)[:, 4:8])
+        self.graph = None   # conditioning buffers changed -> recapture
+
+    def _forward(self):
+        return self.unet.forward_nhwc(self.unet_in, self.t_dev, self.cond)
+
+    def run(self, noise, steps=50, guidance=7.5, image_guidance=1.5):
+        """noise: standard-normal latents NCHW [B,4,h,w] (the pipeline's `latents=` argument before init_noise_sigma scaling).
+        Returns the final fp32 latents NCHW."""
+        sch = self.sch.set_timesteps(steps)
+        self.x.copy_(noise.to(self.x.device, torch.float32))
+        ops.cfg_euler_step(None, self.x, self.unet_in, self.branches, guidance, image_guidance, 1.0, sch.sigmas[0], sch.init_noise_sigma)
+        if self.use_graph and self.graph is None:
+            self.t_dev.fill_(sch.timesteps[0])
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._forward()                      # warm-up outside capture (lazy one-time setup inside the library)
+            torch.cuda.current_stream().wait_stream(s)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.eps = self._forward()
+        for i in range(steps):
+            self.t_dev.fill_(sch.timesteps[i])
+            if self.use_graph:
+                self.graph.replay()
+            else:
+                self.eps = self._forward()
+            ops.cfg_euler_step(self.eps, self.x, self.unet_in, self.branches, guidance, image_guidance, sch.sigmas[i], sch.sigmas[i + 1])
+        return self.x
+
+
+def decode_to_uint8(vae, latents):
+    """latents / scaling_factor -> VAE decode -> (x/2+.5).clamp(0,1) -> uint8 HWC (pipeline...edit.py:965-986)."""
+    img = vae.decode_nhwc(latents, scale=1.0 / vae.cfg["scaling_factor"])
+    return ops.image_to_u8(img)

@@ -1,0 +1,536 @@
+"""Stage 3 host: SDXL UNet2DConditionModel, AutoencoderKL and EulerDiscreteScheduler stand-ins driven through libseedx.so.
+
+The reference instantiates these three classes from diffusers==0.25.0 (src/inference/eval_*.py:97-101) and calls them at
+src/models/detokenizer/pipeline_stable_diffusion_xl_t2i_edit.py:823,828,908,915-922,953,973 and (t2i) inside
+StableDiffusionXLPipeline.__call__ reached from src/models/detokenizer/adapter_modules.py:156-167.  diffusers is not a
+dependency of this engine: the classes below expose the constructor/loader surface the reference scripts use
+(``from_pretrained(path, subfolder=...)``) and ingest diffusers state-dict key names.
+
+HBM layout: activations are NHWC fp16 ([B*H*W, C] token-major, so a feature map IS the A operand of the transformer
+GEMMs); transformer residual stream fp32; sampler state (latents) fp32; all accumulation fp32.
+"""
+import json
+import math
+import os
+
+import torch
+
+from . import ops
+from ._lib import SeedxError
+
+SDXL_UNET = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280), layers_per_block=2,
+                 down_attn=(False, True, True), transformer_layers=(1, 2, 10), heads=(5, 10, 20), cross_attention_dim=2048,
+                 time_embed_dim=1280, addition_time_embed_dim=256, text_embed_dim=1280, groups=32)
+SDXL_VAE = dict(block_out_channels=(128, 256, 512, 512), layers_per_block=2, latent_channels=4, groups=32, scaling_factor=0.13025)
+
+
+def _load_weights_dir(path):
+    """diffusers checkpoint directory -> state dict (safetensors preferred, then .bin)."""
+    for name in ("diffusion_pytorch_model.fp16.safetensors", "diffusion_pytorch_model.safetensors"):
+        f = os.path.join(path, name)
+        if os.path.exists(f):
+            from safetensors.torch import load_file
+            return load_file(f)
+    f = os.path.join(path, "diffusion_pytorch_model.bin")
+    if os.path.exists(f):
+        return torch.load(f, map_location="cpu")
+    raise SeedxError(f"no diffusers weights found under {path}")
+
+
+def _h(t, dev):
+    return t.to(dev, torch.float16).contiguous()
+
+
+def _f(t, dev):
+    return t.float().to(dev).contiguous()
+
+
+def pack_conv(w, dev, cin_pad_to=None):
+    """[Cout, Cin, k, k] -> fp16 [Cout, k*k*Cpad], k index = (kh*k + kw)*Cpad + c, Cpad = roundup(Cin, 64)."""
+    cout, cin, k, _ = w.shape
+    cpad = (cin + 63) // 64 * 64
+    wp = torch.zeros((cout, k, k, cpad), dtype=torch.float16)
+    wp[..., :cin] = w.permute(0, 2, 3, 1).to(torch.float16)
+    return wp.reshape(cout, k * k * cpad).to(dev).contiguous()
+
+
+def pad_rows(w, b, nmin=8):
+    """pad a tiny output dimension up to a multiple of 8 rows (so the NHWC result keeps 16-byte pixels)."""
+    n = w.shape[0]
+    npad = (n + nmin - 1) // nmin * nmin
+    if npad == n:
+        return w, b
+    wp = torch.zeros((npad,) + tuple(w.shape[1:]), dtype=w.dtype)
+    wp[:n] = w
+    bp = torch.zeros((npad,), dtype=b.dtype)
+    bp[:n] = b
+    return wp, bp
+
+
+class _Resnet:
+    def __init__(self, sd, p, dev, eps):
+        self.eps = eps
+        self.n1 = (_f(sd[p + ".norm1.weight"], dev), _f(sd[p + ".norm1.bias"], dev))
+        self.n2 = (_f(sd[p + ".norm2.weight"], dev), _f(sd[p + ".norm2.bias"], dev))
+        self.w1, self.b1 = pack_conv(sd[p + ".conv1.weight"], dev), _f(sd[p + ".conv1.bias"], dev)
+        self.w2, self.b2 = pack_conv(sd[p + ".conv2.weight"], dev), _f(sd[p + ".conv2.bias"], dev)
+        self.wt = self.bt = None
+        if (p + ".time_emb_proj.weight") in sd:
+            self.wt, self.bt = _h(sd[p + ".time_emb_proj.weight"], dev), _f(sd[p + ".time_emb_proj.bias"], dev)
+        self.wsc = self.bsc = None
+        if (p + ".conv_shortcut.weight") in sd:
+            w = sd[p + ".conv_shortcut.weight"]
+            self.wsc, self.bsc = _h(w.reshape(w.shape[0], w.shape[1]), dev), _f(sd[p + ".conv_shortcut.bias"], dev)
+
+    def __call__(self, x, skip, semb, groups, ws):
+        """ResnetBlock2D on NHWC fp16; `skip` (optional) is channel-concatenated behind x (UNet up blocks)."""
+        n, h, w, _ = x.shape
+        raw = None
+        if skip is not None:
+            raw = torch.empty((n, h, w, x.shape[3] + skip.shape[3]), device=x.device, dtype=torch.float16)
+        a = ops.groupnorm_nhwc(x, self.n1[0], self.n1[1], self.eps, x2=skip, silu=True, groups=groups, raw_out=raw, stats_ws=ws)
+        tb = ops.gemm(semb, self.wt, bias=self.bt, out_dtype=torch.float32) if self.wt is not None else None
+        a = ops.conv2d_nhwc(a, self.w1, bias=self.b1, bias_g=tb)
+        a = ops.groupnorm_nhwc(a, self.n2[0], self.n2[1], self.eps, silu=True, groups=groups, stats_ws=ws)
+        xin = raw if raw is not None else x
+        if self.wsc is not None:
+            sc = ops.gemm(xin.view(n * h * w, xin.shape[3]), self.wsc, bias=self.bsc).view(n, h, w, -1)
+        else:
+            sc = xin
+        return ops.conv2d_nhwc(a, self.w2, bias=self.b2, residual=sc)
+
+
+class _Transformer:
+    def __init__(self, sd, p, dev, depth, heads):
+        self.heads = heads
+        self.norm = (_f(sd[p + ".norm.weight"], dev), _f(sd[p + ".norm.bias"], dev))
+        self.w_in, self.b_in = _h(sd[p + ".proj_in.weight"], dev), _f(sd[p + ".proj_in.bias"], dev)
+        self.w_out, self.b_out = _h(sd[p + ".proj_out.weight"], dev), _f(sd[p + ".proj_out.bias"], dev)
+        self.blocks = []
+        for k in range(depth):
+            b = f"{p}.transformer_blocks.{k}"
+            g = lambda s: sd[f"{b}.{s}"]  # noqa: E731
+            w_ff = g("ff.net.0.proj.weight")
+            b_ff = g("ff.net.0.proj.bias")
+            inner = w_ff.shape[0] // 2
+            # GEGLU: interleave [hidden_j, gate_j] rows so the gate sits beside its value in one accumulator tile
+            w_il = torch.stack([w_ff[:inner], w_ff[inner:]], dim=1).reshape(2 * inner, -1)
+            b_il = torch.stack([b_ff[:inner], b_ff[inner:]], dim=1).reshape(2 * inner)
+            self.blocks.append(dict(
+                n1=(_f(g("norm1.weight"), dev), _f(g("norm1.bias"), dev)),
+                n2=(_f(g("norm2.weight"), dev), _f(g("norm2.bias"), dev)),
+                n3=(_f(g("norm3.weight"), dev), _f(g("norm3.bias"), dev)),
+                w_qkv=_h(torch.cat([g("attn1.to_q.weight"), g("attn1.to_k.weight"), g("attn1.to_v.weight")], dim=0), dev),
+                w_o1=_h(g("attn1.to_out.0.weight"), dev), b_o1=_f(g("attn1.to_out.0.bias"), dev),
+                w_q2=_h(g("attn2.to_q.weight"), dev),
+                w_kv2=_h(torch.cat([g("attn2.to_k.weight"), g("attn2.to_v.weight")], dim=0), dev),
+                w_o2=_h(g("attn2.to_out.0.weight"), dev), b_o2=_f(g("attn2.to_out.0.bias"), dev),
+                w_ff1=_h(w_il, dev), b_ff1=_f(b_il, dev),
+                w_ff2=_h(g("ff.net.2.weight"), dev), b_ff2=_f(g("ff.net.2.bias"), dev)))
+
+    def context_kv(self, ctx16):
+        """cross-attention K/V of every block for a step-invariant context [B*T, ctx_dim] (hoisted out of the sampler loop)."""
+        return [ops.gemm(ctx16, blk["w_kv2"]) for blk in self.blocks]
+
+    def __call__(self, x, kv, n_ctx, groups, ws):
+        n, h, w, c = x.shape
+        S, M, H = h * w, n * h * w, self.heads
+        d = c // H
+        scale = d ** -0.5
+        hn = ops.groupnorm_nhwc(x, self.norm[0], self.norm[1], 1e-6, silu=False, groups=groups, stats_ws=ws)
+        hs = ops.gemm(hn.view(M, c), self.w_in, bias=self.b_in, out_dtype=torch.float32)
+        nbuf = torch.empty((M, c), device=x.device, dtype=torch.float16)
+        qkv = torch.empty((M, 3 * c), device=x.device, dtype=torch.float16)
+        obuf = torch.empty((M, c), device=x.device, dtype=torch.float16)
+        qbuf = torch.empty((M, c), device=x.device, dtype=torch.float16)
+        fbuf = torch.empty((M, 4 * c), device=x.device, dtype=torch.float16)
+        q5 = qkv.view(n, S, 3, H, d)
+        q1, k1, v1 = (q5[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        ov = obuf.view(n, S, H, d).permute(0, 2, 1, 3)
+        q2 = qbuf.view(n, S, H, d).permute(0, 2, 1, 3)
+        for blk, kvb in zip(self.blocks, kv):
+            ops.layernorm(hs, blk["n1"][0], blk["n1"][1], 1e-5, out=nbuf)
+            ops.gemm(nbuf, blk["w_qkv"], out=qkv)
+            ops.attention(q1, k1, v1, ov, scale=scale)
+            ops.gemm(obuf, blk["w_o1"], out=hs, bias=blk["b_o1"], residual=hs)
+            ops.layernorm(hs, blk["n2"][0], blk["n2"][1], 1e-5, out=nbuf)
+            ops.gemm(nbuf, blk["w_q2"], out=qbuf)
+            kv5 = kvb.view(n, n_ctx, 2, H, d)
+            ops.attention(q2, kv5[:, :, 0].permute(0, 2, 1, 3), kv5[:, :, 1].permute(0, 2, 1, 3), ov, scale=scale)
+            ops.gemm(obuf, blk["w_o2"], out=hs, bias=blk["b_o2"], residual=hs)
+            ops.layernorm(hs, blk["n3"][0], blk["n3"][1], 1e-5, out=nbuf)
+            ops.gemm(nbuf, blk["w_ff1"], out=fbuf, bias=blk["b_ff1"], act=ops.ACT_GELU, gated=True)
+            ops.gemm(fbuf, blk["w_ff2"], out=hs, bias=blk["b_ff2"], residual=hs)
+        h16 = ops.cast(hs, torch.float16)
+        return ops.gemm(h16, self.w_out, bias=self.b_out, residual=x.view(M, c)).view(n, h, w, c)
+
+
+def _conv_s2(x, w, b, pad_before):
+    """3x3 stride-2 conv = patch gather + GEMM (UNet Downsample2D pad 1; VAE encoder asymmetric pad (0,1))."""
+    n, h, wd, c = x.shape
+    ho, wo = h // 2, wd // 2
+    a = ops.im2col_nhwc(x, 3, 2, pad_before, ho, wo)
+    return ops.gemm(a, w, bias=b).view(n, ho, wo, -1)
+
+
+def pack_conv_dense(w, dev):
+    """[Cout, Cin, k, k] -> fp16 [Cout, k*k*Cin] matching seedx_im2col_nhwc's column order."""
+    cout, cin, k, _ = w.shape
+    return w.permute(0, 2, 3, 1).reshape(cout, k * k * cin).to(dev, torch.float16).contiguous()
+
+
+class UNet2DConditionModel:
+    """SDXL UNet (forward only). ``cfg`` follows SDXL_UNET; in_channels 8 = the edit variant (adapter_modules.py:183-198)."""
+
+    def __init__(self, cfg=None, device="cuda"):
+        self.cfg = dict(SDXL_UNET if cfg is None else cfg)
+        self.device = torch.device(device)
+        self.dtype = torch.float16
+        self._loaded = False
+
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, **kw):
+        d = os.path.join(path, subfolder) if subfolder else path
+        cfg = dict(SDXL_UNET)
+        cj = os.path.join(d, "config.json")
+        if os.path.exists(cj):
+            c = json.load(open(cj))
+            cfg.update(in_channels=c.get("in_channels", 4), out_channels=c.get("out_channels", 4),
+                       block_out_channels=tuple(c["block_out_channels"]), layers_per_block=c["layers_per_block"],
+                       transformer_layers=tuple(c["transformer_layers_per_block"]), heads=tuple(c["attention_head_dim"]),
+                       cross_attention_dim=c["cross_attention_dim"], addition_time_embed_dim=c["addition_time_embed_dim"],
+                       down_attn=tuple("CrossAttn" in t for t in c["down_block_types"]))
+        m = cls(cfg)
+        m.load_state_dict(_load_weights_dir(d))
+        return m
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    def state_shape_in_channels(self):
+        return self.cfg["in_channels"]
+
+    def load_state_dict(self, sd, strict=False):
+        cfg, dev = self.cfg, self.device
+        boc = cfg["block_out_channels"]
+        nb = len(boc)
+        cin = sd["conv_in.weight"].shape[1]
+        self.cfg["in_channels"] = cin
+        if cin > 8:
+            raise SeedxError("conv_in with more than 8 input channels is not supported")
+        self.conv_in = (pack_conv(sd["conv_in.weight"], dev), _f(sd["conv_in.bias"], dev))
+        lin = lambda p: (_h(sd[p + ".weight"], dev), _f(sd[p + ".bias"], dev))  # noqa: E731
+        self.t1, self.t2 = lin("time_embedding.linear_1"), lin("time_embedding.linear_2")
+        self.a1, self.a2 = lin("add_embedding.linear_1"), lin("add_embedding.linear_2")
+        self.down, self.up = [], []
+        for i in range(nb):
+            blk = dict(res=[], att=[], ds=None)
+            for j in range(cfg["layers_per_block"]):
+                blk["res"].append(_Resnet(sd, f"down_blocks.{i}.resnets.{j}", dev, 1e-5))
+                if cfg["down_attn"][i]:
+                    blk["att"].append(_Transformer(sd, f"down_blocks.{i}.attentions.{j}", dev, cfg["transformer_layers"][i], cfg["heads"][i]))
+            if i < nb - 1:
+                p = f"down_blocks.{i}.downsamplers.0.conv"
+                blk["ds"] = (pack_conv_dense(sd[p + ".weight"], dev), _f(sd[p + ".bias"], dev))
+            self.down.append(blk)
+        self.mid = dict(r0=_Resnet(sd, "mid_block.resnets.0", dev, 1e-5),
+                        att=_Transformer(sd, "mid_block.attentions.0", dev, cfg["transformer_layers"][-1], cfg["heads"][-1]),
+                        r1=_Resnet(sd, "mid_block.resnets.1", dev, 1e-5))
+        for i in range(nb):
+            r = nb - 1 - i
+            blk = dict(res=[], att=[], us=None)
+            for j in range(cfg["layers_per_block"] + 1):
+                blk["res"].append(_Resnet(sd, f"up_blocks.{i}.resnets.{j}", dev, 1e-5))
+                if cfg["down_attn"][r]:
+                    blk["att"].append(_Transformer(sd, f"up_blocks.{i}.attentions.{j}", dev, cfg["transformer_layers"][r], cfg["heads"][r]))
+            if i < nb - 1:
+                p = f"up_blocks.{i}.upsamplers.0.conv"
+                blk["us"] = (pack_conv(sd[p + ".weight"], dev), _f(sd[p + ".bias"], dev))
+            self.up.append(blk)
+        self.norm_out = (_f(sd["conv_norm_out.weight"], dev), _f(sd["conv_norm_out.bias"], dev))
+        self.conv_out = (pack_conv(sd["conv_out.weight"], dev), _f(sd["conv_out.bias"], dev))
+        self._loaded = True
+        return [], []
+
+    # ---- step-invariant conditioning ---------------------------------------------------------------------------
+    def prepare_cond(self, ctx, text_embeds, time_ids):
+        """ctx [Be,T,ctx_dim], text_embeds [Be,1280], time_ids [Be,6] (any float dtype, device tensors).  Returns the
+        hoisted cross-attention K/V of every transformer block and the 'text_time' additive embedding."""
+        cfg = self.cfg
+        Be, T, cd = ctx.shape
+        ctx16 = ops.unary_f16(ctx.reshape(Be * T, cd).contiguous())
+        kv = dict(n_ctx=T, down=[[a.context_kv(ctx16) for a in b["att"]] for b in self.down], mid=self.mid["att"].context_kv(ctx16),
+                  up=[[a.context_kv(ctx16) for a in b["att"]] for b in self.up])
+        td = cfg["addition_time_embed_dim"]
+        te = cfg["text_embed_dim"]
+        aug_in = torch.empty((Be, te + 6 * td), device=self.device, dtype=torch.float16)
+        ops.unary_f16(text_embeds.reshape(Be, te).contiguous(), out=aug_in[:, :te])
+        tid = time_ids.reshape(-1).float().contiguous()
+        tid_emb = torch.empty((Be * 6, td), device=self.device, dtype=torch.float16)
+        ops.timestep_embedding(tid, td, tid_emb)                       # row b*6+i = Timesteps(td)(time_ids[b, i])
+        ops.unary_f16(tid_emb.view(Be, 6 * td), out=aug_in[:, te:])    # flatten(1) and concatenate behind text_embeds
+        a = ops.gemm(aug_in, self.a1[0], bias=self.a1[1], act=ops.ACT_SILU)
+        kv["aug"] = ops.gemm(a, self.a2[0], bias=self.a2[1], out_dtype=torch.float32)
+        return kv
+
+    # ---- forward ---------------------------------------------------------------------------------------------------
+    def forward_nhwc(self, x_in, t_dev, cond):
+        """x_in: fp16 NHWC [Be,H,W,8] (scaled latents in channels 0..3, image latents / zeros in 4..7);
+        t_dev: fp32 device tensor [Be] holding the timestep; cond: prepare_cond(...) -> eps fp32 [Be,H,W,4]."""
+        if not self._loaded:
+            raise SeedxError("UNet2DConditionModel: weights not loaded")
+        cfg = self.cfg
+        G = cfg["groups"]
+        Be = x_in.shape[0]
+        nb = len(cfg["block_out_channels"])
+        ws = torch.empty((Be * G * 2,), device=self.device, dtype=torch.float64)
+        T = cond["n_ctx"]
+        temb_in = torch.empty((Be, cfg["block_out_channels"][0]), device=self.device, dtype=torch.float16)
+        ops.timestep_embedding(t_dev, cfg["block_out_channels"][0], temb_in)
+        e1 = ops.gemm(temb_in, self.t1[0], bias=self.t1[1], act=ops.ACT_SILU)
+        emb = ops.gemm(e1, self.t2[0], bias=self.t2[1], residual=cond["aug"], out_dtype=torch.float32)
+        semb = ops.unary_f16(emb, act=ops.ACT_SILU)
+
+        h = ops.conv2d_nhwc(x_in, self.conv_in[0], bias=self.conv_in[1])
+        skips = [h]
+        for i, blk in enumerate(self.down):
+            for j, res in enumerate(blk["res"]):
+                h = res(h, None, semb, G, ws)
+                if blk["att"]:
+                    h = blk["att"][j](h, cond["down"][i][j], T, G, ws)
+                skips.append(h)
+            if blk["ds"] is not None:
+                h = _conv_s2(h, blk["ds"][0], blk["ds"][1], 1)
+                skips.append(h)
+        h = self.mid["r0"](h, None, semb, G, ws)
+        h = self.mid["att"](h, cond["mid"], T, G, ws)
+        h = self.mid["r1"](h, None, semb, G, ws)
+        for i, blk in enumerate(self.up):
+            for j, res in enumerate(blk["res"]):
+                h = res(h, skips.pop(), semb, G, ws)
+                if blk["att"]:
+                    h = blk["att"][j](h, cond["up"][i][j], T, G, ws)
+            if blk["us"] is not None:
+                h = ops.conv2d_nhwc(ops.upsample2x_nhwc(h), blk["us"][0], bias=blk["us"][1])
+        a = ops.groupnorm_nhwc(h, self.norm_out[0], self.norm_out[1], 1e-5, silu=True, groups=G, stats_ws=ws)
+        return ops.conv2d_nhwc(a, self.conv_out[0], bias=self.conv_out[1], out_dtype=torch.float32, tile_n=64)
+
+    def __call__(self, sample, timestep, encoder_hidden_states, added_cond_kwargs=None, **kw):
+        """diffusers-style call on NCHW tensors (used by parity tests): returns eps NCHW fp32."""
+        Be = sample.shape[0]
+        cond = self.prepare_cond(encoder_hidden_states.to(self.device), added_cond_kwargs["text_embeds"].to(self.device),
+                                 added_cond_kwargs["time_ids"].to(self.device))
+        x_in = ops.nchw_to_nhwc_f16(sample.to(self.device).float().contiguous(), 8)
+        t = torch.full((Be,), float(timestep), device=self.device, dtype=torch.float32)
+        eps = self.forward_nhwc(x_in, t, cond)
+        return ops.nhwc_to_nchw_f32(eps, self.cfg["out_channels"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# VAE
+# ------------------------------------------------------------------------------------------------------------------
+class _VaeAttention:
+    def __init__(self, sd, p, dev):
+        self.norm = (_f(sd[p + ".group_norm.weight"], dev), _f(sd[p + ".group_norm.bias"], dev))
+        self.wq, self.bq = _h(sd[p + ".to_q.weight"], dev), _f(sd[p + ".to_q.bias"], dev)
+        self.wk, self.bk = _h(sd[p + ".to_k.weight"], dev), _f(sd[p + ".to_k.bias"], dev)
+        self.wv, self.bv = _h(sd[p + ".to_v.weight"], dev), _f(sd[p + ".to_v.bias"], dev)
+        self.wo, self.bo = _h(sd[p + ".to_out.0.weight"], dev), _f(sd[p + ".to_out.0.bias"], dev)
+
+    def __call__(self, x, groups, ws):
+        """single-head attention over H*W tokens, head dim = C (512): scores are materialised per image (C > 160)."""
+        n, h, w, c = x.shape
+        S = h * w
+        hn = ops.groupnorm_nhwc(x, self.norm[0], self.norm[1], 1e-6, silu=False, groups=groups, stats_ws=ws).view(n, S, c)
+        q = ops.gemm(hn.view(n * S, c), self.wq, bias=self.bq).view(n, S, c)
+        k = ops.gemm(hn.view(n * S, c), self.wk, bias=self.bk).view(n, S, c)
+        out = torch.empty((n, S, c), device=x.device, dtype=torch.float16)
+        scores = torch.empty((S, S), device=x.device, dtype=torch.float32)   # fp32 scores: no fp16 overflow on real VAE weights
+        probs = torch.empty((S, S), device=x.device, dtype=torch.float16)
+        scale = c ** -0.5
+        for i in range(n):
+            vt = ops.gemm(self.wv, hn[i], bias_m=self.bv)                       # V^T [c, S]: K-major operand of P.V
+            ops.gemm(q[i], k[i], out=scores, alpha=scale)
+            ops.softmax_rows(scores, 1.0, out=probs)
+            ops.gemm(probs, vt, out=out[i])
+        xr = x.view(n * S, c)
+        return ops.gemm(out.view(n * S, c), self.wo, bias=self.bo, residual=xr).view(n, h, w, c)
+
+
+class AutoencoderKL:
+    """SDXL VAE (encode -> latent mode, decode).  The reference up-casts the VAE to fp32 (pipeline...edit.py:569-586);
+    here operands are fp16 with fp32 accumulation (DESIGN.md 'precision')."""
+
+    def __init__(self, cfg=None, device="cuda"):
+        self.cfg = dict(SDXL_VAE if cfg is None else cfg)
+        self.device = torch.device(device)
+        self.dtype = torch.float16
+        self._loaded = False
+
+    class _Config:
+        pass
+
+    @property
+    def config(self):
+        c = AutoencoderKL._Config()
+        c.scaling_factor = self.cfg["scaling_factor"]
+        c.force_upcast = False
+        c.block_out_channels = list(self.cfg["block_out_channels"])
+        return c
+
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, **kw):
+        d = os.path.join(path, subfolder) if subfolder else path
+        cfg = dict(SDXL_VAE)
+        cj = os.path.join(d, "config.json")
+        if os.path.exists(cj):
+            c = json.load(open(cj))
+            cfg.update(block_out_channels=tuple(c["block_out_channels"]), layers_per_block=c["layers_per_block"],
+                       latent_channels=c["latent_channels"], scaling_factor=c.get("scaling_factor", 0.13025))
+        m = cls(cfg)
+        m.load_state_dict(_load_weights_dir(d))
+        return m
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    def load_state_dict(self, sd, strict=False):
+        cfg, dev = self.cfg, self.device
+        boc = cfg["block_out_channels"]
+        rev = list(reversed(boc))
+        cv = lambda p: (pack_conv(sd[p + ".weight"], dev), _f(sd[p + ".bias"], dev))  # noqa: E731
+        self.has_decoder = "decoder.conv_in.weight" in sd
+        self.has_encoder = "encoder.conv_in.weight" in sd
+        if self.has_decoder:
+            w, b = pad_rows(sd["post_quant_conv.weight"].reshape(cfg["latent_channels"], -1), sd["post_quant_conv.bias"])
+            wq = torch.zeros((w.shape[0], 8), dtype=w.dtype)
+            wq[:, : w.shape[1]] = w
+            self.post_quant = (_h(wq, dev), _f(b, dev))
+            self.d_conv_in = cv("decoder.conv_in")
+            self.d_mid = (_Resnet(sd, "decoder.mid_block.resnets.0", dev, 1e-6), _VaeAttention(sd, "decoder.mid_block.attentions.0", dev),
+                          _Resnet(sd, "decoder.mid_block.resnets.1", dev, 1e-6))
+            self.d_up = []
+            for i in range(len(rev)):
+                res = [_Resnet(sd, f"decoder.up_blocks.{i}.resnets.{j}", dev, 1e-6) for j in range(cfg["layers_per_block"] + 1)]
+                us = cv(f"decoder.up_blocks.{i}.upsamplers.0.conv") if i < len(rev) - 1 else None
+                self.d_up.append((res, us))
+            self.d_norm_out = (_f(sd["decoder.conv_norm_out.weight"], dev), _f(sd["decoder.conv_norm_out.bias"], dev))
+            self.d_conv_out = cv("decoder.conv_out")
+        if self.has_encoder:
+            w = sd["encoder.conv_in.weight"]
+            self.e_conv_in = cv("encoder.conv_in")
+            self.e_down = []
+            for i in range(len(boc)):
+                res = [_Resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}", dev, 1e-6) for j in range(cfg["layers_per_block"])]
+                ds = None
+                if i < len(boc) - 1:
+                    p = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+                    ds = (pack_conv_dense(sd[p + ".weight"], dev), _f(sd[p + ".bias"], dev))
+                self.e_down.append((res, ds))
+            self.e_mid = (_Resnet(sd, "encoder.mid_block.resnets.0", dev, 1e-6), _VaeAttention(sd, "encoder.mid_block.attentions.0", dev),
+                          _Resnet(sd, "encoder.mid_block.resnets.1", dev, 1e-6))
+            self.e_norm_out = (_f(sd["encoder.conv_norm_out.weight"], dev), _f(sd["encoder.conv_norm_out.bias"], dev))
+            wco, bco = pad_rows(sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"])
+            self.e_conv_out = (pack_conv(wco, dev), _f(bco, dev))
+            L2 = 2 * cfg["latent_channels"]
+            wq, bq = pad_rows(sd["quant_conv.weight"].reshape(L2, L2), sd["quant_conv.bias"])
+            self.quant = (_h(wq, dev), _f(bq, dev))
+        self._loaded = True
+        return [], []
+
+    def decode_nhwc(self, latents, scale=1.0):
+        """latents: fp32 NCHW [B,4,h,w]; z = latents * scale (pass 1/scaling_factor) -> fp32 NHWC image [B,8h,8w,3] in ~[-1,1]."""
+        if not (self._loaded and self.has_decoder):
+            raise SeedxError("AutoencoderKL: decoder weights not loaded")
+        G = self.cfg["groups"]
+        B, _, h, w = latents.shape
+        ws = torch.empty((B * G * 2,), device=self.device, dtype=torch.float64)
+        z = ops.nchw_to_nhwc_f16(latents.to(self.device).float().contiguous(), 8, scale=scale)
+        x = ops.gemm(z.view(B * h * w, 8), self.post_quant[0], bias=self.post_quant[1]).view(B, h, w, -1)
+        x = ops.conv2d_nhwc(x, self.d_conv_in[0], bias=self.d_conv_in[1])
+        x = self.d_mid[0](x, None, None, G, ws)
+        x = self.d_mid[1](x, G, ws)
+        x = self.d_mid[2](x, None, None, G, ws)
+        for res, us in self.d_up:
+            for r in res:
+                x = r(x, None, None, G, ws)
+            if us is not None:
+                x = ops.conv2d_nhwc(ops.upsample2x_nhwc(x), us[0], bias=us[1])
+        a = ops.groupnorm_nhwc(x, self.d_norm_out[0], self.d_norm_out[1], 1e-6, silu=True, groups=G, stats_ws=ws)
+        return ops.conv2d_nhwc(a, self.d_conv_out[0], bias=self.d_conv_out[1], tile_n=64, out_dtype=torch.float32)
+
+    def decode(self, latents, scale=1.0):
+        """-> NCHW fp32 image (diffusers AutoencoderKL.decode(...).sample layout)."""
+        return ops.nhwc_to_nchw_f32(self.decode_nhwc(latents, scale), 3)
+
+    def encode_mode(self, image):
+        """image NCHW fp32 in [-1,1] -> latent_dist.mode() NCHW fp32 [B,4,H/8,W/8] (NOT multiplied by scaling_factor,
+        as at pipeline_stable_diffusion_xl_t2i_edit.py:523)."""
+        if not (self._loaded and self.has_encoder):
+            raise SeedxError("AutoencoderKL: encoder weights not loaded")
+        G = self.cfg["groups"]
+        B = image.shape[0]
+        ws = torch.empty((B * G * 2,), device=self.device, dtype=torch.float64)
+        x = ops.nchw_to_nhwc_f16(image.to(self.device).float().contiguous(), 8)
+        x = ops.conv2d_nhwc(x, self.e_conv_in[0], bias=self.e_conv_in[1])
+        for res, ds in self.e_down:
+            for r in res:
+                x = r(x, None, None, G, ws)
+            if ds is not None:
+                x = _conv_s2(x, ds[0], ds[1], 0)
+        x = self.e_mid[0](x, None, None, G, ws)
+        x = self.e_mid[1](x, G, ws)
+        x = self.e_mid[2](x, None, None, G, ws)
+        a = ops.groupnorm_nhwc(x, self.e_norm_out[0], self.e_norm_out[1], 1e-6, silu=True, groups=G, stats_ws=ws)
+        m = ops.conv2d_nhwc(a, self.e_conv_out[0], bias=self.e_conv_out[1], tile_n=64)
+        n, h, w, c = m.shape
+        mo = ops.gemm(m.view(n * h * w, c), self.quant[0], bias=self.quant[1], out_dtype=torch.float32).view(n, h, w, -1)
+        return ops.nhwc_to_nchw_f32(mo, self.cfg["latent_channels"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# scheduler (host-side constants only; the per-step arithmetic runs in seedx_cfg_euler_step)
+# ------------------------------------------------------------------------------------------------------------------
+class EulerDiscreteScheduler:
+    """SDXL scheduler_config defaults: scaled_linear betas .00085-.012, 1000 train steps, 'leading' spacing, offset 1."""
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, steps_offset=1, **kw):
+        self.num_train, self.steps_offset = num_train_timesteps, steps_offset
+        betas = [(beta_start ** 0.5 + (beta_end ** 0.5 - beta_start ** 0.5) * i / (num_train_timesteps - 1)) ** 2
+                 for i in range(num_train_timesteps)]
+        ac, s = 1.0, []
+        for b in betas:
+            ac *= (1.0 - b)
+            s.append(math.sqrt((1.0 - ac) / ac))
+        self._sig = s
+        self.order = 1
+        self.sigmas = None
+
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, **kw):
+        d = os.path.join(path, subfolder) if subfolder else path
+        cj = os.path.join(d, "scheduler_config.json")
+        if os.path.exists(cj):
+            c = json.load(open(cj))
+            return cls(c.get("num_train_timesteps", 1000), c.get("beta_start", 0.00085), c.get("beta_end", 0.012), c.get("steps_offset", 1))
+        return cls()
+
+    def set_timesteps(self, n, device=None):
+        ratio = self.num_train // n
+        ts = [float(i * ratio + self.steps_offset) for i in range(n)][::-1]
+        sig = []
+        for t in ts:
+            lo = min(int(math.floor(t)), self.num_train - 1)
+            hi = min(lo + 1, self.num_train - 1)
+            w = t - lo
+            sig.append(self._sig[lo] * (1 - w) + self._sig[hi] * w)
+        self.timesteps = ts
+        self.sigmas = sig + [0.0]
+        self.init_noise_sigma = math.sqrt(max(sig) ** 2 + 1.0)
+        return self

@@ -234,3 +234,89 @@ def vae_state_dict(cfg):
     _norm(sd, "decoder.conv_norm_out", ch)
     _conv(sd, "decoder.conv_out", 3, ch, 3)
     return sd
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# LLaMA / agent parameters and a synthetic tokenizer (no tokenizer files exist offline)
+# ----------------------------------------------------------------------------------------------------------------------
+LLAMA_13B = dict(vocab=32330, hidden=5120, layers=40, heads=40, ffn=13824, eps=1e-5)
+TINY_LLAMA = dict(vocab=1024, hidden=256, layers=2, heads=2, ffn=512, eps=1e-5)
+
+
+def llama_state_dict(cfg):
+    """LlamaForCausalLM parameters (modeling_llama_xformer.py), HF key names."""
+    sd = OrderedDict()
+    D, FF, V = cfg["hidden"], cfg["ffn"], cfg["vocab"]
+    d = D // cfg["heads"]
+    sd["model.embed_tokens.weight"] = randn("model.embed_tokens.weight", (V, D), 1.0)
+    for i in range(cfg["layers"]):
+        p = f"model.layers.{i}."
+        for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+            sd[p + f"self_attn.{n}.weight"] = randn(p + f"self_attn.{n}.weight", (D, D), D ** -0.5)
+        sd[p + "self_attn.rotary_emb.inv_freq"] = 1.0 / (10000.0 ** (torch.arange(0, d, 2).float() / d))
+        sd[p + "mlp.gate_proj.weight"] = randn(p + "mlp.gate_proj.weight", (FF, D), D ** -0.5)
+        sd[p + "mlp.up_proj.weight"] = randn(p + "mlp.up_proj.weight", (FF, D), D ** -0.5)
+        sd[p + "mlp.down_proj.weight"] = randn(p + "mlp.down_proj.weight", (D, FF), FF ** -0.5)
+        sd[p + "input_layernorm.weight"] = randn(p + "input_layernorm.weight", (D,), 0.1, 1.0)
+        sd[p + "post_attention_layernorm.weight"] = randn(p + "post_attention_layernorm.weight", (D,), 0.1, 1.0)
+    sd["model.norm.weight"] = randn("model.norm.weight", (D,), 0.1, 1.0)
+    sd["lm_head.weight"] = randn("lm_head.weight", (V, D), D ** -0.5)
+    return sd
+
+
+def agent_state_dict(llm_hidden, vit_dim, sd=None):
+    """ContinuousLVLM parameters besides the LLM (seed_x.py:22-45): input/output Resampler + patch_pos_embed."""
+    sd = OrderedDict() if sd is None else sd
+    resampler_state_dict("input_resampler.", 8, llm_hidden, vit_dim, sd)
+    resampler_state_dict("output_resampler.", 8, vit_dim, llm_hidden, sd)
+    sd["patch_pos_embed"] = randn("patch_pos_embed", (4, llm_hidden), llm_hidden ** -0.5)
+    return sd
+
+
+class SynthTokenizer:
+    """Stand-in for the LlamaTokenizer with the reference's added special tokens: ids [0, base) are text,
+    then <img>, </img>, <patch>, </patch>, <box_start>, <box_end>, <img_00000..00099>, <loc-0..223>."""
+    SPECIALS = ["<img>", "</img>", "<patch>", "</patch>", "<box_start>", "<box_end>"]
+
+    def __init__(self, vocab=32330, n_img=100, n_loc=224):
+        n_special = len(self.SPECIALS) + n_img + n_loc
+        self.base = vocab - n_special
+        assert self.base > 3
+        self.vocab = vocab
+        self.bos_token_id, self.eos_token_id, self.pad_token_id = 1, 2, 0
+        self.tok2id = {s: self.base + i for i, s in enumerate(self.SPECIALS)}
+        for i in range(n_img):
+            self.tok2id["<img_{:05d}>".format(i)] = self.base + len(self.SPECIALS) + i
+        for i in range(n_loc):
+            self.tok2id["<loc-{}>".format(i)] = self.base + len(self.SPECIALS) + n_img + i
+        self.id2tok = {v: k for k, v in self.tok2id.items()}
+
+    def encode(self, text, add_special_tokens=False):
+        """special-token strings map to their ids; any other character maps to a deterministic text id in [3, base)."""
+        ids, i = [], 0
+        if add_special_tokens:
+            ids.append(self.bos_token_id)
+        while i < len(text):
+            if text[i] == "<":
+                j = text.find(">", i)
+                if j > 0 and text[i:j + 1] in self.tok2id:
+                    ids.append(self.tok2id[text[i:j + 1]])
+                    i = j + 1
+                    continue
+            ids.append(3 + (ord(text[i]) * 2654435761 % (self.base - 3)))
+            i += 1
+        return ids
+
+    def __call__(self, text, return_tensors=None):
+        ids = self.encode(text, add_special_tokens=True)
+
+        class _R:
+            pass
+
+        r = _R()
+        r.input_ids = torch.tensor([ids]) if return_tensors == "pt" else ids
+        return r
+
+    def decode(self, ids, skip_special_tokens=False):
+        ids = ids.tolist() if hasattr(ids, "tolist") else list(ids)
+        return "".join(self.id2tok.get(int(i), f"[{int(i)}]") for i in ids)

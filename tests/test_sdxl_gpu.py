@@ -1,0 +1,171 @@
+"""Stage-3 parity: CUDA UNet / VAE / sampler (seedx_b200.sdxl, .sampler) vs the CPU oracle (oracle/sdxl.py, a restatement of
+diffusers 0.25.0 — parity unpinned against real diffusers, see the oracle header) on scaled-down configs with the full topology.
+
+Tolerances: UNet eps and latents: relative Frobenius <= 5e-3 (fp16 activations between layers, as the reference itself runs);
+decoded pixels: PSNR >= 40 dB on the [0,1] image (north_star)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from seedx_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a.float().cpu() - b.float().cpu()).norm() / b.float().cpu().norm()).item()
+
+
+def psnr(a, b):
+    """a, b in [-1,1] -> PSNR of the [0,1] images"""
+    a = (a.float().cpu() / 2 + 0.5).clamp(0, 1)
+    b = (b.float().cpu() / 2 + 0.5).clamp(0, 1)
+    mse = (a - b).pow(2).mean().item()
+    return 10 * math.log10(1.0 / max(mse, 1e-20))
+
+
+def mk(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+def test_small_kernels():
+    from seedx_b200 import ops
+    x = mk((2, 16, 16, 64), 1).half()
+    ref = F.unfold(F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1)), 3, stride=2)          # [n, c*9, L], index c*9 + tap
+    ref = ref.view(2, 64, 9, 64).permute(0, 3, 2, 1).reshape(2 * 64, 9 * 64)
+    assert torch.equal(ops.im2col_nhwc(x, 3, 2, 1, 8, 8), ref.half())
+    ref = F.unfold(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), 3, stride=2).view(2, 64, 9, 64).permute(0, 3, 2, 1).reshape(128, 576)
+    assert torch.equal(ops.im2col_nhwc(x, 3, 2, 0, 8, 8), ref.half())
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(ops.upsample2x_nhwc(x), up.half())
+    from oracle import sdxl as osd
+    t = torch.tensor([981.0, 1.0, 1024.0, 0.0], device="cuda")
+    out = torch.empty((4, 320), device="cuda", dtype=torch.float16)
+    ops.timestep_embedding(t, 320, out)
+    assert (out.float().cpu() - osd.timestep_embedding(t.cpu(), 320)).abs().max() < 2e-3
+    s = mk((300, 1000), 3, 4.0)
+    assert rel(ops.softmax_rows(s, 0.5), torch.softmax(s * 0.5, -1)) < 1e-3
+    img = mk((1, 8, 8, 3), 4)
+    assert (ops.image_to_u8(img).int().cpu() - osd.postprocess(img.permute(0, 3, 1, 2).cpu()).int()).abs().max() <= 1
+
+
+def _unet_inputs(cfg, B, hw, in_ch=4):
+    x = synth.randn("unet_x", (B, in_ch, hw, hw))
+    ctx = synth.randn("unet_ctx", (B, 16, cfg["cross_attention_dim"]))
+    te = synth.randn("unet_te", (B, cfg["text_embed_dim"]))
+    tid = torch.tensor([[1024.0, 1024.0, 0.0, 0.0, 1024.0, 1024.0]]).repeat(B, 1)
+    return x, ctx, te, tid
+
+
+@pytest.mark.parametrize("in_ch", [4, 8])
+def test_unet_tiny_forward(in_ch):
+    from oracle import sdxl as osd
+    from seedx_b200.sdxl import UNet2DConditionModel
+    cfg = dict(synth.TINY_UNET, in_channels=in_ch)
+    sd = synth.unet_state_dict(cfg)
+    B, hw = 2, 64
+    x, ctx, te, tid = _unet_inputs(cfg, B, hw, in_ch)
+    ref = osd.unet_forward(sd, cfg, x, 601.0, ctx, te, tid)
+    m = UNet2DConditionModel(cfg)
+    m.load_state_dict(sd)
+    out = m(x.cuda(), 601.0, ctx.cuda(), added_cond_kwargs=dict(text_embeds=te.cuda(), time_ids=tid.cuda()))
+    e = rel(out, ref)
+    print(f"tiny unet (in_ch={in_ch}) eps rel err = {e:.3e}")
+    assert e < 5e-3, e
+
+
+def test_vae_tiny_decode_encode():
+    from oracle import sdxl as osd
+    from seedx_b200.sdxl import AutoencoderKL
+    cfg = synth.TINY_VAE
+    sd = synth.vae_state_dict(cfg)
+    vae = AutoencoderKL(cfg)
+    vae.load_state_dict(sd)
+    z = synth.randn("vae_z", (2, 4, 32, 32))
+    ref = osd.vae_decode(sd, cfg, z)
+    out = vae.decode(z.cuda())
+    p = psnr(out, ref)
+    print(f"tiny vae decode PSNR = {p:.1f} dB, rel = {rel(out, ref):.3e}")
+    assert p >= 40.0, p
+    img = synth.randn("vae_img", (1, 3, 256, 256), 0.5)
+    refm = osd.vae_encode_mode(sd, cfg, img)
+    m = vae.encode_mode(img.cuda())
+    e = rel(m, refm)
+    print(f"tiny vae encode rel = {e:.3e}")
+    assert e < 5e-3, e
+
+
+def _cond(cfg, B, tag):
+    T = 16
+    return (synth.randn(tag + "p", (B, T, cfg["cross_attention_dim"])), synth.randn(tag + "pp", (B, cfg["text_embed_dim"])),
+            synth.randn(tag + "n", (B, T, cfg["cross_attention_dim"])), synth.randn(tag + "np", (B, cfg["text_embed_dim"])))
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_t2i_sampler_tiny(graph):
+    """8 Euler steps, 2-way CFG 7.5, then VAE decode: latents rel error and pixel PSNR vs the oracle loop."""
+    from oracle import sdxl as osd
+    from seedx_b200.sampler import DenoiseLoop, decode_to_uint8
+    from seedx_b200.sdxl import AutoencoderKL, EulerDiscreteScheduler, UNet2DConditionModel
+    cfg, vcfg = synth.TINY_UNET, synth.TINY_VAE
+    sd, vsd = synth.unet_state_dict(cfg), synth.vae_state_dict(vcfg)
+    B, hw, steps = 2, 32, 8
+    noise = synth.randn("t2i_noise", (B, 4, hw, hw))
+    p, pp, n, npool = _cond(cfg, B, "t2i")
+    ref_lat = osd.t2i_sample(sd, cfg, noise, p, pp, n, npool, steps=steps, guidance=7.5, size=1024)
+    ref_img = osd.vae_decode(vsd, vcfg, ref_lat / vcfg["scaling_factor"])
+    unet, vae = UNet2DConditionModel(cfg), AutoencoderKL(vcfg)
+    unet.load_state_dict(sd)
+    vae.load_state_dict(vsd)
+    loop = DenoiseLoop(unet, EulerDiscreteScheduler(), B, (hw, hw), 2, use_graph=graph)
+    tid = torch.tensor([[1024.0, 1024.0, 0.0, 0.0, 1024.0, 1024.0]]).repeat(2 * B, 1)
+    loop.set_condition(torch.cat([n, p]).cuda(), torch.cat([npool, pp]).cuda(), tid.cuda())
+    lat = loop.run(noise.cuda(), steps=steps, guidance=7.5).clone()
+    e = rel(lat, ref_lat)
+    img = vae.decode(lat, scale=1.0 / vcfg["scaling_factor"])
+    ps = psnr(img, ref_img)
+    print(f"t2i tiny (graph={graph}): latents rel = {e:.3e}, pixels PSNR = {ps:.1f} dB")
+    assert e < 1e-2 and ps >= 40.0, (e, ps)
+    u8 = decode_to_uint8(vae, lat)
+    assert u8.shape == (B, hw * 8, hw * 8, 3) and u8.dtype == torch.uint8
+    assert (u8.int().cpu() - osd.postprocess(ref_img).int()).abs().float().mean() < 1.5
+    if graph:   # replaying the captured graph with new noise must still be correct
+        noise2 = synth.randn("t2i_noise2", (B, 4, hw, hw))
+        ref2 = osd.t2i_sample(sd, cfg, noise2, p, pp, n, npool, steps=steps, guidance=7.5, size=1024)
+        assert rel(loop.run(noise2.cuda(), steps=steps, guidance=7.5), ref2) < 1e-2
+
+
+def test_edit_sampler_tiny():
+    """3-way CFG (text 7.5 / image 1.5) in sigma space with 8-channel conv_in, 6 steps."""
+    from oracle import sdxl as osd
+    from seedx_b200.sampler import DenoiseLoop
+    from seedx_b200.sdxl import EulerDiscreteScheduler, UNet2DConditionModel
+    cfg = dict(synth.TINY_UNET, in_channels=8)
+    sd = synth.unet_state_dict(cfg)
+    B, hw, steps = 1, 32, 6
+    noise = synth.randn("edit_noise", (B, 4, hw, hw))
+    il = synth.randn("edit_il", (B, 4, hw, hw), 0.7)
+    p, pp, n, npool = _cond(cfg, B, "edit")
+    ref = osd.edit_sample(sd, cfg, noise, il, p, pp, n, npool, steps=steps)
+    unet = UNet2DConditionModel(cfg)
+    unet.load_state_dict(sd)
+    loop = DenoiseLoop(unet, EulerDiscreteScheduler(), B, (hw, hw), 3, use_graph=False)
+    tid = torch.tensor([[1024.0, 1024.0, 0.0, 0.0, 1024.0, 1024.0]]).repeat(3 * B, 1)
+    loop.set_condition(torch.cat([p, n, n]).cuda(), torch.cat([pp, npool, npool]).cuda(), tid.cuda(), image_latents=il.cuda())
+    lat = loop.run(noise.cuda(), steps=steps, guidance=7.5, image_guidance=1.5)
+    e = rel(lat, ref)
+    print(f"edit tiny: latents rel = {e:.3e}")
+    assert e < 1e-2, e
+
+
+def test_scheduler_tables_match_oracle():
+    from oracle import sdxl as osd
+    from seedx_b200.sdxl import EulerDiscreteScheduler
+    a = EulerDiscreteScheduler().set_timesteps(50)
+    b = osd.Euler().set_timesteps(50)
+    assert a.timesteps[0] == 981.0 and a.timesteps[-1] == 1.0
+    assert max(abs(x - float(y)) for x, y in zip(a.sigmas, b.sigmas)) < 1e-5
+    assert abs(a.init_noise_sigma - b.init_noise_sigma) < 1e-5
