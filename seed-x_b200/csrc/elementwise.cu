@@ -225,6 +225,19 @@ __global__ void cfg_euler_kernel(const float* __restrict__ eps, float* __restric
   }
 }
 
+
+// out[r, :] = fp16( a[r, :] + b[r % b_rows, :] )   (positional-embedding add of AttentionPool2d, resampler.py:93)
+template <typename TA>
+__global__ void add_bcast_kernel(const TA* __restrict__ a, const float* __restrict__ b, long long rows, int cols, int b_rows,
+                                 __half* __restrict__ out) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    out[i] = __float2half_rn((float)a[i] + b[(r % b_rows) * cols + c]);
+  }
+}
+
 }  // namespace seedx
 using namespace seedx;
 
@@ -355,4 +368,16 @@ extern "C" int seedx_cfg_euler_step(const float* eps, float* x, void* unet_in, i
                                                                                    guidance, image_guidance, sigma, sigma_next, init_sigma);
   count_launch();
   return check_cuda(cudaGetLastError(), "cfg_euler launch");
+}
+
+extern "C" int seedx_add_bcast_f16(const void* a, int a_dtype, const float* b, int64_t rows, int64_t cols, int64_t b_rows, void* out,
+                                   void* stream) {
+  SEEDX_REQUIRE(a && b && out && rows > 0 && cols > 0 && b_rows > 0, "seedx_add_bcast_f16: bad arguments");
+  const int g = grid_for(rows * cols, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (a_dtype == SEEDX_F16) add_bcast_kernel<__half><<<g, 256, 0, st>>>((const __half*)a, b, rows, (int)cols, (int)b_rows, (__half*)out);
+  else if (a_dtype == SEEDX_F32) add_bcast_kernel<float><<<g, 256, 0, st>>>((const float*)a, b, rows, (int)cols, (int)b_rows, (__half*)out);
+  else SEEDX_REQUIRE(false, "seedx_add_bcast_f16: bad dtype");
+  count_launch();
+  return check_cuda(cudaGetLastError(), "add_bcast launch");
 }

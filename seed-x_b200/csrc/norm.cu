@@ -15,7 +15,8 @@ namespace seedx {
 void count_launch();
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm / RMSNorm : one CTA (256 threads) per row, row cached in registers (cols <= 8192)
+// LayerNorm / RMSNorm.  TPR threads cooperate on one row (32 = a warp, 4 rows per CTA; 256 = a whole CTA); every thread keeps
+// NV 4-element vectors of the row in registers (two-pass statistics on the cached row), 16-byte loads, 8/16-byte stores.
 // ------------------------------------------------------------------------------------------------
 constexpr int LN_THREADS = 256;
 constexpr int LN_MAXPT = 32;
@@ -31,6 +32,80 @@ SEEDX_DEVINL float block_sum(float v, float* sh) {
   return t;
 }
 
+SEEDX_DEVINL float4 ld4(const float* p) { return *(const float4*)p; }
+SEEDX_DEVINL float4 ld4(const __half* p) {
+  const uint2 q = *(const uint2*)p;
+  const float2 a = __half22float2(*(const __half2*)&q.x), b = __half22float2(*(const __half2*)&q.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+SEEDX_DEVINL void st4(float* p, float4 v) { *(float4*)p = v; }
+SEEDX_DEVINL void st4(__half* p, float4 v) {
+  uint2 q;
+  *(__half2*)&q.x = __floats2half2_rn(v.x, v.y);
+  *(__half2*)&q.y = __floats2half2_rn(v.z, v.w);
+  *(uint2*)p = q;
+}
+
+template <typename TI, typename TO, int TPR, int NV>
+__global__ void __launch_bounds__(LN_THREADS)
+layernorm_vec_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     TO* __restrict__ out, long long ldo, TO* __restrict__ out2, const float* __restrict__ add, int add_rows,
+                     long long rows, int cols, float eps, int rms) {
+  __shared__ float sh[8];
+  constexpr int RPB = LN_THREADS / TPR;  // rows per block
+  const int sub = threadIdx.x / TPR, t = threadIdx.x % TPR;
+  const long long row = (long long)blockIdx.x * RPB + sub;
+  const bool row_ok = row < rows;
+  const TI* xr = x + (row_ok ? row : 0) * ldx;
+  const int nvec = cols >> 2;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = t + i * TPR;
+    v[i] = (c < nvec && row_ok) ? ld4(xr + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  float mean = 0.f;
+  if (!rms) mean = (TPR == 32 ? warp_sum(s) : block_sum(s, sh)) / (float)cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = t + i * TPR;
+    if (c < nvec) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + cc * cc + d * d;
+    }
+  }
+  const float var = (TPR == 32 ? warp_sum(q) : block_sum(q, sh)) / (float)cols;
+  const float rstd = rsqrtf(var + eps);
+  if (!row_ok) return;
+  TO* orow = out + row * ldo;
+  TO* orow2 = out2 ? out2 + row * ldo : nullptr;
+  const float* arow = add ? add + (long long)(row % add_rows) * cols : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = t + i * TPR;
+    if (c < nvec) {
+      float4 y = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd);
+      if (gamma) {
+        const float4 g = *(const float4*)(gamma + c * 4);
+        y.x *= g.x, y.y *= g.y, y.z *= g.z, y.w *= g.w;
+      }
+      if (beta) {
+        const float4 bb = *(const float4*)(beta + c * 4);
+        y.x += bb.x, y.y += bb.y, y.z += bb.z, y.w += bb.w;
+      }
+      st4(orow + c * 4, y);
+      if (orow2) {
+        const float4 aa = *(const float4*)(arow + c * 4);
+        st4(orow2 + c * 4, make_float4(y.x + aa.x, y.y + aa.y, y.z + aa.z, y.w + aa.w));
+      }
+    }
+  }
+}
+
+// scalar fallback (cols not a multiple of 4 or unaligned rows): one CTA per row
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(LN_THREADS)
 layernorm_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -78,10 +153,8 @@ layernorm_kernel(const TI* __restrict__ x, long long ldx, const float* __restric
 // GroupNorm on NHWC fp16, 2 passes: (1) per-(image, group) sum / sum-of-squares (fp32 partials, fp64 atomics),
 // (2) apply per-channel scale/shift (+SiLU).  Input may be the channel concatenation of two tensors.
 // ------------------------------------------------------------------------------------------------
-constexpr int GN_PIX_PER_BLOCK = 64;
-
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int hw, int groups,
+gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int hw, int groups, int pix_per_block,
                 double* __restrict__ stats /*[n][groups][2]*/) {
   extern __shared__ float gsm[];  // [groups][2]
   const int n = blockIdx.y;
@@ -89,38 +162,49 @@ gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
   const int cpg = C / groups;
   for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) gsm[i] = 0.f;
   __syncthreads();
-  const int p0 = blockIdx.x * GN_PIX_PER_BLOCK;
-  const int p1 = min(p0 + GN_PIX_PER_BLOCK, hw);
-  const int vec_per_pix = C >> 3;  // 8 halves per 16-byte vector; c1, c2 multiples of 8
-  const int total = (p1 - p0) * vec_per_pix;
-  // each thread owns a fixed channel-vector when blockDim % vec_per_pix == 0 is not guaranteed -> accumulate per element
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int pix = p0 + idx / vec_per_pix;
-    const int cv = (idx % vec_per_pix) * 8;
-    const __half* src = (cv < c1) ? x1 + ((long long)n * hw + pix) * c1 + cv : x2 + ((long long)n * hw + pix) * c2 + (cv - c1);
-    const uint4 q = *(const uint4*)src;
-    const __half2* h = (const __half2*)&q;
-    float f[8];
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, hw);
+  const int vpp = C >> 3;  // 16-byte channel vectors per pixel (c1, c2 multiples of 8)
+  // thread -> (pixel lane, channel vector): a thread keeps ONE channel vector and strides over pixels, so the 8 per-channel
+  // partial sums live in registers and shared-memory atomics happen once per thread, not once per element
+  const bool wide = vpp >= 256;
+  const int lanes = wide ? 1 : 256 / vpp;
+  const int p_lane = wide ? 0 : (int)threadIdx.x / vpp;
+  const int cv_step = wide ? 256 : vpp;
+  if (p_lane < lanes) {
+    for (int cv = wide ? (int)threadIdx.x : (int)threadIdx.x % vpp; cv < vpp; cv += cv_step) {
+      const int ch = cv * 8;
+      const bool first = ch < c1;
+      const __half* base = first ? x1 + (long long)n * hw * c1 + ch : x2 + (long long)n * hw * c2 + (ch - c1);
+      const int cstride = first ? c1 : c2;
+      float s[8], ss[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 t = __half22float2(h[j]);
-      f[2 * j] = t.x, f[2 * j + 1] = t.y;
-    }
-    // the 8 channels span at most two groups when cpg >= 8, more when cpg < 8: handle generally
-    int g_prev = cv / cpg;
-    float s = 0.f, ss = 0.f;
+      for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+      for (int pix = p0 + p_lane; pix < p1; pix += lanes) {
+        const uint4 q = *(const uint4*)(base + (long long)pix * cstride);
+        const __half2* h = (const __half2*)&q;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (cv + j) / cpg;
-      if (g != g_prev) {
-        atomicAdd(&gsm[2 * g_prev], s);
-        atomicAdd(&gsm[2 * g_prev + 1], ss);
-        s = 0.f, ss = 0.f, g_prev = g;
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(h[j]);
+          s[2 * j] += t.x, ss[2 * j] += t.x * t.x;
+          s[2 * j + 1] += t.y, ss[2 * j + 1] += t.y * t.y;
+        }
       }
-      s += f[j], ss += f[j] * f[j];
+      int g_prev = ch / cpg;
+      float a = 0.f, aa = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int g = (ch + j) / cpg;
+        if (g != g_prev) {
+          atomicAdd(&gsm[2 * g_prev], a);
+          atomicAdd(&gsm[2 * g_prev + 1], aa);
+          a = 0.f, aa = 0.f, g_prev = g;
+        }
+        a += s[j], aa += ss[j];
+      }
+      atomicAdd(&gsm[2 * g_prev], a);
+      atomicAdd(&gsm[2 * g_prev + 1], aa);
     }
-    atomicAdd(&gsm[2 * g_prev], s);
-    atomicAdd(&gsm[2 * g_prev + 1], ss);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&stats[(long long)n * groups * 2 + i], (double)gsm[i]);
@@ -187,16 +271,40 @@ extern "C" int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const fl
   SEEDX_REQUIRE((out2 == nullptr) == (add == nullptr), "seedx_layernorm: out2 and add go together");
   if (add) SEEDX_REQUIRE(add_rows > 0, "seedx_layernorm: add_rows must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t in_sz = x_dtype == SEEDX_F32 ? 4 : 2, out_sz = out_dtype == SEEDX_F32 ? 4 : 2;
+  const bool vec_ok = cols % 4 == 0 && ((uintptr_t)x % 16 == 0) && ((ldx * in_sz) % (4 * in_sz) == 0) && ((uintptr_t)out % 16 == 0) &&
+                      ((ldo * out_sz) % (4 * out_sz) == 0) && (!out2 || (uintptr_t)out2 % 16 == 0) && (!gamma || (uintptr_t)gamma % 16 == 0) &&
+                      (!beta || (uintptr_t)beta % 16 == 0) && (!add || (uintptr_t)add % 16 == 0) && cols <= 8192;
+#define LN_VEC(TI, TO, TPR, NV)                                                                                              \
+  layernorm_vec_kernel<TI, TO, TPR, NV><<<(unsigned)((rows + (LN_THREADS / TPR) - 1) / (LN_THREADS / TPR)), LN_THREADS, 0, st>>>( \
+      (const TI*)x, ldx, gamma, beta, (TO*)out, ldo, (TO*)out2, add, (int)(add ? add_rows : 1), rows, (int)cols, eps, rms)
+#define LN_VEC_DISPATCH(TI, TO)                  \
+  do {                                           \
+    if (cols <= 256) LN_VEC(TI, TO, 32, 2);      \
+    else if (cols <= 512) LN_VEC(TI, TO, 32, 4); \
+    else if (cols <= 1024) LN_VEC(TI, TO, 32, 8);\
+    else if (cols <= 2048) LN_VEC(TI, TO, 32, 16);\
+    else if (cols <= 4096) LN_VEC(TI, TO, 256, 4);\
+    else LN_VEC(TI, TO, 256, 8);                 \
+  } while (0)
   dim3 grid((unsigned)rows);
 #define LN_LAUNCH(TI, TO)                                                                                                  \
   layernorm_kernel<TI, TO><<<grid, LN_THREADS, 0, st>>>((const TI*)x, ldx, gamma, beta, (TO*)out, ldo, (TO*)out2, add, \
                                                         (int)(add ? add_rows : 1), (int)cols, eps, rms)
-  if (x_dtype == SEEDX_F32 && out_dtype == SEEDX_F16) LN_LAUNCH(float, __half);
-  else if (x_dtype == SEEDX_F32 && out_dtype == SEEDX_F32) LN_LAUNCH(float, float);
-  else if (x_dtype == SEEDX_F16 && out_dtype == SEEDX_F16) LN_LAUNCH(__half, __half);
-  else if (x_dtype == SEEDX_F16 && out_dtype == SEEDX_F32) LN_LAUNCH(__half, float);
+#define LN_BOTH(TI, TO)            \
+  do {                             \
+    if (vec_ok) LN_VEC_DISPATCH(TI, TO); \
+    else LN_LAUNCH(TI, TO);        \
+  } while (0)
+  if (x_dtype == SEEDX_F32 && out_dtype == SEEDX_F16) LN_BOTH(float, __half);
+  else if (x_dtype == SEEDX_F32 && out_dtype == SEEDX_F32) LN_BOTH(float, float);
+  else if (x_dtype == SEEDX_F16 && out_dtype == SEEDX_F16) LN_BOTH(__half, __half);
+  else if (x_dtype == SEEDX_F16 && out_dtype == SEEDX_F32) LN_BOTH(__half, float);
   else SEEDX_REQUIRE(false, "seedx_layernorm: bad dtype combination");
 #undef LN_LAUNCH
+#undef LN_VEC
+#undef LN_VEC_DISPATCH
+#undef LN_BOTH
   count_launch();
   return check_cuda(cudaGetLastError(), "layernorm_kernel launch");
 }
@@ -212,8 +320,11 @@ extern "C" int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, 
   SEEDX_REQUIRE(n > 0 && n <= 65535 && hw > 0, "seedx_groupnorm_nhwc: bad n/hw");
   cudaStream_t st = (cudaStream_t)stream;
   SEEDX_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * groups * n, st));
-  dim3 g1((unsigned)((hw + GN_PIX_PER_BLOCK - 1) / GN_PIX_PER_BLOCK), (unsigned)n);
-  gn_stats_kernel<<<g1, 256, groups * 2 * sizeof(float), st>>>((const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw, groups,
+  int64_t spb = (hw * n + 148 * 4 - 1) / (148 * 4);  // ~4 waves of CTAs; >= 32 pixels each so the register partials amortise the atomics
+  if (spb < 32) spb = 32;
+  if (spb > hw) spb = hw;
+  dim3 g1((unsigned)((hw + spb - 1) / spb), (unsigned)n);
+  gn_stats_kernel<<<g1, 256, groups * 2 * sizeof(float), st>>>((const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw, groups, (int)spb,
                                                                (double*)stats_ws);
   count_launch();
   SEEDX_CUDA(cudaGetLastError());

@@ -1,0 +1,226 @@
+"""Stage 2 host: LLaMA causal LM (prefill on the tensor-core GEMM, token loop on HBM-bound GEMV kernels) behind the
+surface of the reference class ``src.models.mllm.modeling_llama_xformer.LlamaForCausalLM``
+(/root/reference/src/models/mllm/modeling_llama_xformer.py:612-779): ``from_pretrained``, ``get_input_embeddings``,
+and a greedy ``generate`` that reproduces what seed_x.py:184-197 consumes (sequences + last-layer hidden states).
+
+HBM layout: weights fp16 ([q|k|v] fused, [up_j,gate_j] row-interleaved for the SwiGLU epilogue); residual stream fp32;
+KV cache fp16, one [max_len, H*d] slab per layer and tensor, appended in place (the reference re-copies it with
+torch.cat every step, :215-218); sampler state (sequence, length, EOS marker) device resident.
+"""
+import json
+import os
+
+import torch
+
+from . import ops
+from ._lib import SeedxError
+
+LLAMA_13B = dict(vocab=32330, hidden=5120, layers=40, heads=40, ffn=13824, eps=1e-5)
+
+
+class _Embedding:
+    def __init__(self, llm):
+        self.llm = llm
+
+    def __call__(self, input_ids):
+        """ids [1,P] or [P] (any device / list) -> fp32 device tensor [1,P,D] (the reference returns model-dtype rows)."""
+        ids = torch.as_tensor(input_ids).reshape(-1).to(self.llm.device, torch.int32)
+        out = torch.empty((1, ids.numel(), self.llm.cfg["hidden"]), device=self.llm.device, dtype=torch.float32)
+        ops.embed_rows(self.llm.embed, out, ids=ids)
+        return out
+
+
+class GreedyOutput:
+    def __init__(self, sequences, hidden, n_generated):
+        self.sequences = sequences          # [1, P + n] int64 (host)
+        self.last_hidden_states = hidden    # fp32 device [n - 1, D]: post-norm state of the position that consumed generated token j
+        self.n_generated = n_generated
+
+
+class LlamaForCausalLM:
+    def __init__(self, cfg=None, max_len=2048, device="cuda"):
+        self.cfg = dict(LLAMA_13B if cfg is None else cfg)
+        self.device = torch.device(device)
+        self.max_len = max_len
+        self.dtype = torch.float16
+        self._loaded = False
+        self._graph = None
+
+    # ---- reference-compatible plumbing --------------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, low_cpu_mem_usage=True, torch_dtype=None, **kw):
+        d = pretrained_model_name_or_path
+        c = json.load(open(os.path.join(d, "config.json")))
+        cfg = dict(vocab=c["vocab_size"], hidden=c["hidden_size"], layers=c["num_hidden_layers"], heads=c["num_attention_heads"],
+                   ffn=c["intermediate_size"], eps=c.get("rms_norm_eps", 1e-5))
+        m = cls(cfg)
+        sd = {}
+        idx = os.path.join(d, "pytorch_model.bin.index.json")
+        sidx = os.path.join(d, "model.safetensors.index.json")
+        if os.path.exists(sidx):
+            from safetensors.torch import load_file
+            for f in sorted(set(json.load(open(sidx))["weight_map"].values())):
+                sd.update(load_file(os.path.join(d, f)))
+        elif os.path.exists(idx):
+            for f in sorted(set(json.load(open(idx))["weight_map"].values())):
+                sd.update(torch.load(os.path.join(d, f), map_location="cpu"))
+        elif os.path.exists(os.path.join(d, "model.safetensors")):
+            from safetensors.torch import load_file
+            sd = load_file(os.path.join(d, "model.safetensors"))
+        else:
+            sd = torch.load(os.path.join(d, "pytorch_model.bin"), map_location="cpu")
+        m.load_state_dict(sd)
+        return m
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def get_input_embeddings(self):
+        return _Embedding(self)
+
+    def load_state_dict(self, sd, strict=False, device_generator=None):
+        cfg, dev = self.cfg, self.device
+        D, H = cfg["hidden"], cfg["heads"]
+        if D // H != 128:
+            raise SeedxError("the decode kernels are specialised for head_dim 128 (LLaMA)")
+        h = lambda t: t.to(dev, torch.float16).contiguous()  # noqa: E731
+        f = lambda t: t.float().to(dev).contiguous()  # noqa: E731
+        self.embed = h(sd["model.embed_tokens.weight"])
+        self.layers = []
+        for i in range(cfg["layers"]):
+            p = f"model.layers.{i}."
+            up, gate = sd[p + "mlp.up_proj.weight"], sd[p + "mlp.gate_proj.weight"]
+            self.layers.append(dict(
+                ln1=f(sd[p + "input_layernorm.weight"]), ln2=f(sd[p + "post_attention_layernorm.weight"]),
+                wqkv=h(torch.cat([sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"], sd[p + "self_attn.v_proj.weight"]], 0)),
+                wo=h(sd[p + "self_attn.o_proj.weight"]),
+                wgu=h(torch.stack([up, gate], dim=1).reshape(2 * up.shape[0], -1)),   # rows [up_0, gate_0, up_1, gate_1, ...]
+                wdown=h(sd[p + "mlp.down_proj.weight"])))
+        self.norm = f(sd["model.norm.weight"])
+        self.lm_head = h(sd["lm_head.weight"])
+        d = D // H
+        self.inv_freq = (1.0 / (10000.0 ** (torch.arange(0, d, 2).float() / d))).to(dev)   # modeling_llama_xformer.py:101
+        self._alloc_state()
+        self._loaded = True
+        return [], []
+
+    def _alloc_state(self):
+        cfg, dev = self.cfg, self.device
+        D, L = cfg["hidden"], cfg["layers"]
+        self.kcache = [torch.zeros((self.max_len, D), device=dev, dtype=torch.float16) for _ in range(L)]
+        self.vcache = [torch.zeros((self.max_len, D), device=dev, dtype=torch.float16) for _ in range(L)]
+        self.seq = torch.zeros((self.max_len,), device=dev, dtype=torch.int32)
+        self.state = torch.zeros((4,), device=dev, dtype=torch.int32)
+        self.xa = torch.zeros((D,), device=dev, dtype=torch.float32)
+        self.xb = torch.zeros((D,), device=dev, dtype=torch.float32)
+        self.qkv1 = torch.zeros((3 * D,), device=dev, dtype=torch.float32)
+        self.att1 = torch.zeros((D,), device=dev, dtype=torch.float32)
+        self.g1 = torch.zeros((cfg["ffn"],), device=dev, dtype=torch.float32)
+        self.hn1 = torch.zeros((1, D), device=dev, dtype=torch.float32)
+        self.logits = torch.zeros((cfg["vocab"],), device=dev, dtype=torch.float32)
+
+    # ---- prefill: tensor-core path ---------------------------------------------------------------------------------------
+    def prefill(self, x, pos0=0):
+        """x: fp32 device [P, D] input embeddings for positions pos0..; fills the KV cache; returns the fp32 residual stream [P, D]."""
+        cfg = self.cfg
+        D, H = cfg["hidden"], cfg["heads"]
+        d = D // H
+        P = x.shape[0]
+        if pos0 + P > self.max_len:
+            raise SeedxError(f"sequence length {pos0 + P} exceeds the KV cache ({self.max_len})")
+        x = x.contiguous().clone()
+        n = torch.empty((P, D), device=x.device, dtype=torch.float16)
+        qkv = torch.empty((P, 3 * D), device=x.device, dtype=torch.float16)
+        o = torch.empty((P, D), device=x.device, dtype=torch.float16)
+        gu = torch.empty((P, cfg["ffn"]), device=x.device, dtype=torch.float16)
+        q4 = qkv.view(1, P, 3, H, d)
+        qv, kv, vv = (q4[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        ov = o.view(1, P, H, d).permute(0, 2, 1, 3)
+        for li, L in enumerate(self.layers):
+            ops.layernorm(x, L["ln1"], None, cfg["eps"], out=n, rms=True)
+            ops.gemm(n, L["wqkv"], out=qkv)
+            ops.rope_kv_prefill(qkv, pos0, H, d, self.inv_freq, self.kcache[li], self.vcache[li])
+            if pos0 == 0:
+                ops.attention(qv, kv, vv, ov, scale=d ** -0.5, causal=True)
+            else:   # chunked prefill: keys/values come from the cache (positions 0..pos0+P-1)
+                kc = self.kcache[li][: pos0 + P].view(1, pos0 + P, H, d).permute(0, 2, 1, 3)
+                vc = self.vcache[li][: pos0 + P].view(1, pos0 + P, H, d).permute(0, 2, 1, 3)
+                ops.attention(qv, kc, vc, ov, scale=d ** -0.5, causal=True)
+            ops.gemm(o, L["wo"], out=x, residual=x)
+            ops.layernorm(x, L["ln2"], None, cfg["eps"], out=n, rms=True)
+            ops.gemm(n, L["wgu"], out=gu, act=ops.ACT_SILU, gated=True)
+            ops.gemm(gu, L["wdown"], out=x, residual=x)
+        return x
+
+    def logits_all(self, x):
+        """final RMSNorm + lm_head over every row of the residual stream (parity checks; LlamaForCausalLM.forward :702-707)."""
+        hn = ops.layernorm(x, self.norm, None, self.cfg["eps"], out_dtype=torch.float32, rms=True)
+        h16 = ops.cast(hn, torch.float16)
+        return ops.gemm(h16, self.lm_head, out_dtype=torch.float32), hn
+
+    # ---- token loop: HBM-bound path ----------------------------------------------------------------------------------------
+    def _decode_step(self, prompt_len, hidden, img_ids, eos_id, suppress_eos):
+        cfg = self.cfg
+        H = cfg["heads"]
+        d = cfg["hidden"] // H
+        ops.embed_rows(self.embed, self.xa, state=self.state, seq=self.seq)
+        for li, L in enumerate(self.layers):
+            ops.gemv(L["wqkv"], self.xa, self.qkv1, rms_w=L["ln1"], eps=cfg["eps"])
+            ops.decode_attention(self.qkv1, self.state, self.inv_freq, self.kcache[li], self.vcache[li], self.att1, H, d)
+            ops.gemv(L["wo"], self.att1, self.xb, residual=self.xa)
+            ops.gemv(L["wgu"], self.xb, self.g1, rms_w=L["ln2"], eps=cfg["eps"], gated=True)
+            ops.gemv(L["wdown"], self.g1, self.xa, residual=self.xb)
+        ops.layernorm(self.xa.view(1, -1), self.norm, None, cfg["eps"], out=self.hn1, rms=True)
+        ops.store_hidden(self.hn1, self.state, prompt_len, hidden)
+        ops.gemv(self.lm_head, self.hn1.view(-1), self.logits)
+        ops.logits_argmax(self.logits, img_ids, self.seq, self.state, eos_id, suppress_eos)
+
+    def generate_greedy(self, input_ids, inputs_embeds, img_ids=None, max_new_tokens=120, eos_id=None, suppress_eos=False,
+                        use_graph=True, sync_every=32):
+        """HF greedy_search as used at seed_x.py:184-189: inputs_embeds [P, D] feed step 0, then the last id each step.
+        img_ids: token ids of <img><img_0>...<img_63></img> for the AutoImageTokenGenerationProcessor (None = no processor)."""
+        if not self._loaded:
+            raise SeedxError("LlamaForCausalLM: weights not loaded")
+        dev = self.device
+        ids = torch.as_tensor(input_ids).reshape(-1)
+        P = ids.numel()
+        if P + max_new_tokens > self.max_len:
+            raise SeedxError("prompt + max_new_tokens exceeds the KV cache")
+        x = inputs_embeds.reshape(P, -1).to(dev, torch.float32)
+        img_dev = torch.as_tensor(img_ids, dtype=torch.int32).to(dev) if img_ids is not None else None
+        self.seq[:P].copy_(ids.to(dev, torch.int32))
+        self.state.copy_(torch.tensor([P, 0, 0, 0], dtype=torch.int32))
+        hidden = torch.zeros((max(max_new_tokens - 1, 1), self.cfg["hidden"]), device=dev, dtype=torch.float32)
+        xs = self.prefill(x)
+        ops.gemv(self.lm_head, xs[P - 1], self.logits, rms_w=self.norm, eps=self.cfg["eps"])
+        ops.logits_argmax(self.logits, img_dev, self.seq, self.state, eos_id, suppress_eos)
+        steps = max_new_tokens - 1
+        if steps > 0:
+            key = (P, hidden.data_ptr(), None if img_dev is None else img_dev.data_ptr(), eos_id, suppress_eos)
+            if use_graph:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    self._decode_step(P, hidden, img_dev, eos_id, suppress_eos)
+                torch.cuda.current_stream().wait_stream(s)
+                self._graph = (key, g, hidden, img_dev)
+            done = 0
+            for i in range(steps):
+                if use_graph:
+                    g.replay()
+                else:
+                    self._decode_step(P, hidden, img_dev, eos_id, suppress_eos)
+                if eos_id is not None and not suppress_eos and (i + 1) % sync_every == 0:
+                    done = int(self.state[1].item())
+                    if done:
+                        break
+        st = self.state.cpu().tolist()
+        n_gen = st[2]
+        if st[1]:
+            n_gen = st[1]          # stop at (and include) the first EOS, like HF greedy_search
+        seq = self.seq[: P + n_gen].cpu().to(torch.int64)
+        return GreedyOutput(seq.unsqueeze(0), hidden[: max(n_gen - 1, 0)], n_gen)

@@ -313,3 +313,66 @@ def cfg_euler_step(eps, x, unet_in, branches, guidance, image_guidance, sigma, s
                                      C.c_float(image_guidance), C.c_float(sigma), C.c_float(sigma_next), C.c_float(init_sigma), _stream()),
           "seedx_cfg_euler_step")
     return x
+
+
+def gemv(W, x, out, *, rms_w=None, eps=1e-5, residual=None, gated=False):
+    """out fp32 = epi(W[N,K] . (rmsnorm(x)*rms_w | x)); W fp16, x fp32 [K]."""
+    _require_cuda(W, x, out)
+    assert W.dtype == torch.float16 and W.is_contiguous() and x.dtype == torch.float32 and out.dtype == torch.float32
+    N, K = W.shape
+    check(lib().seedx_gemv_f16(_ptr(W), _ptr(x), _ptr(rms_w), C.c_float(eps), _ptr(residual), _ptr(out), _i64(N), _i64(K), C.c_int(int(gated)),
+                               _stream()), "seedx_gemv_f16")
+    return out
+
+
+def decode_attention(qkv, state, inv_freq, kcache, vcache, out, heads, head_dim):
+    check(lib().seedx_decode_attention(_ptr(qkv), _ptr(state), _ptr(inv_freq), _ptr(kcache), _ptr(vcache), _ptr(out), C.c_int(heads),
+                                       C.c_int(head_dim), C.c_float(head_dim ** -0.5), _stream()), "seedx_decode_attention")
+    return out
+
+
+def rope_kv_prefill(qkv, pos0, heads, head_dim, inv_freq, kcache, vcache):
+    assert qkv.dtype == torch.float16 and qkv.is_contiguous()
+    check(lib().seedx_rope_kv_prefill(_ptr(qkv), _i64(qkv.shape[0]), _i64(pos0), C.c_int(heads), C.c_int(head_dim), _ptr(inv_freq), _ptr(kcache),
+                                      _ptr(vcache), _stream()), "seedx_rope_kv_prefill")
+
+
+def embed_rows(table, out, *, ids=None, state=None, seq=None):
+    n, dim = out.reshape(-1, out.shape[-1]).shape
+    assert table.dtype == torch.float16 and out.dtype == torch.float32 and out.is_contiguous()
+    if ids is not None:
+        assert ids.dtype == torch.int32 and ids.numel() == n
+    check(lib().seedx_embed_rows(_ptr(table), _ptr(ids), _ptr(state), _ptr(seq), _i64(n), _i64(dim), _ptr(out), _stream()), "seedx_embed_rows")
+    return out
+
+
+def scatter_rows(src, idx, dst, src_idx=None):
+    assert idx.dtype == torch.int32 and dst.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
+    if src_idx is not None:
+        assert src_idx.dtype == torch.int32 and src_idx.numel() == idx.numel()
+    check(lib().seedx_scatter_rows(_ptr(src), _dt(src), _ptr(src_idx), _ptr(idx), _i64(idx.numel()), _i64(dst.shape[-1]), _ptr(dst), _stream()),
+          "seedx_scatter_rows")
+    return dst
+
+
+def store_hidden(x, state, prompt_len, hidden):
+    check(lib().seedx_store_hidden(_ptr(x), _ptr(state), _i64(prompt_len), _i64(hidden.shape[0]), _i64(hidden.shape[1]), _ptr(hidden), _stream()),
+          "seedx_store_hidden")
+
+
+def logits_argmax(logits, img_ids, seq, state, eos_id, suppress_eos):
+    check(lib().seedx_logits_argmax(_ptr(logits), _i64(logits.numel()), _ptr(img_ids), C.c_int(0 if img_ids is None else img_ids.numel()), _ptr(seq),
+                                    _ptr(state), C.c_int(eos_id if eos_id is not None else -1), C.c_int(int(suppress_eos)), _i64(seq.numel()),
+                                    _stream()), "seedx_logits_argmax")
+
+
+def add_bcast_f16(a, b, out=None):
+    """fp16 out[r,:] = a[r,:] + b[r % b_rows,:] (b fp32)."""
+    _require_cuda(a, b, out)
+    assert a.is_contiguous() and b.dtype == torch.float32 and b.is_contiguous()
+    a2 = a.reshape(-1, a.shape[-1])
+    if out is None:
+        out = torch.empty(a2.shape, device=a.device, dtype=torch.float16)
+    check(lib().seedx_add_bcast_f16(_ptr(a2), _dt(a2), _ptr(b), _i64(a2.shape[0]), _i64(a2.shape[1]), _i64(b.shape[0]), _ptr(out), _stream()),
+          "seedx_add_bcast_f16")
+    return out

@@ -320,3 +320,37 @@ class SynthTokenizer:
     def decode(self, ids, skip_special_tokens=False):
         ids = ids.tolist() if hasattr(ids, "tolist") else list(ids)
         return "".join(self.id2tok.get(int(i), f"[{int(i)}]") for i in ids)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# ResamplerXLV2 (de-tokenizer front, resampler.py:226-286)
+# ----------------------------------------------------------------------------------------------------------------------
+RESAMPLER_XL = dict(dim=1024, depth=4, dim_head=64, heads=16, num_queries=64, embedding_dim=4096, output1_dim=768, output2_dim=1280, ff_mult=4)
+TINY_RESAMPLER_XL = dict(dim=256, depth=2, dim_head=64, heads=4, num_queries=64, embedding_dim=320, output1_dim=96, output2_dim=160, ff_mult=4)
+
+
+def resampler_xl_state_dict(cfg, prefix=""):
+    sd = OrderedDict()
+    D, inner = cfg["dim"], cfg["dim_head"] * cfg["heads"]
+    sd["latents"] = randn(prefix + "latents", (1, cfg["num_queries"], D), D ** -0.5 * 4)
+    _lin(sd, "proj_in", D, cfg["embedding_dim"])
+    _norm(sd, "norm_out", D)
+    for i in range(cfg["depth"]):
+        a, f = f"layers.{i}.0", f"layers.{i}.1"
+        _norm(sd, a + ".norm1", D)
+        _norm(sd, a + ".norm2", D)
+        _lin(sd, a + ".to_q", inner, D, bias=False)
+        _lin(sd, a + ".to_kv", 2 * inner, D, bias=False)
+        _lin(sd, a + ".to_out", D, inner, bias=False, gain=0.5)
+        _norm(sd, f + ".0", D)
+        _lin(sd, f + ".1", int(D * cfg["ff_mult"]), D, bias=False)
+        _lin(sd, f + ".3", D, int(D * cfg["ff_mult"]), bias=False, gain=0.5)
+    _lin(sd, "unet_proj_1", cfg["output1_dim"], D)
+    _lin(sd, "unet_proj_2", cfg["output2_dim"], D)
+    sd["unet_attnpool.positional_embedding"] = randn("unet_attnpool.positional_embedding", (cfg["num_queries"] + 1, D), D ** -0.5)
+    for n in ("k_proj", "q_proj", "v_proj"):
+        _lin(sd, "unet_attnpool." + n, D, D)
+    _lin(sd, "unet_attnpool.c_proj", cfg["output2_dim"], D)
+    if prefix:
+        sd = OrderedDict((prefix + k, v) for k, v in sd.items())
+    return sd

@@ -58,9 +58,92 @@ def golden_resamplers():
     print("resamplers", {k: tuple(v.shape) for k, v in out.items()})
 
 
+def golden_llama():
+    """Reference LlamaForCausalLM (xformers stub = exact SDPA) on the tiny config: prefill logits/hidden, 3 cached decode steps,
+    and a 40-token greedy loop driven around the reference forward with the reference's own AutoImageTokenGenerationProcessor."""
+    from transformers import LlamaConfig
+    mod = ref_module("src.models.mllm.modeling_llama_xformer")
+    gen = ref_module("src.models.mllm.generation")
+    cfg = synth.TINY_LLAMA
+    hc = LlamaConfig(vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], intermediate_size=cfg["ffn"], num_hidden_layers=cfg["layers"],
+                     num_attention_heads=cfg["heads"], rms_norm_eps=cfg["eps"], max_position_embeddings=2048)
+    hc.pad_token_id = 0
+    model = mod.LlamaForCausalLM(hc).eval()
+    sd = synth.llama_state_dict(cfg)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("rotary" in m for m in missing), (missing, unexpected)
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    proc = gen.AutoImageTokenGenerationProcessor(tok, num_img_gen_tokens=64)
+    P = 45
+    ids = [tok.bos_token_id] + [int(v) for v in (synth.randn("llama_ids", (P - 1,)).abs() * 1000).long() % (tok.base - 3) + 3]
+    emb = model.get_input_embeddings()(torch.tensor([ids])).detach()
+    emb[0, 5:15] = synth.randn("llama_img_rows", (10, cfg["hidden"]))          # some rows replaced by "image" embeddings
+    out = {"ids": ids, "embeds": emb[0].clone()}
+
+    def fwd(**kw):
+        with torch.no_grad():
+            return model(use_cache=True, output_hidden_states=True, return_dict=True, **kw)
+
+    o = fwd(inputs_embeds=emb, attention_mask=torch.ones(1, P, dtype=torch.long), position_ids=torch.arange(P)[None])
+    out["prefill_logits"] = o.logits[0].float()
+    out["prefill_hidden"] = o.hidden_states[-1][0].float()
+    # greedy loop (HF 4.30 greedy_search semantics, SURVEY.md B.1) around the reference forward + the reference's processor
+    def greedy(ids_, emb_, n_new):
+        o_ = fwd(inputs_embeds=emb_, attention_mask=torch.ones(1, len(ids_), dtype=torch.long), position_ids=torch.arange(len(ids_))[None])
+        seq, past, logits = list(ids_), o_.past_key_values, o_.logits[:, -1, :]
+        gen_ids, hiddens, step_logits = [], [], []
+        for step in range(n_new):
+            nxt = int(proc(torch.tensor([seq]), logits.clone()).argmax(-1))
+            gen_ids.append(nxt)
+            seq.append(nxt)
+            if step == n_new - 1:
+                break
+            o_ = fwd(input_ids=torch.tensor([[nxt]]), past_key_values=past, attention_mask=torch.ones(1, len(seq), dtype=torch.long),
+                     position_ids=torch.tensor([[len(seq) - 1]]))
+            past, logits = o_.past_key_values, o_.logits[:, -1, :]
+            hiddens.append(o_.hidden_states[-1][0, -1].float())
+            step_logits.append(o_.logits[0, -1].float())
+        return gen_ids, torch.stack(hiddens), torch.stack(step_logits)
+
+    g, h, sl = greedy(ids, emb, 16)
+    out["text_gen_ids"], out["text_hidden"], out["text_step_logits"] = g, h, sl
+    # prompt ending in <img>: the processor forces <img_00000..00063></img>, then free text
+    ids_b = ids + [tok.encode("<img>")[0]]
+    emb_b = torch.cat([emb, model.get_input_embeddings()(torch.tensor([[ids_b[-1]]])).detach()], dim=1)
+    g, h, sl = greedy(ids_b, emb_b, 72)
+    out["img_gen_ids"], out["img_hidden"] = g, h
+    assert g[:65] == tok.encode("".join("<img_{:05d}>".format(i) for i in range(64)) + "</img>"), g[:66]
+    # the reference processor on two hand-made rows (pins the restated processor)
+    s = synth.randn("proc_scores", (1, cfg["vocab"]))
+    out["proc_in"] = s.clone()
+    out["proc_out_text"] = proc(torch.tensor([[5, 6, 7]]), s.clone())
+    out["proc_out_img"] = proc(torch.tensor([[5, tok.encode("<img_00010>")[0]]]), s.clone())
+    torch.save(out, os.path.join(HERE, "llama_tiny.pt"))
+    print("llama_tiny: text", out["text_gen_ids"][:8], "img-span tail", out["img_gen_ids"][62:])
+
+
+def golden_resampler_xl():
+    rs = ref_module("src.models.detokenizer.resampler")
+    out = {}
+    for name, cfg in (("tiny", synth.TINY_RESAMPLER_XL), ("full", synth.RESAMPLER_XL)):
+        m = rs.ResamplerXLV2(normalize=False, **cfg).eval()
+        m.load_state_dict(synth.resampler_xl_state_dict(cfg), strict=True)
+        for n_tok in (64, 256):
+            x = synth.randn(f"rxl_{name}_{n_tok}", (2, n_tok, cfg["embedding_dim"]))
+            with torch.no_grad():
+                p, pooled = m(x)
+            out[f"{name}_{n_tok}_prompt"], out[f"{name}_{n_tok}_pooled"] = p.float().half(), pooled.float()
+    torch.save(out, os.path.join(HERE, "resampler_xl.pt"))
+    print("resampler_xl", {k: tuple(v.shape) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["vit", "resamplers"]
+    which = sys.argv[1:] or ["vit", "resamplers", "llama", "resampler_xl"]
     if "vit" in which:
         golden_vit()
     if "resamplers" in which:
         golden_resamplers()
+    if "llama" in which:
+        golden_llama()
+    if "resampler_xl" in which:
+        golden_resampler_xl()

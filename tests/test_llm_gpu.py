@@ -1,0 +1,125 @@
+"""Stage-2 parity: CUDA LLaMA (prefill GEMM path + GEMV token loop) and the ContinuousLVLM agent vs the reference's own
+outputs (tests/golden/llama_tiny.pt) and the CPU oracle.  Tolerance = north_star: logits / hidden states <= 1e-3 relative
+Frobenius; greedy token ids exact."""
+import os
+
+import pytest
+import torch
+
+from seedx_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3
+
+
+def rel(a, b):
+    return ((a.float().cpu() - b.float().cpu()).norm() / b.float().cpu().norm()).item()
+
+
+def mk(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+@pytest.mark.parametrize("N,K", [(5120, 5120), (15360, 5120), (27648, 5120), (5120, 13824), (32330, 5120), (7, 64)])
+def test_gemv(N, K):
+    from seedx_b200 import ops
+    W = mk((N, K), 1, K ** -0.5).half()
+    x = mk((K,), 2)
+    res = mk((N,), 3)
+    rw = mk((K,), 4) + 1.0
+    out = torch.empty((N,), device="cuda")
+    ops.gemv(W, x, out, residual=res)
+    assert rel(out, W.float() @ x + res) < 1e-5
+    xn = x * torch.rsqrt(x.pow(2).mean() + 1e-5) * rw
+    ops.gemv(W, x, out, rms_w=rw, eps=1e-5)
+    assert rel(out, W.float() @ xn) < 1e-5
+    if N % 2 == 0:
+        o2 = torch.empty((N // 2,), device="cuda")
+        ops.gemv(W, x, o2, gated=True)
+        r = W.float() @ x
+        assert rel(o2, r[0::2] * torch.nn.functional.silu(r[1::2])) < 1e-5
+
+
+def _llm():
+    from seedx_b200.llm import LlamaForCausalLM
+    cfg = synth.TINY_LLAMA
+    m = LlamaForCausalLM(cfg, max_len=512)
+    m.load_state_dict(synth.llama_state_dict(cfg))
+    return m, cfg
+
+
+def test_llama_prefill_matches_reference_golden():
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    m, cfg = _llm()
+    xs = m.prefill(g["embeds"].cuda())
+    logits, hid = m.logits_all(xs)
+    e1, e2 = rel(logits, g["prefill_logits"]), rel(hid, g["prefill_hidden"])
+    print(f"llama tiny prefill: logits rel = {e1:.3e}, hidden rel = {e2:.3e}")
+    assert e1 < TOL and e2 < TOL
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_llama_greedy_matches_reference_golden(graph):
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    m, cfg = _llm()
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    img_ids = tok.encode("".join(["<img>"] + ["<img_{:05d}>".format(i) for i in range(64)] + ["</img>"]))
+    out = m.generate_greedy(g["ids"], g["embeds"].cuda(), img_ids=img_ids, max_new_tokens=16, use_graph=graph)
+    assert out.sequences[0][len(g["ids"]):].tolist() == g["text_gen_ids"]
+    e = rel(out.last_hidden_states, g["text_hidden"])
+    print(f"llama tiny greedy (graph={graph}): hidden rel = {e:.3e}")
+    assert e < TOL
+    # prompt ending in <img>: 64 forced image tokens + </img>, then free text
+    sd = synth.llama_state_dict(cfg)
+    ids_b = g["ids"] + [tok.encode("<img>")[0]]
+    emb_b = torch.cat([g["embeds"], sd["model.embed_tokens.weight"][ids_b[-1]][None]])
+    out = m.generate_greedy(ids_b, emb_b.cuda(), img_ids=img_ids, max_new_tokens=72, use_graph=graph)
+    assert out.sequences[0][len(ids_b):].tolist() == g["img_gen_ids"]
+    assert rel(out.last_hidden_states, g["img_hidden"]) < TOL
+
+
+def test_llama_chunked_prefill_and_decode_consistency():
+    """size-independent property: prefill(P) == prefill(P-8) followed by a cached chunk of 8 (same logits for the tail)."""
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    m, cfg = _llm()
+    emb = g["embeds"].cuda()
+    full, _ = m.logits_all(m.prefill(emb))
+    m.prefill(emb[:-8])
+    tail, _ = m.logits_all(m.prefill(emb[-8:], pos0=emb.shape[0] - 8))
+    assert rel(tail, full[-8:]) < 1e-3
+
+
+def test_agent_generate_vs_oracle():
+    """ContinuousLVLM.generate: image embeds -> input resampler (+patch pos) -> scatter -> greedy with forced image span ->
+    hidden-state harvest -> output resampler, against oracle/llm.py::lvlm_generate."""
+    from oracle import llm as ollm
+    from seedx_b200.agent import ContinuousLVLM, Resampler
+    m, cfg = _llm()
+    vit_dim = 320
+    llm_sd = synth.llama_state_dict(cfg)
+    agent_sd = synth.agent_state_dict(cfg["hidden"], vit_dim)
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    agent = ContinuousLVLM.from_pretrained(llm=m, input_resampler=Resampler(8, cfg["hidden"], 2, vit_dim),
+                                           output_resampler=Resampler(8, vit_dim, 2, cfg["hidden"]), add_patch_pos=True, vit_down=True)
+    agent.load_state_dict(agent_sd)
+    N = 2
+    image_embeds = synth.randn("agent_img", (N, 256, vit_dim))
+    patch_pos = torch.tensor([[0.5, 0.5], [0.5, 0.5]])
+    prompt = "<patch>" + "".join("<img_{:05d}>".format(i) for i in range(64)) + "</patch>" + "<img>" + \
+        "".join("<img_{:05d}>".format(i) for i in range(64)) + "</img>" + "draw it again<img>"
+    ids = [tok.bos_token_id] + tok.encode(prompt)
+    ids_t = torch.tensor(ids)
+    first_img = tok.tok2id["<img_00000>"]
+    ids_cmp_mask = ((ids_t >= first_img) & (ids_t < first_img + 64)).unsqueeze(0)
+    embeds_cmp_mask = torch.ones((N, 64), dtype=torch.bool)
+    ref = ollm.lvlm_generate(llm_sd, agent_sd, cfg, tok, ids, image_embeds, ids_cmp_mask[0], embeds_cmp_mask, patch_pos, 70)
+    out = agent.generate(tokenizer=tok, input_ids=ids_t.unsqueeze(0), image_embeds=image_embeds.cuda(), embeds_cmp_mask=embeds_cmp_mask,
+                         ids_cmp_mask=ids_cmp_mask, patch_positions=patch_pos, max_new_tokens=70)
+    assert out["ids"] == ref["ids"]
+    assert out["has_img_output"] and ref["has_img_output"] and out["num_gen_imgs"] == 1
+    assert out["text"] == ref["text"]
+    e = rel(out["img_gen_feat"], ref["img_gen_feat"])
+    print(f"agent img_gen_feat rel = {e:.3e}")
+    assert e < TOL

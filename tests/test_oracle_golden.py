@@ -38,3 +38,37 @@ def test_resampler_oracle_matches_reference():
         x = synth.randn(f"res_{name}_x", (3, nkv, kv_dim))
         out = vit.resampler(sd, f"res_{name}.", x, heads, 1e-5)
         assert rel(out, g[name]) < 2e-5, name
+
+
+def test_llama_oracle_matches_reference():
+    """forward (prefill logits / hidden), cached decode, logits processor and the greedy loop vs the reference's own outputs."""
+    from oracle import llm
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    cfg = synth.TINY_LLAMA
+    sd = synth.llama_state_dict(cfg)
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    logits, hid, cache = llm.llama_forward(sd, cfg, g["embeds"], 0, None)
+    assert rel(logits, g["prefill_logits"]) < 2e-5 and rel(hid, g["prefill_hidden"]) < 2e-5
+    img_ids = tok.encode("".join(["<img>"] + ["<img_{:05d}>".format(i) for i in range(64)] + ["</img>"]))
+    # processor restatement
+    assert torch.equal(llm.image_token_processor(img_ids, 7, g["proc_in"][0]), g["proc_out_text"][0])
+    assert torch.equal(llm.image_token_processor(img_ids, tok.encode("<img_00010>")[0], g["proc_in"][0]), g["proc_out_img"][0])
+    # greedy loops
+    gen, h = llm.greedy_generate(sd, cfg, g["ids"], g["embeds"], img_ids, 16)
+    assert gen == g["text_gen_ids"] and rel(h, g["text_hidden"]) < 2e-5
+    ids_b = g["ids"] + [tok.encode("<img>")[0]]
+    emb_b = torch.cat([g["embeds"], sd["model.embed_tokens.weight"][ids_b[-1]][None]])
+    gen, h = llm.greedy_generate(sd, cfg, ids_b, emb_b, img_ids, 72)
+    assert gen == g["img_gen_ids"] and rel(h, g["img_hidden"]) < 2e-5
+
+
+def test_resampler_xl_oracle_matches_reference():
+    from oracle import resampler_xl as orx
+    g = torch.load(os.path.join(GOLD, "resampler_xl.pt"))
+    for name, cfg in (("tiny", synth.TINY_RESAMPLER_XL), ("full", synth.RESAMPLER_XL)):
+        sd = synth.resampler_xl_state_dict(cfg)
+        for n_tok in (64, 256):
+            x = synth.randn(f"rxl_{name}_{n_tok}", (2, n_tok, cfg["embedding_dim"]))
+            p, pooled = orx.resampler_xl(sd, cfg, x)
+            assert rel(p, g[f"{name}_{n_tok}_prompt"]) < 5e-4          # golden prompt stored as fp16
+            assert rel(pooled, g[f"{name}_{n_tok}_pooled"]) < 2e-5
