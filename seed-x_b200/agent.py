@@ -52,7 +52,7 @@ class ContinuousLVLM:
         self.output_resampler = ResamplerWeights(sd, "output_resampler.", self.out_cfg.num_heads, 1e-5, dev)
         if self.add_patch_pos:
             w = sd["patch_pos_embed"].float()                     # [4, D]; x @ W == gemm(x, W^T); K padded 4 -> 8 for 16-byte rows
-            wt = torch.zeros((w.shape[1], 8), dtype=torch.float16)
+            wt = torch.zeros((w.shape[1], 8), dtype=torch.float16, device=w.device)
             wt[:, :4] = w.t().to(torch.float16)
             self.patch_w = wt.to(dev)
         self._loaded = True
@@ -104,7 +104,10 @@ class ContinuousLVLM:
             assert embeds_cmp_mask is not None and ids_cmp_mask is not None
             lm = self.encode_images(image_embeds, patch_positions)                  # [N*64, D] fp32
             dst = torch.nonzero(torch.as_tensor(ids_cmp_mask).reshape(-1).cpu()).reshape(-1).to(torch.int32).to(self.device)
-            src = torch.nonzero(torch.as_tensor(embeds_cmp_mask).reshape(-1).cpu()).reshape(-1).to(torch.int32).to(self.device)
+            em = torch.as_tensor(embeds_cmp_mask).cpu()
+            if em.dim() == 1:                      # one flag per view (eval_img2text_seed_x_i.py:134) -> all 64 rows of that view
+                em = em[:, None].expand(-1, lm.shape[0] // em.shape[0])
+            src = torch.nonzero(em.reshape(-1)).reshape(-1).to(torch.int32).to(self.device)
             if dst.numel() != src.numel():
                 raise SeedxError("ids_cmp_mask and embeds_cmp_mask select different numbers of rows")
             ops.scatter_rows(lm, dst, x, src_idx=src)

@@ -10,6 +10,8 @@
 // (im2col-free implicit GEMM).
 //
 // Reference call sites replaced: see include/seedx.h (seedx_gemm_f16).
+#include <math.h>
+
 #include "common.cuh"
 #include "../../include/seedx.h"
 
@@ -27,7 +29,7 @@ struct GemmParams {
   long long ldd, strideD, ldr, strideR;
   int res_row_mod, bias_g_rows;
   float alpha;
-  int act, gated, out_f32, res_f32, vec_ok, b_batched;
+  int act, gated, out_f32, res_f32, vec_ok, b_batched, bias_vec;
   // conv
   int conv, taps_w, c_chunks, conv_w, conv_h, tile_w, tile_h, tiles_per_img, tiles_w, pad, imgs_per_tile;
 };
@@ -36,23 +38,32 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 
+constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 = TMA, warp 1 = MMA, warps 2..9 = epilogue
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
+
 template <int BN>
 struct TileCfg {
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N for M=128: multiple of 16, <= 256");
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;  // power of two: 128 / 256 / 512
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - 1024 - 256) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  // two accumulator stages; the last 32-column epilogue chunk of a stage may over-read up to 16 columns -> keep them allocated
+  static constexpr int TMEM_COLS = pow2_cols(2 * BN + 16);
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 SEEDX_DEVINL float apply_act(float x, int act) {
-  if (act == SEEDX_ACT_GELU_ERF) return gelu_erf(x);
+  if (act == SEEDX_ACT_GELU_ERF) return gelu_erf_fast(x);
   if (act == SEEDX_ACT_SILU) return silu(x);
   return x;
 }
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = TileCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
@@ -78,7 +89,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), EPI_WARPS);
     }
     mbar_fence_init();
   }
@@ -172,10 +183,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ------------------------------------------------ epilogue warps (TMEM -> regs -> global)
-    const int lane_grp = warp & 3;  // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    const int lane_grp = warp & 3;            // TMEM lanes [32*lane_grp, +32) are accessible to this warp
+    const int chunk0 = ((warp - 2) >> 2) * 32;  // warps 2..5 take even 32-column chunks, warps 6..9 the odd ones
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int n_out = p.gated ? (p.N >> 1) : p.N;
+    const int n_out_all = p.gated ? (p.N >> 1) : p.N;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int b = t / tiles_per_batch;
       const int r = t - b * tiles_per_batch;
@@ -194,8 +206,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int rrow = p.res_row_mod ? (row % p.res_row_mod) : row;
 
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        if (n0 + c >= p.N) break;  // warp-uniform
+      const int col_end = min(p.N, n0 + BN);   // columns of this tile that exist
+      for (int c = chunk0; c < BN; c += 64) {
+        if (n0 + c >= col_end) break;  // warp-uniform
         __syncwarp();              // tcgen05.ld is warp-collective: reconverge after the predicated stores
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
@@ -204,15 +217,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) * p.alpha + bm;
         const int col0 = n0 + c;
+        const bool chunk_full = col0 + 32 <= col_end;
         if (p.bias_n != nullptr) {
+          if (chunk_full && p.bias_vec) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) x[i] += __ldg(p.bias_n + col0 + i);
+            for (int i = 0; i < 32; i += 4) {
+              const float4 q = __ldg((const float4*)(p.bias_n + col0 + i));
+              x[i] += q.x, x[i + 1] += q.y, x[i + 2] += q.z, x[i + 3] += q.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < col_end) x[i] += __ldg(p.bias_n + col0 + i);
+          }
         }
         if (bg != nullptr) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (col0 + i < p.N) x[i] += __ldg(bg + col0 + i);
+            if (col0 + i < col_end) x[i] += __ldg(bg + col0 + i);
         }
         int nvals = 32;
         int ocol0 = col0;
@@ -226,6 +248,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 32; ++i) x[i] = apply_act(x[i], p.act);
         }
         if (!row_ok) continue;
+        const int n_out = p.gated ? (col_end >> 1) : col_end;  // output columns of this tile end here
         const bool full = (ocol0 + nvals <= n_out) && p.vec_ok;
         if (p.residual != nullptr) {
           if (p.res_f32) {
@@ -327,9 +350,37 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int tiles = p.m_blocks * p.n_blocks * p.batch;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
+}
+
+static const int kTileN[] = {64, 96, 128, 144, 160, 192, 208, 224, 240, 256};
+
+static bool valid_tile_n(int bn) {
+  for (int t : kTileN)
+    if (t == bn) return true;
+  return false;
+}
+
+// Pick the N tile that minimises a simple cycle model of the persistent kernel:
+//   waves = ceil(tiles / SMs); per tile max(MMA issue, epilogue drain) cycles; plus the un-overlapped epilogue of the last tile.
+// MMA: 128 x BN x 16 per instruction = BN/2 cycles, but never faster than shared memory can feed A+B (128 B/clk).
+static int choose_tile_n(int m_tiles, int N, int k_blocks, bool heavy_epilogue) {
+  const int sms = num_sms();
+  double best = 1e30;
+  int best_bn = 256;
+  for (int bn : kTileN) {
+    const int n_blocks = (N + bn - 1) / bn;
+    const long long tiles = (long long)m_tiles * n_blocks;
+    const long long waves = (tiles + sms - 1) / sms;
+    const double mma_k16 = fmax(bn / 2.0, (4096.0 + 32.0 * bn) / 128.0);
+    const double mma = k_blocks * 4.0 * mma_k16;
+    const double epi = bn * (heavy_epilogue ? 14.0 : 8.0) + 300.0;
+    const double cost = waves * (fmax(mma, epi) + 150.0) + epi;
+    if (cost < best - 1e-9 || (fabs(cost - best) <= 1e-9 && bn > best_bn)) best = cost, best_bn = bn;
+  }
+  return best_bn;
 }
 
 }  // namespace seedx
@@ -347,8 +398,7 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
   const bool conv = a->conv_taps_h > 0;
   GemmParams p{};
   int bn = a->tile_n;
-  if (bn == 0) bn = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
-  SEEDX_REQUIRE(bn == 64 || bn == 128 || bn == 256, "seedx_gemm_f16: tile_n must be 64/128/256");
+  SEEDX_REQUIRE(bn == 0 || valid_tile_n(bn), "seedx_gemm_f16: tile_n must be 0 (auto) or one of 64/96/128/144/160/192/208/224/240/256");
   if (a->gated) SEEDX_REQUIRE(a->N % 2 == 0, "seedx_gemm_f16: gated epilogue needs even N");
 
   CUtensorMap ta, tb;
@@ -363,6 +413,7 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
       return e;
     p.k_blocks = (int)((a->K + BK - 1) / BK);
     p.m_blocks = (int)((a->M + BM - 1) / BM);
+    if (bn == 0) bn = choose_tile_n(p.m_blocks * (int)a->batch, (int)a->N, p.k_blocks, a->act != SEEDX_ACT_NONE);
   } else {
     const int64_t C = a->conv_c, W = a->conv_w, H = a->conv_h, NI = a->conv_n;
     SEEDX_REQUIRE(C % 8 == 0 && C > 0, "seedx_gemm_f16(conv): channels must be a multiple of 8");
@@ -388,6 +439,7 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
                   (long long)a->conv_taps_h * a->conv_taps_w * cchunks * BK);
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
     uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    if (bn == 0) bn = choose_tile_n((int)((a->M + BM - 1) / BM), (int)a->N, a->conv_taps_h * a->conv_taps_w * cchunks, a->act != SEEDX_ACT_NONE);
     uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
     if (int e = encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a->A, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
@@ -437,8 +489,18 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
     vec = vec && ((uintptr_t)a->residual % 16 == 0) && (a->ldr % re == 0) && (a->strideR % re == 0);
   }
   p.vec_ok = vec ? 1 : 0;
+  p.bias_vec = (a->bias_n && (uintptr_t)a->bias_n % 16 == 0) ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (bn == 256) return launch_gemm<256>(ta, tb, p, st);
-  if (bn == 128) return launch_gemm<128>(ta, tb, p, st);
-  return launch_gemm<64>(ta, tb, p, st);
+  switch (bn) {
+    case 64: return launch_gemm<64>(ta, tb, p, st);
+    case 96: return launch_gemm<96>(ta, tb, p, st);
+    case 128: return launch_gemm<128>(ta, tb, p, st);
+    case 144: return launch_gemm<144>(ta, tb, p, st);
+    case 160: return launch_gemm<160>(ta, tb, p, st);
+    case 192: return launch_gemm<192>(ta, tb, p, st);
+    case 208: return launch_gemm<208>(ta, tb, p, st);
+    case 224: return launch_gemm<224>(ta, tb, p, st);
+    case 240: return launch_gemm<240>(ta, tb, p, st);
+    default: return launch_gemm<256>(ta, tb, p, st);
+  }
 }

@@ -49,7 +49,7 @@ def pack_conv(w, dev, cin_pad_to=None):
     """[Cout, Cin, k, k] -> fp16 [Cout, k*k*Cpad], k index = (kh*k + kw)*Cpad + c, Cpad = roundup(Cin, 64)."""
     cout, cin, k, _ = w.shape
     cpad = (cin + 63) // 64 * 64
-    wp = torch.zeros((cout, k, k, cpad), dtype=torch.float16)
+    wp = torch.zeros((cout, k, k, cpad), dtype=torch.float16, device=w.device)
     wp[..., :cin] = w.permute(0, 2, 3, 1).to(torch.float16)
     return wp.reshape(cout, k * k * cpad).to(dev).contiguous()
 
@@ -60,9 +60,9 @@ def pad_rows(w, b, nmin=8):
     npad = (n + nmin - 1) // nmin * nmin
     if npad == n:
         return w, b
-    wp = torch.zeros((npad,) + tuple(w.shape[1:]), dtype=w.dtype)
+    wp = torch.zeros((npad,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
     wp[:n] = w
-    bp = torch.zeros((npad,), dtype=b.dtype)
+    bp = torch.zeros((npad,), dtype=b.dtype, device=b.device)
     bp[:n] = b
     return wp, bp
 
@@ -409,7 +409,7 @@ class AutoencoderKL:
         self.has_encoder = "encoder.conv_in.weight" in sd
         if self.has_decoder:
             w, b = pad_rows(sd["post_quant_conv.weight"].reshape(cfg["latent_channels"], -1), sd["post_quant_conv.bias"])
-            wq = torch.zeros((w.shape[0], 8), dtype=w.dtype)
+            wq = torch.zeros((w.shape[0], 8), dtype=w.dtype, device=w.device)
             wq[:, : w.shape[1]] = w
             self.post_quant = (_h(wq, dev), _f(b, dev))
             self.d_conv_in = cv("decoder.conv_in")

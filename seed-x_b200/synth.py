@@ -21,7 +21,23 @@ def _gen(name, seed):
     return g
 
 
+_DEVICE = "cpu"
+
+
+def set_device(device):
+    """'cpu' (default): bit-reproducible fp32 tensors shared by oracle, goldens and CUDA path.  'cuda': tensors are drawn directly
+    on the GPU in fp16 (a different stream of values) — used to materialise the 13 B-parameter benchmark models in seconds."""
+    global _DEVICE
+    _DEVICE = device
+
+
 def randn(name, shape, std=1.0, mean=0.0, seed=SEED):
+    if _DEVICE != "cpu":
+        h = hashlib.sha256(f"{seed}:{name}".encode()).digest()
+        g = torch.Generator(device=_DEVICE)
+        g.manual_seed(int.from_bytes(h[:8], "little") & ((1 << 62) - 1))
+        t = torch.randn(tuple(shape), generator=g, device=_DEVICE, dtype=torch.float16)
+        return t.mul_(std).add_(mean) if (std != 1.0 or mean != 0.0) else t
     t = torch.randn(tuple(shape), generator=_gen(name, seed), dtype=torch.float32)
     # fp16-representable values: the reference checkpoints are fp16 tensors, so the oracle (fp32 math) and the CUDA path
     # (fp16 operands) start from bit-identical parameters and inputs

@@ -122,7 +122,7 @@ class VisionTransformerWithAttnPool:
         h = lambda t: t.to(dev, torch.float16).contiguous()  # noqa: E731
         f = lambda t: t.float().to(dev).contiguous()  # noqa: E731
         w = sd["conv1.weight"].reshape(self.width, -1)
-        wp = torch.zeros((self.width, self.kpad), dtype=torch.float16)
+        wp = torch.zeros((self.width, self.kpad), dtype=torch.float16, device=w.device)
         wp[:, : w.shape[1]] = w.to(torch.float16)
         self.w_patch = wp.to(dev)
         self.pos_cpu = sd["positional_embedding"].float().cpu()

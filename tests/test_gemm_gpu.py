@@ -21,7 +21,7 @@ def mk(shape, seed, scale=1.0):
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (1024, 1664, 1664), (200, 328, 72),
                                    (2048, 4992, 1664), (174, 5120, 5120), (77, 40, 8), (1, 32330, 256)])
-@pytest.mark.parametrize("tile_n", [0, 64, 128])
+@pytest.mark.parametrize("tile_n", [0, 64, 96, 128, 144, 160, 192, 208, 224, 240, 256])
 def test_gemm_plain(M, N, K, tile_n):
     from seedx_b200 import ops
     a = mk((M, K), 1).half()
@@ -33,9 +33,13 @@ def test_gemm_plain(M, N, K, tile_n):
     assert rel(out16, ref) < 2e-3
 
 
-def test_gemm_epilogues():
+@pytest.mark.parametrize("tile_n", [0, 144, 208])
+def test_gemm_epilogues(tile_n):
     from seedx_b200 import ops
+    import functools
     M, N, K = 384, 768, 320
+    ops = type("O", (), {k: getattr(ops, k) for k in dir(ops)})
+    ops.gemm = functools.partial(ops.gemm, tile_n=tile_n)
     a = mk((M, K), 3).half()
     w = mk((N, K), 4, K ** -0.5).half()
     bias = mk((N,), 5)
