@@ -151,6 +151,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from seedx_b200 import _lib, synth
+    from seedx_b200 import dist as sdist
     from seedx_b200.engine import SeedXEngine
     log = (lambda *a: print("[bench]", *a, file=sys.stderr, flush=True)) if rank == 0 else None
     tensor_peak, hbm_peak, peak_src = peaks()
@@ -198,9 +199,7 @@ def main():
         u8 = eng.generate(v, patch_pos, text_ids, steps=args.denoise_steps, n_views=n_views)
         nonlocal gather_buf
         if world > 1:                                  # the only collective: gather finished images on every rank (NCCL / NVLink)
-            if gather_buf is None:
-                gather_buf = torch.empty((world,) + tuple(u8.shape), device=u8.device, dtype=torch.uint8)
-            dist.all_gather_into_tensor(gather_buf, u8)
+            gather_buf = sdist.gather_images(u8, gather_buf)
         if e2e:
             if out_host is not None:
                 out_host.copy_(u8, non_blocking=True)
@@ -230,12 +229,10 @@ def main():
             stages.append(eng._events)
         e1.record()
         sync()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = sdist.max_over_ranks(e0.elapsed_time(e1), "cuda")
         st = {k: statistics.mean(a.elapsed_time(b) for (a, b) in [(ev[i], ev[i + 1]) for ev in stages])
               for i, k in enumerate(("vit_ms", "llm_ms", "detok_ms"))}
-        return float(ms.item()), _lib.launch_count() - n0, st
+        return ms, _lib.launch_count() - n0, st
 
     with ClockSampler(local) as cs:
         ms_dev, launches, stages = timed(e2e=False)

@@ -101,6 +101,9 @@ typedef struct seedx_attn_args {
 } seedx_attn_args;
 
 int seedx_attention_f16(const seedx_attn_args* args, void* stream);
+/* implementation switch for A/B tests: 0 = auto (tcgen05/TMEM kernel when d <= 128 and sq >= 128, else mma.sync), 1 = always mma.sync */
+void seedx_attention_set_impl(int impl);
+int seedx_attention_last_impl(void); /* 2 = tcgen05 kernel, 1 = mma.sync kernel (most recent call) */
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm (rms=0) / RMSNorm (rms=1) over the last dimension, fp32 statistics.
@@ -159,31 +162,32 @@ int seedx_cfg_euler_step(const float* eps, float* x, void* unet_in, int64_t batc
                          float image_guidance, float sigma, float sigma_next, float init_sigma, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * LLaMA token loop (batch-1 greedy decode; HBM-bound) and prefill glue.  Device-resident sampler state:
- *   seq   int32 [max_len]  prompt ids followed by generated ids
- *   state int32 [4]        [0] current length, [1] 1-based index of the generated EOS (0 = none), [2] #generated
+ * LLaMA token loop (greedy decode of up to 8 sequences in lock-step; HBM-bound) and prefill glue.  Device-resident state:
+ *   seq   int32 [batch][max_len]  prompt ids followed by generated ids
+ *   state int32 [batch][4]        [0] current length, [1] 1-based index of the generated EOS (0 = none), [2] #generated, [3] prompt length
  * ---------------------------------------------------------------------------------------------- */
-/* out[N or N/2] = epi(W[N,K] . (rms_w ? rmsnorm(x)*rms_w : x)); gated: out[j] = r[2j] * silu(r[2j+1]); else += residual.
+/* out[b][N or N/2] = epi(W[N,K] . (rms_w ? rmsnorm(x[b])*rms_w : x[b])), b < batch (1, 2, 4 or 8); the fp16 weight matrix is
+ * streamed once for all sequences.  gated: out[j] = r[2j] * silu(r[2j+1]); else += residual[b].  Row strides ldx/ldr/ldo in elements.
  * replaces the M=1 projections of modeling_llama_xformer.py:204-206,239,166-167,707 (+ LlamaRMSNorm :258-259,443) */
-int seedx_gemv_f16(const void* W, const float* x, const float* rms_w, float eps, const float* residual, float* out, int64_t N, int64_t K,
-                   int gated, void* stream);
-/* one new token: RoPE(q,k) (:141-149), append k,v at position state[0]-1 (replaces torch.cat :215-218), attention over the
- * cache (:225-237, unmasked decode).  qkv fp32 [3*H*d]; caches fp16 [max_len, H*d]; out fp32 [H*d] */
-int seedx_decode_attention(const float* qkv, const int32_t* state, const float* inv_freq, void* kcache, void* vcache, float* out, int heads,
-                           int head_dim, float scale, void* stream);
+int seedx_gemv_f16(const void* W, const float* x, int64_t ldx, const float* rms_w, float eps, const float* residual, int64_t ldr, float* out,
+                   int64_t ldo, int64_t N, int64_t K, int batch, int gated, void* stream);
+/* one new token per sequence: RoPE(q,k) (:141-149), append k,v at position state[b][0]-1 (replaces torch.cat :215-218), attention
+ * over the cache (:225-237).  qkv fp32 [batch][3*H*d]; caches fp16 [batch][max_len, H*d] (cache_stride elements apart); out fp32 [batch][H*d] */
+int seedx_decode_attention(const float* qkv, const int32_t* state, const float* inv_freq, void* kcache, void* vcache, int64_t cache_stride,
+                           float* out, int batch, int heads, int head_dim, float scale, void* stream);
 /* prefill: RoPE q,k in place on fp16 [tokens, 3*H*d] for positions pos0.., and copy k,v rows into the caches */
 int seedx_rope_kv_prefill(void* qkv, int64_t tokens, int64_t pos0, int heads, int head_dim, const float* inv_freq, void* kcache, void* vcache,
                           void* stream);
-/* embedding rows -> fp32 [n, dim]; ids == NULL: one row for the last token of the device sequence (seq[state[0]-1]) */
-int seedx_embed_rows(const void* table, const int32_t* ids, const int32_t* state, const int32_t* seq, int64_t n, int64_t dim, float* out,
-                     void* stream);
+/* embedding rows -> fp32 [n, dim]; ids == NULL: row b = last token of device sequence b (seq[b*seq_stride + state[b][0]-1]) */
+int seedx_embed_rows(const void* table, const int32_t* ids, const int32_t* state, const int32_t* seq, int64_t seq_stride, int64_t n, int64_t dim,
+                     float* out, void* stream);
 /* dst[idx[r], :] = src[src_idx ? src_idx[r] : r, :]  (input_embeds[ids_cmp_mask] = image_embeds_lm[embeds_cmp_mask], seed_x.py:173) */
 int seedx_scatter_rows(const void* src, int src_dtype, const int32_t* src_idx, const int32_t* idx, int64_t n, int64_t dim, float* dst,
                        void* stream);
-/* hidden[state[0] - prompt_len - 1, :] = x  (last_hidden_states harvest, seed_x.py:196-197) */
-int seedx_store_hidden(const float* x, const int32_t* state, int64_t prompt_len, int64_t max_rows, int64_t dim, float* hidden, void* stream);
-/* AutoImageTokenGenerationProcessor (generation.py:19-31) + argmax + append to seq/state, no host sync */
-int seedx_logits_argmax(float* logits, int64_t vocab, const int32_t* img_ids, int n_img_ids, int32_t* seq, int32_t* state, int eos_id,
+/* hidden[b][state[b][0] - state[b][3] - 1, :] = x[b]  (last_hidden_states harvest, seed_x.py:196-197) */
+int seedx_store_hidden(const float* x, const int32_t* state, int batch, int64_t max_rows, int64_t dim, float* hidden, void* stream);
+/* AutoImageTokenGenerationProcessor (generation.py:19-31) + argmax + append to seq/state per sequence, no host sync */
+int seedx_logits_argmax(float* logits, int64_t vocab, const int32_t* img_ids, int n_img_ids, int32_t* seq, int32_t* state, int batch, int eos_id,
                         int suppress_eos, int64_t max_len, void* stream);
 
 /* out[r,:] = fp16(a[r,:] + b[r % b_rows,:]), b fp32 (AttentionPool2d positional add, src/models/detokenizer/resampler.py:93) */

@@ -89,13 +89,8 @@ class ContinuousLVLM:
                       v.view(batch, n_kv, H, d).permute(0, 2, 1, 3), o.view(batch, Nq, H, d).permute(0, 2, 1, 3), scale=d ** -0.5)
         return ops.gemm(o, r.wo, bias=r.bo, out_dtype=torch.float32, bias_g=bias_g, bias_g_rows=Nq if bias_g is not None else 0)
 
-    def generate(self, tokenizer, prompt=None, input_ids=None, image_embeds=None, embeds_cmp_mask=None, ids_cmp_mask=None,
-                 logits_processor=None, num_img_gen_tokens=64, temperature=0.7, num_beams=1, max_new_tokens=120, top_p=0.5,
-                 dtype=torch.float16, device="cuda", patch_positions=None, suppress_eos=False):
-        if not self._loaded:
-            raise SeedxError("ContinuousLVLM: weights not loaded")
-        if prompt is not None:
-            input_ids = tokenizer(prompt, return_tensors="pt").input_ids
+    def _embed_request(self, input_ids, image_embeds, embeds_cmp_mask, ids_cmp_mask, patch_positions):
+        """prompt embeddings with the resampled image features scattered into the <img_k> rows (seed_x.py:157-173)"""
         ids = torch.as_tensor(input_ids).reshape(-1).cpu()
         P = ids.numel()
         D = self.llm.cfg["hidden"]
@@ -111,10 +106,11 @@ class ContinuousLVLM:
             if dst.numel() != src.numel():
                 raise SeedxError("ids_cmp_mask and embeds_cmp_mask select different numbers of rows")
             ops.scatter_rows(lm, dst, x, src_idx=src)
-        img_str = "".join([BOI_TOKEN] + [IMG_TOKEN.format(i) for i in range(num_img_gen_tokens)] + [EOI_TOKEN])
-        img_ids = tokenizer.encode(img_str, add_special_tokens=False)
-        eos = getattr(tokenizer, "eos_token_id", None)
-        out = self.llm.generate_greedy(ids, x, img_ids=img_ids, max_new_tokens=max_new_tokens, eos_id=eos, suppress_eos=suppress_eos)
+        return ids, x
+
+    def _harvest(self, tokenizer, out, P, num_img_gen_tokens):
+        """split generated ids into text / image spans and run the output resampler on the harvested hidden rows (seed_x.py:191-223)"""
+        D = self.llm.cfg["hidden"]
         gen = out.sequences[0][P:]
         boi = tokenizer.encode(BOI_TOKEN, add_special_tokens=False)[0]
         eoi = tokenizer.encode(EOI_TOKEN, add_special_tokens=False)[0]
@@ -134,3 +130,33 @@ class ContinuousLVLM:
         text_mask[gen == boi] = False
         text = tokenizer.decode(gen[text_mask], skip_special_tokens=False)
         return {"text": text, "has_img_output": bool(eoi_idx), "img_gen_feat": feat, "num_gen_imgs": len(eoi_idx), "ids": gen.tolist()}
+
+    def generate_batch(self, tokenizer, requests, num_img_gen_tokens=64, max_new_tokens=120, suppress_eos=False):
+        """Several independent requests decoded in lock-step (the LLM weights are read once per step for all of them).
+        requests: list of dicts with the per-request keyword arguments of generate()."""
+        if not self._loaded:
+            raise SeedxError("ContinuousLVLM: weights not loaded")
+        img_str = "".join([BOI_TOKEN] + [IMG_TOKEN.format(i) for i in range(num_img_gen_tokens)] + [EOI_TOKEN])
+        img_ids = tokenizer.encode(img_str, add_special_tokens=False)
+        eos = getattr(tokenizer, "eos_token_id", None)
+        results = []
+        for c0 in range(0, len(requests), 8):
+            chunk = requests[c0:c0 + 8]
+            pairs = [self._embed_request(r.get("input_ids"), r.get("image_embeds"), r.get("embeds_cmp_mask"), r.get("ids_cmp_mask"),
+                                         r.get("patch_positions")) for r in chunk]
+            outs = self.llm.generate_greedy_batch([p[0] for p in pairs], [p[1] for p in pairs], img_ids=img_ids, max_new_tokens=max_new_tokens,
+                                                  eos_id=eos, suppress_eos=suppress_eos)
+            results += [self._harvest(tokenizer, o, p[0].numel(), num_img_gen_tokens) for o, p in zip(outs, pairs)]
+        return results
+
+    def generate(self, tokenizer, prompt=None, input_ids=None, image_embeds=None, embeds_cmp_mask=None, ids_cmp_mask=None,
+                 logits_processor=None, num_img_gen_tokens=64, temperature=0.7, num_beams=1, max_new_tokens=120, top_p=0.5,
+                 dtype=torch.float16, device="cuda", patch_positions=None, suppress_eos=False):
+        """reference signature (seed_x.py:130-145); temperature / top_p / num_beams are accepted and ignored exactly as the reference
+        ignores them (do_sample=False greedy search, Appendix D.13)."""
+        if prompt is not None:
+            input_ids = tokenizer(prompt, return_tensors="pt").input_ids
+        req = dict(input_ids=input_ids, image_embeds=image_embeds, embeds_cmp_mask=embeds_cmp_mask, ids_cmp_mask=ids_cmp_mask,
+                   patch_positions=patch_positions)
+        return self.generate_batch(tokenizer, [req], num_img_gen_tokens=num_img_gen_tokens, max_new_tokens=max_new_tokens,
+                                   suppress_eos=suppress_eos)[0]

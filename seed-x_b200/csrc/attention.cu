@@ -271,7 +271,15 @@ static int launch_attn(const AttnParams& p, int B, int H, cudaStream_t st) {
 
 }  // namespace seedx
 
+namespace seedx {
+int attention_tc_try(const seedx_attn_args* a, cudaStream_t st);
+static int g_attn_impl = 0;  // 0 = auto (tcgen05 kernel when eligible), 1 = force the mma.sync kernel
+static int g_attn_last = 0;  // implementation used by the most recent call: 2 = tcgen05, 1 = mma.sync
+}
 using namespace seedx;
+
+extern "C" void seedx_attention_set_impl(int impl) { seedx::g_attn_impl = impl; }
+extern "C" int seedx_attention_last_impl(void) { return seedx::g_attn_last; }
 
 extern "C" int seedx_attention_f16(const seedx_attn_args* a, void* stream) {
   SEEDX_REQUIRE(a && a->q && a->k && a->v && a->o, "seedx_attention_f16: null pointer");
@@ -294,6 +302,14 @@ extern "C" int seedx_attention_f16(const seedx_attn_args* a, void* stream) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.causal = a->causal;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_attn_impl == 0) {
+    const int rc = attention_tc_try(a, st);
+    if (rc >= 0) {
+      g_attn_last = 2;
+      return rc;
+    }
+  }
+  g_attn_last = 1;
   if (a->d <= 64) return launch_attn<64>(p, a->batch, a->heads, st);
   if (a->d <= 112) return launch_attn<112>(p, a->batch, a->heads, st);
   if (a->d <= 128) return launch_attn<128>(p, a->batch, a->heads, st);

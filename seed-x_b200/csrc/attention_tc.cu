@@ -1,0 +1,318 @@
+// seedx-b200: tcgen05 flash attention (forward) for sm_100a.
+//
+//   O[b,h,i,:] = softmax_j( scale * Q[b,h,i,:].K[b,h,j,:] (+causal) ) V[b,h,j,:]         fp16 in/out, fp32 softmax/accumulate
+//
+// One CTA = 128 query rows of one (batch, head).  Warp 0: TMA producer (Q once, K/V tiles of 128 keys through two mbarrier
+// rings).  Warp 1: single-thread MMA issuer: S_j = Q K_j^T into a double-buffered TMEM accumulator (2 x 128 columns), then
+// O += P_j V_j with P_j read back as the TMEM A-operand and V_j as an MN-major shared-memory B-operand.  Warps 2..5: softmax —
+// thread = query row (TMEM lane), so row max / row sum need no shuffles; P_j (fp16) overwrites the first 64 columns of S_j;
+// the O accumulator (TMEM) is rescaled only when a row maximum moved.  QK^T of tile j+1 overlaps the softmax of tile j.
+//
+// Replaces the same reference call sites as seedx_attention_f16 (include/seedx.h) for head dims <= 128 and long sequences.
+#include "common.cuh"
+#include "../../include/seedx.h"
+
+namespace seedx {
+void count_launch();
+
+struct FaParams {
+  __half* o;
+  long long o_sb, o_sh, o_ss;
+  int sq, sk, d;
+  float scale_log2;
+  int causal, q_batched;
+};
+
+template <int D>
+struct FaCfg {
+  static constexpr int BM = 128, BN = 128;
+  static constexpr int HALVES = D / 64;
+  static constexpr int HALF_BYTES = 128 * 64 * 2;           // one [128 rows x 64 fp16] swizzled tile
+  static constexpr int TILE_BYTES = HALVES * HALF_BYTES;    // Q, K or V tile
+  static constexpr int KV_STAGES = (D == 64) ? 3 : 2;
+  static constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES) + 1024 + 256;
+  static constexpr uint32_t S_COL0 = 0, S_COL1 = 128, O_COL = 256;
+};
+
+template <int D>
+__global__ void __launch_bounds__(192, 1)
+flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                     const FaParams p) {
+  using Cfg = FaCfg<D>;
+  constexpr int KS = Cfg::KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = smem_base;
+  const uint32_t sK0 = sQ + Cfg::TILE_BYTES;
+  const uint32_t sV0 = sK0 + KS * Cfg::TILE_BYTES;
+  const uint32_t bar = sV0 + KS * Cfg::TILE_BYTES;
+  // barriers: q_full, k_full[KS], k_empty[KS], v_full[KS], v_empty[KS], s_full[2], p_full[2], pv_done[2]
+  const uint32_t q_full = bar;
+  auto k_full = [&](int s) { return bar + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bar + 8u * (1 + KS + s); };
+  auto v_full = [&](int s) { return bar + 8u * (1 + 2 * KS + s); };
+  auto v_empty = [&](int s) { return bar + 8u * (1 + 3 * KS + s); };
+  auto s_full = [&](int s) { return bar + 8u * (1 + 4 * KS + s); };
+  auto p_full = [&](int s) { return bar + 8u * (3 + 4 * KS + s); };
+  auto pv_done = [&](int s) { return bar + 8u * (5 + 4 * KS + s); };
+  const uint32_t tmem_slot = bar + 8u * (7 + 4 * KS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * Cfg::BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KS; ++s) {
+      mbar_init(k_full(s), 1), mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1), mbar_init(v_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(s_full(s), 1);
+      mbar_init(p_full(s), 128);
+      mbar_init(pv_done(s), 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  int n_tiles = (p.sk + Cfg::BN - 1) / Cfg::BN;
+  const int causal_off = p.sk - p.sq;
+  if (p.causal) {
+    const int lim = (m0 + Cfg::BM - 1 + causal_off) / Cfg::BN + 1;
+    if (lim < n_tiles) n_tiles = lim < 1 ? 1 : lim;
+  }
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Cfg::TILE_BYTES);
+#pragma unroll
+      for (int hf = 0; hf < Cfg::HALVES; ++hf) tma_load_4d(sQ + hf * Cfg::HALF_BYTES, &tmQ, q_full, hf * 64, m0, h, p.q_batched ? b : 0);
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(k_empty(st), ph ^ 1u);
+        mbar_expect_tx(k_full(st), Cfg::TILE_BYTES);
+#pragma unroll
+        for (int hf = 0; hf < Cfg::HALVES; ++hf)
+          tma_load_4d(sK0 + st * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmK, k_full(st), hf * 64, j * Cfg::BN, h, b);
+        mbar_wait(v_empty(st), ph ^ 1u);
+        mbar_expect_tx(v_full(st), Cfg::TILE_BYTES);
+#pragma unroll
+        for (int hf = 0; hf < Cfg::HALVES; ++hf)
+          tma_load_4d(sV0 + st * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmV, v_full(st), hf * 64, j * Cfg::BN, h, b);
+        if (++st == KS) st = 0, ph ^= 1u;
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, D) | (1u << 16);  // B operand MN-major
+      const uint32_t tO = tmem_base + Cfg::O_COL;
+      auto issue_pv = [&](int j, int vst) {
+        const uint32_t tP = tmem_base + ((j & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
+        const uint32_t vb = sV0 + vst * Cfg::TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < Cfg::BN / 16; ++kk)  // 16 keys per MMA: A advances 8 TMEM columns, B 16 rows of 128 B
+          umma_f16_ts(tO, tP + (uint32_t)(kk * 8), umma_desc_mn_sw128(vb + kk * 2048, Cfg::HALF_BYTES), idesc_pv, (j | kk) != 0);
+      };
+      mbar_wait(q_full, 0);
+      int kst = 0, vst = 0;
+      uint32_t kph = 0, vph = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(k_full(kst), kph);
+        tc_fence_after();
+        const uint32_t tS = tmem_base + ((j & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
+        const uint32_t kb = sK0 + kst * Cfg::TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t off = (uint32_t)((ks >> 2) * Cfg::HALF_BYTES + (ks & 3) * 32);
+          umma_f16(tS, umma_desc_k_sw128(sQ + off), umma_desc_k_sw128(kb + off), idesc_qk, ks != 0);
+        }
+        umma_commit(k_empty(kst));
+        umma_commit(s_full(j & 1));
+        if (++kst == KS) kst = 0, kph ^= 1u;
+        if (j >= 1) {
+          mbar_wait(p_full((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
+          mbar_wait(v_full(vst), vph);
+          tc_fence_after();
+          issue_pv(j - 1, vst);
+          umma_commit(v_empty(vst));
+          umma_commit(pv_done((j - 1) & 1));
+          if (++vst == KS) vst = 0, vph ^= 1u;
+        }
+      }
+      const int jl = n_tiles - 1;
+      mbar_wait(p_full(jl & 1), (uint32_t)((jl >> 1) & 1));
+      mbar_wait(v_full(vst), vph);
+      tc_fence_after();
+      issue_pv(jl, vst);
+      umma_commit(v_empty(vst));
+      umma_commit(pv_done(jl & 1));
+    }
+  } else {
+    // ------------------------------------------------------------ softmax / correction / epilogue: thread = query row
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int qrow = m0 + row;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tO = tmem_base + lane_addr + Cfg::O_COL;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const uint32_t tS = tmem_base + lane_addr + ((j & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
+      mbar_wait(s_full(j & 1), (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      float s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(v[i]) * p.scale_log2;
+      }
+      const int key0 = j * Cfg::BN;
+      const bool need_mask = (key0 + Cfg::BN > p.sk) || (p.causal && (key0 + Cfg::BN - 1 > m0 + causal_off));
+      if (need_mask) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) {
+          const int key = key0 + i;
+          if (key >= p.sk || (p.causal && key > qrow + causal_off)) s[i] = -INFINITY;
+        }
+      }
+      float m_tile = s[0];
+#pragma unroll
+      for (int i = 1; i < 128; ++i) m_tile = fmaxf(m_tile, s[i]);
+      const float m_new = fmaxf(m_run, m_tile);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha = fast_exp2(m_run - m_use);  // m_run = -inf -> 0
+      if (j > 0) {
+        mbar_wait(pv_done((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));  // O is quiescent: PV_{j-1} retired
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, m_new > m_run)) {                      // some row of this warp moved its maximum: rescale O
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + (uint32_t)(c * 32), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(tO + (uint32_t)(c * 32), v);
+          }
+        }
+      }
+      // P_j = exp2(S_j - m) as fp16 pairs over the first 64 columns of S_j (every S value is already in registers)
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float a = fast_exp2(s[c * 32 + 2 * i] - m_use), c2 = fast_exp2(s[c * 32 + 2 * i + 1] - m_use);
+          rs += a + c2;
+          __half2 hh = __floats2half2_rn(a, c2);
+          v[i] = *(uint32_t*)&hh;
+        }
+        tmem_st16(tS + (uint32_t)(c * 16), v);
+      }
+      tmem_st_wait();
+      l_run = l_run * alpha + rs;
+      m_run = m_new;
+      tc_fence_before();
+      mbar_arrive(p_full(j & 1));
+    }
+    // ---- epilogue
+    const int jl = n_tiles - 1;
+    mbar_wait(pv_done(jl & 1), (uint32_t)((jl >> 1) & 1));
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    __half* orow = p.o + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)qrow * p.o_ss;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + (uint32_t)(c * 32), v);
+      tmem_ld_wait();
+      if (qrow < p.sq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const int col = c * 32 + i;
+          if (col + 8 <= p.d) {
+            uint4 q;
+            __half2* hh = (__half2*)&q;
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              hh[t] = __floats2half2_rn(__uint_as_float(v[i + 2 * t]) * inv, __uint_as_float(v[i + 2 * t + 1]) * inv);
+            *(uint4*)(orow + col) = q;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int D>
+static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FaParams& p, int B, int H, cudaStream_t st) {
+  using Cfg = FaCfg<D>;
+  static bool attr = false;
+  if (!attr) {
+    SEEDX_CUDA(cudaFuncSetAttribute(flash_attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr = true;
+  }
+  dim3 grid((p.sq + Cfg::BM - 1) / Cfg::BM, H, B);
+  flash_attn_tc_kernel<D><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "flash_attn_tc_kernel launch");
+}
+
+static int make_map(CUtensorMap* m, const void* ptr, int d, int s, int H, int B, long long ss, long long sh, long long sb) {
+  uint64_t dims[4] = {(uint64_t)d, (uint64_t)s, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)ss * 2, (uint64_t)(H > 1 ? sh : ss * s) * 2, (uint64_t)(B > 1 ? sb : ss * s) * 2};
+  uint32_t box[4] = {64, 128, 1, 1};
+  return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// returns -1 when the problem is not eligible for the tensor-memory kernel (caller falls back to the mma.sync kernel)
+int attention_tc_try(const seedx_attn_args* a, cudaStream_t st) {
+  if (a->d > 128 || a->d % 8 != 0 || a->sq < 128 || a->sk < 1) return -1;
+  if (a->o_stride_s % 8 || a->o_stride_h % 8 || a->o_stride_b % 8 || (uintptr_t)a->o % 16) return -1;
+  const long long str[] = {a->q_stride_s, a->q_stride_h, a->q_stride_b, a->k_stride_s, a->k_stride_h, a->k_stride_b,
+                           a->v_stride_s, a->v_stride_h, a->v_stride_b};
+  for (long long s : str)
+    if (s % 8 != 0 || s < 0) return -1;
+  if (a->q_stride_s == 0 || a->k_stride_s == 0 || a->v_stride_s == 0) return -1;
+  if ((a->heads > 1 && (a->q_stride_h == 0 || a->k_stride_h == 0 || a->v_stride_h == 0)) ||
+      (a->batch > 1 && (a->k_stride_b == 0 || a->v_stride_b == 0)))
+    return -1;
+  const bool qb = !(a->batch > 1 && a->q_stride_b == 0);
+  CUtensorMap tq, tk, tv;
+  if (make_map(&tq, a->q, a->d, a->sq, a->heads, qb ? a->batch : 1, a->q_stride_s, a->q_stride_h, a->q_stride_b)) return -1;
+  if (make_map(&tk, a->k, a->d, a->sk, a->heads, a->batch, a->k_stride_s, a->k_stride_h, a->k_stride_b)) return -1;
+  if (make_map(&tv, a->v, a->d, a->sk, a->heads, a->batch, a->v_stride_s, a->v_stride_h, a->v_stride_b)) return -1;
+  FaParams p;
+  p.o = (__half*)a->o;
+  p.o_sb = a->o_stride_b, p.o_sh = a->o_stride_h, p.o_ss = a->o_stride_s;
+  p.sq = a->sq, p.sk = a->sk, p.d = a->d;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.causal = a->causal;
+  p.q_batched = qb ? 1 : 0;
+  if (a->d <= 64) return launch_fa<64>(tq, tk, tv, p, a->batch, a->heads, st);
+  return launch_fa<128>(tq, tk, tv, p, a->batch, a->heads, st);
+}
+
+}  // namespace seedx

@@ -365,7 +365,8 @@ static bool valid_tile_n(int bn) {
 
 // Pick the N tile that minimises a simple cycle model of the persistent kernel:
 //   waves = ceil(tiles / SMs); per tile max(MMA issue, epilogue drain) cycles; plus the un-overlapped epilogue of the last tile.
-// MMA: 128 x BN x 16 per instruction = BN/2 cycles, but never faster than shared memory can feed A+B (128 B/clk).
+// MMA: 128 x BN x 16 per instruction = BN/2 cycles, but never faster than shared memory can feed A+B; the effective operand
+// bandwidth measured on B200 (8192^3: BN=128 runs at 0.71x the BN=256 rate) is ~91 B/clk.
 static int choose_tile_n(int m_tiles, int N, int k_blocks, bool heavy_epilogue) {
   const int sms = num_sms();
   double best = 1e30;
@@ -374,7 +375,7 @@ static int choose_tile_n(int m_tiles, int N, int k_blocks, bool heavy_epilogue) 
     const int n_blocks = (N + bn - 1) / bn;
     const long long tiles = (long long)m_tiles * n_blocks;
     const long long waves = (tiles + sms - 1) / sms;
-    const double mma_k16 = fmax(bn / 2.0, (4096.0 + 32.0 * bn) / 128.0);
+    const double mma_k16 = fmax(bn / 2.0, (4096.0 + 32.0 * bn) / 91.0);
     const double mma = k_blocks * 4.0 * mma_k16;
     const double epi = bn * (heavy_epilogue ? 14.0 : 8.0) + 300.0;
     const double cost = waves * (fmax(mma, epi) + 150.0) + epi;

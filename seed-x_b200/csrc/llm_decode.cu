@@ -15,70 +15,140 @@ namespace seedx {
 void count_launch();
 
 // ------------------------------------------------------------------------------------------------
-// GEMV: out = epi( W[N,K] . norm(x) ),  W fp16 row-major, x fp32.  One warp owns a pair of rows at a time.
+// Batched GEMV: out[b][n] = epi( W[n,:] . norm(x[b,:]) ) for NB <= 8 sequences.  W fp16 row-major is streamed exactly once
+// (128-bit ld.global.cs) and reused for all NB activations, which sit in shared memory as fp16.  A CTA owns a contiguous,
+// balanced range of 4-row groups; its 8 warps split K, so the work per CTA is even for any N (no whole-row quantisation).
 // ------------------------------------------------------------------------------------------------
 constexpr int GEMV_THREADS = 256;
+constexpr int GEMV_WARPS = GEMV_THREADS / 32;
+constexpr int GEMV_R = 4;  // weight rows per iteration (two gated pairs)
 
-__global__ void __launch_bounds__(GEMV_THREADS)
-gemv_kernel(const __half* __restrict__ W, const float* __restrict__ x, const float* __restrict__ rms_w, float eps,
-            const float* __restrict__ residual, float* __restrict__ out, int N, int K, int gated) {
-  extern __shared__ float xs[];  // K floats
-  __shared__ float red[GEMV_THREADS / 32];
-  float ss = 0.f;
-  for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
-    const float v = x[k];
-    xs[k] = v;
-    ss += v * v;
-  }
-  if (rms_w != nullptr) {
-    ss = warp_sum(ss);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-    __syncthreads();
-    float tot = 0.f;
+// v[NV] per lane -> lane l (l < NV) returns the warp-wide sum of v[l]; NV-1 + (5 - log2 NV) shuffles
+template <int NV>
+SEEDX_DEVINL float warp_reduce_multi(float (&v)[NV]) {
 #pragma unroll
-    for (int i = 0; i < GEMV_THREADS / 32; ++i) tot += red[i];
-    const float r = rsqrtf(tot / (float)K + eps);
-    for (int k = threadIdx.x; k < K; k += GEMV_THREADS) xs[k] = xs[k] * r * rms_w[k];
+  for (int s = NV / 2; s >= 1; s >>= 1) {
+    const bool upper = (threadIdx.x & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float keep = upper ? v[i + s] : v[i];
+      const float send = upper ? v[i] : v[i + s];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  float r = v[0];
+#pragma unroll
+  for (int o = NV; o < 32; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;  // value index = lane & (NV-1)
+}
+
+template <int NB>
+__global__ void __launch_bounds__(GEMV_THREADS)
+gemv_batched_kernel(const __half* __restrict__ W, const float* __restrict__ x, long long ldx, const float* __restrict__ rms_w, float eps,
+                    const float* __restrict__ residual, long long ldr, float* __restrict__ out, long long ldo, int N, int K, int gated) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  __half* xs = (__half*)gsm;                                  // [NB][K]
+  __shared__ float part[2][GEMV_WARPS][GEMV_R * NB];
+  __shared__ float red[GEMV_WARPS][NB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- prologue: activations -> (RMSNorm) -> fp16 in shared memory
+  float ss[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) ss[b] = 0.f;
+  if (rms_w != nullptr) {
+    for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const float v = x[b * ldx + k];
+        ss[b] += v * v;
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      ss[b] = warp_sum(ss[b]);
+      if (lane == 0) red[warp][b] = ss[b];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < GEMV_WARPS; ++w) t += red[w][b];
+      ss[b] = rsqrtf(t / (float)K + eps);
+    }
+  }
+  for (int k = threadIdx.x; k < K; k += GEMV_THREADS) {
+    const float g = rms_w ? rms_w[k] : 1.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const float v = x[b * ldx + k];
+      xs[b * K + k] = __float2half_rn(rms_w ? v * ss[b] * g : v);
+    }
   }
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warps_total = gridDim.x * (GEMV_THREADS / 32);
-  const int chunks = K >> 3;  // 16-byte chunks per row
-  for (int pair = blockIdx.x * (GEMV_THREADS / 32) + warp; pair * 2 < N; pair += warps_total) {
-    const int r0 = pair * 2;
-    const bool has1 = (r0 + 1) < N;
-    const uint4* w0 = (const uint4*)(W + (long long)r0 * K);
-    const uint4* w1 = (const uint4*)(W + (long long)(has1 ? r0 + 1 : r0) * K);
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll 4
-    for (int c = lane; c < chunks; c += 32) {
-      const uint4 q0 = __ldcs(w0 + c);  // streaming: every weight is read exactly once per token
-      const uint4 q1 = __ldcs(w1 + c);
-      const float4 xa = *(const float4*)(xs + c * 8);
-      const float4 xb = *(const float4*)(xs + c * 8 + 4);
-      const __half2* h0 = (const __half2*)&q0;
-      const __half2* h1 = (const __half2*)&q1;
-      float2 f;
-      f = __half22float2(h0[0]); a0 += f.x * xa.x + f.y * xa.y;
-      f = __half22float2(h0[1]); a0 += f.x * xa.z + f.y * xa.w;
-      f = __half22float2(h0[2]); a0 += f.x * xb.x + f.y * xb.y;
-      f = __half22float2(h0[3]); a0 += f.x * xb.z + f.y * xb.w;
-      f = __half22float2(h1[0]); a1 += f.x * xa.x + f.y * xa.y;
-      f = __half22float2(h1[1]); a1 += f.x * xa.z + f.y * xa.w;
-      f = __half22float2(h1[2]); a1 += f.x * xb.x + f.y * xb.y;
-      f = __half22float2(h1[3]); a1 += f.x * xb.z + f.y * xb.w;
-    }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    if (lane == 0) {
-      if (gated) {
-        out[pair] = a0 * silu(a1);  // rows interleaved [up_j, gate_j]: down(silu(gate(x)) * up(x)), :166-167
-      } else {
-        out[r0] = a0 + (residual ? residual[r0] : 0.f);
-        if (has1) out[r0 + 1] = a1 + (residual ? residual[r0 + 1] : 0.f);
+  // ---- main loop over this CTA's row groups
+  const int groups = (N + GEMV_R - 1) / GEMV_R;
+  const int g_begin = (int)((long long)blockIdx.x * groups / gridDim.x);
+  const int g_end = (int)((long long)(blockIdx.x + 1) * groups / gridDim.x);
+  const int chunks = K >> 3;
+  const int c_begin = (int)((long long)warp * chunks / GEMV_WARPS), c_end = (int)((long long)(warp + 1) * chunks / GEMV_WARPS);
+  int buf = 0;
+  for (int g = g_begin; g < g_end; ++g, buf ^= 1) {
+    const int row0 = g * GEMV_R;
+    const uint4* wrow[GEMV_R];
+#pragma unroll
+    for (int r = 0; r < GEMV_R; ++r) wrow[r] = (const uint4*)(W + (long long)min(row0 + r, N - 1) * K);
+    float acc[GEMV_R * NB];
+#pragma unroll
+    for (int i = 0; i < GEMV_R * NB; ++i) acc[i] = 0.f;
+#pragma unroll 2
+    for (int c = c_begin + lane; c < c_end; c += 32) {
+      uint4 wq[GEMV_R];
+#pragma unroll
+      for (int r = 0; r < GEMV_R; ++r) wq[r] = __ldcs(wrow[r] + c);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const uint4 xq = *(const uint4*)(xs + b * K + c * 8);
+        const __half2* xh = (const __half2*)&xq;
+        float2 xf[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xf[j] = __half22float2(xh[j]);
+#pragma unroll
+        for (int r = 0; r < GEMV_R; ++r) {
+          const __half2* wh = (const __half2*)&wq[r];
+          float a = acc[r * NB + b];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 wf = __half22float2(wh[j]);
+            a = fmaf(wf.x, xf[j].x, a);
+            a = fmaf(wf.y, xf[j].y, a);
+          }
+          acc[r * NB + b] = a;
+        }
       }
     }
+    const float tot = warp_reduce_multi<GEMV_R * NB>(acc);
+    if (lane < GEMV_R * NB) part[buf][warp][lane] = tot;
+    __syncthreads();
+    // finalize: thread t -> (row r, batch b) for the plain epilogue, (pair p, batch b) for the gated one
+    if (threadIdx.x < GEMV_R * NB) {
+      const int r = threadIdx.x / NB, b = threadIdx.x % NB;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < GEMV_WARPS; ++w) v += part[buf][w][r * NB + b];
+      const int row = row0 + r;
+      if (!gated) {
+        if (row < N) out[b * ldo + row] = v + (residual ? residual[b * ldr + row] : 0.f);
+      } else if ((r & 1) == 0 && row + 1 < N) {
+        float gate = 0.f;
+#pragma unroll
+        for (int w = 0; w < GEMV_WARPS; ++w) gate += part[buf][w][(r + 1) * NB + b];
+        out[b * ldo + (row >> 1)] = v * silu(gate);  // rows interleaved [up_j, gate_j]: silu(gate(x)) * up(x), :166-167
+      }
+    }
+    // the next iteration writes the other partial buffer; its __syncthreads orders this iteration's reads before buffer reuse
   }
 }
 
@@ -91,14 +161,21 @@ constexpr int DA_THREADS = 256;
 constexpr int DA_GROUPS = DA_THREADS / 16;  // half-warps
 
 __global__ void __launch_bounds__(DA_THREADS)
-decode_attn_kernel(const float* __restrict__ qkv, const int* __restrict__ state, const float* __restrict__ inv_freq,
-                   __half* __restrict__ kcache, __half* __restrict__ vcache, float* __restrict__ out, int H, float scale) {
+decode_attn_kernel(const float* __restrict__ qkv_all, const int* __restrict__ state_all, const float* __restrict__ inv_freq,
+                   __half* __restrict__ kcache_all, __half* __restrict__ vcache_all, long long cache_stride, float* __restrict__ out_all, int H,
+                   float scale) {
   constexpr int HD = 128;
   __shared__ float qs[HD];
   __shared__ float gm[DA_GROUPS], gl[DA_GROUPS];
   __shared__ float gacc[DA_GROUPS][HD];
   const int h = blockIdx.x;
   const int D = H * HD;
+  const int bidx = blockIdx.y;                    // sequence slot
+  const float* qkv = qkv_all + (long long)bidx * 3 * D;
+  const int* state = state_all + bidx * 4;
+  __half* kcache = kcache_all + (long long)bidx * cache_stride;
+  __half* vcache = vcache_all + (long long)bidx * cache_stride;
+  float* out = out_all + (long long)bidx * D;
   const int pos = state[0] - 1;
   const int tid = threadIdx.x;
   if (tid < HD / 2) {
@@ -206,10 +283,10 @@ __global__ void rope_kv_prefill_kernel(__half* __restrict__ qkv, int T, int pos0
 
 // rows of the embedding table -> fp32.  ids == NULL: single row for the last token of the device-resident sequence
 __global__ void embed_rows_kernel(const __half* __restrict__ table, const int* __restrict__ ids, const int* __restrict__ state,
-                                  const int* __restrict__ seq, int n, int D, float* __restrict__ out) {
+                                  const int* __restrict__ seq, int seq_stride, int n, int D, float* __restrict__ out) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n * D; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / D), c = (int)(i - (long long)r * D);
-    const int id = ids ? ids[r] : seq[state[0] - 1];
+    const int id = ids ? ids[r] : seq[(long long)r * seq_stride + state[r * 4] - 1];
     out[i] = __half2float(table[(long long)id * D + c]);
   }
 }
@@ -225,18 +302,23 @@ __global__ void scatter_rows_kernel(const TS* __restrict__ src, const int* __res
 }
 
 // hidden[(state[0] - prompt_len - 1) * D + i] = x[i]   (post-norm last hidden state of the position consuming generated token j)
-__global__ void store_hidden_kernel(const float* __restrict__ x, const int* __restrict__ state, int prompt_len, int max_rows, int D,
+__global__ void store_hidden_kernel(const float* __restrict__ x, const int* __restrict__ state, int max_rows, int D,
                                     float* __restrict__ hidden) {
-  const int row = state[0] - prompt_len - 1;
+  const int b = blockIdx.y;                       // state[b][3] = prompt length of sequence b
+  const int row = state[b * 4] - state[b * 4 + 3] - 1;
   if (row < 0 || row >= max_rows) return;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x) hidden[(long long)row * D + i] = x[i];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < D; i += gridDim.x * blockDim.x)
+    hidden[((long long)b * max_rows + row) * D + i] = x[(long long)b * D + i];
 }
 
 // logits processor (generation.py:19-31) + greedy argmax + sequence append, all on the device.
 // state[0] = sequence length, state[1] = done flag (EOS seen), state[2] = number of generated tokens
 __global__ void __launch_bounds__(1024)
-logits_argmax_kernel(float* __restrict__ logits, int V, const int* __restrict__ img_ids, int n_img_ids, int* __restrict__ seq,
-                     int* __restrict__ state, int eos_id, int suppress_eos, int max_len) {
+logits_argmax_kernel(float* __restrict__ logits_all, int V, const int* __restrict__ img_ids, int n_img_ids, int* __restrict__ seq_all,
+                     int* __restrict__ state_all, int eos_id, int suppress_eos, int max_len) {
+  float* logits = logits_all + (long long)blockIdx.x * V;      // one CTA per sequence
+  int* seq = seq_all + (long long)blockIdx.x * max_len;
+  int* state = state_all + blockIdx.x * 4;
   __shared__ float smax[32];
   __shared__ int sidx[32];
   __shared__ int forced;
@@ -244,13 +326,13 @@ logits_argmax_kernel(float* __restrict__ logits, int V, const int* __restrict__ 
   const int last = seq[len - 1];
   if (threadIdx.x == 0) forced = -1;
   __syncthreads();
-  if (threadIdx.x < n_img_ids - 1 && img_ids[threadIdx.x] == last) forced = img_ids[threadIdx.x + 1];
+  if ((int)threadIdx.x < n_img_ids - 1 && img_ids[threadIdx.x] == last) forced = img_ids[threadIdx.x + 1];
   __syncthreads();
   int next;
   if (forced >= 0) {
     next = forced;  // scores[next] = max + 10 -> argmax is `next`
   } else {
-    if (threadIdx.x >= 1 && threadIdx.x < n_img_ids) logits[img_ids[threadIdx.x]] = 0.0f;  // img_ids[1:] <- 0.0 (not -inf!)
+    if (threadIdx.x >= 1 && (int)threadIdx.x < n_img_ids) logits[img_ids[threadIdx.x]] = 0.0f;  // img_ids[1:] <- 0.0 (not -inf!)
     if (suppress_eos && threadIdx.x == 0 && eos_id >= 0 && eos_id < V) logits[eos_id] = -INFINITY;
     __syncthreads();
     float best = -INFINITY;
@@ -298,32 +380,46 @@ static inline int ew_grid(long long work, int threads) {
   return (int)(b > cap ? cap : (b < 1 ? 1 : b));
 }
 
-extern "C" int seedx_gemv_f16(const void* W, const float* x, const float* rms_w, float eps, const float* residual, float* out, int64_t N,
-                              int64_t K, int gated, void* stream) {
+extern "C" int seedx_gemv_f16(const void* W, const float* x, int64_t ldx, const float* rms_w, float eps, const float* residual, int64_t ldr,
+                              float* out, int64_t ldo, int64_t N, int64_t K, int batch, int gated, void* stream) {
   SEEDX_REQUIRE(W && x && out, "seedx_gemv_f16: null pointer");
-  SEEDX_REQUIRE(K % 8 == 0 && K > 0 && N > 0 && K * 4 <= 200 * 1024, "seedx_gemv_f16: K=%lld unsupported (multiple of 8, <= 51200)", (long long)K);
+  SEEDX_REQUIRE(batch >= 1 && batch <= 8, "seedx_gemv_f16: batch %d out of range (1..8)", batch);
+  SEEDX_REQUIRE(K % 8 == 0 && K > 0 && N > 0, "seedx_gemv_f16: K=%lld must be a positive multiple of 8", (long long)K);
   SEEDX_REQUIRE((uintptr_t)W % 16 == 0, "seedx_gemv_f16: W must be 16B aligned");
   if (gated) SEEDX_REQUIRE(N % 2 == 0 && residual == nullptr, "seedx_gemv_f16: gated needs even N and no residual");
-  static bool attr = false;
-  if (!attr) {
-    SEEDX_CUDA(cudaFuncSetAttribute(gemv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
-  const long long pairs = (N + 1) / 2;
-  long long blocks = (pairs + (GEMV_THREADS / 32) - 1) / (GEMV_THREADS / 32);
-  const long long cap = (long long)num_sms() * 2;
-  if (blocks > cap) blocks = cap;
-  gemv_kernel<<<(unsigned)blocks, GEMV_THREADS, (size_t)K * 4, (cudaStream_t)stream>>>((const __half*)W, x, rms_w, eps, residual, out, (int)N,
-                                                                                       (int)K, gated);
+  const int nb = batch <= 1 ? 1 : batch <= 2 ? 2 : batch <= 4 ? 4 : 8;
+  SEEDX_REQUIRE(nb == batch, "seedx_gemv_f16: batch must be 1, 2, 4 or 8 (pad the sequence slots)");
+  const size_t smem = (size_t)nb * K * 2;
+  SEEDX_REQUIRE(smem <= 220 * 1024, "seedx_gemv_f16: batch*K too large for shared memory");
+  const long long groups = (N + GEMV_R - 1) / GEMV_R;
+  long long blocks = (long long)num_sms() * (smem > 100 * 1024 ? 1 : 2);
+  if (blocks > groups) blocks = groups;
+  cudaStream_t st = (cudaStream_t)stream;
+#define GEMV_LAUNCH(NBV)                                                                                                                   \
+  do {                                                                                                                                     \
+    static bool attr = false;                                                                                                              \
+    if (!attr) {                                                                                                                           \
+      SEEDX_CUDA(cudaFuncSetAttribute(gemv_batched_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                 \
+      attr = true;                                                                                                                         \
+    }                                                                                                                                      \
+    gemv_batched_kernel<NBV><<<(unsigned)blocks, GEMV_THREADS, smem, st>>>((const __half*)W, x, ldx, rms_w, eps, residual, ldr, out, ldo, \
+                                                                           (int)N, (int)K, gated);                                          \
+  } while (0)
+  if (nb == 1) GEMV_LAUNCH(1);
+  else if (nb == 2) GEMV_LAUNCH(2);
+  else if (nb == 4) GEMV_LAUNCH(4);
+  else GEMV_LAUNCH(8);
+#undef GEMV_LAUNCH
   count_launch();
   return check_cuda(cudaGetLastError(), "gemv launch");
 }
 
-extern "C" int seedx_decode_attention(const float* qkv, const int32_t* state, const float* inv_freq, void* kcache, void* vcache, float* out,
-                                      int heads, int head_dim, float scale, void* stream) {
-  SEEDX_REQUIRE(qkv && state && inv_freq && kcache && vcache && out, "seedx_decode_attention: null pointer");
+extern "C" int seedx_decode_attention(const float* qkv, const int32_t* state, const float* inv_freq, void* kcache, void* vcache,
+                                      int64_t cache_stride, float* out, int batch, int heads, int head_dim, float scale, void* stream) {
+  SEEDX_REQUIRE(qkv && state && inv_freq && kcache && vcache && out && batch >= 1, "seedx_decode_attention: bad arguments");
   SEEDX_REQUIRE(head_dim == 128, "seedx_decode_attention: head_dim must be 128 (LLaMA)");
-  decode_attn_kernel<<<heads, DA_THREADS, 0, (cudaStream_t)stream>>>(qkv, state, inv_freq, (__half*)kcache, (__half*)vcache, out, heads, scale);
+  decode_attn_kernel<<<dim3(heads, batch), DA_THREADS, 0, (cudaStream_t)stream>>>(qkv, state, inv_freq, (__half*)kcache, (__half*)vcache,
+                                                                                  cache_stride, out, heads, scale);
   count_launch();
   return check_cuda(cudaGetLastError(), "decode_attention launch");
 }
@@ -338,10 +434,11 @@ extern "C" int seedx_rope_kv_prefill(void* qkv, int64_t tokens, int64_t pos0, in
   return check_cuda(cudaGetLastError(), "rope_kv_prefill launch");
 }
 
-extern "C" int seedx_embed_rows(const void* table, const int32_t* ids, const int32_t* state, const int32_t* seq, int64_t n, int64_t dim,
-                                float* out, void* stream) {
+extern "C" int seedx_embed_rows(const void* table, const int32_t* ids, const int32_t* state, const int32_t* seq, int64_t seq_stride, int64_t n,
+                                int64_t dim, float* out, void* stream) {
   SEEDX_REQUIRE(table && out && n > 0 && (ids || (state && seq)), "seedx_embed_rows: bad arguments");
-  embed_rows_kernel<<<ew_grid(n * dim, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)table, ids, state, seq, (int)n, (int)dim, out);
+  embed_rows_kernel<<<ew_grid(n * dim, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)table, ids, state, seq, (int)seq_stride, (int)n,
+                                                                             (int)dim, out);
   count_launch();
   return check_cuda(cudaGetLastError(), "embed_rows launch");
 }
@@ -357,19 +454,18 @@ extern "C" int seedx_scatter_rows(const void* src, int src_dtype, const int32_t*
   return check_cuda(cudaGetLastError(), "scatter_rows launch");
 }
 
-extern "C" int seedx_store_hidden(const float* x, const int32_t* state, int64_t prompt_len, int64_t max_rows, int64_t dim, float* hidden,
-                                  void* stream) {
-  SEEDX_REQUIRE(x && state && hidden, "seedx_store_hidden: null pointer");
-  store_hidden_kernel<<<ew_grid(dim, 256), 256, 0, (cudaStream_t)stream>>>(x, state, (int)prompt_len, (int)max_rows, (int)dim, hidden);
+extern "C" int seedx_store_hidden(const float* x, const int32_t* state, int batch, int64_t max_rows, int64_t dim, float* hidden, void* stream) {
+  SEEDX_REQUIRE(x && state && hidden && batch >= 1, "seedx_store_hidden: bad arguments");
+  store_hidden_kernel<<<dim3(ew_grid(dim, 256), batch), 256, 0, (cudaStream_t)stream>>>(x, state, (int)max_rows, (int)dim, hidden);
   count_launch();
   return check_cuda(cudaGetLastError(), "store_hidden launch");
 }
 
-extern "C" int seedx_logits_argmax(float* logits, int64_t vocab, const int32_t* img_ids, int n_img_ids, int32_t* seq, int32_t* state, int eos_id,
-                                   int suppress_eos, int64_t max_len, void* stream) {
-  SEEDX_REQUIRE(logits && seq && state && vocab > 0, "seedx_logits_argmax: bad arguments");
+extern "C" int seedx_logits_argmax(float* logits, int64_t vocab, const int32_t* img_ids, int n_img_ids, int32_t* seq, int32_t* state, int batch,
+                                   int eos_id, int suppress_eos, int64_t max_len, void* stream) {
+  SEEDX_REQUIRE(logits && seq && state && vocab > 0 && batch >= 1, "seedx_logits_argmax: bad arguments");
   SEEDX_REQUIRE(n_img_ids >= 0 && n_img_ids <= 1024, "seedx_logits_argmax: too many image token ids");
-  logits_argmax_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, (int)vocab, img_ids, n_img_ids, seq, state, eos_id, suppress_eos, (int)max_len);
+  logits_argmax_kernel<<<batch, 1024, 0, (cudaStream_t)stream>>>(logits, (int)vocab, img_ids, n_img_ids, seq, state, eos_id, suppress_eos, (int)max_len);
   count_launch();
   return check_cuda(cudaGetLastError(), "logits_argmax launch");
 }

@@ -93,16 +93,16 @@ class SeedXEngine:
         e0 = self._ev()
         feats = self.vit(views)                                                   # [B*n_views, 256, 4096] fp16
         e1 = self._ev()
-        gen_feats = []
+        reqs = []
         for b in range(B):
             ids, mask = self.build_prompt(n_views, text_ids[b])
-            f = feats[b * n_views:(b + 1) * n_views]
-            out = self.agent.generate(tokenizer=self.tok, input_ids=ids.unsqueeze(0), image_embeds=f,
-                                      embeds_cmp_mask=torch.ones((n_views, 64), dtype=torch.bool), ids_cmp_mask=mask.unsqueeze(0),
-                                      patch_positions=patch_pos[b * n_views:(b + 1) * n_views], max_new_tokens=66, suppress_eos=True)
-            if not out["has_img_output"]:
-                raise RuntimeError("the forced image span was not produced")
-            gen_feats.append(out["img_gen_feat"])
+            reqs.append(dict(input_ids=ids.unsqueeze(0), image_embeds=feats[b * n_views:(b + 1) * n_views],
+                             embeds_cmp_mask=torch.ones((n_views, 64), dtype=torch.bool), ids_cmp_mask=mask.unsqueeze(0),
+                             patch_positions=patch_pos[b * n_views:(b + 1) * n_views]))
+        outs = self.agent.generate_batch(self.tok, reqs, max_new_tokens=66, suppress_eos=True)   # lock-step decode of the B requests
+        if not all(o["has_img_output"] for o in outs):
+            raise RuntimeError("the forced image span was not produced")
+        gen_feats = [o["img_gen_feat"] for o in outs]
         e2 = self._ev()
         img_feats = torch.cat(gen_feats, dim=0)                                   # [B, 64, 4096] fp32
         u8 = self.adapter.generate(image_embeds=img_feats, num_inference_steps=steps, guidance_scale=guidance, latents=noise,

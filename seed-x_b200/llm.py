@@ -107,24 +107,22 @@ class LlamaForCausalLM:
         self._loaded = True
         return [], []
 
-    def _alloc_state(self):
+    def _alloc_state(self, slots=1):
         cfg, dev = self.cfg, self.device
         D, L = cfg["hidden"], cfg["layers"]
-        self.kcache = [torch.zeros((self.max_len, D), device=dev, dtype=torch.float16) for _ in range(L)]
-        self.vcache = [torch.zeros((self.max_len, D), device=dev, dtype=torch.float16) for _ in range(L)]
-        self.seq = torch.zeros((self.max_len,), device=dev, dtype=torch.int32)
-        self.state = torch.zeros((4,), device=dev, dtype=torch.int32)
-        self.xa = torch.zeros((D,), device=dev, dtype=torch.float32)
-        self.xb = torch.zeros((D,), device=dev, dtype=torch.float32)
-        self.qkv1 = torch.zeros((3 * D,), device=dev, dtype=torch.float32)
-        self.att1 = torch.zeros((D,), device=dev, dtype=torch.float32)
-        self.g1 = torch.zeros((cfg["ffn"],), device=dev, dtype=torch.float32)
-        self.hn1 = torch.zeros((1, D), device=dev, dtype=torch.float32)
-        self.logits = torch.zeros((cfg["vocab"],), device=dev, dtype=torch.float32)
+        self.slots = slots
+        self.kcache = [torch.zeros((slots, self.max_len, D), device=dev, dtype=torch.float16) for _ in range(L)]
+        self.vcache = [torch.zeros((slots, self.max_len, D), device=dev, dtype=torch.float16) for _ in range(L)]
+        self.seq = torch.zeros((slots, self.max_len), device=dev, dtype=torch.int32)
+        self.state = torch.zeros((slots, 4), device=dev, dtype=torch.int32)
+        z = lambda n: torch.zeros((slots, n), device=dev, dtype=torch.float32)  # noqa: E731
+        self.xa, self.xb, self.qkv1, self.att1, self.g1, self.hn1 = z(D), z(D), z(3 * D), z(D), z(cfg["ffn"]), z(D)
+        self.logits = z(cfg["vocab"])
 
     # ---- prefill: tensor-core path ---------------------------------------------------------------------------------------
-    def prefill(self, x, pos0=0):
-        """x: fp32 device [P, D] input embeddings for positions pos0..; fills the KV cache; returns the fp32 residual stream [P, D]."""
+    def prefill(self, x, pos0=0, slot=0):
+        """x: fp32 device [P, D] input embeddings for positions pos0.. of sequence slot `slot`; fills its KV cache; returns the fp32
+        residual stream [P, D]."""
         cfg = self.cfg
         D, H = cfg["hidden"], cfg["heads"]
         d = D // H
@@ -142,12 +140,12 @@ class LlamaForCausalLM:
         for li, L in enumerate(self.layers):
             ops.layernorm(x, L["ln1"], None, cfg["eps"], out=n, rms=True)
             ops.gemm(n, L["wqkv"], out=qkv)
-            ops.rope_kv_prefill(qkv, pos0, H, d, self.inv_freq, self.kcache[li], self.vcache[li])
+            ops.rope_kv_prefill(qkv, pos0, H, d, self.inv_freq, self.kcache[li][slot], self.vcache[li][slot])
             if pos0 == 0:
                 ops.attention(qv, kv, vv, ov, scale=d ** -0.5, causal=True)
             else:   # chunked prefill: keys/values come from the cache (positions 0..pos0+P-1)
-                kc = self.kcache[li][: pos0 + P].view(1, pos0 + P, H, d).permute(0, 2, 1, 3)
-                vc = self.vcache[li][: pos0 + P].view(1, pos0 + P, H, d).permute(0, 2, 1, 3)
+                kc = self.kcache[li][slot, : pos0 + P].view(1, pos0 + P, H, d).permute(0, 2, 1, 3)
+                vc = self.vcache[li][slot, : pos0 + P].view(1, pos0 + P, H, d).permute(0, 2, 1, 3)
                 ops.attention(qv, kc, vc, ov, scale=d ** -0.5, causal=True)
             ops.gemm(o, L["wo"], out=x, residual=x)
             ops.layernorm(x, L["ln2"], None, cfg["eps"], out=n, rms=True)
@@ -162,7 +160,8 @@ class LlamaForCausalLM:
         return ops.gemm(h16, self.lm_head, out_dtype=torch.float32), hn
 
     # ---- token loop: HBM-bound path ----------------------------------------------------------------------------------------
-    def _decode_step(self, prompt_len, hidden, img_ids, eos_id, suppress_eos):
+    def _decode_step(self, hidden, img_ids, eos_id, suppress_eos):
+        """one token for every sequence slot: the fp16 weights are streamed once and shared by all slots"""
         cfg = self.cfg
         H = cfg["heads"]
         d = cfg["hidden"] // H
@@ -173,54 +172,68 @@ class LlamaForCausalLM:
             ops.gemv(L["wo"], self.att1, self.xb, residual=self.xa)
             ops.gemv(L["wgu"], self.xb, self.g1, rms_w=L["ln2"], eps=cfg["eps"], gated=True)
             ops.gemv(L["wdown"], self.g1, self.xa, residual=self.xb)
-        ops.layernorm(self.xa.view(1, -1), self.norm, None, cfg["eps"], out=self.hn1, rms=True)
-        ops.store_hidden(self.hn1, self.state, prompt_len, hidden)
-        ops.gemv(self.lm_head, self.hn1.view(-1), self.logits)
+        ops.layernorm(self.xa, self.norm, None, cfg["eps"], out=self.hn1, rms=True)
+        ops.store_hidden(self.hn1, self.state, hidden)
+        ops.gemv(self.lm_head, self.hn1, self.logits)
         ops.logits_argmax(self.logits, img_ids, self.seq, self.state, eos_id, suppress_eos)
 
-    def generate_greedy(self, input_ids, inputs_embeds, img_ids=None, max_new_tokens=120, eos_id=None, suppress_eos=False,
-                        use_graph=True, sync_every=32):
-        """HF greedy_search as used at seed_x.py:184-189: inputs_embeds [P, D] feed step 0, then the last id each step.
-        img_ids: token ids of <img><img_0>...<img_63></img> for the AutoImageTokenGenerationProcessor (None = no processor)."""
+    def generate_greedy_batch(self, input_ids_list, inputs_embeds_list, img_ids=None, max_new_tokens=120, eos_id=None, suppress_eos=False,
+                              use_graph=True, sync_every=32):
+        """Greedy decoding of up to 8 independent requests in lock-step (HF greedy_search per request, seed_x.py:184-189):
+        request r's inputs_embeds [P_r, D] feed its prefill, then its last id each step.  Returns a list of GreedyOutput."""
         if not self._loaded:
             raise SeedxError("LlamaForCausalLM: weights not loaded")
         dev = self.device
-        ids = torch.as_tensor(input_ids).reshape(-1)
-        P = ids.numel()
-        if P + max_new_tokens > self.max_len:
-            raise SeedxError("prompt + max_new_tokens exceeds the KV cache")
-        x = inputs_embeds.reshape(P, -1).to(dev, torch.float32)
+        n_req = len(input_ids_list)
+        if not 1 <= n_req <= 8:
+            raise SeedxError("generate_greedy_batch handles 1..8 requests per call")
+        slots = 1 if n_req == 1 else 2 if n_req == 2 else 4 if n_req <= 4 else 8
+        if slots != self.slots:
+            self._alloc_state(slots)
         img_dev = torch.as_tensor(img_ids, dtype=torch.int32).to(dev) if img_ids is not None else None
-        self.seq[:P].copy_(ids.to(dev, torch.int32))
-        self.state.copy_(torch.tensor([P, 0, 0, 0], dtype=torch.int32))
-        hidden = torch.zeros((max(max_new_tokens - 1, 1), self.cfg["hidden"]), device=dev, dtype=torch.float32)
-        xs = self.prefill(x)
-        ops.gemv(self.lm_head, xs[P - 1], self.logits, rms_w=self.norm, eps=self.cfg["eps"])
+        hidden = torch.zeros((slots, max(max_new_tokens - 1, 1), self.cfg["hidden"]), device=dev, dtype=torch.float32)
+        st0, plens = [], []
+        for s in range(slots):
+            r = min(s, n_req - 1)                       # padding slots replay the last request
+            ids = torch.as_tensor(input_ids_list[r]).reshape(-1)
+            P = ids.numel()
+            if P + max_new_tokens > self.max_len:
+                raise SeedxError("prompt + max_new_tokens exceeds the KV cache")
+            plens.append(P)
+            st0.append([P, 0, 0, P])
+            self.seq[s, :P].copy_(ids.to(dev, torch.int32))
+            xs = self.prefill(inputs_embeds_list[r].reshape(P, -1).to(dev, torch.float32), slot=s)
+            ops.gemv(self.lm_head, xs[P - 1], self.logits[s], rms_w=self.norm, eps=self.cfg["eps"])
+        self.state.copy_(torch.tensor(st0, dtype=torch.int32))
         ops.logits_argmax(self.logits, img_dev, self.seq, self.state, eos_id, suppress_eos)
         steps = max_new_tokens - 1
         if steps > 0:
-            key = (P, hidden.data_ptr(), None if img_dev is None else img_dev.data_ptr(), eos_id, suppress_eos)
+            g = None
             if use_graph:
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
+                s_ = torch.cuda.Stream()
+                s_.wait_stream(torch.cuda.current_stream())
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=s):
-                    self._decode_step(P, hidden, img_dev, eos_id, suppress_eos)
-                torch.cuda.current_stream().wait_stream(s)
-                self._graph = (key, g, hidden, img_dev)
-            done = 0
+                with torch.cuda.graph(g, stream=s_):
+                    self._decode_step(hidden, img_dev, eos_id, suppress_eos)
+                torch.cuda.current_stream().wait_stream(s_)
             for i in range(steps):
-                if use_graph:
+                if g is not None:
                     g.replay()
                 else:
-                    self._decode_step(P, hidden, img_dev, eos_id, suppress_eos)
+                    self._decode_step(hidden, img_dev, eos_id, suppress_eos)
                 if eos_id is not None and not suppress_eos and (i + 1) % sync_every == 0:
-                    done = int(self.state[1].item())
-                    if done:
+                    if bool((self.state[:n_req, 1] != 0).all().item()):
                         break
         st = self.state.cpu().tolist()
-        n_gen = st[2]
-        if st[1]:
-            n_gen = st[1]          # stop at (and include) the first EOS, like HF greedy_search
-        seq = self.seq[: P + n_gen].cpu().to(torch.int64)
-        return GreedyOutput(seq.unsqueeze(0), hidden[: max(n_gen - 1, 0)], n_gen)
+        seq_host = self.seq.cpu()
+        outs = []
+        for r in range(n_req):
+            n_gen = st[r][1] if st[r][1] else st[r][2]   # stop at (and include) the first EOS, like HF greedy_search
+            outs.append(GreedyOutput(seq_host[r, : plens[r] + n_gen].to(torch.int64).unsqueeze(0), hidden[r, : max(n_gen - 1, 0)], n_gen))
+        return outs
+
+    def generate_greedy(self, input_ids, inputs_embeds, img_ids=None, max_new_tokens=120, eos_id=None, suppress_eos=False, use_graph=True,
+                        sync_every=32):
+        """single-request form of generate_greedy_batch"""
+        return self.generate_greedy_batch([input_ids], [inputs_embeds], img_ids=img_ids, max_new_tokens=max_new_tokens, eos_id=eos_id,
+                                          suppress_eos=suppress_eos, use_graph=use_graph, sync_every=sync_every)[0]

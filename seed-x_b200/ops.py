@@ -316,18 +316,25 @@ def cfg_euler_step(eps, x, unet_in, branches, guidance, image_guidance, sigma, s
 
 
 def gemv(W, x, out, *, rms_w=None, eps=1e-5, residual=None, gated=False):
-    """out fp32 = epi(W[N,K] . (rmsnorm(x)*rms_w | x)); W fp16, x fp32 [K]."""
+    """out[b] fp32 = epi(W[N,K] . (rmsnorm(x[b])*rms_w | x[b])); W fp16; x fp32 [K] or [B,K] with B in {1,2,4,8} (weights streamed once)."""
     _require_cuda(W, x, out)
     assert W.dtype == torch.float16 and W.is_contiguous() and x.dtype == torch.float32 and out.dtype == torch.float32
     N, K = W.shape
-    check(lib().seedx_gemv_f16(_ptr(W), _ptr(x), _ptr(rms_w), C.c_float(eps), _ptr(residual), _ptr(out), _i64(N), _i64(K), C.c_int(int(gated)),
-                               _stream()), "seedx_gemv_f16")
+    x2 = x.reshape(-1, K)
+    o2 = out.reshape(x2.shape[0], -1)
+    r2 = residual.reshape(x2.shape[0], -1) if residual is not None else None
+    assert x2.stride(1) == 1 and o2.stride(1) == 1
+    check(lib().seedx_gemv_f16(_ptr(W), _ptr(x2), _i64(x2.stride(0)), _ptr(rms_w), C.c_float(eps), _ptr(r2), _i64(r2.stride(0) if r2 is not None else 0),
+                               _ptr(o2), _i64(o2.stride(0)), _i64(N), _i64(K), C.c_int(x2.shape[0]), C.c_int(int(gated)), _stream()), "seedx_gemv_f16")
     return out
 
 
 def decode_attention(qkv, state, inv_freq, kcache, vcache, out, heads, head_dim):
-    check(lib().seedx_decode_attention(_ptr(qkv), _ptr(state), _ptr(inv_freq), _ptr(kcache), _ptr(vcache), _ptr(out), C.c_int(heads),
-                                       C.c_int(head_dim), C.c_float(head_dim ** -0.5), _stream()), "seedx_decode_attention")
+    """qkv fp32 [B, 3*H*d]; kcache/vcache fp16 [B, max_len, H*d]; state int32 [B,4]; out fp32 [B, H*d]."""
+    B = qkv.shape[0]
+    check(lib().seedx_decode_attention(_ptr(qkv), _ptr(state), _ptr(inv_freq), _ptr(kcache), _ptr(vcache), _i64(kcache.stride(0)), _ptr(out),
+                                       C.c_int(B), C.c_int(heads), C.c_int(head_dim), C.c_float(head_dim ** -0.5), _stream()),
+          "seedx_decode_attention")
     return out
 
 
@@ -342,7 +349,8 @@ def embed_rows(table, out, *, ids=None, state=None, seq=None):
     assert table.dtype == torch.float16 and out.dtype == torch.float32 and out.is_contiguous()
     if ids is not None:
         assert ids.dtype == torch.int32 and ids.numel() == n
-    check(lib().seedx_embed_rows(_ptr(table), _ptr(ids), _ptr(state), _ptr(seq), _i64(n), _i64(dim), _ptr(out), _stream()), "seedx_embed_rows")
+    check(lib().seedx_embed_rows(_ptr(table), _ptr(ids), _ptr(state), _ptr(seq), _i64(seq.stride(0) if seq is not None else 0), _i64(n), _i64(dim),
+                                 _ptr(out), _stream()), "seedx_embed_rows")
     return out
 
 
@@ -355,24 +363,15 @@ def scatter_rows(src, idx, dst, src_idx=None):
     return dst
 
 
-def store_hidden(x, state, prompt_len, hidden):
-    check(lib().seedx_store_hidden(_ptr(x), _ptr(state), _i64(prompt_len), _i64(hidden.shape[0]), _i64(hidden.shape[1]), _ptr(hidden), _stream()),
-          "seedx_store_hidden")
+def store_hidden(x, state, hidden):
+    """hidden fp32 [B, max_rows, D]; x fp32 [B, D]"""
+    B, R, D = hidden.shape
+    check(lib().seedx_store_hidden(_ptr(x), _ptr(state), C.c_int(B), _i64(R), _i64(D), _ptr(hidden), _stream()), "seedx_store_hidden")
 
 
 def logits_argmax(logits, img_ids, seq, state, eos_id, suppress_eos):
-    check(lib().seedx_logits_argmax(_ptr(logits), _i64(logits.numel()), _ptr(img_ids), C.c_int(0 if img_ids is None else img_ids.numel()), _ptr(seq),
-                                    _ptr(state), C.c_int(eos_id if eos_id is not None else -1), C.c_int(int(suppress_eos)), _i64(seq.numel()),
-                                    _stream()), "seedx_logits_argmax")
-
-
-def add_bcast_f16(a, b, out=None):
-    """fp16 out[r,:] = a[r,:] + b[r % b_rows,:] (b fp32)."""
-    _require_cuda(a, b, out)
-    assert a.is_contiguous() and b.dtype == torch.float32 and b.is_contiguous()
-    a2 = a.reshape(-1, a.shape[-1])
-    if out is None:
-        out = torch.empty(a2.shape, device=a.device, dtype=torch.float16)
-    check(lib().seedx_add_bcast_f16(_ptr(a2), _dt(a2), _ptr(b), _i64(a2.shape[0]), _i64(a2.shape[1]), _i64(b.shape[0]), _ptr(out), _stream()),
-          "seedx_add_bcast_f16")
-    return out
+    """logits fp32 [B, V]; seq int32 [B, max_len]; state int32 [B, 4]"""
+    B, V = logits.shape
+    check(lib().seedx_logits_argmax(_ptr(logits), _i64(V), _ptr(img_ids), C.c_int(0 if img_ids is None else img_ids.numel()), _ptr(seq),
+                                    _ptr(state), C.c_int(B), C.c_int(eos_id if eos_id is not None else -1), C.c_int(int(suppress_eos)),
+                                    _i64(seq.shape[1]), _stream()), "seedx_logits_argmax")

@@ -30,16 +30,59 @@ def test_gemv(N, K):
     res = mk((N,), 3)
     rw = mk((K,), 4) + 1.0
     out = torch.empty((N,), device="cuda")
+    x16 = x.half().float()                      # activations are staged as fp16 in shared memory (like the prefill GEMM operands)
     ops.gemv(W, x, out, residual=res)
-    assert rel(out, W.float() @ x + res) < 1e-5
-    xn = x * torch.rsqrt(x.pow(2).mean() + 1e-5) * rw
+    assert rel(out, W.float() @ x16 + res) < 1e-5
+    xn = (x * torch.rsqrt(x.pow(2).mean() + 1e-5) * rw).half().float()
     ops.gemv(W, x, out, rms_w=rw, eps=1e-5)
     assert rel(out, W.float() @ xn) < 1e-5
     if N % 2 == 0:
         o2 = torch.empty((N // 2,), device="cuda")
         ops.gemv(W, x, o2, gated=True)
-        r = W.float() @ x
+        r = W.float() @ x16
         assert rel(o2, r[0::2] * torch.nn.functional.silu(r[1::2])) < 1e-5
+
+
+@pytest.mark.parametrize("B", [2, 4, 8])
+def test_gemv_batched(B):
+    from seedx_b200 import ops
+    N, K = 5120, 13824
+    W = mk((N, K), 1, K ** -0.5).half()
+    x = mk((B, K), 2)
+    res = mk((B, N), 3)
+    rw = mk((K,), 4) + 1.0
+    out = torch.empty((B, N), device="cuda")
+    ops.gemv(W, x, out, residual=res)
+    x16 = x.half().float()                      # activations are staged as fp16 in shared memory
+    assert rel(out, x16 @ W.float().t() + res) < 1e-5
+    xn = (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5) * rw).half().float()
+    ops.gemv(W, x, out, rms_w=rw, eps=1e-5)
+    assert rel(out, xn @ W.float().t()) < 1e-5
+    o2 = torch.empty((B, N // 2), device="cuda")
+    ops.gemv(W, x, o2, gated=True)
+    r = x16 @ W.float().t()
+    assert rel(o2, r[:, 0::2] * torch.nn.functional.silu(r[:, 1::2])) < 1e-5
+
+
+def test_llama_batched_decode_matches_single():
+    """lock-step decode of 3 requests with different prompt lengths == each request decoded alone (ids exact, hidden <= 1e-3)"""
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    m, cfg = _llm()
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    img_ids = tok.encode("".join(["<img>"] + ["<img_{:05d}>".format(i) for i in range(64)] + ["</img>"]))
+    sd = synth.llama_state_dict(cfg)
+    ids_a = g["ids"]
+    emb_a = g["embeds"]
+    ids_b = g["ids"] + [tok.encode("<img>")[0]]
+    emb_b = torch.cat([g["embeds"], sd["model.embed_tokens.weight"][ids_b[-1]][None]])
+    ids_c = g["ids"][:20]
+    emb_c = g["embeds"][:20]
+    outs = m.generate_greedy_batch([ids_a, ids_b, ids_c], [emb_a.cuda(), emb_b.cuda(), emb_c.cuda()], img_ids=img_ids, max_new_tokens=72)
+    assert outs[0].sequences[0][len(ids_a):len(ids_a) + 16].tolist() == g["text_gen_ids"]
+    assert outs[1].sequences[0][len(ids_b):].tolist() == g["img_gen_ids"]
+    assert rel(outs[1].last_hidden_states, g["img_hidden"]) < TOL
+    single = m.generate_greedy(ids_c, emb_c.cuda(), img_ids=img_ids, max_new_tokens=72)
+    assert outs[2].sequences.tolist() == single.sequences.tolist()
 
 
 def _llm():

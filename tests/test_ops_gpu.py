@@ -30,8 +30,11 @@ def mk(shape, seed, scale=1.0):
     (2, 16, 1, 65, 64, False),         # AttentionPool2d (single query)
     (1, 3, 77, 33, 72, False),
 ])
-def test_attention(B, H, Sq, Sk, D, causal):
+@pytest.mark.parametrize("impl", ["tcgen05", "mma_sync"])
+def test_attention(B, H, Sq, Sk, D, causal, impl):
     from seedx_b200 import ops
+    from seedx_b200._lib import lib
+    lib().seedx_attention_set_impl(1 if impl == "mma_sync" else 0)
     shared_q = (Sq == 256 and Sk == 1024)
     q = mk((1 if shared_q else B, Sq, H, D), 1).half()
     k = mk((B, Sk, H, D), 2).half()
@@ -40,8 +43,12 @@ def test_attention(B, H, Sq, Sk, D, causal):
     scale = D ** -0.5
     ops.attention(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), o.permute(0, 2, 1, 3), scale=scale, causal=causal)
     qf = q.float().expand(B, -1, -1, -1).permute(0, 2, 1, 3)
+    used = lib().seedx_attention_last_impl()
+    lib().seedx_attention_set_impl(0)
     ref = F.scaled_dot_product_attention(qf, k.float().permute(0, 2, 1, 3), v.float().permute(0, 2, 1, 3), is_causal=causal, scale=scale)
     assert rel(o.permute(0, 2, 1, 3), ref) < 2e-3
+    if impl == "tcgen05" and Sq >= 128 and D <= 128:
+        assert used == 2, "the tcgen05 kernel should have handled this shape"
 
 
 def test_attention_strided_qkv():
