@@ -4,9 +4,10 @@
 //
 // One CTA = 128 query rows of one (batch, head).  Warp 0: TMA producer (Q once, K/V tiles of 128 keys through two mbarrier
 // rings).  Warp 1: single-thread MMA issuer: S_j = Q K_j^T into a double-buffered TMEM accumulator (2 x 128 columns), then
-// O += P_j V_j with P_j read back as the TMEM A-operand and V_j as an MN-major shared-memory B-operand.  Warps 2..5: softmax —
-// thread = query row (TMEM lane), so row max / row sum need no shuffles; P_j (fp16) overwrites the first 64 columns of S_j;
-// the O accumulator (TMEM) is rescaled only when a row maximum moved.  QK^T of tile j+1 overlaps the softmax of tile j.
+// O += P_j V_j with P_j read back as the TMEM A-operand and V_j as an MN-major shared-memory B-operand.  Warps 2..9: softmax —
+// two threads per query row (TMEM lane), each owning 64 of the 128 score columns, so a row max is one shared-memory exchange and
+// needs no shuffles; P_j (fp16) overwrites the first 64 columns of S_j; the O accumulator (TMEM) is rescaled only when a row
+// maximum moved.  QK^T of tile j+1 overlaps the softmax of tile j.
 //
 // Replaces the same reference call sites as seedx_attention_f16 (include/seedx.h) for head dims <= 128 and long sequences.
 #include "common.cuh"
@@ -35,7 +36,7 @@ struct FaCfg {
 };
 
 template <int D>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const FaParams p) {
   using Cfg = FaCfg<D>;
@@ -72,7 +73,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(s_full(s), 1);
-      mbar_init(p_full(s), 128);
+      mbar_init(p_full(s), 256);
       mbar_init(pv_done(s), 1);
     }
     mbar_fence_init();
@@ -161,47 +162,60 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       umma_commit(pv_done(jl & 1));
     }
   } else {
-    // ------------------------------------------------------------ softmax / correction / epilogue: thread = query row
+    // ------------------------------------------------------------ softmax / correction / epilogue
+    // row = TMEM lane; warps 2..5 own score columns [0,64) and O columns [0,D/2), warps 6..9 the upper halves
+    __shared__ float xch_max[2][2][128];   // [tile parity][column half][row]
+    __shared__ float xch_sum[2][128];
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const int qrow = m0 + row;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tO = tmem_base + lane_addr + Cfg::O_COL;
+    const uint32_t tO = tmem_base + lane_addr + Cfg::O_COL + (uint32_t)(half * (D / 2));
+    constexpr int OC = D / 2;              // O columns per thread
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
-      const uint32_t tS = tmem_base + lane_addr + ((j & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
+      const uint32_t tSb = tmem_base + lane_addr + ((j & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
       mbar_wait(s_full(j & 1), (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      float s[128];
+      float s[64];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(tS + (uint32_t)(c * 32), v);
+        tmem_ld32(tSb + (uint32_t)(half * 64 + c * 32), v);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(v[i]) * p.scale_log2;
       }
-      const int key0 = j * Cfg::BN;
-      const bool need_mask = (key0 + Cfg::BN > p.sk) || (p.causal && (key0 + Cfg::BN - 1 > m0 + causal_off));
+      const int key0 = j * Cfg::BN + half * 64;
+      const bool need_mask = (j * Cfg::BN + Cfg::BN > p.sk) || (p.causal && (j * Cfg::BN + Cfg::BN - 1 > m0 + causal_off));
       if (need_mask) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
+        for (int i = 0; i < 64; ++i) {
           const int key = key0 + i;
           if (key >= p.sk || (p.causal && key > qrow + causal_off)) s[i] = -INFINITY;
         }
       }
       float m_tile = s[0];
 #pragma unroll
-      for (int i = 1; i < 128; ++i) m_tile = fmaxf(m_tile, s[i]);
-      const float m_new = fmaxf(m_run, m_tile);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = fast_exp2(m_run - m_use);  // m_run = -inf -> 0
-      if (j > 0) {
-        mbar_wait(pv_done((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));  // O is quiescent: PV_{j-1} retired
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, m_new > m_run)) {                      // some row of this warp moved its maximum: rescale O
+      for (int i = 1; i < 64; ++i) m_tile = fmaxf(m_tile, s[i]);
+      xch_max[j & 1][half][row] = m_tile;
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");                   // the 8 softmax warps only
+      m_tile = fmaxf(m_tile, xch_max[j & 1][half ^ 1][row]);
+      // Lazy rescaling: the reference maximum m_run only moves when some row of this warp exceeds it by more than 2^8 (P then stays
+      // <= 256, exact in fp16 range; sums and O are fp32).  Only then does the softmax have to wait for PV_{j-1} and touch O, so in
+      // the steady state softmax_j does not depend on the tensor pipe at all and the MMA -> softmax -> MMA round trip disappears.
+      const bool grow = m_tile > m_run + 8.0f;       // also true for j == 0 (m_run = -inf) unless the whole row is masked
+      float alpha = 1.0f;
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = fmaxf(m_run, m_tile);
+        const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
+        alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_ref);
+        if (j > 0) {
+          mbar_wait(pv_done((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));  // O is quiescent: PV_{j-1} retired
+          tc_fence_after();
 #pragma unroll
-          for (int c = 0; c < D / 32; ++c) {
+          for (int c = 0; c < OC / 32; ++c) {
             uint32_t v[32];
             tmem_ld32(tO + (uint32_t)(c * 32), v);
             tmem_ld_wait();
@@ -210,11 +224,15 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             tmem_st32(tO + (uint32_t)(c * 32), v);
           }
         }
+        m_run = m_new;
       }
-      // P_j = exp2(S_j - m) as fp16 pairs over the first 64 columns of S_j (every S value is already in registers)
+      const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+      // P_j = exp2(S_j - m) as fp16 pairs: my 64 scores -> 32 packed columns at [half*32, half*32+32) of the S_j buffer.
+      // (the other half-row thread may still be reading S columns >= 64 only if it is `half`=1: its columns are never overwritten by
+      //  P (P occupies columns 0..63), and a `half`=0 thread has already pulled columns 0..63 into registers before the bar.sync.)
       float rs = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
@@ -223,36 +241,38 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           __half2 hh = __floats2half2_rn(a, c2);
           v[i] = *(uint32_t*)&hh;
         }
-        tmem_st16(tS + (uint32_t)(c * 16), v);
+        tmem_st16(tSb + (uint32_t)(half * 32 + c * 16), v);
       }
       tmem_st_wait();
       l_run = l_run * alpha + rs;
-      m_run = m_new;
       tc_fence_before();
       mbar_arrive(p_full(j & 1));
     }
-    // ---- epilogue
+    // ---- epilogue: combine the two half-row sums, normalise and store my half of the output columns
+    xch_sum[half][row] = l_run;
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    const float l_tot = l_run + xch_sum[half ^ 1][row];
     const int jl = n_tiles - 1;
     mbar_wait(pv_done(jl & 1), (uint32_t)((jl >> 1) & 1));
     tc_fence_after();
-    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-    __half* orow = p.o + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)qrow * p.o_ss;
+    const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+    __half* orow = p.o + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)qrow * p.o_ss + half * OC;
 #pragma unroll
-    for (int c = 0; c < D / 32; ++c) {
+    for (int c = 0; c < OC / 32; ++c) {
       uint32_t v[32];
       tmem_ld32(tO + (uint32_t)(c * 32), v);
       tmem_ld_wait();
       if (qrow < p.sq) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          const int col = c * 32 + i;
+          const int col = half * OC + c * 32 + i;
           if (col + 8 <= p.d) {
             uint4 q;
             __half2* hh = (__half2*)&q;
 #pragma unroll
             for (int t = 0; t < 4; ++t)
               hh[t] = __floats2half2_rn(__uint_as_float(v[i + 2 * t]) * inv, __uint_as_float(v[i + 2 * t + 1]) * inv);
-            *(uint4*)(orow + col) = q;
+            *(uint4*)(orow + c * 32 + i) = q;
           }
         }
       }
@@ -275,7 +295,7 @@ static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
     attr = true;
   }
   dim3 grid((p.sq + Cfg::BM - 1) / Cfg::BM, H, B);
-  flash_attn_tc_kernel<D><<<grid, 192, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  flash_attn_tc_kernel<D><<<grid, 320, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "flash_attn_tc_kernel launch");
 }
@@ -289,7 +309,8 @@ static int make_map(CUtensorMap* m, const void* ptr, int d, int s, int H, int B,
 
 // returns -1 when the problem is not eligible for the tensor-memory kernel (caller falls back to the mma.sync kernel)
 int attention_tc_try(const seedx_attn_args* a, cudaStream_t st) {
-  if (a->d > 128 || a->d % 8 != 0 || a->sq < 128 || a->sk < 1) return -1;
+  // short key sequences (UNet cross-attention over 64 context tokens) would fill under half of one 128-key tile: mma.sync kernel is faster
+  if (a->d > 128 || a->d % 8 != 0 || a->sq < 128 || a->sk < 96) return -1;
   if (a->o_stride_s % 8 || a->o_stride_h % 8 || a->o_stride_b % 8 || (uintptr_t)a->o % 16) return -1;
   const long long str[] = {a->q_stride_s, a->q_stride_h, a->q_stride_b, a->k_stride_s, a->k_stride_h, a->k_stride_b,
                            a->v_stride_s, a->v_stride_h, a->v_stride_b};

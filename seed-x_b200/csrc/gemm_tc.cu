@@ -44,10 +44,10 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int BN>
+template <int BN, int CL = 1>
 struct TileCfg {
-  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N for M=128: multiple of 16, <= 256");
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N for M=128/256: multiple of 16, <= 256");
+  static constexpr int B_STAGE_BYTES = (BN / CL) * BK * 2;   // a CTA of a pair stages only its half of the B tile
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES_FIT = (SMEM_LIMIT - 1024 - 256) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
@@ -62,10 +62,16 @@ SEEDX_DEVINL float apply_act(float x, int act) {
   return x;
 }
 
-template <int BN>
+// CL = CTAs per MMA (1, or 2 = a CTA pair on one 256 x BN tile, tcgen05 cta_group::2).  In pair mode each CTA stages its own 128 rows
+// of A and only HALF of the B tile (BN/2 rows); the leader CTA (cluster rank 0) issues tcgen05.mma.cta_group::2, which reads both
+// CTAs' shared memory and writes both CTAs' tensor memory (128 accumulator rows each).  Operand bytes an SM has to ingest per FLOP
+// drop by a third, which is what bounds the single-CTA kernel (measured: TMA multicast of B does NOT help, cta_group::2 does).
+// All TMA transaction bytes of the pair complete on the leader's `full` barrier; the leader's commits arrive on both CTAs' `empty`
+// and `tmem_full` barriers; both CTAs' epilogue warps arrive on the leader's `tmem_empty` barrier.
+template <int BN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, CL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -79,6 +85,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int crank = (CL > 1) ? (int)cluster_ctarank() : 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -89,30 +96,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), EPI_WARPS);
+      mbar_init(tempty_bar(s), EPI_WARPS * CL);  // pair mode: the leader's barrier collects both CTAs' epilogue warps
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if (warp == 1) {
+    if (CL == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc_2sm<Cfg::TMEM_COLS>(tmem_slot);   // the same warp id in both CTAs of the pair
+  }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // peer barriers are initialised before any remote arrive / transaction can reach them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int tiles_per_batch = p.m_blocks * p.n_blocks;
+  // tile space: (batch, n block, m group) with CL consecutive m blocks per group; a cluster walks groups, CTA `crank` takes m = group*CL + crank
+  const int m_groups = (p.m_blocks + CL - 1) / CL;
+  const int tiles_per_batch = m_groups * p.n_blocks;
   const int num_tiles = tiles_per_batch * p.batch;
+  const int tile0 = (int)blockIdx.x / CL, tile_step = (int)gridDim.x / CL;
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = tile0; t < num_tiles; t += tile_step) {
         const int b = t / tiles_per_batch;
         const int r = t - b * tiles_per_batch;
-        const int n_blk = r / p.m_blocks;
-        const int m_blk = r - n_blk * p.m_blocks;
+        const int n_blk = r / m_groups;
+        const int m_blk = (r - n_blk * m_groups) * CL + crank;
         int img = 0, h0 = 0, w0 = 0;
         if (p.conv) {
           if (p.imgs_per_tile > 1) {
@@ -129,17 +143,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
-          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          if (p.conv) {
-            const int tap = kb / p.c_chunks;
-            const int cc = kb - tap * p.c_chunks;
-            const int kh = tap / p.taps_w;
-            const int kw = tap - kh * p.taps_w;
-            tma_load_4d(sa, &tmA, full_bar(stage), cc * BK, w0 + kw - p.pad, h0 + kh - p.pad, img);
+          if (CL == 1) {
+            mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            if (p.conv) {
+              const int tap = kb / p.c_chunks;
+              const int cc = kb - tap * p.c_chunks;
+              const int kh = tap / p.taps_w;
+              const int kw = tap - kh * p.taps_w;
+              tma_load_4d(sa, &tmA, full_bar(stage), cc * BK, w0 + kw - p.pad, h0 + kh - p.pad, img);
+            } else {
+              tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM, b);
+            }
+            tma_load_3d(sb, &tmB, full_bar(stage), kb * BK, n_blk * BN, p.b_batched ? b : 0);
           } else {
-            tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM, b);
+            // pair mode: the leader arms its barrier for the bytes of BOTH CTAs; every load names the leader's barrier
+            const uint32_t lbar = mapa_cluster(full_bar(stage), 0);
+            if (crank == 0) mbar_expect_tx(full_bar(stage), CL * Cfg::STAGE_BYTES);
+            if (p.conv) {
+              const int tap = kb / p.c_chunks;
+              const int cc = kb - tap * p.c_chunks;
+              const int kh = tap / p.taps_w;
+              const int kw = tap - kh * p.taps_w;
+              tma_load_4d_2sm(sa, &tmA, lbar, cc * BK, w0 + kw - p.pad, h0 + kh - p.pad, img);
+            } else {
+              tma_load_3d_2sm(sa, &tmA, lbar, kb * BK, m_blk * BM, b);
+            }
+            tma_load_3d_2sm(sb, &tmB, lbar, kb * BK, n_blk * BN + crank * (BN / CL), p.b_batched ? b : 0);   // my half of the B tile
           }
-          tma_load_3d(sb, &tmB, full_bar(stage), kb * BK, n_blk * BN, p.b_batched ? b : 0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -148,14 +178,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    // ------------------------------------------------ MMA issuer (single thread; pair mode: the leader CTA only)
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM * CL, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = tile0; t < num_tiles; t += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -168,15 +198,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 fp16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            if (CL == 1) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            else umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
           }
-          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          if (CL == 1) umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+          else umma_commit_2sm(empty_bar(stage));      // ... in both CTAs
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete
+        if (CL == 1) umma_commit(tfull_bar(acc));  // accumulator complete
+        else umma_commit_2sm(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -188,16 +221,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     const int n_out_all = p.gated ? (p.N >> 1) : p.N;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = tile0; t < num_tiles; t += tile_step) {
       const int b = t / tiles_per_batch;
       const int r = t - b * tiles_per_batch;
-      const int n_blk = r / p.m_blocks;
-      const int m_blk = r - n_blk * p.m_blocks;
+      const int n_blk = r / m_groups;
+      const int m_blk = (r - n_blk * m_groups) * CL + crank;
       const int row = m_blk * BM + lane_grp * 32 + lane;
       const bool row_ok = row < p.M;
       const int n0 = n_blk * BN;
 
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait_relaxed(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
 
@@ -321,7 +354,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CL == 1) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));  // the leader's MMA thread owns the accumulator hand-shake
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -329,9 +365,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while its peer may still read its shared memory / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (CL == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -340,20 +378,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 void count_launch();
 
-template <int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  using Cfg = TileCfg<BN>;
+template <int BN, int CL>
+static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using Cfg = TileCfg<BN, CL>;
   static bool attr_done = false;
   if (!attr_done) {
-    SEEDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    SEEDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_done = true;
   }
-  const int tiles = p.m_blocks * p.n_blocks * p.batch;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, st>>>(ta, tb, p);
+  const int groups = ((p.m_blocks + CL - 1) / CL) * p.n_blocks * p.batch;
+  const int max_clusters = num_sms() / CL;
+  const int grid = (groups < max_clusters ? groups : max_clusters) * CL;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, ta, tb, p);
   count_launch();
-  return check_cuda(cudaGetLastError(), "gemm_tc_kernel launch");
+  return check_cuda(e != cudaSuccess ? e : cudaGetLastError(), "gemm_tc_kernel launch");
 }
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int cl, cudaStream_t st) {
+  if (cl == 2) return launch_gemm_cl<BN, 2>(ta, tb, p, st);
+  return launch_gemm_cl<BN, 1>(ta, tb, p, st);
+}
+
+static int g_gemm_cluster = 1;  // 0 = never cluster, 1 = auto, 2 = always when legal
 
 static const int kTileN[] = {64, 96, 128, 144, 160, 192, 208, 224, 240, 256};
 
@@ -388,6 +445,8 @@ static int choose_tile_n(int m_tiles, int N, int k_blocks, bool heavy_epilogue) 
 
 using namespace seedx;
 
+extern "C" void seedx_gemm_set_cluster(int mode) { seedx::g_gemm_cluster = mode; }
+
 extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
   SEEDX_REQUIRE(a != nullptr, "seedx_gemm_f16: null args");
   SEEDX_REQUIRE(a->A && a->B && a->D, "seedx_gemm_f16: null operand pointer");
@@ -403,6 +462,7 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
   if (a->gated) SEEDX_REQUIRE(a->N % 2 == 0, "seedx_gemm_f16: gated epilogue needs even N");
 
   CUtensorMap ta, tb;
+  int cl = 1;
   if (!conv) {
     SEEDX_REQUIRE(a->lda % 8 == 0 && a->lda >= a->K, "seedx_gemm_f16: lda must be >= K and a multiple of 8");
     uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->batch};
@@ -463,7 +523,11 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
     uint64_t bstride = bb ? (uint64_t)a->strideB * 2 : (uint64_t)a->ldb * 2 * (uint64_t)a->N;
     SEEDX_REQUIRE(bstride % 16 == 0, "seedx_gemm_f16: strideB must be a multiple of 8 elements");
     uint64_t strides[2] = {(uint64_t)a->ldb * 2, bstride};
-    uint32_t box[3] = {BK, (uint32_t)bn, 1};
+    // CTA pairs (cta_group::2) when every SM still gets work and the B tile splits into two 16-row-aligned halves
+    const long long groups2 = (long long)((p.m_blocks + 1) / 2) * ((a->N + bn - 1) / bn) * a->batch;
+    cl = (g_gemm_cluster != 0 && p.m_blocks >= 2 && bn % 32 == 0 && groups2 >= num_sms() / 2) ? 2 : 1;
+    if (g_gemm_cluster == 2 && p.m_blocks >= 2 && bn % 32 == 0) cl = 2;  // forced (tests)
+    uint32_t box[3] = {BK, (uint32_t)(bn / cl), 1};
     if (int e = encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a->B, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
     p.b_batched = bb ? 1 : 0;
@@ -493,15 +557,15 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
   p.bias_vec = (a->bias_n && (uintptr_t)a->bias_n % 16 == 0) ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   switch (bn) {
-    case 64: return launch_gemm<64>(ta, tb, p, st);
-    case 96: return launch_gemm<96>(ta, tb, p, st);
-    case 128: return launch_gemm<128>(ta, tb, p, st);
-    case 144: return launch_gemm<144>(ta, tb, p, st);
-    case 160: return launch_gemm<160>(ta, tb, p, st);
-    case 192: return launch_gemm<192>(ta, tb, p, st);
-    case 208: return launch_gemm<208>(ta, tb, p, st);
-    case 224: return launch_gemm<224>(ta, tb, p, st);
-    case 240: return launch_gemm<240>(ta, tb, p, st);
-    default: return launch_gemm<256>(ta, tb, p, st);
+    case 64: return launch_gemm<64>(ta, tb, p, cl, st);
+    case 96: return launch_gemm<96>(ta, tb, p, cl, st);
+    case 128: return launch_gemm<128>(ta, tb, p, cl, st);
+    case 144: return launch_gemm<144>(ta, tb, p, cl, st);
+    case 160: return launch_gemm<160>(ta, tb, p, cl, st);
+    case 192: return launch_gemm<192>(ta, tb, p, cl, st);
+    case 208: return launch_gemm<208>(ta, tb, p, cl, st);
+    case 224: return launch_gemm<224>(ta, tb, p, cl, st);
+    case 240: return launch_gemm<240>(ta, tb, p, cl, st);
+    default: return launch_gemm<256>(ta, tb, p, cl, st);
   }
 }

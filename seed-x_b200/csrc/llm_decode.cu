@@ -15,40 +15,34 @@ namespace seedx {
 void count_launch();
 
 // ------------------------------------------------------------------------------------------------
-// Batched GEMV: out[b][n] = epi( W[n,:] . norm(x[b,:]) ) for NB <= 8 sequences.  W fp16 row-major is streamed exactly once
-// (128-bit ld.global.cs) and reused for all NB activations, which sit in shared memory as fp16.  A CTA owns a contiguous,
-// balanced range of 4-row groups; its 8 warps split K, so the work per CTA is even for any N (no whole-row quantisation).
+// Batched GEMV: out[b][n] = epi( W[n,:] . norm(x[b,:]) ) for up to 8 sequences.  The fp16 weight matrix is streamed from HBM exactly
+// once (one 128-bit ld.global.cs per lane per 8x32 weight block) and multiplied on the tensor cores: mma.sync.m16n8k16 with the
+// weight block as the A operand (8 rows used), the activations of the 8 sequence slots as the B operand (from shared memory, fp16)
+// and fp32 accumulators — so the instruction stream per byte is ~10x shorter than scalar FMAs and decode stays HBM-bound for 8
+// sequences as well as for 1.  The dot product is order-independent in k, so a lane's 16 contiguous bytes of a weight row serve
+// as the k-slots {2q,2q+1,2q+8,2q+9} of two consecutive MMAs and the activations are read with the same permutation.
+// One CTA per SM (16 warps split K); a CTA owns a balanced contiguous range of 8-row tiles.
 // ------------------------------------------------------------------------------------------------
-constexpr int GEMV_THREADS = 256;
+constexpr int GEMV_THREADS = 512;
 constexpr int GEMV_WARPS = GEMV_THREADS / 32;
-constexpr int GEMV_R = 4;  // weight rows per iteration (two gated pairs)
+constexpr int GEMV_ROWS = 8;    // weight rows per tile
+constexpr int GEMV_MAXKB = 14;  // 32-wide k blocks a warp keeps in registers (16 B per lane each)
 
-// v[NV] per lane -> lane l (l < NV) returns the warp-wide sum of v[l]; NV-1 + (5 - log2 NV) shuffles
-template <int NV>
-SEEDX_DEVINL float warp_reduce_multi(float (&v)[NV]) {
-#pragma unroll
-  for (int s = NV / 2; s >= 1; s >>= 1) {
-    const bool upper = (threadIdx.x & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float keep = upper ? v[i + s] : v[i];
-      const float send = upper ? v[i] : v[i + s];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  float r = v[0];
-#pragma unroll
-  for (int o = NV; o < 32; o <<= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
-  return r;  // value index = lane & (NV-1)
+SEEDX_DEVINL void mma16816_f32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int NB>
-__global__ void __launch_bounds__(GEMV_THREADS)
-gemv_batched_kernel(const __half* __restrict__ W, const float* __restrict__ x, long long ldx, const float* __restrict__ rms_w, float eps,
-                    const float* __restrict__ residual, long long ldr, float* __restrict__ out, long long ldo, int N, int K, int gated) {
+template <int NB>  // sequence slots held in shared memory: 1, 2, 4 or 8
+__global__ void __launch_bounds__(GEMV_THREADS, 1)
+gemv_mma_kernel(const __half* __restrict__ W, const float* __restrict__ x, long long ldx, const float* __restrict__ rms_w, float eps,
+                const float* __restrict__ residual, long long ldr, float* __restrict__ out, long long ldo, int N, int K, int gated) {
   extern __shared__ __align__(16) uint8_t gsm[];
-  __half* xs = (__half*)gsm;                                  // [NB][K]
-  __shared__ float part[2][GEMV_WARPS][GEMV_R * NB];
+  __half* xs = (__half*)gsm;                                   // [NB][K + 8]: rows 16 B apart in bank space (conflict-free LDS.128)
+  const int KP = K + 8;
+  __shared__ float part_sm[2][GEMV_WARPS][GEMV_ROWS * 8];
   __shared__ float red[GEMV_WARPS][NB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -83,72 +77,70 @@ gemv_batched_kernel(const __half* __restrict__ W, const float* __restrict__ x, l
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
       const float v = x[b * ldx + k];
-      xs[b * K + k] = __float2half_rn(rms_w ? v * ss[b] * g : v);
+      xs[b * KP + k] = __float2half_rn(rms_w ? v * ss[b] * g : v);
     }
   }
   __syncthreads();
 
-  // ---- main loop over this CTA's row groups
-  const int groups = (N + GEMV_R - 1) / GEMV_R;
-  const int g_begin = (int)((long long)blockIdx.x * groups / gridDim.x);
-  const int g_end = (int)((long long)(blockIdx.x + 1) * groups / gridDim.x);
-  const int chunks = K >> 3;
-  const int c_begin = (int)((long long)warp * chunks / GEMV_WARPS), c_end = (int)((long long)(warp + 1) * chunks / GEMV_WARPS);
+  const int g = lane >> 2, q = lane & 3;   // g: weight row inside the tile AND sequence slot of the B fragment; q: 16-byte k-chunk
+  const int tiles = (N + GEMV_ROWS - 1) / GEMV_ROWS;
+  const int t_begin = (int)((long long)blockIdx.x * tiles / gridDim.x);
+  const int t_end = (int)((long long)(blockIdx.x + 1) * tiles / gridDim.x);
+  const int kblocks = K >> 5;              // 32-wide k blocks (K % 32 == 0 checked on the host)
+  const int kb_begin = (int)((long long)warp * kblocks / GEMV_WARPS), kb_end = (int)((long long)(warp + 1) * kblocks / GEMV_WARPS);
+  const int kparts = (((kblocks + GEMV_WARPS - 1) / GEMV_WARPS) + GEMV_MAXKB - 1) / GEMV_MAXKB;   // block-uniform
+  const bool has_x = g < NB;
+  const __half* xrow = xs + (has_x ? g : 0) * KP + q * 8;
+
+  // The weight stream is software-pipelined across tiles: the registers of unit u+1 (a tile's k-part) are requested right after
+  // unit u has been fed to the tensor cores, i.e. BEFORE the cross-warp reduction and its barrier, so HBM requests never drain.
+  uint4 wreg[GEMV_MAXKB];
+  auto load_unit = [&](int t, int part) {
+    const int row = min(t * GEMV_ROWS + g, N - 1);
+    const uint4* wrow = (const uint4*)(W + (long long)row * K) + q;
+    const int kb0 = kb_begin + part * GEMV_MAXKB;
+#pragma unroll
+    for (int i = 0; i < GEMV_MAXKB; ++i)
+      if (kb0 + i < kb_end) wreg[i] = __ldcs(wrow + (kb0 + i) * 4);   // 8 consecutive halves of weight row g: k = kb*32 + q*8 ..
+  };
+  if (t_begin < t_end) load_unit(t_begin, 0);
   int buf = 0;
-  for (int g = g_begin; g < g_end; ++g, buf ^= 1) {
-    const int row0 = g * GEMV_R;
-    const uint4* wrow[GEMV_R];
+  for (int t = t_begin; t < t_end; ++t, buf ^= 1) {
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int part = 0; part < kparts; ++part) {
+      const int kb0 = kb_begin + part * GEMV_MAXKB;
 #pragma unroll
-    for (int r = 0; r < GEMV_R; ++r) wrow[r] = (const uint4*)(W + (long long)min(row0 + r, N - 1) * K);
-    float acc[GEMV_R * NB];
-#pragma unroll
-    for (int i = 0; i < GEMV_R * NB; ++i) acc[i] = 0.f;
-#pragma unroll 2
-    for (int c = c_begin + lane; c < c_end; c += 32) {
-      uint4 wq[GEMV_R];
-#pragma unroll
-      for (int r = 0; r < GEMV_R; ++r) wq[r] = __ldcs(wrow[r] + c);
-#pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        const uint4 xq = *(const uint4*)(xs + b * K + c * 8);
-        const __half2* xh = (const __half2*)&xq;
-        float2 xf[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) xf[j] = __half22float2(xh[j]);
-#pragma unroll
-        for (int r = 0; r < GEMV_R; ++r) {
-          const __half2* wh = (const __half2*)&wq[r];
-          float a = acc[r * NB + b];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 wf = __half22float2(wh[j]);
-            a = fmaf(wf.x, xf[j].x, a);
-            a = fmaf(wf.y, xf[j].y, a);
-          }
-          acc[r * NB + b] = a;
+      for (int i = 0; i < GEMV_MAXKB; ++i) {
+        if (kb0 + i < kb_end) {
+          uint4 xq = make_uint4(0, 0, 0, 0);
+          if (has_x) xq = *(const uint4*)(xrow + (kb0 + i) * 32);       // the same k positions of sequence g
+          mma16816_f32(c, wreg[i].x, 0u, wreg[i].y, 0u, xq.x, xq.y);
+          mma16816_f32(c, wreg[i].z, 0u, wreg[i].w, 0u, xq.z, xq.w);
         }
       }
+      if (part + 1 < kparts) load_unit(t, part + 1);
+      else if (t + 1 < t_end) load_unit(t + 1, 0);
     }
-    const float tot = warp_reduce_multi<GEMV_R * NB>(acc);
-    if (lane < GEMV_R * NB) part[buf][warp][lane] = tot;
+    // c[0], c[1] = partial dot products of weight row g with sequences 2q, 2q+1
+    part_sm[buf][warp][g * 8 + 2 * q] = c[0];
+    part_sm[buf][warp][g * 8 + 2 * q + 1] = c[1];
     __syncthreads();
-    // finalize: thread t -> (row r, batch b) for the plain epilogue, (pair p, batch b) for the gated one
-    if (threadIdx.x < GEMV_R * NB) {
+    if (threadIdx.x < GEMV_ROWS * NB) {
       const int r = threadIdx.x / NB, b = threadIdx.x % NB;
       float v = 0.f;
 #pragma unroll
-      for (int w = 0; w < GEMV_WARPS; ++w) v += part[buf][w][r * NB + b];
-      const int row = row0 + r;
+      for (int w = 0; w < GEMV_WARPS; ++w) v += part_sm[buf][w][r * 8 + b];
+      const int orow = t * GEMV_ROWS + r;
       if (!gated) {
-        if (row < N) out[b * ldo + row] = v + (residual ? residual[b * ldr + row] : 0.f);
-      } else if ((r & 1) == 0 && row + 1 < N) {
+        if (orow < N) out[b * ldo + orow] = v + (residual ? residual[b * ldr + orow] : 0.f);
+      } else if ((r & 1) == 0 && orow + 1 < N) {
         float gate = 0.f;
 #pragma unroll
-        for (int w = 0; w < GEMV_WARPS; ++w) gate += part[buf][w][(r + 1) * NB + b];
-        out[b * ldo + (row >> 1)] = v * silu(gate);  // rows interleaved [up_j, gate_j]: silu(gate(x)) * up(x), :166-167
+        for (int w = 0; w < GEMV_WARPS; ++w) gate += part_sm[buf][w][(r + 1) * 8 + b];
+        out[b * ldo + (orow >> 1)] = v * silu(gate);  // rows interleaved [up_j, gate_j]: silu(gate(x)) * up(x), :166-167
       }
     }
-    // the next iteration writes the other partial buffer; its __syncthreads orders this iteration's reads before buffer reuse
+    // the next tile writes the other partial buffer; its __syncthreads orders these reads before the buffer is reused
   }
 }
 
@@ -384,26 +376,26 @@ extern "C" int seedx_gemv_f16(const void* W, const float* x, int64_t ldx, const 
                               float* out, int64_t ldo, int64_t N, int64_t K, int batch, int gated, void* stream) {
   SEEDX_REQUIRE(W && x && out, "seedx_gemv_f16: null pointer");
   SEEDX_REQUIRE(batch >= 1 && batch <= 8, "seedx_gemv_f16: batch %d out of range (1..8)", batch);
-  SEEDX_REQUIRE(K % 8 == 0 && K > 0 && N > 0, "seedx_gemv_f16: K=%lld must be a positive multiple of 8", (long long)K);
+  SEEDX_REQUIRE(K % 32 == 0 && K > 0 && N > 0, "seedx_gemv_f16: K=%lld must be a positive multiple of 32", (long long)K);
   SEEDX_REQUIRE((uintptr_t)W % 16 == 0, "seedx_gemv_f16: W must be 16B aligned");
   if (gated) SEEDX_REQUIRE(N % 2 == 0 && residual == nullptr, "seedx_gemv_f16: gated needs even N and no residual");
   const int nb = batch <= 1 ? 1 : batch <= 2 ? 2 : batch <= 4 ? 4 : 8;
   SEEDX_REQUIRE(nb == batch, "seedx_gemv_f16: batch must be 1, 2, 4 or 8 (pad the sequence slots)");
-  const size_t smem = (size_t)nb * K * 2;
-  SEEDX_REQUIRE(smem <= 220 * 1024, "seedx_gemv_f16: batch*K too large for shared memory");
-  const long long groups = (N + GEMV_R - 1) / GEMV_R;
-  long long blocks = (long long)num_sms() * (smem > 100 * 1024 ? 1 : 2);
-  if (blocks > groups) blocks = groups;
+  const size_t smem = (size_t)nb * (K + 8) * 2;
+  SEEDX_REQUIRE(smem <= 216 * 1024, "seedx_gemv_f16: batch*K = %d*%lld does not fit in shared memory", nb, (long long)K);
+  const long long tiles = (N + GEMV_ROWS - 1) / GEMV_ROWS;
+  long long blocks = num_sms();
+  if (blocks > tiles) blocks = tiles;
   cudaStream_t st = (cudaStream_t)stream;
-#define GEMV_LAUNCH(NBV)                                                                                                                   \
-  do {                                                                                                                                     \
-    static bool attr = false;                                                                                                              \
-    if (!attr) {                                                                                                                           \
-      SEEDX_CUDA(cudaFuncSetAttribute(gemv_batched_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                 \
-      attr = true;                                                                                                                         \
-    }                                                                                                                                      \
-    gemv_batched_kernel<NBV><<<(unsigned)blocks, GEMV_THREADS, smem, st>>>((const __half*)W, x, ldx, rms_w, eps, residual, ldr, out, ldo, \
-                                                                           (int)N, (int)K, gated);                                          \
+#define GEMV_LAUNCH(NBV)                                                                                                               \
+  do {                                                                                                                                 \
+    static bool attr = false;                                                                                                          \
+    if (!attr) {                                                                                                                       \
+      SEEDX_CUDA(cudaFuncSetAttribute(gemv_mma_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));                 \
+      attr = true;                                                                                                                     \
+    }                                                                                                                                  \
+    gemv_mma_kernel<NBV><<<(unsigned)blocks, GEMV_THREADS, smem, st>>>((const __half*)W, x, ldx, rms_w, eps, residual, ldr, out, ldo, \
+                                                                       (int)N, (int)K, gated);                                          \
   } while (0)
   if (nb == 1) GEMV_LAUNCH(1);
   else if (nb == 2) GEMV_LAUNCH(2);

@@ -375,3 +375,15 @@ def logits_argmax(logits, img_ids, seq, state, eos_id, suppress_eos):
     check(lib().seedx_logits_argmax(_ptr(logits), _i64(V), _ptr(img_ids), C.c_int(0 if img_ids is None else img_ids.numel()), _ptr(seq),
                                     _ptr(state), C.c_int(B), C.c_int(eos_id if eos_id is not None else -1), C.c_int(int(suppress_eos)),
                                     _i64(seq.shape[1]), _stream()), "seedx_logits_argmax")
+
+
+def add_bcast_f16(a, b, out=None):
+    """fp16 out[r,:] = a[r,:] + b[r % b_rows,:] (b fp32)."""
+    _require_cuda(a, b, out)
+    assert a.is_contiguous() and b.dtype == torch.float32 and b.is_contiguous()
+    a2 = a.reshape(-1, a.shape[-1])
+    if out is None:
+        out = torch.empty(a2.shape, device=a.device, dtype=torch.float16)
+    check(lib().seedx_add_bcast_f16(_ptr(a2), _dt(a2), _ptr(b), _i64(a2.shape[0]), _i64(a2.shape[1]), _i64(b.shape[0]), _ptr(out), _stream()),
+          "seedx_add_bcast_f16")
+    return out

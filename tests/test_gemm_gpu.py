@@ -19,10 +19,19 @@ def mk(shape, seed, scale=1.0):
     return (torch.randn(shape, generator=g) * scale).cuda()
 
 
+@pytest.fixture(params=["single_cta", "cluster2"])
+def cluster_mode(request):
+    """run each GEMM test with the 2-CTA cluster / TMA-multicast variant forced off and forced on"""
+    from seedx_b200._lib import lib
+    lib().seedx_gemm_set_cluster(0 if request.param == "single_cta" else 2)
+    yield request.param
+    lib().seedx_gemm_set_cluster(1)
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (1024, 1664, 1664), (200, 328, 72),
                                    (2048, 4992, 1664), (174, 5120, 5120), (77, 40, 8), (1, 32330, 256)])
 @pytest.mark.parametrize("tile_n", [0, 64, 96, 128, 144, 160, 192, 208, 224, 240, 256])
-def test_gemm_plain(M, N, K, tile_n):
+def test_gemm_plain(M, N, K, tile_n, cluster_mode):
     from seedx_b200 import ops
     a = mk((M, K), 1).half()
     w = mk((N, K), 2, K ** -0.5).half()
@@ -34,7 +43,7 @@ def test_gemm_plain(M, N, K, tile_n):
 
 
 @pytest.mark.parametrize("tile_n", [0, 144, 208])
-def test_gemm_epilogues(tile_n):
+def test_gemm_epilogues(tile_n, cluster_mode):
     from seedx_b200 import ops
     import functools
     M, N, K = 384, 768, 320
@@ -70,7 +79,7 @@ def test_gemm_epilogues(tile_n):
     assert rel(o, acc + pos.repeat(3, 1) + bg.repeat_interleave(128, 0)) < 1e-5
 
 
-def test_gemm_batched_strided():
+def test_gemm_batched_strided(cluster_mode):
     from seedx_b200 import ops
     B, M, N, K = 5, 200, 136, 104
     a_full = mk((B, M, 3 * K + 8), 11).half()
@@ -87,7 +96,7 @@ def test_gemm_batched_strided():
 @pytest.mark.parametrize("n,h,w,c,cout,taps", [(2, 32, 32, 128, 192, 3), (1, 64, 64, 320, 320, 3), (2, 128, 128, 64, 64, 3),
                                                (1, 256, 256, 128, 24, 3), (3, 16, 16, 8, 320, 3), (2, 32, 32, 960, 640, 1),
                                                (1, 128, 128, 8, 320, 3)])
-def test_conv_nhwc(n, h, w, c, cout, taps):
+def test_conv_nhwc(n, h, w, c, cout, taps, cluster_mode):
     from seedx_b200 import ops
     x = mk((n, c, h, w), 21).half()
     wt = mk((cout, c, taps, taps), 22, (c * taps * taps) ** -0.5).half()

@@ -169,3 +169,56 @@ def test_scheduler_tables_match_oracle():
     assert a.timesteps[0] == 981.0 and a.timesteps[-1] == 1.0
     assert max(abs(x - float(y)) for x, y in zip(a.sigmas, b.sigmas)) < 1e-5
     assert abs(a.init_noise_sigma - b.init_noise_sigma) < 1e-5
+
+
+@pytest.mark.parametrize("name", ["tiny", "full"])
+def test_resampler_xl_matches_reference_golden(name):
+    """ResamplerXLV2 (perceiver + attention pool) vs the reference module's own outputs (tests/golden/resampler_xl.pt)."""
+    import os
+    from seedx_b200.resampler_xl import ResamplerXLV2
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "resampler_xl.pt"))
+    cfg = synth.TINY_RESAMPLER_XL if name == "tiny" else synth.RESAMPLER_XL
+    m = ResamplerXLV2(normalize=False, **cfg)
+    m.load_state_dict(synth.resampler_xl_state_dict(cfg))
+    for n_tok in (64, 256):
+        x = synth.randn(f"rxl_{name}_{n_tok}", (2, n_tok, cfg["embedding_dim"]))
+        p, pooled = m(x.cuda())
+        e1, e2 = rel(p, g[f"{name}_{n_tok}_prompt"]), rel(pooled, g[f"{name}_{n_tok}_pooled"])
+        print(f"resampler_xl {name} n={n_tok}: prompt rel = {e1:.3e}, pooled rel = {e2:.3e}")
+        assert e1 < 2e-3 and e2 < 2e-3
+
+
+def test_adapter_t2i_tiny_end_to_end():
+    """SDXLAdapter.generate(image_embeds=...) on tiny models: negative = avg-pooled ViT(zeros), resampler, 6-step CFG loop, VAE, uint8."""
+    from seedx_b200.adapter import SDXLAdapter
+    from seedx_b200.resampler_xl import ResamplerXLV2
+    from seedx_b200.sdxl import AutoencoderKL, EulerDiscreteScheduler, UNet2DConditionModel
+    from seedx_b200.vit import VisionTransformerWithAttnPool
+    from oracle import resampler_xl as orx, sdxl as osd, vit as ovit
+    vcfg = dict(width=208, layers=2, heads=2, mlp_width=520, output_dim=256, n_queries=256, patch=14)
+    rcfg = dict(synth.TINY_RESAMPLER_XL, embedding_dim=256)
+    ucfg = dict(synth.TINY_UNET, cross_attention_dim=256, text_embed_dim=160)
+    vit_sd, r_sd, u_sd, v_sd = synth.vit_state_dict(**vcfg), synth.resampler_xl_state_dict(rcfg), synth.unet_state_dict(ucfg), synth.vae_state_dict(synth.TINY_VAE)
+    vit = VisionTransformerWithAttnPool(image_size=448, patch_size=14, width=208, layers=2, heads=2, mlp_ratio=2.5, output_dim=256)
+    vit.load_state_dict(vit_sd)
+    rx = ResamplerXLV2(normalize=False, **rcfg)
+    rx.load_state_dict(r_sd)
+    unet, vae = UNet2DConditionModel(ucfg), AutoencoderKL(synth.TINY_VAE)
+    unet.load_state_dict(u_sd)
+    vae.load_state_dict(v_sd)
+    ad = SDXLAdapter(unet=unet, resampler=rx, vit_down=True)
+    ad.init_pipe(vae=vae, scheduler=EulerDiscreteScheduler(), visual_encoder=vit, image_transform=None)
+    feats = synth.randn("adapter_feats", (2, 64, 256))
+    noise = synth.randn("adapter_noise", (2, 4, 32, 32))
+    lat = ad.generate(image_embeds=feats.cuda(), num_inference_steps=6, height=256, width=256, latents=noise.cuda(), input_image_size=224,
+                      output_type="latent")
+    # oracle: same composition (adapter_modules.py:96-169)
+    neg = ovit.vit_down(ovit.vit_forward(vit_sd, torch.zeros(1, 3, 224, 224), 2))
+    allf = torch.cat([feats, neg.expand(2, -1, -1)])
+    prompt, pooled = orx.resampler_xl(r_sd, rcfg, allf)
+    ref = osd.t2i_sample(u_sd, ucfg, noise, prompt[:2], pooled[:2], prompt[2:], pooled[2:], steps=6, guidance=7.5, size=256)
+    e = rel(lat, ref)
+    print(f"adapter t2i tiny: latents rel = {e:.3e}")
+    assert e < 1e-2
+    imgs = ad.generate(image_embeds=feats.cuda(), num_inference_steps=2, height=256, width=256, latents=noise.cuda(), input_image_size=224)
+    assert len(imgs) == 2 and imgs[0].size == (256, 256)

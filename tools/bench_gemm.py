@@ -43,6 +43,8 @@ def run_conv(name, n, h, w, c, cout, tiles=(0,)):
 
 
 T = tuple(int(t) for t in os.environ.get("TILES", "0,128,256").split(","))
+from seedx_b200._lib import lib
+lib().seedx_gemm_set_cluster(int(os.environ.get("CLUSTER", "1")))
 run_gemm("square 8192", 8192, 8192, 8192, T)
 run_gemm("square 4096", 4096, 4096, 4096, T)
 Be = 2
