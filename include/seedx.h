@@ -81,6 +81,8 @@ typedef struct seedx_gemm_args {
 int seedx_gemm_f16(const seedx_gemm_args* args, void* stream);
 /* A/B switch for the 2-CTA cluster (TMA multicast of the B tile) variant: 0 = off, 1 = auto (default), 2 = whenever legal */
 void seedx_gemm_set_cluster(int mode);
+/* A/B switch for the epilogue: 1 (default) = output/residual tiles staged in shared memory and moved by TMA, 0 = direct row-per-thread stores */
+void seedx_gemm_set_tma_epilogue(int on);
 
 
 /* ------------------------------------------------------------------------------------------------

@@ -134,6 +134,27 @@ SEEDX_DEVINL void umma_commit(uint32_t bar) {
 }
 
 
+
+// ---- TMA stores (shared -> global), bulk async groups, proxy fence ---------------------------------
+SEEDX_DEVINL void tma_store_3d(const void* tmap, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+SEEDX_DEVINL void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+SEEDX_DEVINL void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+SEEDX_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+SEEDX_DEVINL uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+SEEDX_DEVINL void sts128(uint32_t a, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ---- thread-block clusters -----------------------------------------------------------------------
 SEEDX_DEVINL uint32_t cluster_ctarank() {
   uint32_t r;

@@ -30,6 +30,7 @@ struct GemmParams {
   int res_row_mod, bias_g_rows;
   float alpha;
   int act, gated, out_f32, res_f32, vec_ok, b_batched, bias_vec;
+  int tma_epi, epi_row_bytes, r_batched;  // TMA epilogue: output (and residual) tiles of 32 rows x epi_row_bytes staged in shared memory
   // conv
   int conv, taps_w, c_chunks, conv_w, conv_h, tile_w, tile_h, tiles_per_img, tiles_w, pad, imgs_per_tile;
 };
@@ -41,6 +42,8 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, alternating 32-column chunks
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 = TMA, warp 1 = MMA, warps 2..9 = epilogue
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int EPI_WARP_BYTES = 8192;                     // per epilogue warp: 4 KB of output tiles + 4 KB of residual tiles
+constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_WARP_BYTES;
 
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
@@ -49,11 +52,11 @@ struct TileCfg {
   static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N for M=128/256: multiple of 16, <= 256");
   static constexpr int B_STAGE_BYTES = (BN / CL) * BK * 2;   // a CTA of a pair stages only its half of the B tile
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES_FIT = (SMEM_LIMIT - 1024 - 256) / STAGE_BYTES;
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - 1024 - 512 - EPI_STAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   // two accumulator stages; the last 32-column epilogue chunk of a stage may over-read up to 16 columns -> keep them allocated
   static constexpr int TMEM_COLS = pow2_cols(2 * BN + 16);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 SEEDX_DEVINL float apply_act(float x, int act) {
@@ -70,18 +73,21 @@ SEEDX_DEVINL float apply_act(float x, int act) {
 // and `tmem_full` barriers; both CTAs' epilogue warps arrive on the leader's `tmem_empty` barrier.
 template <int BN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+               const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using Cfg = TileCfg<BN, CL>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned
+  const uint32_t bar_base = epi_base + EPI_STAGE_BYTES;
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto res_bar = [&](int w, int i) { return bar_base + 8u * (2 * STAGES + 6 + 2 * w + i); };  // residual tile landed (per epilogue warp, 2 buffers)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -97,6 +103,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), EPI_WARPS * CL);  // pair mode: the leader's barrier collects both CTAs' epilogue warps
+    }
+    for (int w = 0; w < EPI_WARPS; ++w) {
+      mbar_init(res_bar(w, 0), 1);
+      mbar_init(res_bar(w, 1), 1);
     }
     mbar_fence_init();
   }
@@ -220,7 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int chunk0 = ((warp - 2) >> 2) * 32;  // warps 2..5 take even 32-column chunks, warps 6..9 the odd ones
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int n_out_all = p.gated ? (p.N >> 1) : p.N;
+    uint32_t epi_res_phase = 0;   // parity bits of this warp's two residual barriers
     for (int t = tile0; t < num_tiles; t += tile_step) {
       const int b = t / tiles_per_batch;
       const int r = t - b * tiles_per_batch;
@@ -230,16 +240,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = row < p.M;
       const int n0 = n_blk * BN;
 
-      mbar_wait_relaxed(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
 
       const float bm = (p.bias_m != nullptr && row_ok) ? p.bias_m[row] : 0.f;
       const float* bg = (p.bias_g != nullptr && row_ok) ? p.bias_g + (long long)(row / p.bias_g_rows) * p.N : nullptr;
       const int rrow = p.res_row_mod ? (row % p.res_row_mod) : row;
 
-#pragma unroll 1
       const int col_end = min(p.N, n0 + BN);   // columns of this tile that exist
+      // ---- TMA epilogue state: tiles of 32 rows x RB bytes in this warp's staging area, XOR-swizzled like the tensor maps
+      const int ew = warp - 2;
+      const uint32_t stg_out = epi_base + (uint32_t)ew * EPI_WARP_BYTES, stg_res = stg_out + 4096u;
+      const int RB = p.epi_row_bytes;
+      const uint32_t tile_bytes = 32u * (uint32_t)RB;
+      const int nbuf = tile_bytes <= 2048u ? 2 : 1;
+      const uint32_t swz_mask = (uint32_t)(RB / 16 - 1);
+      const int row_base = m_blk * BM + lane_grp * 32;
+      const bool tma_res = p.tma_epi && p.residual != nullptr;
+      int n_chunks = 0;
+      for (int c = chunk0; c < BN && n0 + c < col_end; c += 64) ++n_chunks;
+      auto out_col = [&](int k) { const int col0 = n0 + chunk0 + 64 * k; return p.gated ? (col0 >> 1) : col0; };
+      auto issue_res = [&](int k) {  // lane 0: fetch the residual tile of chunk k into residual buffer k % nbuf
+        const int rb = k % nbuf;
+        mbar_expect_tx(res_bar(ew, rb), tile_bytes);
+        tma_load_3d(stg_res + (uint32_t)rb * tile_bytes, &tmR, res_bar(ew, rb), out_col(k), p.res_row_mod ? (row_base % p.res_row_mod) : row_base,
+                    p.r_batched ? b : 0);
+      };
+      if (tma_res && lane == 0)
+        for (int k = 0; k < nbuf && k < n_chunks; ++k) issue_res(k);  // in flight while the main loop of this tile is still running
+      int kchunk = 0;
+      mbar_wait_relaxed(tfull_bar(acc), acc_phase);   // accumulator of this tile complete
+      tc_fence_after();
+#pragma unroll 1
       for (int c = chunk0; c < BN; c += 64) {
         if (n0 + c >= col_end) break;  // warp-uniform
         __syncwarp();              // tcgen05.ld is warp-collective: reconverge after the predicated stores
@@ -280,8 +311,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = apply_act(x[i], p.act);
         }
-        if (!row_ok) continue;
         const int n_out = p.gated ? (col_end >> 1) : col_end;  // output columns of this tile end here
+        if (!row_ok) continue;
         const bool full = (ocol0 + nvals <= n_out) && p.vec_ok;
         if (p.residual != nullptr) {
           if (p.res_f32) {
@@ -361,6 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (p.tma_epi && lane == 0) bulk_wait_read<0>();  // shared memory stays alive until the last TMA store has read it
   }
 
   tc_fence_before();
@@ -379,7 +411,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 void count_launch();
 
 template <int BN, int CL>
-static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p,
+                          cudaStream_t st) {
   using Cfg = TileCfg<BN, CL>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -399,18 +432,20 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const Ge
   attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, ta, tb, p);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, ta, tb, td, tr, p);
   count_launch();
   return check_cuda(e != cudaSuccess ? e : cudaGetLastError(), "gemm_tc_kernel launch");
 }
 
 template <int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int cl, cudaStream_t st) {
-  if (cl == 2) return launch_gemm_cl<BN, 2>(ta, tb, p, st);
-  return launch_gemm_cl<BN, 1>(ta, tb, p, st);
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p, int cl,
+                       cudaStream_t st) {
+  if (cl == 2) return launch_gemm_cl<BN, 2>(ta, tb, td, tr, p, st);
+  return launch_gemm_cl<BN, 1>(ta, tb, td, tr, p, st);
 }
 
 static int g_gemm_cluster = 1;  // 0 = never cluster, 1 = auto, 2 = always when legal
+static int g_gemm_tma_epi = 1;  // 0 = row-per-thread direct stores, 1 = TMA-store epilogue when eligible
 
 static const int kTileN[] = {64, 96, 128, 144, 160, 192, 208, 224, 240, 256};
 
@@ -424,11 +459,12 @@ static bool valid_tile_n(int bn) {
 //   waves = ceil(tiles / SMs); per tile max(MMA issue, epilogue drain) cycles; plus the un-overlapped epilogue of the last tile.
 // MMA: 128 x BN x 16 per instruction = BN/2 cycles, but never faster than shared memory can feed A+B; the effective operand
 // bandwidth measured on B200 (8192^3: BN=128 runs at 0.71x the BN=256 rate) is ~91 B/clk.
-static int choose_tile_n(int m_tiles, int N, int k_blocks, bool heavy_epilogue) {
+static int choose_tile_n(int m_tiles, int N, int k_blocks, bool heavy_epilogue, bool only32) {
   const int sms = num_sms();
   double best = 1e30;
   int best_bn = 256;
   for (int bn : kTileN) {
+    if (only32 && bn % 32 != 0) continue;  // the TMA epilogue stores whole 32-column chunks
     const int n_blocks = (N + bn - 1) / bn;
     const long long tiles = (long long)m_tiles * n_blocks;
     const long long waves = (tiles + sms - 1) / sms;
@@ -446,6 +482,7 @@ static int choose_tile_n(int m_tiles, int N, int k_blocks, bool heavy_epilogue) 
 using namespace seedx;
 
 extern "C" void seedx_gemm_set_cluster(int mode) { seedx::g_gemm_cluster = mode; }
+extern "C" void seedx_gemm_set_tma_epilogue(int on) { seedx::g_gemm_tma_epi = on; }
 
 extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
   SEEDX_REQUIRE(a != nullptr, "seedx_gemm_f16: null args");
@@ -461,7 +498,17 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
   SEEDX_REQUIRE(bn == 0 || valid_tile_n(bn), "seedx_gemm_f16: tile_n must be 0 (auto) or one of 64/96/128/144/160/192/208/224/240/256");
   if (a->gated) SEEDX_REQUIRE(a->N % 2 == 0, "seedx_gemm_f16: gated epilogue needs even N");
 
-  CUtensorMap ta, tb;
+  // ---- TMA epilogue eligibility (output / residual tiles go through shared memory and cp.async.bulk.tensor stores)
+  const int out_es = a->out_dtype == SEEDX_F32 ? 4 : 2;
+  const long long n_out_ll = a->gated ? a->N / 2 : a->N;
+  bool tma_epi = g_gemm_tma_epi && ((uintptr_t)a->D % 16 == 0) && ((a->ldd * out_es) % 16 == 0) && (a->batch == 1 || (a->strideD * out_es) % 16 == 0) &&
+                 (a->N % 2 == 0);
+  if (a->residual) {
+    tma_epi = tma_epi && !a->gated && a->residual_dtype == a->out_dtype && ((uintptr_t)a->residual % 16 == 0) && ((a->ldr * out_es) % 16 == 0) &&
+              (a->res_row_mod % 32 == 0) && (a->batch == 1 || a->strideR == 0 || (a->strideR * out_es) % 16 == 0);
+  }
+  if (bn != 0 && bn % 32 != 0) tma_epi = false;
+  CUtensorMap ta, tb, td, tr;
   int cl = 1;
   if (!conv) {
     SEEDX_REQUIRE(a->lda % 8 == 0 && a->lda >= a->K, "seedx_gemm_f16: lda must be >= K and a multiple of 8");
@@ -474,7 +521,7 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
       return e;
     p.k_blocks = (int)((a->K + BK - 1) / BK);
     p.m_blocks = (int)((a->M + BM - 1) / BM);
-    if (bn == 0) bn = choose_tile_n(p.m_blocks * (int)a->batch, (int)a->N, p.k_blocks, a->act != SEEDX_ACT_NONE);
+    if (bn == 0) bn = choose_tile_n(p.m_blocks * (int)a->batch, (int)a->N, p.k_blocks, a->act != SEEDX_ACT_NONE, tma_epi);
   } else {
     const int64_t C = a->conv_c, W = a->conv_w, H = a->conv_h, NI = a->conv_n;
     SEEDX_REQUIRE(C % 8 == 0 && C > 0, "seedx_gemm_f16(conv): channels must be a multiple of 8");
@@ -500,7 +547,7 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
                   (long long)a->conv_taps_h * a->conv_taps_w * cchunks * BK);
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NI};
     uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-    if (bn == 0) bn = choose_tile_n((int)((a->M + BM - 1) / BM), (int)a->N, a->conv_taps_h * a->conv_taps_w * cchunks, a->act != SEEDX_ACT_NONE);
+    if (bn == 0) bn = choose_tile_n((int)((a->M + BM - 1) / BM), (int)a->N, a->conv_taps_h * a->conv_taps_w * cchunks, a->act != SEEDX_ACT_NONE, tma_epi);
     uint32_t box[4] = {BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tn};
     if (int e = encode_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, a->A, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
@@ -555,17 +602,40 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
   }
   p.vec_ok = vec ? 1 : 0;
   p.bias_vec = (a->bias_n && (uintptr_t)a->bias_n % 16 == 0) ? 1 : 0;
+  p.tma_epi = tma_epi ? 1 : 0;
+  td = ta, tr = ta;  // placeholders when the TMA epilogue is off (never dereferenced)
+  if (tma_epi) {
+    const int cols = a->gated ? 16 : 32;                    // output columns per 32-column accumulator chunk
+    const int rb = cols * out_es;                           // staged row bytes: 32, 64 or 128
+    const CUtensorMapSwizzle sw = rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (rb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMapDataType dt = out_es == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    p.epi_row_bytes = rb;
+    uint32_t box[3] = {(uint32_t)cols, 32, 1};
+    {
+      uint64_t dims[3] = {(uint64_t)n_out_ll, (uint64_t)a->M, (uint64_t)a->batch};
+      uint64_t strides[2] = {(uint64_t)a->ldd * out_es, (uint64_t)(a->batch > 1 ? a->strideD : a->ldd * a->M) * out_es};
+      if (int e = encode_tmap(&td, dt, 3, a->D, dims, strides, box, sw)) return e;
+    }
+    if (a->residual) {
+      const bool rbat = a->batch > 1 && a->strideR != 0;
+      const uint64_t rrows = (uint64_t)(a->res_row_mod ? a->res_row_mod : a->M);
+      uint64_t dims[3] = {(uint64_t)n_out_ll, rrows, (uint64_t)(rbat ? a->batch : 1)};
+      uint64_t strides[2] = {(uint64_t)a->ldr * out_es, (uint64_t)(rbat ? a->strideR : a->ldr * (long long)rrows) * out_es};
+      if (int e = encode_tmap(&tr, dt, 3, a->residual, dims, strides, box, sw)) return e;
+      p.r_batched = rbat ? 1 : 0;
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   switch (bn) {
-    case 64: return launch_gemm<64>(ta, tb, p, cl, st);
-    case 96: return launch_gemm<96>(ta, tb, p, cl, st);
-    case 128: return launch_gemm<128>(ta, tb, p, cl, st);
-    case 144: return launch_gemm<144>(ta, tb, p, cl, st);
-    case 160: return launch_gemm<160>(ta, tb, p, cl, st);
-    case 192: return launch_gemm<192>(ta, tb, p, cl, st);
-    case 208: return launch_gemm<208>(ta, tb, p, cl, st);
-    case 224: return launch_gemm<224>(ta, tb, p, cl, st);
-    case 240: return launch_gemm<240>(ta, tb, p, cl, st);
-    default: return launch_gemm<256>(ta, tb, p, cl, st);
+    case 64: return launch_gemm<64>(ta, tb, td, tr, p, cl, st);
+    case 96: return launch_gemm<96>(ta, tb, td, tr, p, cl, st);
+    case 128: return launch_gemm<128>(ta, tb, td, tr, p, cl, st);
+    case 144: return launch_gemm<144>(ta, tb, td, tr, p, cl, st);
+    case 160: return launch_gemm<160>(ta, tb, td, tr, p, cl, st);
+    case 192: return launch_gemm<192>(ta, tb, td, tr, p, cl, st);
+    case 208: return launch_gemm<208>(ta, tb, td, tr, p, cl, st);
+    case 224: return launch_gemm<224>(ta, tb, td, tr, p, cl, st);
+    case 240: return launch_gemm<240>(ta, tb, td, tr, p, cl, st);
+    default: return launch_gemm<256>(ta, tb, td, tr, p, cl, st);
   }
 }

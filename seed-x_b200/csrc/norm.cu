@@ -32,12 +32,19 @@ SEEDX_DEVINL float block_sum(float v, float* sh) {
   return t;
 }
 
-SEEDX_DEVINL float4 ld4(const float* p) { return *(const float4*)p; }
-SEEDX_DEVINL float4 ld4(const __half* p) {
-  const uint2 q = *(const uint2*)p;
+// a row is cached in registers in its STORAGE format (fp16 rows cost half the registers -> more resident CTAs to hide HBM latency)
+template <typename T> struct Raw4;
+template <> struct Raw4<float> { typedef float4 type; };
+template <> struct Raw4<__half> { typedef uint2 type; };
+SEEDX_DEVINL float4 ldraw(const float* p) { return *(const float4*)p; }
+SEEDX_DEVINL uint2 ldraw(const __half* p) { return *(const uint2*)p; }
+SEEDX_DEVINL float4 unpack4(float4 q) { return q; }
+SEEDX_DEVINL float4 unpack4(uint2 q) {
   const float2 a = __half22float2(*(const __half2*)&q.x), b = __half22float2(*(const __half2*)&q.y);
   return make_float4(a.x, a.y, b.x, b.y);
 }
+SEEDX_DEVINL float4 zero_raw(float4*) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+SEEDX_DEVINL uint2 zero_raw(uint2*) { return make_uint2(0u, 0u); }
 SEEDX_DEVINL void st4(float* p, float4 v) { *(float4*)p = v; }
 SEEDX_DEVINL void st4(__half* p, float4 v) {
   uint2 q;
@@ -58,13 +65,18 @@ layernorm_vec_kernel(const TI* __restrict__ x, long long ldx, const float* __res
   const bool row_ok = row < rows;
   const TI* xr = x + (row_ok ? row : 0) * ldx;
   const int nvec = cols >> 2;
-  float4 v[NV];
+  typedef typename Raw4<TI>::type RawT;
+  RawT raw[NV];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = t + i * TPR;
-    v[i] = (c < nvec && row_ok) ? ld4(xr + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-    s += v[i].x + v[i].y + v[i].z + v[i].w;
+    raw[i] = (c < nvec && row_ok) ? ldraw(xr + c * 4) : zero_raw((RawT*)nullptr);
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 v = unpack4(raw[i]);
+    s += v.x + v.y + v.z + v.w;
   }
   float mean = 0.f;
   if (!rms) mean = (TPR == 32 ? warp_sum(s) : block_sum(s, sh)) / (float)cols;
@@ -73,7 +85,8 @@ layernorm_vec_kernel(const TI* __restrict__ x, long long ldx, const float* __res
   for (int i = 0; i < NV; ++i) {
     const int c = t + i * TPR;
     if (c < nvec) {
-      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      const float4 v = unpack4(raw[i]);
+      const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
       q += a * a + b * b + cc * cc + d * d;
     }
   }
@@ -87,7 +100,8 @@ layernorm_vec_kernel(const TI* __restrict__ x, long long ldx, const float* __res
   for (int i = 0; i < NV; ++i) {
     const int c = t + i * TPR;
     if (c < nvec) {
-      float4 y = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd);
+      const float4 v = unpack4(raw[i]);
+      float4 y = make_float4((v.x - mean) * rstd, (v.y - mean) * rstd, (v.z - mean) * rstd, (v.w - mean) * rstd);
       if (gamma) {
         const float4 g = *(const float4*)(gamma + c * 4);
         y.x *= g.x, y.y *= g.y, y.z *= g.z, y.w *= g.w;

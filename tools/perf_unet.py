@@ -10,7 +10,7 @@ B = int(os.environ.get("B", "1"))
 branches = int(os.environ.get("BR", "2"))
 t0 = time.time()
 cfg = dict(SDXL_UNET)
-sd = synth.unet_state_dict(cfg)
+synth.set_device('cuda'); sd = synth.unet_state_dict(cfg); synth.set_device('cpu')
 print("synth weights", time.time() - t0, "s", flush=True)
 unet = UNet2DConditionModel(cfg)
 unet.load_state_dict(sd)
