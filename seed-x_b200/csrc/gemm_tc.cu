@@ -31,6 +31,7 @@ struct GemmParams {
   float alpha;
   int act, gated, out_f32, res_f32, vec_ok, b_batched, bias_vec;
   int tma_epi, epi_row_bytes, r_batched;  // TMA epilogue: output (and residual) tiles of 32 rows x epi_row_bytes staged in shared memory
+  int stages, epi_warp_bytes;             // pipeline depth and per-epilogue-warp staging bytes, sized on the host to fill shared memory
   // conv
   int conv, taps_w, c_chunks, conv_w, conv_h, tile_w, tile_h, tiles_per_img, tiles_w, pad, imgs_per_tile;
 };
@@ -42,8 +43,9 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int EPI_WARPS = 8;                       // two warps per TMEM lane quarter, alternating 32-column chunks
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;  // warp 0 = TMA, warp 1 = MMA, warps 2..9 = epilogue
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int EPI_WARP_BYTES = 8192;                     // per epilogue warp: 4 KB of output tiles + 4 KB of residual tiles
-constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_WARP_BYTES;
+constexpr int EPI_OUT_BYTES = 4096;                      // per epilogue warp: output tiles (2 x <=2 KB, or 1 x 4 KB)
+constexpr int EPI_RES_BYTES = 8192;                      // per epilogue warp: residual tiles, ideally every chunk of a 256-wide tile in flight
+constexpr int MAX_STAGES = 8;
 
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
@@ -52,11 +54,14 @@ struct TileCfg {
   static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N for M=128/256: multiple of 16, <= 256");
   static constexpr int B_STAGE_BYTES = (BN / CL) * BK * 2;   // a CTA of a pair stages only its half of the B tile
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES_FIT = (SMEM_LIMIT - 1024 - 512 - EPI_STAGE_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+  // pipeline depth for a given amount of epilogue staging (runtime: depends on whether a residual is streamed through shared memory)
+  static int stages_for(int epi_bytes) {
+    const int fit = (SMEM_LIMIT - 1024 - 512 - epi_bytes) / STAGE_BYTES;
+    return fit > MAX_STAGES ? MAX_STAGES : fit;
+  }
+  static int smem_for(int stages, int epi_bytes) { return stages * STAGE_BYTES + epi_bytes + 1024 /*align slack*/ + 512 /*barriers*/; }
   // two accumulator stages; the last 32-column epilogue chunk of a stage may over-read up to 16 columns -> keep them allocated
   static constexpr int TMEM_COLS = pow2_cols(2 * BN + 16);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 SEEDX_DEVINL float apply_act(float x, int act) {
@@ -76,18 +81,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using Cfg = TileCfg<BN, CL>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = p.stages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned
-  const uint32_t bar_base = epi_base + EPI_STAGE_BYTES;
+  const uint32_t bar_base = epi_base + (uint32_t)(EPI_WARPS * p.epi_warp_bytes);
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
-  auto res_bar = [&](int w, int i) { return bar_base + 8u * (2 * STAGES + 6 + 2 * w + i); };  // residual tile landed (per epilogue warp, 2 buffers)
+  auto res_bar = [&](int w, int i) { return bar_base + 8u * (2 * STAGES + 6 + 4 * w + i); };  // residual tile landed (per epilogue warp, <= 4 buffers)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,10 +109,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), EPI_WARPS * CL);  // pair mode: the leader's barrier collects both CTAs' epilogue warps
     }
-    for (int w = 0; w < EPI_WARPS; ++w) {
-      mbar_init(res_bar(w, 0), 1);
-      mbar_init(res_bar(w, 1), 1);
-    }
+    for (int w = 0; w < EPI_WARPS; ++w)
+      for (int i = 0; i < 4; ++i) mbar_init(res_bar(w, i), 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -249,24 +252,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int col_end = min(p.N, n0 + BN);   // columns of this tile that exist
       // ---- TMA epilogue state: tiles of 32 rows x RB bytes in this warp's staging area, XOR-swizzled like the tensor maps
       const int ew = warp - 2;
-      const uint32_t stg_out = epi_base + (uint32_t)ew * EPI_WARP_BYTES, stg_res = stg_out + 4096u;
+      const uint32_t stg_out = epi_base + (uint32_t)(ew * p.epi_warp_bytes), stg_res = stg_out + (uint32_t)EPI_OUT_BYTES;
       const int RB = p.epi_row_bytes;
       const uint32_t tile_bytes = 32u * (uint32_t)RB;
-      const int nbuf = tile_bytes <= 2048u ? 2 : 1;
+      const int nbuf = tile_bytes <= 2048u ? 2 : 1;                 // output buffers (EPI_OUT_BYTES)
+      int nres = (int)(EPI_RES_BYTES / tile_bytes);                 // residual buffers: 8/4/2 -> clamp to 4
+      nres = nres > 4 ? 4 : nres;
       const uint32_t swz_mask = (uint32_t)(RB / 16 - 1);
       const int row_base = m_blk * BM + lane_grp * 32;
       const bool tma_res = p.tma_epi && p.residual != nullptr;
       int n_chunks = 0;
       for (int c = chunk0; c < BN && n0 + c < col_end; c += 64) ++n_chunks;
       auto out_col = [&](int k) { const int col0 = n0 + chunk0 + 64 * k; return p.gated ? (col0 >> 1) : col0; };
-      auto issue_res = [&](int k) {  // lane 0: fetch the residual tile of chunk k into residual buffer k % nbuf
-        const int rb = k % nbuf;
+      auto issue_res = [&](int k) {  // lane 0: fetch the residual tile of chunk k into residual buffer k % nres
+        const int rb = k % nres;
         mbar_expect_tx(res_bar(ew, rb), tile_bytes);
         tma_load_3d(stg_res + (uint32_t)rb * tile_bytes, &tmR, res_bar(ew, rb), out_col(k), p.res_row_mod ? (row_base % p.res_row_mod) : row_base,
                     p.r_batched ? b : 0);
       };
       if (tma_res && lane == 0)
-        for (int k = 0; k < nbuf && k < n_chunks; ++k) issue_res(k);  // in flight while the main loop of this tile is still running
+        for (int k = 0; k < nres && k < n_chunks; ++k) issue_res(k);  // in flight while the main loop of this tile is still running
       int kchunk = 0;
       mbar_wait_relaxed(tfull_bar(acc), acc_phase);   // accumulator of this tile complete
       tc_fence_after();
@@ -411,21 +416,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 void count_launch();
 
 template <int BN, int CL>
-static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p,
+static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p_in,
                           cudaStream_t st) {
   using Cfg = TileCfg<BN, CL>;
   static bool attr_done = false;
   if (!attr_done) {
-    SEEDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    SEEDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
+  GemmParams p = p_in;
+  const int epi_bytes = EPI_WARPS * p.epi_warp_bytes;
+  p.stages = Cfg::stages_for(epi_bytes);
+  if (p.stages < 2) {
+    set_error("seedx_gemm_f16: tile %dx%d does not fit in shared memory with %d B of epilogue staging", BM * CL, BN, epi_bytes);
+    return 5;
+  }
+  const int smem_bytes = Cfg::smem_for(p.stages, epi_bytes);
   const int groups = ((p.m_blocks + CL - 1) / CL) * p.n_blocks * p.batch;
   const int max_clusters = num_sms() / CL;
   const int grid = (groups < max_clusters ? groups : max_clusters) * CL;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -574,6 +587,8 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
     const long long groups2 = (long long)((p.m_blocks + 1) / 2) * ((a->N + bn - 1) / bn) * a->batch;
     cl = (g_gemm_cluster != 0 && p.m_blocks >= 2 && bn % 32 == 0 && groups2 >= num_sms() / 2) ? 2 : 1;
     if (g_gemm_cluster == 2 && p.m_blocks >= 2 && bn % 32 == 0) cl = 2;  // forced (tests)
+    // a single CTA with residual staging (96 KB) keeps only 2 stages of a 256-wide tile: use a narrower tile there
+    if (cl == 1 && tma_epi && a->residual && bn > 160 && a->tile_n == 0) bn = 160;
     uint32_t box[3] = {BK, (uint32_t)(bn / cl), 1};
     if (int e = encode_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, a->B, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
       return e;
@@ -603,6 +618,7 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
   p.vec_ok = vec ? 1 : 0;
   p.bias_vec = (a->bias_n && (uintptr_t)a->bias_n % 16 == 0) ? 1 : 0;
   p.tma_epi = tma_epi ? 1 : 0;
+  p.epi_warp_bytes = tma_epi ? (EPI_OUT_BYTES + (a->residual ? EPI_RES_BYTES : 0)) : 0;
   td = ta, tr = ta;  // placeholders when the TMA epilogue is off (never dereferenced)
   if (tma_epi) {
     const int cols = a->gated ? 16 : 32;                    // output columns per 32-column accumulator chunk
