@@ -119,6 +119,81 @@ layernorm_vec_kernel(const TI* __restrict__ x, long long ldx, const float* __res
   }
 }
 
+// Warp-persistent variant for narrow rows (cols <= 2048): gamma/beta are staged once per CTA in shared memory (they are 2-4x the bytes of an
+// fp16 row and were re-read from L1/L2 for every row), each warp walks rows with a grid stride and requests row r+stride while it reduces
+// and writes row r, so HBM latency is hidden by the warp's own next row instead of by occupancy.
+template <typename TI, typename TO, int NV>
+__global__ void __launch_bounds__(LN_THREADS)
+layernorm_rows_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      TO* __restrict__ out, long long ldo, TO* __restrict__ out2, const float* __restrict__ add, int add_rows,
+                      long long rows, int cols, float eps, int rms) {
+  extern __shared__ __align__(16) float gb[];  // gamma[cols] | beta[cols]
+  float* sg = gb;
+  float* sb = gb + cols;
+  for (int c = threadIdx.x; c < cols; c += LN_THREADS) {
+    sg[c] = gamma ? gamma[c] : 1.f;
+    sb[c] = beta ? beta[c] : 0.f;
+  }
+  __syncthreads();
+  typedef typename Raw4<TI>::type RawT;
+  const int lane = threadIdx.x & 31;
+  const int nvec = cols >> 2;
+  const long long wstride = (long long)gridDim.x * (LN_THREADS / 32);
+  long long row = (long long)blockIdx.x * (LN_THREADS / 32) + (threadIdx.x >> 5);
+  RawT cur[NV], nxt[NV];
+  auto load_row = [&](RawT (&dst)[NV], long long r) {
+    const TI* xr = x + r * ldx;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      dst[i] = (c < nvec) ? ldraw(xr + c * 4) : zero_raw((RawT*)nullptr);
+    }
+  };
+  if (row < rows) load_row(cur, row);
+  for (; row < rows; row += wstride) {
+    const long long rn = row + wstride;
+    if (rn < rows) load_row(nxt, rn);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 v = unpack4(cur[i]);
+      s += v.x + v.y + v.z + v.w;
+    }
+    const float mean = rms ? 0.f : warp_sum(s) / (float)cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nvec) {
+        const float4 v = unpack4(cur[i]);
+        const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+        q += a * a + b * b + cc * cc + d * d;
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
+    TO* orow = out + row * ldo;
+    TO* orow2 = out2 ? out2 + row * ldo : nullptr;
+    const float* arow = add ? add + (long long)(row % add_rows) * cols : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        const float4 v = unpack4(cur[i]);
+        const float4 g = *(const float4*)(sg + c * 4);
+        const float4 bb = *(const float4*)(sb + c * 4);
+        const float4 y = make_float4((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y, (v.z - mean) * rstd * g.z + bb.z,
+                                     (v.w - mean) * rstd * g.w + bb.w);
+        st4(orow + c * 4, y);
+        if (orow2) {
+          const float4 aa = *(const float4*)(arow + c * 4);
+          st4(orow2 + c * 4, make_float4(y.x + aa.x, y.y + aa.y, y.z + aa.z, y.w + aa.w));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cur[i] = nxt[i];
+  }
+}
+
 // scalar fallback (cols not a multiple of 4 or unaligned rows): one CTA per row
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(LN_THREADS)
@@ -292,15 +367,27 @@ extern "C" int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const fl
 #define LN_VEC(TI, TO, TPR, NV)                                                                                              \
   layernorm_vec_kernel<TI, TO, TPR, NV><<<(unsigned)((rows + (LN_THREADS / TPR) - 1) / (LN_THREADS / TPR)), LN_THREADS, 0, st>>>( \
       (const TI*)x, ldx, gamma, beta, (TO*)out, ldo, (TO*)out2, add, (int)(add ? add_rows : 1), rows, (int)cols, eps, rms)
+#define LN_ROWS(TI, TO, NV)                                                                                                          \
+  layernorm_rows_kernel<TI, TO, NV><<<rows_grid, LN_THREADS, (size_t)cols * 8, st>>>((const TI*)x, ldx, gamma, beta, (TO*)out, ldo, (TO*)out2, \
+                                                                                   add, (int)(add ? add_rows : 1), rows, (int)cols, eps, rms)
 #define LN_VEC_DISPATCH(TI, TO)                  \
   do {                                           \
-    if (cols <= 256) LN_VEC(TI, TO, 32, 2);      \
+    if (cols <= 2048 && rows >= 64) {            \
+      if (cols <= 512) LN_ROWS(TI, TO, 4);       \
+      else if (cols <= 1024) LN_ROWS(TI, TO, 8); \
+      else if (cols <= 1536) LN_ROWS(TI, TO, 12);\
+      else LN_ROWS(TI, TO, 16);                  \
+    }                                            \
+    else if (cols <= 256) LN_VEC(TI, TO, 32, 2); \
     else if (cols <= 512) LN_VEC(TI, TO, 32, 4); \
     else if (cols <= 1024) LN_VEC(TI, TO, 32, 8);\
     else if (cols <= 2048) LN_VEC(TI, TO, 32, 16);\
     else if (cols <= 4096) LN_VEC(TI, TO, 256, 4);\
     else LN_VEC(TI, TO, 256, 8);                 \
   } while (0)
+  long long rg = (rows + (LN_THREADS / 32) - 1) / (LN_THREADS / 32);
+  if (rg > (long long)num_sms() * 4) rg = (long long)num_sms() * 4;
+  const unsigned rows_grid = (unsigned)rg;
   dim3 grid((unsigned)rows);
 #define LN_LAUNCH(TI, TO)                                                                                                  \
   layernorm_kernel<TI, TO><<<grid, LN_THREADS, 0, st>>>((const TI*)x, ldx, gamma, beta, (TO*)out, ldo, (TO*)out2, add, \
@@ -316,6 +403,7 @@ extern "C" int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const fl
   else if (x_dtype == SEEDX_F16 && out_dtype == SEEDX_F32) LN_BOTH(__half, float);
   else SEEDX_REQUIRE(false, "seedx_layernorm: bad dtype combination");
 #undef LN_LAUNCH
+#undef LN_ROWS
 #undef LN_VEC
 #undef LN_VEC_DISPATCH
 #undef LN_BOTH

@@ -44,7 +44,8 @@ class LlamaForCausalLM:
         self.max_len = max_len
         self.dtype = torch.float16
         self._loaded = False
-        self._graph = None
+        self._graphs = {}
+        self._hidden = None
 
     # ---- reference-compatible plumbing --------------------------------------------------------------------------------
     @classmethod
@@ -111,6 +112,8 @@ class LlamaForCausalLM:
         cfg, dev = self.cfg, self.device
         D, L = cfg["hidden"], cfg["layers"]
         self.slots = slots
+        self._graphs = {}          # captured decode graphs reference the state buffers below
+        self._hidden = None
         self.kcache = [torch.zeros((slots, self.max_len, D), device=dev, dtype=torch.float16) for _ in range(L)]
         self.vcache = [torch.zeros((slots, self.max_len, D), device=dev, dtype=torch.float16) for _ in range(L)]
         self.seq = torch.zeros((slots, self.max_len), device=dev, dtype=torch.int32)
@@ -190,8 +193,17 @@ class LlamaForCausalLM:
         slots = 1 if n_req == 1 else 2 if n_req == 2 else 4 if n_req <= 4 else 8
         if slots != self.slots:
             self._alloc_state(slots)
-        img_dev = torch.as_tensor(img_ids, dtype=torch.int32).to(dev) if img_ids is not None else None
-        hidden = torch.zeros((slots, max(max_new_tokens - 1, 1), self.cfg["hidden"]), device=dev, dtype=torch.float32)
+        # static device state shared by every call with the same slot count, so the captured decode graph can be replayed across calls
+        ikey = tuple(int(i) for i in img_ids) if img_ids is not None else None
+        if getattr(self, "_img_key", "unset") != ikey:
+            self._img_key = ikey
+            self._img_dev = torch.tensor(list(ikey), dtype=torch.int32, device=dev) if ikey is not None else None
+            self._graphs = {}
+        img_dev = self._img_dev
+        if getattr(self, "_hidden", None) is None or self._hidden.shape[0] != slots:
+            self._hidden = torch.zeros((slots, self.max_len, self.cfg["hidden"]), device=dev, dtype=torch.float32)
+            self._graphs = {}
+        hidden = self._hidden
         st0, plens = [], []
         for s in range(slots):
             r = min(s, n_req - 1)                       # padding slots replay the last request
@@ -210,12 +222,16 @@ class LlamaForCausalLM:
         if steps > 0:
             g = None
             if use_graph:
-                s_ = torch.cuda.Stream()
-                s_.wait_stream(torch.cuda.current_stream())
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=s_):
-                    self._decode_step(hidden, img_dev, eos_id, suppress_eos)
-                torch.cuda.current_stream().wait_stream(s_)
+                gkey = (slots, eos_id, bool(suppress_eos))
+                g = self._graphs.get(gkey)
+                if g is None:   # one capture per (slot count, stop rule): the step reads lengths / prompt lengths from device state
+                    s_ = torch.cuda.Stream()
+                    s_.wait_stream(torch.cuda.current_stream())
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=s_):
+                        self._decode_step(hidden, img_dev, eos_id, suppress_eos)
+                    torch.cuda.current_stream().wait_stream(s_)
+                    self._graphs[gkey] = g
             for i in range(steps):
                 if g is not None:
                     g.replay()
@@ -229,7 +245,7 @@ class LlamaForCausalLM:
         outs = []
         for r in range(n_req):
             n_gen = st[r][1] if st[r][1] else st[r][2]   # stop at (and include) the first EOS, like HF greedy_search
-            outs.append(GreedyOutput(seq_host[r, : plens[r] + n_gen].to(torch.int64).unsqueeze(0), hidden[r, : max(n_gen - 1, 0)], n_gen))
+            outs.append(GreedyOutput(seq_host[r, : plens[r] + n_gen].to(torch.int64).unsqueeze(0), hidden[r, : max(n_gen - 1, 0)].clone(), n_gen))
         return outs
 
     def generate_greedy(self, input_ids, inputs_embeds, img_ids=None, max_new_tokens=120, eos_id=None, suppress_eos=False, use_graph=True,

@@ -137,8 +137,31 @@ def golden_resampler_xl():
     print("resampler_xl", {k: tuple(v.shape) for k, v in out.items()})
 
 
+def golden_preprocess():
+    """reference host pre-processing (transforms.get_transform + any_res.process_anyres_image) on seeded noise images: store
+    shapes, patch positions and float64 checksums (the tensors themselves are large)."""
+    import numpy as np
+    from PIL import Image
+    ar, tr = ref_module("src.inference.any_res"), ref_module("src.processer.transforms")
+    base = 448
+    grids = [[base * int(g.split("x")[0]), base * int(g.split("x")[1])] for g in ["1x1", "1x2", "1x3", "2x1", "3x1", "1x4", "4x1", "2x2"]]
+    rng = np.random.RandomState(0)
+    out = {"grids": grids, "cases": []}
+    for (w, h) in [(448, 448), (1024, 1024), (896, 896), (1300, 500), (300, 1200), (640, 480), (2000, 900), (333, 777)]:
+        arr = rng.randint(0, 255, (h, w, 3), dtype=np.uint8)
+        img = Image.fromarray(arr)
+        t = tr.get_transform("clip", keep_ratio=False, image_size=base)
+        views, pos = ar.process_anyres_image(img, t, grids, base)
+        tk = tr.get_transform("clip", keep_ratio=True, image_size=base)(img)
+        out["cases"].append(dict(size=(w, h), shape=tuple(views.shape), pos=pos.clone(), sum=float(views.double().sum()),
+                                 abssum=float(views.double().abs().sum()), first=views[0, :, :4, :4].clone(), last=views[-1, :, -4:, -4:].clone(),
+                                 keep_sum=float(tk.double().sum())))
+    torch.save(out, os.path.join(HERE, "preprocess.pt"))
+    print("preprocess", [c["shape"] for c in out["cases"]])
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["vit", "resamplers", "llama", "resampler_xl"]
+    which = sys.argv[1:] or ["vit", "resamplers", "llama", "resampler_xl", "preprocess"]
     if "vit" in which:
         golden_vit()
     if "resamplers" in which:
@@ -147,3 +170,5 @@ if __name__ == "__main__":
         golden_llama()
     if "resampler_xl" in which:
         golden_resampler_xl()
+    if "preprocess" in which:
+        golden_preprocess()

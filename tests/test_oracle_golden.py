@@ -72,3 +72,21 @@ def test_resampler_xl_oracle_matches_reference():
             p, pooled = orx.resampler_xl(sd, cfg, x)
             assert rel(p, g[f"{name}_{n_tok}_prompt"]) < 5e-4          # golden prompt stored as fp16
             assert rel(pooled, g[f"{name}_{n_tok}_pooled"]) < 2e-5
+
+
+def test_host_preprocessing_matches_reference():
+    """seedx_b200.preprocess (get_transform, process_anyres_image) vs the reference functions' outputs on seeded noise images."""
+    import numpy as np
+    from PIL import Image
+    from seedx_b200 import preprocess as pp
+    g = torch.load(os.path.join(GOLD, "preprocess.pt"))
+    rng = np.random.RandomState(0)
+    for c in g["cases"]:
+        w, h = c["size"]
+        img = Image.fromarray(rng.randint(0, 255, (h, w, 3), dtype=np.uint8))
+        views, pos = pp.process_anyres_image(img, pp.get_transform("clip", keep_ratio=False, image_size=448), g["grids"], 448)
+        assert tuple(views.shape) == c["shape"] and torch.equal(pos, c["pos"])
+        assert abs(float(views.double().sum()) - c["sum"]) < 1e-6 * max(1.0, abs(c["abssum"]))
+        assert torch.equal(views[0, :, :4, :4], c["first"]) and torch.equal(views[-1, :, -4:, -4:], c["last"])
+        tk = pp.get_transform("clip", keep_ratio=True, image_size=448)(img)
+        assert abs(float(tk.double().sum()) - c["keep_sum"]) < 1e-6 * max(1.0, abs(c["abssum"]))
