@@ -34,6 +34,10 @@ const char* seedx_last_error(void);
 int seedx_abi_version(void);
 /* number of kernels launched by this process through the library since load (bench.py's gpu_launches) */
 int64_t seedx_launch_count(void);
+/* Programmatic dependent launch for every kernel of the library (default on; env SEEDX_PDL=0 turns it off): each kernel is launched
+ * with the programmatic-stream-serialization attribute and issues griddepcontrol.wait before its first dependent memory access, so
+ * its launch and prologue overlap the tail of the kernel before it.  No reference counterpart (the reference runs eager PyTorch). */
+int seedx_set_pdl(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core GEMM / implicit-GEMM convolution (tcgen05 + TMEM accumulators + TMA operand staging)
@@ -121,13 +125,16 @@ int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const float* gamma,
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ optional SiLU) on NHWC fp16 images; the input may be the channel-concatenation [x1 | x2] (UNet skip
- * connections); raw_out (optional) receives the un-normalised concatenation.  stats_ws: n*groups*2 doubles.
+ * connections); raw_out (optional) receives the un-normalised concatenation.  stats_ws: seedx_groupnorm_ws_bytes(n, groups) bytes of
+ * scratch, 8-byte aligned (contents need not be initialised).  The statistics are reduced in a fixed order: results are
+ * bit-reproducible run to run, like torch's GroupNorm.
  * replaces diffusers ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm, UNet conv_norm_out, VAE norms
  *   (SURVEY.md Appendix B.2), reached from pipeline_stable_diffusion_xl_t2i_edit.py:915-922,973.
  * ---------------------------------------------------------------------------------------------- */
 int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, int64_t c2, int64_t n, int64_t hw, int groups,
                          const float* gamma, const float* beta, float eps, int silu_act, void* out, void* raw_out,
                          void* stats_ws, void* stream);
+int64_t seedx_groupnorm_ws_bytes(int64_t n, int groups);
 
 /* ------------------------------------------------------------------------------------------------
  * Small HBM-bound data-movement kernels

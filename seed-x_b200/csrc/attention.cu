@@ -84,6 +84,8 @@ SEEDX_DEVINL void load_tile(uint32_t sdst, const __half* g, long long gs, int ro
 
 template <int DPAD>
 __global__ void __launch_bounds__(128) flash_attn_kernel(const AttnParams p) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int LD = AttnSmem<DPAD>::LD;
   constexpr int KSTEPS = DPAD / 16;  // k16 steps over the head dim
   constexpr int DTILES = DPAD / 8;   // n8 tiles of the output
@@ -264,7 +266,7 @@ static int launch_attn(const AttnParams& p, int B, int H, cudaStream_t st) {
     attr_done = true;
   }
   dim3 grid((p.sq + ATT_BM - 1) / ATT_BM, H, B);
-  flash_attn_kernel<DPAD><<<grid, 128, AttnSmem<DPAD>::BYTES, st>>>(p);
+  launch_k(flash_attn_kernel<DPAD>, grid, 128, AttnSmem<DPAD>::BYTES, st, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "flash_attn_kernel launch");
 }

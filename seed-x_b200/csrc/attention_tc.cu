@@ -2,7 +2,7 @@
 //
 //   O[b,h,i,:] = softmax_j( scale * Q[b,h,i,:].K[b,h,j,:] (+causal) ) V[b,h,j,:]         fp16 in/out, fp32 softmax/accumulate
 //
-// One CTA = 128 query rows of one (batch, head).  Warp 0: TMA producer (Q once, K/V tiles of 128 keys through two mbarrier
+// One work item = 128 query rows of one (batch, head); CTAs are persistent (one per SM) and walk the item list.  Warp 0: TMA producer (Q once, K/V tiles of 128 keys through two mbarrier
 // rings).  Warp 1: single-thread MMA issuer: S_j = Q K_j^T into a double-buffered TMEM accumulator (2 x 128 columns), then
 // O += P_j V_j with P_j read back as the TMEM A-operand and V_j as an MN-major shared-memory B-operand.  Warps 2..9: softmax —
 // two threads per query row (TMEM lane), each owning 64 of the 128 score columns, so a row max is one shared-memory exchange and
@@ -22,6 +22,7 @@ struct FaParams {
   int sq, sk, d;
   float scale_log2;
   int causal, q_batched;
+  int m_tiles, heads, items;   // work items = m_tiles * heads * batch, q-tile fastest
 };
 
 template <int D>
@@ -31,10 +32,13 @@ struct FaCfg {
   static constexpr int HALF_BYTES = 128 * 64 * 2;           // one [128 rows x 64 fp16] swizzled tile
   static constexpr int TILE_BYTES = HALVES * HALF_BYTES;    // Q, K or V tile
   static constexpr int KV_STAGES = (D == 64) ? 3 : 2;
-  static constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES) + 1024 + 256;
-  static constexpr uint32_t S_COL0 = 0, S_COL1 = 128, O_COL = 256;
+  static constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256;
+  static constexpr uint32_t S_COL0 = 0, S_COL1 = 128, O_COL0 = 256, O_COL1 = 256 + D;
 };
 
+// Persistent: grid = min(items, SMs); CTA c walks items c, c+grid, ...  Q tiles and O accumulators are double-buffered so the
+// TMA loads, the first QK^T of the next item and the output store of the previous one overlap; the S/P buffers, the K/V rings and
+// their barrier phases run on one global tile counter `g` straight through item boundaries.
 template <int D>
 __global__ void __launch_bounds__(320, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -43,38 +47,40 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   constexpr int KS = Cfg::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = smem_base;
-  const uint32_t sK0 = sQ + Cfg::TILE_BYTES;
+  const uint32_t sQ0 = smem_base;
+  const uint32_t sK0 = sQ0 + 2 * Cfg::TILE_BYTES;
   const uint32_t sV0 = sK0 + KS * Cfg::TILE_BYTES;
   const uint32_t bar = sV0 + KS * Cfg::TILE_BYTES;
-  // barriers: q_full, k_full[KS], k_empty[KS], v_full[KS], v_empty[KS], s_full[2], p_full[2], pv_done[2]
-  const uint32_t q_full = bar;
-  auto k_full = [&](int s) { return bar + 8u * (1 + s); };
-  auto k_empty = [&](int s) { return bar + 8u * (1 + KS + s); };
-  auto v_full = [&](int s) { return bar + 8u * (1 + 2 * KS + s); };
-  auto v_empty = [&](int s) { return bar + 8u * (1 + 3 * KS + s); };
-  auto s_full = [&](int s) { return bar + 8u * (1 + 4 * KS + s); };
-  auto p_full = [&](int s) { return bar + 8u * (3 + 4 * KS + s); };
-  auto pv_done = [&](int s) { return bar + 8u * (5 + 4 * KS + s); };
-  const uint32_t tmem_slot = bar + 8u * (7 + 4 * KS);
+  // barriers: k_full[KS], k_empty[KS], v_full[KS], v_empty[KS], then pairs: q_full, q_empty, s_full, p_full, pv_done, o_free
+  auto k_full = [&](int s) { return bar + 8u * (s); };
+  auto k_empty = [&](int s) { return bar + 8u * (KS + s); };
+  auto v_full = [&](int s) { return bar + 8u * (2 * KS + s); };
+  auto v_empty = [&](int s) { return bar + 8u * (3 * KS + s); };
+  auto q_full = [&](int s) { return bar + 8u * (4 * KS + s); };
+  auto q_empty = [&](int s) { return bar + 8u * (4 * KS + 2 + s); };
+  auto s_full = [&](int s) { return bar + 8u * (4 * KS + 4 + s); };
+  auto p_full = [&](int s) { return bar + 8u * (4 * KS + 6 + s); };
+  auto pv_done = [&](int s) { return bar + 8u * (4 * KS + 8 + s); };
+  auto o_free = [&](int s) { return bar + 8u * (4 * KS + 10 + s); };
+  const uint32_t tmem_slot = bar + 8u * (4 * KS + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * Cfg::BM;
-  const int h = blockIdx.y, b = blockIdx.z;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
     for (int s = 0; s < KS; ++s) {
       mbar_init(k_full(s), 1), mbar_init(k_empty(s), 1);
       mbar_init(v_full(s), 1), mbar_init(v_empty(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
       mbar_init(s_full(s), 1);
       mbar_init(p_full(s), 256);
       mbar_init(pv_done(s), 1);
+      mbar_init(o_free(s), 256);
     }
     mbar_fence_init();
   }
@@ -84,34 +90,50 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();      // prologue above overlapped the previous kernel's tail (programmatic dependent launch)
+  pdl_trigger();
 
-  int n_tiles = (p.sk + Cfg::BN - 1) / Cfg::BN;
   const int causal_off = p.sk - p.sq;
-  if (p.causal) {
-    const int lim = (m0 + Cfg::BM - 1 + causal_off) / Cfg::BN + 1;
-    if (lim < n_tiles) n_tiles = lim < 1 ? 1 : lim;
-  }
+  const int kv_tiles = (p.sk + Cfg::BN - 1) / Cfg::BN;
+  auto tiles_of = [&](int m0) {
+    int n = kv_tiles;
+    if (p.causal) {
+      const int lim = (m0 + Cfg::BM - 1 + causal_off) / Cfg::BN + 1;
+      if (lim < n) n = lim < 1 ? 1 : lim;
+    }
+    return n;
+  };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, Cfg::TILE_BYTES);
-#pragma unroll
-      for (int hf = 0; hf < Cfg::HALVES; ++hf) tma_load_4d(sQ + hf * Cfg::HALF_BYTES, &tmQ, q_full, hf * 64, m0, h, p.q_batched ? b : 0);
       int st = 0;
       uint32_t ph = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(k_empty(st), ph ^ 1u);
-        mbar_expect_tx(k_full(st), Cfg::TILE_BYTES);
+      int n = 0;
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+        const int mt = it % p.m_tiles, hb = it / p.m_tiles;
+        const int h = hb % p.heads, b = hb / p.heads;
+        const int m0 = mt * Cfg::BM;
+        const int qi = n & 1;
+        mbar_wait(q_empty(qi), (uint32_t)(((n >> 1) & 1) ^ 1));
+        mbar_expect_tx(q_full(qi), Cfg::TILE_BYTES);
 #pragma unroll
         for (int hf = 0; hf < Cfg::HALVES; ++hf)
-          tma_load_4d(sK0 + st * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmK, k_full(st), hf * 64, j * Cfg::BN, h, b);
-        mbar_wait(v_empty(st), ph ^ 1u);
-        mbar_expect_tx(v_full(st), Cfg::TILE_BYTES);
+          tma_load_4d(sQ0 + qi * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmQ, q_full(qi), hf * 64, m0, h, p.q_batched ? b : 0);
+        const int n_tiles = tiles_of(m0);
+        for (int j = 0; j < n_tiles; ++j) {
+          mbar_wait(k_empty(st), ph ^ 1u);
+          mbar_expect_tx(k_full(st), Cfg::TILE_BYTES);
 #pragma unroll
-        for (int hf = 0; hf < Cfg::HALVES; ++hf)
-          tma_load_4d(sV0 + st * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmV, v_full(st), hf * 64, j * Cfg::BN, h, b);
-        if (++st == KS) st = 0, ph ^= 1u;
+          for (int hf = 0; hf < Cfg::HALVES; ++hf)
+            tma_load_4d(sK0 + st * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmK, k_full(st), hf * 64, j * Cfg::BN, h, b);
+          mbar_wait(v_empty(st), ph ^ 1u);
+          mbar_expect_tx(v_full(st), Cfg::TILE_BYTES);
+#pragma unroll
+          for (int hf = 0; hf < Cfg::HALVES; ++hf)
+            tma_load_4d(sV0 + st * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmV, v_full(st), hf * 64, j * Cfg::BN, h, b);
+          if (++st == KS) st = 0, ph ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
@@ -119,47 +141,54 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, D) | (1u << 16);  // B operand MN-major
-      const uint32_t tO = tmem_base + Cfg::O_COL;
-      auto issue_pv = [&](int j, int vst) {
-        const uint32_t tP = tmem_base + ((j & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
+      int kst = 0, vst = 0;
+      uint32_t kph = 0, vph = 0;
+      uint32_t g = 0;                 // global tile counter
+      bool pend = false;              // a PV whose P is still being produced: issued after the next QK^T so the two overlap
+      uint32_t pend_g = 0, pend_tO = 0;
+      bool pend_first = false;
+      auto flush_pv = [&]() {
+        mbar_wait(p_full(pend_g & 1), (pend_g >> 1) & 1u);
+        mbar_wait(v_full(vst), vph);
+        tc_fence_after();
+        const uint32_t tP = tmem_base + ((pend_g & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
         const uint32_t vb = sV0 + vst * Cfg::TILE_BYTES;
 #pragma unroll
         for (int kk = 0; kk < Cfg::BN / 16; ++kk)  // 16 keys per MMA: A advances 8 TMEM columns, B 16 rows of 128 B
-          umma_f16_ts(tO, tP + (uint32_t)(kk * 8), umma_desc_mn_sw128(vb + kk * 2048, Cfg::HALF_BYTES), idesc_pv, (j | kk) != 0);
+          umma_f16_ts(pend_tO, tP + (uint32_t)(kk * 8), umma_desc_mn_sw128(vb + kk * 2048, Cfg::HALF_BYTES), idesc_pv,
+                      !(pend_first && kk == 0));
+        umma_commit(v_empty(vst));
+        umma_commit(pv_done(pend_g & 1));
+        if (++vst == KS) vst = 0, vph ^= 1u;
       };
-      mbar_wait(q_full, 0);
-      int kst = 0, vst = 0;
-      uint32_t kph = 0, vph = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(k_full(kst), kph);
-        tc_fence_after();
-        const uint32_t tS = tmem_base + ((j & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
-        const uint32_t kb = sK0 + kst * Cfg::TILE_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) {
-          const uint32_t off = (uint32_t)((ks >> 2) * Cfg::HALF_BYTES + (ks & 3) * 32);
-          umma_f16(tS, umma_desc_k_sw128(sQ + off), umma_desc_k_sw128(kb + off), idesc_qk, ks != 0);
-        }
-        umma_commit(k_empty(kst));
-        umma_commit(s_full(j & 1));
-        if (++kst == KS) kst = 0, kph ^= 1u;
-        if (j >= 1) {
-          mbar_wait(p_full((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));
-          mbar_wait(v_full(vst), vph);
+      int n = 0;
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+        const int m0 = (it % p.m_tiles) * Cfg::BM;
+        const int n_tiles = tiles_of(m0);
+        const int qi = n & 1;
+        const uint32_t sQ = sQ0 + qi * Cfg::TILE_BYTES;
+        mbar_wait(q_full(qi), (uint32_t)((n >> 1) & 1));
+        mbar_wait(o_free(qi), (uint32_t)(((n >> 1) & 1) ^ 1));   // epilogue of item n-2 has drained this O accumulator
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          mbar_wait(k_full(kst), kph);
           tc_fence_after();
-          issue_pv(j - 1, vst);
-          umma_commit(v_empty(vst));
-          umma_commit(pv_done((j - 1) & 1));
-          if (++vst == KS) vst = 0, vph ^= 1u;
+          const uint32_t tS = tmem_base + ((g & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
+          const uint32_t kb = sK0 + kst * Cfg::TILE_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < D / 16; ++ks) {
+            const uint32_t off = (uint32_t)((ks >> 2) * Cfg::HALF_BYTES + (ks & 3) * 32);
+            umma_f16(tS, umma_desc_k_sw128(sQ + off), umma_desc_k_sw128(kb + off), idesc_qk, ks != 0);
+          }
+          umma_commit(k_empty(kst));
+          if (j == n_tiles - 1) umma_commit(q_empty(qi));
+          umma_commit(s_full(g & 1));
+          if (++kst == KS) kst = 0, kph ^= 1u;
+          if (pend) flush_pv();
+          pend = true, pend_g = g, pend_first = (j == 0);
+          pend_tO = tmem_base + (qi ? Cfg::O_COL1 : Cfg::O_COL0);
         }
       }
-      const int jl = n_tiles - 1;
-      mbar_wait(p_full(jl & 1), (uint32_t)((jl >> 1) & 1));
-      mbar_wait(v_full(vst), vph);
-      tc_fence_after();
-      issue_pv(jl, vst);
-      umma_commit(v_empty(vst));
-      umma_commit(pv_done(jl & 1));
+      if (pend) flush_pv();
     }
   } else {
     // ------------------------------------------------------------ softmax / correction / epilogue
@@ -169,110 +198,122 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
-    const int qrow = m0 + row;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t tO = tmem_base + lane_addr + Cfg::O_COL + (uint32_t)(half * (D / 2));
     constexpr int OC = D / 2;              // O columns per thread
-    float m_run = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      const uint32_t tSb = tmem_base + lane_addr + ((j & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
-      mbar_wait(s_full(j & 1), (uint32_t)((j >> 1) & 1));
-      tc_fence_after();
-      float s[64];
+    uint32_t g = 0;
+    int n = 0;
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+      const int mt = it % p.m_tiles, hb = it / p.m_tiles;
+      const int h = hb % p.heads, b = hb / p.heads;
+      const int m0 = mt * Cfg::BM;
+      const int n_tiles = tiles_of(m0);
+      const int qrow = m0 + row;
+      const uint32_t tO = tmem_base + lane_addr + ((n & 1) ? Cfg::O_COL1 : Cfg::O_COL0) + (uint32_t)(half * OC);
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++g) {
+        const uint32_t tSb = tmem_base + lane_addr + ((g & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
+        mbar_wait(s_full(g & 1), (g >> 1) & 1u);
+        tc_fence_after();
+        float s[64];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tSb + (uint32_t)(half * 64 + c * 32), v);
-        tmem_ld_wait();
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tSb + (uint32_t)(half * 64 + c * 32), v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(v[i]) * p.scale_log2;
-      }
-      const int key0 = j * Cfg::BN + half * 64;
-      const bool need_mask = (j * Cfg::BN + Cfg::BN > p.sk) || (p.causal && (j * Cfg::BN + Cfg::BN - 1 > m0 + causal_off));
-      if (need_mask) {
-#pragma unroll
-        for (int i = 0; i < 64; ++i) {
-          const int key = key0 + i;
-          if (key >= p.sk || (p.causal && key > qrow + causal_off)) s[i] = -INFINITY;
+          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(v[i]) * p.scale_log2;
         }
-      }
-      float m_tile = s[0];
+        const int key0 = j * Cfg::BN + half * 64;
+        const bool need_mask = (j * Cfg::BN + Cfg::BN > p.sk) || (p.causal && (j * Cfg::BN + Cfg::BN - 1 > m0 + causal_off));
+        if (need_mask) {
 #pragma unroll
-      for (int i = 1; i < 64; ++i) m_tile = fmaxf(m_tile, s[i]);
-      xch_max[j & 1][half][row] = m_tile;
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");                   // the 8 softmax warps only
-      m_tile = fmaxf(m_tile, xch_max[j & 1][half ^ 1][row]);
-      // Lazy rescaling: the reference maximum m_run only moves when some row of this warp exceeds it by more than 2^8 (P then stays
-      // <= 256, exact in fp16 range; sums and O are fp32).  Only then does the softmax have to wait for PV_{j-1} and touch O, so in
-      // the steady state softmax_j does not depend on the tensor pipe at all and the MMA -> softmax -> MMA round trip disappears.
-      const bool grow = m_tile > m_run + 8.0f;       // also true for j == 0 (m_run = -inf) unless the whole row is masked
-      float alpha = 1.0f;
-      if (__any_sync(0xffffffffu, grow)) {
-        const float m_new = fmaxf(m_run, m_tile);
-        const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
-        alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_ref);
-        if (j > 0) {
-          mbar_wait(pv_done((j - 1) & 1), (uint32_t)(((j - 1) >> 1) & 1));  // O is quiescent: PV_{j-1} retired
-          tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < OC / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tO + (uint32_t)(c * 32), v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st32(tO + (uint32_t)(c * 32), v);
+          for (int i = 0; i < 64; ++i) {
+            const int key = key0 + i;
+            if (key >= p.sk || (p.causal && key > qrow + causal_off)) s[i] = -INFINITY;
           }
         }
-        m_run = m_new;
-      }
-      const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-      // P_j = exp2(S_j - m) as fp16 pairs: my 64 scores -> 32 packed columns at [half*32, half*32+32) of the S_j buffer.
-      // (the other half-row thread may still be reading S columns >= 64 only if it is `half`=1: its columns are never overwritten by
-      //  P (P occupies columns 0..63), and a `half`=0 thread has already pulled columns 0..63 into registers before the bar.sync.)
-      float rs = 0.f;
+        float m_tile = s[0];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[16];
+        for (int i = 1; i < 64; ++i) m_tile = fmaxf(m_tile, s[i]);
+        xch_max[g & 1][half][row] = m_tile;
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");                   // the 8 softmax warps only
+        m_tile = fmaxf(m_tile, xch_max[g & 1][half ^ 1][row]);
+        // Lazy rescaling: the reference maximum m_run only moves when some row of this warp exceeds it by more than 2^8 (P then stays
+        // <= 256, exact in fp16 range; sums and O are fp32).  Only then does the softmax have to wait for PV_{j-1} and touch O, so in
+        // the steady state softmax_j does not depend on the tensor pipe at all and the MMA -> softmax -> MMA round trip disappears.
+        const bool grow = m_tile > m_run + 8.0f;       // also true for j == 0 (m_run = -inf) unless the whole row is masked
+        float alpha = 1.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = fmaxf(m_run, m_tile);
+          const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
+          alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_ref);
+          if (j > 0) {
+            mbar_wait(pv_done((g - 1) & 1), ((g - 1) >> 1) & 1u);  // O is quiescent: PV_{j-1} retired
+            tc_fence_after();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float a = fast_exp2(s[c * 32 + 2 * i] - m_use), c2 = fast_exp2(s[c * 32 + 2 * i + 1] - m_use);
-          rs += a + c2;
-          __half2 hh = __floats2half2_rn(a, c2);
-          v[i] = *(uint32_t*)&hh;
+            for (int c = 0; c < OC / 32; ++c) {
+              uint32_t v[32];
+              tmem_ld32(tO + (uint32_t)(c * 32), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st32(tO + (uint32_t)(c * 32), v);
+            }
+          }
+          m_run = m_new;
         }
-        tmem_st16(tSb + (uint32_t)(half * 32 + c * 16), v);
+        const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+        // P_j = exp2(S_j - m) as fp16 pairs: my 64 scores -> 32 packed columns at [half*32, half*32+32) of the S_j buffer.
+        // (the other half-row thread may still be reading S columns >= 64 only if it is `half`=1: its columns are never overwritten
+        //  by P (P occupies columns 0..63), and a `half`=0 thread has already pulled columns 0..63 into registers before the bar.sync.)
+        float rs = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a = fast_exp2(s[c * 32 + 2 * i] - m_use), c2 = fast_exp2(s[c * 32 + 2 * i + 1] - m_use);
+            rs += a + c2;
+            __half2 hh = __floats2half2_rn(a, c2);
+            v[i] = *(uint32_t*)&hh;
+          }
+          tmem_st16(tSb + (uint32_t)(half * 32 + c * 16), v);
+        }
+        tmem_st_wait();
+        l_run = l_run * alpha + rs;
+        tc_fence_before();
+        mbar_arrive(p_full(g & 1));
       }
-      tmem_st_wait();
-      l_run = l_run * alpha + rs;
-      tc_fence_before();
-      mbar_arrive(p_full(j & 1));
-    }
-    // ---- epilogue: combine the two half-row sums, normalise and store my half of the output columns
-    xch_sum[half][row] = l_run;
-    asm volatile("bar.sync 1, 256;\n" ::: "memory");
-    const float l_tot = l_run + xch_sum[half ^ 1][row];
-    const int jl = n_tiles - 1;
-    mbar_wait(pv_done(jl & 1), (uint32_t)((jl >> 1) & 1));
-    tc_fence_after();
-    const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-    __half* orow = p.o + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)qrow * p.o_ss + half * OC;
+      // ---- epilogue: combine the two half-row sums, normalise and store my half of the output columns
+      xch_sum[half][row] = l_run;
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      const float l_tot = l_run + xch_sum[half ^ 1][row];
+      const uint32_t gl = g - 1;
+      mbar_wait(pv_done(gl & 1), (gl >> 1) & 1u);
+      tc_fence_after();
+      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      __half* orow = p.o + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)qrow * p.o_ss + half * OC;
 #pragma unroll
-    for (int c = 0; c < OC / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tO + (uint32_t)(c * 32), v);
-      tmem_ld_wait();
-      if (qrow < p.sq) {
+      for (int c = 0; c < OC / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tO + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (c == OC / 32 - 1) {            // accumulator drained into registers: the MMA warp may start item n+2 on it
+          tc_fence_before();
+          mbar_arrive(o_free(n & 1));
+        }
+        if (qrow < p.sq) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          const int col = half * OC + c * 32 + i;
-          if (col + 8 <= p.d) {
-            uint4 q;
-            __half2* hh = (__half2*)&q;
+          for (int i = 0; i < 32; i += 8) {
+            const int col = half * OC + c * 32 + i;
+            if (col + 8 <= p.d) {
+              uint4 q;
+              __half2* hh = (__half2*)&q;
 #pragma unroll
-            for (int t = 0; t < 4; ++t)
-              hh[t] = __floats2half2_rn(__uint_as_float(v[i + 2 * t]) * inv, __uint_as_float(v[i + 2 * t + 1]) * inv);
-            *(uint4*)(orow + c * 32 + i) = q;
+              for (int t = 0; t < 4; ++t)
+                hh[t] = __floats2half2_rn(__uint_as_float(v[i + 2 * t]) * inv, __uint_as_float(v[i + 2 * t + 1]) * inv);
+              *(uint4*)(orow + c * 32 + i) = q;
+            }
           }
         }
       }
@@ -287,15 +328,24 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 template <int D>
-static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const FaParams& p, int B, int H, cudaStream_t st) {
+static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, FaParams p, int B, int H, cudaStream_t st) {
   using Cfg = FaCfg<D>;
   static bool attr = false;
+  static int sms = 0;
   if (!attr) {
     SEEDX_CUDA(cudaFuncSetAttribute(flash_attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int dev = 0;
+    SEEDX_CUDA(cudaGetDevice(&dev));
+    SEEDX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     attr = true;
   }
-  dim3 grid((p.sq + Cfg::BM - 1) / Cfg::BM, H, B);
-  flash_attn_tc_kernel<D><<<grid, 320, Cfg::SMEM_BYTES, st>>>(tq, tk, tv, p);
+  p.m_tiles = (p.sq + Cfg::BM - 1) / Cfg::BM;
+  p.heads = H;
+  const long long items = (long long)p.m_tiles * H * B;
+  if (items > 0x7fffffffLL) return -1;
+  p.items = (int)items;
+  const int grid = p.items < sms ? p.items : sms;
+  launch_k(flash_attn_tc_kernel<D>, grid, 320, Cfg::SMEM_BYTES, st, tq, tk, tv, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "flash_attn_tc_kernel launch");
 }

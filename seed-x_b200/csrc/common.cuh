@@ -15,6 +15,26 @@ namespace seedx {
 // ----------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
+
+// ---- programmatic dependent launch (PDL).  Every kernel of this library is launched through launch_k() with the
+// programmatic-stream-serialization attribute and begins its data-dependent part with pdl_wait(): a kernel's launch latency and
+// prologue (barrier init, TMEM allocation, descriptor prefetch, weight prefetch) then overlap the tail of its predecessor, in
+// eager streams and inside captured CUDA graphs alike.  seedx_set_pdl(0) (or SEEDX_PDL=0) turns the attribute off.
+int pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+template <typename... KA, typename... A>
+static inline cudaError_t launch_k(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+}
+
 #define SEEDX_CUDA(x)                                          \
   do {                                                         \
     int _e = ::seedx::check_cuda((x), #x);                     \

@@ -16,6 +16,8 @@ static inline int grid_for(long long work, int threads) {
 
 template <typename TI>
 __global__ void patchify_kernel(const TI* __restrict__ x, int n, int c, int h, int w, int patch, __half* __restrict__ out, int kpad) {
+  pdl_wait();
+  pdl_trigger();
   const int gh = h / patch, gw = w / patch;
   const long long total = (long long)n * gh * gw * kpad;
   const int kreal = c * patch * patch;
@@ -39,12 +41,16 @@ __global__ void patchify_kernel(const TI* __restrict__ x, int n, int c, int h, i
 
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI* __restrict__ s, TO* __restrict__ d, long long n) {
+  pdl_wait();
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     d[i] = (TO)(float)s[i];
 }
 
 template <typename T>
 __global__ void avgpool_tokens_kernel(const T* __restrict__ x, long long n_out_rows, int c, int k, T* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = n_out_rows * c;
   const float inv = 1.f / (float)k;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -60,6 +66,8 @@ __global__ void avgpool_tokens_kernel(const T* __restrict__ x, long long n_out_r
 // im2col for strided convs on NHWC fp16 (k x k taps, stride s, pad_before on top/left, zero fill), 8 channels / thread
 __global__ void im2col_nhwc_kernel(const __half* __restrict__ x, int n, int h, int w, int c, int k, int stride, int pad, int ho, int wo,
                                    __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int cv = c >> 3;
   const long long total = (long long)n * ho * wo * k * k * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -79,6 +87,8 @@ __global__ void im2col_nhwc_kernel(const __half* __restrict__ x, int n, int h, i
 }
 
 __global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, int n, int h, int w, int c, __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const int cv = c >> 3;
   const long long total = (long long)n * (2 * h) * (2 * w) * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -94,6 +104,8 @@ __global__ void upsample2x_nhwc_kernel(const __half* __restrict__ x, int n, int 
 
 // diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): out[i, :] = [cos(t_i f_j) | sin(t_i f_j)]
 __global__ void timestep_embedding_kernel(const float* __restrict__ t, int count, int dim, __half* __restrict__ out, long long ldo) {
+  pdl_wait();
+  pdl_trigger();
   const int half_dim = dim >> 1;
   const int total = count * half_dim;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -107,6 +119,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int count
 
 template <typename TI>
 __global__ void unary_kernel(const TI* __restrict__ x, long long rows, int cols, long long ldx, __half* __restrict__ out, long long ldo, int act) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols;
@@ -122,6 +136,8 @@ __global__ void unary_kernel(const TI* __restrict__ x, long long rows, int cols,
 template <typename TI>
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const TI* __restrict__ x, long long ldx, int cols, float scale, __half* __restrict__ out,
                                                            long long ldo) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sh[8];
   const TI* xr = x + (long long)blockIdx.x * ldx;
   __half* orow = out + (long long)blockIdx.x * ldo;
@@ -148,6 +164,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const TI* __restrict_
 
 // NCHW fp32 -> NHWC fp16 with channel padding and scale
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, int hw, int cpad, float scale, __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)n * hw * cpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ch = (int)(i % cpad);
@@ -160,6 +178,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int n, int c, i
 
 template <typename TI>
 __global__ void nhwc_to_nchw_kernel(const TI* __restrict__ x, int n, int c, int hw, int ldc, float scale, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)n * c * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(i % hw);
@@ -173,6 +193,8 @@ __global__ void nhwc_to_nchw_kernel(const TI* __restrict__ x, int n, int c, int 
 // VaeImageProcessor.postprocess: (x/2 + 0.5).clamp(0,1) -> uint8 (round half to even like torch .round())
 template <typename TI>
 __global__ void image_to_u8_kernel(const TI* __restrict__ x, long long pixels, int ldc, uint8_t* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = pixels * 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long p = i / 3;
@@ -191,6 +213,8 @@ __global__ void image_to_u8_kernel(const TI* __restrict__ x, long long pixels, i
 //   mode 3 (edit, branches [text, image, uncond]): sigma-space combine, pipeline_stable_diffusion_xl_t2i_edit.py:928-950
 __global__ void cfg_euler_kernel(const float* __restrict__ eps, float* __restrict__ x, __half* __restrict__ unet_in, int B, int hw, int mode,
                                  float g, float ig, float sigma, float sigma_next, float init_sigma) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = (long long)B * hw * 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ch = (int)(i & 3);
@@ -230,6 +254,8 @@ __global__ void cfg_euler_kernel(const float* __restrict__ eps, float* __restric
 template <typename TA>
 __global__ void add_bcast_kernel(const TA* __restrict__ a, const float* __restrict__ b, long long rows, int cols, int b_rows,
                                  __half* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   const long long total = rows * cols;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols;
@@ -251,9 +277,9 @@ extern "C" int seedx_patchify(const void* x, int x_dtype, int64_t n, int64_t c, 
   const int g = grid_for(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == SEEDX_F32)
-    patchify_kernel<float><<<g, 256, 0, st>>>((const float*)x, (int)n, (int)c, (int)h, (int)w, (int)patch, (__half*)out, (int)kpad);
+    launch_k(patchify_kernel<float>, g, 256, 0, st, (const float*)x, (int)n, (int)c, (int)h, (int)w, (int)patch, (__half*)out, (int)kpad);
   else if (x_dtype == SEEDX_F16)
-    patchify_kernel<__half><<<g, 256, 0, st>>>((const __half*)x, (int)n, (int)c, (int)h, (int)w, (int)patch, (__half*)out, (int)kpad);
+    launch_k(patchify_kernel<__half>, g, 256, 0, st, (const __half*)x, (int)n, (int)c, (int)h, (int)w, (int)patch, (__half*)out, (int)kpad);
   else
     SEEDX_REQUIRE(false, "seedx_patchify: bad dtype");
   count_launch();
@@ -264,8 +290,8 @@ extern "C" int seedx_cast(const void* src, int sd, void* dst, int dd, int64_t co
   SEEDX_REQUIRE(src && dst && count > 0, "seedx_cast: bad arguments");
   const int g = grid_for(count, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (sd == SEEDX_F32 && dd == SEEDX_F16) cast_kernel<float, __half><<<g, 256, 0, st>>>((const float*)src, (__half*)dst, count);
-  else if (sd == SEEDX_F16 && dd == SEEDX_F32) cast_kernel<__half, float><<<g, 256, 0, st>>>((const __half*)src, (float*)dst, count);
+  if (sd == SEEDX_F32 && dd == SEEDX_F16) launch_k(cast_kernel<float, __half>, g, 256, 0, st, (const float*)src, (__half*)dst, count);
+  else if (sd == SEEDX_F16 && dd == SEEDX_F32) launch_k(cast_kernel<__half, float>, g, 256, 0, st, (const __half*)src, (float*)dst, count);
   else SEEDX_REQUIRE(false, "seedx_cast: unsupported conversion %d -> %d", sd, dd);
   count_launch();
   return check_cuda(cudaGetLastError(), "cast launch");
@@ -276,8 +302,8 @@ extern "C" int seedx_avgpool_tokens(const void* x, int dtype, int64_t n, int64_t
   const long long rows = n * (t / k);
   const int g = grid_for(rows * c, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == SEEDX_F16) avgpool_tokens_kernel<__half><<<g, 256, 0, st>>>((const __half*)x, rows, (int)c, (int)k, (__half*)out);
-  else if (dtype == SEEDX_F32) avgpool_tokens_kernel<float><<<g, 256, 0, st>>>((const float*)x, rows, (int)c, (int)k, (float*)out);
+  if (dtype == SEEDX_F16) launch_k(avgpool_tokens_kernel<__half>, g, 256, 0, st, (const __half*)x, rows, (int)c, (int)k, (__half*)out);
+  else if (dtype == SEEDX_F32) launch_k(avgpool_tokens_kernel<float>, g, 256, 0, st, (const float*)x, rows, (int)c, (int)k, (float*)out);
   else SEEDX_REQUIRE(false, "seedx_avgpool_tokens: bad dtype");
   count_launch();
   return check_cuda(cudaGetLastError(), "avgpool launch");
@@ -287,7 +313,7 @@ extern "C" int seedx_im2col_nhwc(const void* x, int64_t n, int64_t h, int64_t w,
                                  int64_t wo, void* out, void* stream) {
   SEEDX_REQUIRE(x && out && c % 8 == 0 && k > 0 && stride > 0, "seedx_im2col_nhwc: bad arguments");
   const long long total = n * ho * wo * k * k * (c / 8);
-  im2col_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (int)n, (int)h, (int)w, (int)c, k, stride,
+  launch_k(im2col_nhwc_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __half*)x, (int)n, (int)h, (int)w, (int)c, k, stride,
                                                                             pad_before, (int)ho, (int)wo, (__half*)out);
   count_launch();
   return check_cuda(cudaGetLastError(), "im2col launch");
@@ -296,14 +322,14 @@ extern "C" int seedx_im2col_nhwc(const void* x, int64_t n, int64_t h, int64_t w,
 extern "C" int seedx_upsample2x_nhwc(const void* x, int64_t n, int64_t h, int64_t w, int64_t c, void* out, void* stream) {
   SEEDX_REQUIRE(x && out && c % 8 == 0, "seedx_upsample2x_nhwc: bad arguments");
   const long long total = n * 4 * h * w * (c / 8);
-  upsample2x_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (int)n, (int)h, (int)w, (int)c, (__half*)out);
+  launch_k(upsample2x_nhwc_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, (const __half*)x, (int)n, (int)h, (int)w, (int)c, (__half*)out);
   count_launch();
   return check_cuda(cudaGetLastError(), "upsample launch");
 }
 
 extern "C" int seedx_timestep_embedding(const float* t, int64_t count, int dim, void* out, int64_t ldo, void* stream) {
   SEEDX_REQUIRE(t && out && count > 0 && dim > 0 && dim % 2 == 0, "seedx_timestep_embedding: bad arguments");
-  timestep_embedding_kernel<<<grid_for(count * dim / 2, 128), 128, 0, (cudaStream_t)stream>>>(t, (int)count, dim, (__half*)out, ldo);
+  launch_k(timestep_embedding_kernel, grid_for(count * dim / 2, 128), 128, 0, (cudaStream_t)stream, t, (int)count, dim, (__half*)out, ldo);
   count_launch();
   return check_cuda(cudaGetLastError(), "timestep_embedding launch");
 }
@@ -312,8 +338,8 @@ extern "C" int seedx_unary_f16(const void* x, int x_dtype, int64_t rows, int64_t
   SEEDX_REQUIRE(x && out && rows > 0 && cols > 0, "seedx_unary_f16: bad arguments");
   const int g = grid_for(rows * cols, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == SEEDX_F32) unary_kernel<float><<<g, 256, 0, st>>>((const float*)x, rows, (int)cols, ldx, (__half*)out, ldo, act);
-  else if (x_dtype == SEEDX_F16) unary_kernel<__half><<<g, 256, 0, st>>>((const __half*)x, rows, (int)cols, ldx, (__half*)out, ldo, act);
+  if (x_dtype == SEEDX_F32) launch_k(unary_kernel<float>, g, 256, 0, st, (const float*)x, rows, (int)cols, ldx, (__half*)out, ldo, act);
+  else if (x_dtype == SEEDX_F16) launch_k(unary_kernel<__half>, g, 256, 0, st, (const __half*)x, rows, (int)cols, ldx, (__half*)out, ldo, act);
   else SEEDX_REQUIRE(false, "seedx_unary_f16: bad dtype");
   count_launch();
   return check_cuda(cudaGetLastError(), "unary launch");
@@ -323,8 +349,8 @@ extern "C" int seedx_softmax_rows(const void* x, int x_dtype, int64_t ldx, int64
                                   void* stream) {
   SEEDX_REQUIRE(x && out && rows > 0 && cols > 0, "seedx_softmax_rows: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == SEEDX_F32) softmax_rows_kernel<float><<<(unsigned)rows, 256, 0, st>>>((const float*)x, ldx, (int)cols, scale, (__half*)out, ldo);
-  else if (x_dtype == SEEDX_F16) softmax_rows_kernel<__half><<<(unsigned)rows, 256, 0, st>>>((const __half*)x, ldx, (int)cols, scale, (__half*)out, ldo);
+  if (x_dtype == SEEDX_F32) launch_k(softmax_rows_kernel<float>, (unsigned)rows, 256, 0, st, (const float*)x, ldx, (int)cols, scale, (__half*)out, ldo);
+  else if (x_dtype == SEEDX_F16) launch_k(softmax_rows_kernel<__half>, (unsigned)rows, 256, 0, st, (const __half*)x, ldx, (int)cols, scale, (__half*)out, ldo);
   else SEEDX_REQUIRE(false, "seedx_softmax_rows: bad dtype");
   count_launch();
   return check_cuda(cudaGetLastError(), "softmax launch");
@@ -332,7 +358,7 @@ extern "C" int seedx_softmax_rows(const void* x, int x_dtype, int64_t ldx, int64
 
 extern "C" int seedx_nchw_to_nhwc_f16(const float* x, int64_t n, int64_t c, int64_t hw, int64_t cpad, float scale, void* out, void* stream) {
   SEEDX_REQUIRE(x && out && cpad >= c, "seedx_nchw_to_nhwc_f16: bad arguments");
-  nchw_to_nhwc_kernel<<<grid_for(n * hw * cpad, 256), 256, 0, (cudaStream_t)stream>>>(x, (int)n, (int)c, (int)hw, (int)cpad, scale, (__half*)out);
+  launch_k(nchw_to_nhwc_kernel, grid_for(n * hw * cpad, 256), 256, 0, (cudaStream_t)stream, x, (int)n, (int)c, (int)hw, (int)cpad, scale, (__half*)out);
   count_launch();
   return check_cuda(cudaGetLastError(), "nchw_to_nhwc launch");
 }
@@ -342,8 +368,8 @@ extern "C" int seedx_nhwc_to_nchw_f32(const void* x, int x_dtype, int64_t n, int
   SEEDX_REQUIRE(x && out && ldc >= c, "seedx_nhwc_to_nchw_f32: bad arguments");
   const int g = grid_for(n * c * hw, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == SEEDX_F32) nhwc_to_nchw_kernel<float><<<g, 256, 0, st>>>((const float*)x, (int)n, (int)c, (int)hw, (int)ldc, scale, out);
-  else if (x_dtype == SEEDX_F16) nhwc_to_nchw_kernel<__half><<<g, 256, 0, st>>>((const __half*)x, (int)n, (int)c, (int)hw, (int)ldc, scale, out);
+  if (x_dtype == SEEDX_F32) launch_k(nhwc_to_nchw_kernel<float>, g, 256, 0, st, (const float*)x, (int)n, (int)c, (int)hw, (int)ldc, scale, out);
+  else if (x_dtype == SEEDX_F16) launch_k(nhwc_to_nchw_kernel<__half>, g, 256, 0, st, (const __half*)x, (int)n, (int)c, (int)hw, (int)ldc, scale, out);
   else SEEDX_REQUIRE(false, "seedx_nhwc_to_nchw_f32: bad dtype");
   count_launch();
   return check_cuda(cudaGetLastError(), "nhwc_to_nchw launch");
@@ -353,8 +379,8 @@ extern "C" int seedx_image_to_u8(const void* x, int x_dtype, int64_t pixels, int
   SEEDX_REQUIRE(x && out && pixels > 0 && ldc >= 3, "seedx_image_to_u8: bad arguments");
   const int g = grid_for(pixels * 3, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (x_dtype == SEEDX_F32) image_to_u8_kernel<float><<<g, 256, 0, st>>>((const float*)x, pixels, (int)ldc, out);
-  else if (x_dtype == SEEDX_F16) image_to_u8_kernel<__half><<<g, 256, 0, st>>>((const __half*)x, pixels, (int)ldc, out);
+  if (x_dtype == SEEDX_F32) launch_k(image_to_u8_kernel<float>, g, 256, 0, st, (const float*)x, pixels, (int)ldc, out);
+  else if (x_dtype == SEEDX_F16) launch_k(image_to_u8_kernel<__half>, g, 256, 0, st, (const __half*)x, pixels, (int)ldc, out);
   else SEEDX_REQUIRE(false, "seedx_image_to_u8: bad dtype");
   count_launch();
   return check_cuda(cudaGetLastError(), "image_to_u8 launch");
@@ -364,7 +390,7 @@ extern "C" int seedx_cfg_euler_step(const float* eps, float* x, void* unet_in, i
                                     float image_guidance, float sigma, float sigma_next, float init_sigma, void* stream) {
   SEEDX_REQUIRE(x && unet_in && (branches == 2 || branches == 3), "seedx_cfg_euler_step: bad arguments");
   if (eps) SEEDX_REQUIRE(sigma > 0.f, "seedx_cfg_euler_step: sigma must be > 0");
-  cfg_euler_kernel<<<grid_for(batch * hw * 4, 256), 256, 0, (cudaStream_t)stream>>>(eps, x, (__half*)unet_in, (int)batch, (int)hw, branches,
+  launch_k(cfg_euler_kernel, grid_for(batch * hw * 4, 256), 256, 0, (cudaStream_t)stream, eps, x, (__half*)unet_in, (int)batch, (int)hw, branches,
                                                                                    guidance, image_guidance, sigma, sigma_next, init_sigma);
   count_launch();
   return check_cuda(cudaGetLastError(), "cfg_euler launch");
@@ -375,8 +401,8 @@ extern "C" int seedx_add_bcast_f16(const void* a, int a_dtype, const float* b, i
   SEEDX_REQUIRE(a && b && out && rows > 0 && cols > 0 && b_rows > 0, "seedx_add_bcast_f16: bad arguments");
   const int g = grid_for(rows * cols, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  if (a_dtype == SEEDX_F16) add_bcast_kernel<__half><<<g, 256, 0, st>>>((const __half*)a, b, rows, (int)cols, (int)b_rows, (__half*)out);
-  else if (a_dtype == SEEDX_F32) add_bcast_kernel<float><<<g, 256, 0, st>>>((const float*)a, b, rows, (int)cols, (int)b_rows, (__half*)out);
+  if (a_dtype == SEEDX_F16) launch_k(add_bcast_kernel<__half>, g, 256, 0, st, (const __half*)a, b, rows, (int)cols, (int)b_rows, (__half*)out);
+  else if (a_dtype == SEEDX_F32) launch_k(add_bcast_kernel<float>, g, 256, 0, st, (const float*)a, b, rows, (int)cols, (int)b_rows, (__half*)out);
   else SEEDX_REQUIRE(false, "seedx_add_bcast_f16: bad dtype");
   count_launch();
   return check_cuda(cudaGetLastError(), "add_bcast launch");

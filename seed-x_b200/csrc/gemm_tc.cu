@@ -123,6 +123,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
+  // everything above touched only this CTA's shared/tensor memory: under programmatic dependent launch it ran while the previous
+  // kernel was still draining.  Operands, residual and output may be that kernel's data: wait for it here.
+  pdl_wait();
+  pdl_trigger();
 
   // tile space: (batch, n block, m group) with CL consecutive m blocks per group; a cluster walks groups, CTA `crank` takes m = group*CL + crank
   const int m_groups = (p.m_blocks + CL - 1) / CL;
@@ -440,11 +444,13 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, ta, tb, td, tr, p);
   count_launch();
   return check_cuda(e != cudaSuccess ? e : cudaGetLastError(), "gemm_tc_kernel launch");

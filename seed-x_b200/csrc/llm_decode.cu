@@ -46,6 +46,31 @@ gemv_mma_kernel(const __half* __restrict__ W, const float* __restrict__ x, long 
   __shared__ float red[GEMV_WARPS][NB];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  const int g = lane >> 2, q = lane & 3;   // g: weight row inside the tile AND sequence slot of the B fragment; q: 16-byte k-chunk
+  const int tiles = (N + GEMV_ROWS - 1) / GEMV_ROWS;
+  const int t_begin = (int)((long long)blockIdx.x * tiles / gridDim.x);
+  const int t_end = (int)((long long)(blockIdx.x + 1) * tiles / gridDim.x);
+  const int kblocks = K >> 5;              // 32-wide k blocks (K % 32 == 0 checked on the host)
+  const int kb_begin = (int)((long long)warp * kblocks / GEMV_WARPS), kb_end = (int)((long long)(warp + 1) * kblocks / GEMV_WARPS);
+  const int kparts = (((kblocks + GEMV_WARPS - 1) / GEMV_WARPS) + GEMV_MAXKB - 1) / GEMV_MAXKB;   // block-uniform
+  const bool has_x = g < NB;
+
+  // The weight stream is software-pipelined across tiles: the registers of unit u+1 (a tile's k-part) are requested right after
+  // unit u has been fed to the tensor cores, i.e. BEFORE the cross-warp reduction and its barrier, so HBM requests never drain.
+  uint4 wreg[GEMV_MAXKB];
+  auto load_unit = [&](int t, int part) {
+    const int row = min(t * GEMV_ROWS + g, N - 1);
+    const uint4* wrow = (const uint4*)(W + (long long)row * K) + q;
+    const int kb0 = kb_begin + part * GEMV_MAXKB;
+#pragma unroll
+    for (int i = 0; i < GEMV_MAXKB; ++i)
+      if (kb0 + i < kb_end) wreg[i] = __ldcs(wrow + (kb0 + i) * 4);   // 8 consecutive halves of weight row g: k = kb*32 + q*8 ..
+  };
+  // Weights never depend on the previous kernel: the first unit is requested before the programmatic-dependent-launch wait, so
+  // the HBM stream is already running while the producer of `x` drains.
+  if (t_begin < t_end) load_unit(t_begin, 0);
+  pdl_wait();
+  pdl_trigger();
   // ---- prologue: activations -> (RMSNorm) -> fp16 in shared memory
   float ss[NB];
 #pragma unroll
@@ -82,28 +107,7 @@ gemv_mma_kernel(const __half* __restrict__ W, const float* __restrict__ x, long 
   }
   __syncthreads();
 
-  const int g = lane >> 2, q = lane & 3;   // g: weight row inside the tile AND sequence slot of the B fragment; q: 16-byte k-chunk
-  const int tiles = (N + GEMV_ROWS - 1) / GEMV_ROWS;
-  const int t_begin = (int)((long long)blockIdx.x * tiles / gridDim.x);
-  const int t_end = (int)((long long)(blockIdx.x + 1) * tiles / gridDim.x);
-  const int kblocks = K >> 5;              // 32-wide k blocks (K % 32 == 0 checked on the host)
-  const int kb_begin = (int)((long long)warp * kblocks / GEMV_WARPS), kb_end = (int)((long long)(warp + 1) * kblocks / GEMV_WARPS);
-  const int kparts = (((kblocks + GEMV_WARPS - 1) / GEMV_WARPS) + GEMV_MAXKB - 1) / GEMV_MAXKB;   // block-uniform
-  const bool has_x = g < NB;
   const __half* xrow = xs + (has_x ? g : 0) * KP + q * 8;
-
-  // The weight stream is software-pipelined across tiles: the registers of unit u+1 (a tile's k-part) are requested right after
-  // unit u has been fed to the tensor cores, i.e. BEFORE the cross-warp reduction and its barrier, so HBM requests never drain.
-  uint4 wreg[GEMV_MAXKB];
-  auto load_unit = [&](int t, int part) {
-    const int row = min(t * GEMV_ROWS + g, N - 1);
-    const uint4* wrow = (const uint4*)(W + (long long)row * K) + q;
-    const int kb0 = kb_begin + part * GEMV_MAXKB;
-#pragma unroll
-    for (int i = 0; i < GEMV_MAXKB; ++i)
-      if (kb0 + i < kb_end) wreg[i] = __ldcs(wrow + (kb0 + i) * 4);   // 8 consecutive halves of weight row g: k = kb*32 + q*8 ..
-  };
-  if (t_begin < t_end) load_unit(t_begin, 0);
   int buf = 0;
   for (int t = t_begin; t < t_end; ++t, buf ^= 1) {
     float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -156,6 +160,8 @@ __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_kernel(const float* __restrict__ qkv_all, const int* __restrict__ state_all, const float* __restrict__ inv_freq,
                    __half* __restrict__ kcache_all, __half* __restrict__ vcache_all, long long cache_stride, float* __restrict__ out_all, int H,
                    float scale) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int HD = 128;
   __shared__ float qs[HD];
   __shared__ float gm[DA_GROUPS], gl[DA_GROUPS];
@@ -246,6 +252,8 @@ decode_attn_kernel(const float* __restrict__ qkv_all, const int* __restrict__ st
 // RoPE on the prefill q/k (in place, fp16 [T, 3D] = [q | k | v]) + copy of k, v into the cache rows pos0..pos0+T-1
 __global__ void rope_kv_prefill_kernel(__half* __restrict__ qkv, int T, int pos0, int H, const float* __restrict__ inv_freq,
                                        __half* __restrict__ kcache, __half* __restrict__ vcache) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int HD = 128;
   const int D = H * HD;
   const long long total = (long long)T * H * (HD / 2);
@@ -276,6 +284,8 @@ __global__ void rope_kv_prefill_kernel(__half* __restrict__ qkv, int T, int pos0
 // rows of the embedding table -> fp32.  ids == NULL: single row for the last token of the device-resident sequence
 __global__ void embed_rows_kernel(const __half* __restrict__ table, const int* __restrict__ ids, const int* __restrict__ state,
                                   const int* __restrict__ seq, int seq_stride, int n, int D, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n * D; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / D), c = (int)(i - (long long)r * D);
     const int id = ids ? ids[r] : seq[(long long)r * seq_stride + state[r * 4] - 1];
@@ -286,6 +296,8 @@ __global__ void embed_rows_kernel(const __half* __restrict__ table, const int* _
 template <typename TS>
 __global__ void scatter_rows_kernel(const TS* __restrict__ src, const int* __restrict__ src_idx, const int* __restrict__ idx, int n, int D,
                                     float* __restrict__ dst) {
+  pdl_wait();
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)n * D; i += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(i / D), c = (int)(i - (long long)r * D);
     const long long sr = src_idx ? src_idx[r] : r;
@@ -296,6 +308,8 @@ __global__ void scatter_rows_kernel(const TS* __restrict__ src, const int* __res
 // hidden[(state[0] - prompt_len - 1) * D + i] = x[i]   (post-norm last hidden state of the position consuming generated token j)
 __global__ void store_hidden_kernel(const float* __restrict__ x, const int* __restrict__ state, int max_rows, int D,
                                     float* __restrict__ hidden) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;                       // state[b][3] = prompt length of sequence b
   const int row = state[b * 4] - state[b * 4 + 3] - 1;
   if (row < 0 || row >= max_rows) return;
@@ -308,6 +322,8 @@ __global__ void store_hidden_kernel(const float* __restrict__ x, const int* __re
 __global__ void __launch_bounds__(1024)
 logits_argmax_kernel(float* __restrict__ logits_all, int V, const int* __restrict__ img_ids, int n_img_ids, int* __restrict__ seq_all,
                      int* __restrict__ state_all, int eos_id, int suppress_eos, int max_len) {
+  pdl_wait();
+  pdl_trigger();
   float* logits = logits_all + (long long)blockIdx.x * V;      // one CTA per sequence
   int* seq = seq_all + (long long)blockIdx.x * max_len;
   int* state = state_all + blockIdx.x * 4;
@@ -394,7 +410,7 @@ extern "C" int seedx_gemv_f16(const void* W, const float* x, int64_t ldx, const 
       SEEDX_CUDA(cudaFuncSetAttribute(gemv_mma_kernel<NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));                 \
       attr = true;                                                                                                                     \
     }                                                                                                                                  \
-    gemv_mma_kernel<NBV><<<(unsigned)blocks, GEMV_THREADS, smem, st>>>((const __half*)W, x, ldx, rms_w, eps, residual, ldr, out, ldo, \
+    launch_k(gemv_mma_kernel<NBV>, (unsigned)blocks, GEMV_THREADS, smem, st, (const __half*)W, x, ldx, rms_w, eps, residual, ldr, out, ldo, \
                                                                        (int)N, (int)K, gated);                                          \
   } while (0)
   if (nb == 1) GEMV_LAUNCH(1);
@@ -410,7 +426,7 @@ extern "C" int seedx_decode_attention(const float* qkv, const int32_t* state, co
                                       int64_t cache_stride, float* out, int batch, int heads, int head_dim, float scale, void* stream) {
   SEEDX_REQUIRE(qkv && state && inv_freq && kcache && vcache && out && batch >= 1, "seedx_decode_attention: bad arguments");
   SEEDX_REQUIRE(head_dim == 128, "seedx_decode_attention: head_dim must be 128 (LLaMA)");
-  decode_attn_kernel<<<dim3(heads, batch), DA_THREADS, 0, (cudaStream_t)stream>>>(qkv, state, inv_freq, (__half*)kcache, (__half*)vcache,
+  launch_k(decode_attn_kernel, dim3(heads, batch), DA_THREADS, 0, (cudaStream_t)stream, qkv, state, inv_freq, (__half*)kcache, (__half*)vcache,
                                                                                   cache_stride, out, heads, scale);
   count_launch();
   return check_cuda(cudaGetLastError(), "decode_attention launch");
@@ -420,7 +436,7 @@ extern "C" int seedx_rope_kv_prefill(void* qkv, int64_t tokens, int64_t pos0, in
                                      void* vcache, void* stream) {
   SEEDX_REQUIRE(qkv && inv_freq && kcache && vcache && tokens > 0, "seedx_rope_kv_prefill: bad arguments");
   SEEDX_REQUIRE(head_dim == 128, "seedx_rope_kv_prefill: head_dim must be 128 (LLaMA)");
-  rope_kv_prefill_kernel<<<ew_grid(tokens * heads * 64, 256), 256, 0, (cudaStream_t)stream>>>((__half*)qkv, (int)tokens, (int)pos0, heads, inv_freq,
+  launch_k(rope_kv_prefill_kernel, ew_grid(tokens * heads * 64, 256), 256, 0, (cudaStream_t)stream, (__half*)qkv, (int)tokens, (int)pos0, heads, inv_freq,
                                                                                              (__half*)kcache, (__half*)vcache);
   count_launch();
   return check_cuda(cudaGetLastError(), "rope_kv_prefill launch");
@@ -429,7 +445,7 @@ extern "C" int seedx_rope_kv_prefill(void* qkv, int64_t tokens, int64_t pos0, in
 extern "C" int seedx_embed_rows(const void* table, const int32_t* ids, const int32_t* state, const int32_t* seq, int64_t seq_stride, int64_t n,
                                 int64_t dim, float* out, void* stream) {
   SEEDX_REQUIRE(table && out && n > 0 && (ids || (state && seq)), "seedx_embed_rows: bad arguments");
-  embed_rows_kernel<<<ew_grid(n * dim, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)table, ids, state, seq, (int)seq_stride, (int)n,
+  launch_k(embed_rows_kernel, ew_grid(n * dim, 256), 256, 0, (cudaStream_t)stream, (const __half*)table, ids, state, seq, (int)seq_stride, (int)n,
                                                                              (int)dim, out);
   count_launch();
   return check_cuda(cudaGetLastError(), "embed_rows launch");
@@ -439,8 +455,8 @@ extern "C" int seedx_scatter_rows(const void* src, int src_dtype, const int32_t*
                                   void* stream) {
   SEEDX_REQUIRE(src && idx && dst && n > 0, "seedx_scatter_rows: bad arguments");
   const int g = ew_grid(n * dim, 256);
-  if (src_dtype == SEEDX_F32) scatter_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)src, src_idx, idx, (int)n, (int)dim, dst);
-  else if (src_dtype == SEEDX_F16) scatter_rows_kernel<__half><<<g, 256, 0, (cudaStream_t)stream>>>((const __half*)src, src_idx, idx, (int)n, (int)dim, dst);
+  if (src_dtype == SEEDX_F32) launch_k(scatter_rows_kernel<float>, g, 256, 0, (cudaStream_t)stream, (const float*)src, src_idx, idx, (int)n, (int)dim, dst);
+  else if (src_dtype == SEEDX_F16) launch_k(scatter_rows_kernel<__half>, g, 256, 0, (cudaStream_t)stream, (const __half*)src, src_idx, idx, (int)n, (int)dim, dst);
   else SEEDX_REQUIRE(false, "seedx_scatter_rows: bad dtype");
   count_launch();
   return check_cuda(cudaGetLastError(), "scatter_rows launch");
@@ -448,7 +464,7 @@ extern "C" int seedx_scatter_rows(const void* src, int src_dtype, const int32_t*
 
 extern "C" int seedx_store_hidden(const float* x, const int32_t* state, int batch, int64_t max_rows, int64_t dim, float* hidden, void* stream) {
   SEEDX_REQUIRE(x && state && hidden && batch >= 1, "seedx_store_hidden: bad arguments");
-  store_hidden_kernel<<<dim3(ew_grid(dim, 256), batch), 256, 0, (cudaStream_t)stream>>>(x, state, (int)max_rows, (int)dim, hidden);
+  launch_k(store_hidden_kernel, dim3(ew_grid(dim, 256), batch), 256, 0, (cudaStream_t)stream, x, state, (int)max_rows, (int)dim, hidden);
   count_launch();
   return check_cuda(cudaGetLastError(), "store_hidden launch");
 }
@@ -457,7 +473,7 @@ extern "C" int seedx_logits_argmax(float* logits, int64_t vocab, const int32_t* 
                                    int eos_id, int suppress_eos, int64_t max_len, void* stream) {
   SEEDX_REQUIRE(logits && seq && state && vocab > 0 && batch >= 1, "seedx_logits_argmax: bad arguments");
   SEEDX_REQUIRE(n_img_ids >= 0 && n_img_ids <= 1024, "seedx_logits_argmax: too many image token ids");
-  logits_argmax_kernel<<<batch, 1024, 0, (cudaStream_t)stream>>>(logits, (int)vocab, img_ids, n_img_ids, seq, state, eos_id, suppress_eos, (int)max_len);
+  launch_k(logits_argmax_kernel, batch, 1024, 0, (cudaStream_t)stream, logits, (int)vocab, img_ids, n_img_ids, seq, state, eos_id, suppress_eos, (int)max_len);
   count_launch();
   return check_cuda(cudaGetLastError(), "logits_argmax launch");
 }

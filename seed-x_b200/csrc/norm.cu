@@ -58,6 +58,8 @@ __global__ void __launch_bounds__(LN_THREADS)
 layernorm_vec_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
                      TO* __restrict__ out, long long ldo, TO* __restrict__ out2, const float* __restrict__ add, int add_rows,
                      long long rows, int cols, float eps, int rms) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sh[8];
   constexpr int RPB = LN_THREADS / TPR;  // rows per block
   const int sub = threadIdx.x / TPR, t = threadIdx.x % TPR;
@@ -130,11 +132,13 @@ layernorm_rows_kernel(const TI* __restrict__ x, long long ldx, const float* __re
   extern __shared__ __align__(16) float gb[];  // gamma[cols] | beta[cols]
   float* sg = gb;
   float* sb = gb + cols;
-  for (int c = threadIdx.x; c < cols; c += LN_THREADS) {
+  for (int c = threadIdx.x; c < cols; c += LN_THREADS) {   // parameters: staged before the dependency wait
     sg[c] = gamma ? gamma[c] : 1.f;
     sb[c] = beta ? beta[c] : 0.f;
   }
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
   typedef typename Raw4<TI>::type RawT;
   const int lane = threadIdx.x & 31;
   const int nvec = cols >> 2;
@@ -200,6 +204,8 @@ __global__ void __launch_bounds__(LN_THREADS)
 layernorm_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
                  TO* __restrict__ out, long long ldo, TO* __restrict__ out2, const float* __restrict__ add, int add_rows,
                  int cols, float eps, int rms) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float sh[8];
   const long long row = blockIdx.x;
   const TI* xr = x + row * ldx;
@@ -239,23 +245,27 @@ layernorm_kernel(const TI* __restrict__ x, long long ldx, const float* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm on NHWC fp16, 2 passes: (1) per-(image, group) sum / sum-of-squares (fp32 partials, fp64 atomics),
-// (2) apply per-channel scale/shift (+SiLU).  Input may be the channel concatenation of two tensors.
+// GroupNorm on NHWC fp16, 2 passes: (1) per-(image, group) sum / sum-of-squares, (2) apply per-channel scale/shift (+SiLU).
+// Input may be the channel concatenation of two tensors.  The statistics are reduced in a FIXED order at every level (thread ->
+// shared-memory slots -> shuffle tree -> per-CTA partial in global memory -> the last CTA of an image sums the partials in index
+// order, fp64), so the result is bit-reproducible run to run: no floating-point atomics anywhere.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int hw, int groups, int pix_per_block,
-                double* __restrict__ stats /*[n][groups][2]*/) {
-  extern __shared__ float gsm[];  // [groups][2]
+                double* __restrict__ stats /*[n][groups][2]*/, float* __restrict__ partials /*[n][blocks][groups][2]*/,
+                unsigned* __restrict__ tickets /*[n], zeroed by the launcher*/, int tpp /*threads per (group, stat) pair*/) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ float gsm[];  // [lanes][C][2] per-channel partials of this CTA
+  __shared__ bool is_last;
   const int n = blockIdx.y;
   const int C = c1 + c2;
   const int cpg = C / groups;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) gsm[i] = 0.f;
-  __syncthreads();
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(p0 + pix_per_block, hw);
   const int vpp = C >> 3;  // 16-byte channel vectors per pixel (c1, c2 multiples of 8)
   // thread -> (pixel lane, channel vector): a thread keeps ONE channel vector and strides over pixels, so the 8 per-channel
-  // partial sums live in registers and shared-memory atomics happen once per thread, not once per element
+  // partial sums live in registers and reach shared memory once per thread, each in its own slot
   const bool wide = vpp >= 256;
   const int lanes = wide ? 1 : 256 / vpp;
   const int p_lane = wide ? 0 : (int)threadIdx.x / vpp;
@@ -279,30 +289,44 @@ gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
           s[2 * j + 1] += t.y, ss[2 * j + 1] += t.y * t.y;
         }
       }
-      int g_prev = ch / cpg;
-      float a = 0.f, aa = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int g = (ch + j) / cpg;
-        if (g != g_prev) {
-          atomicAdd(&gsm[2 * g_prev], a);
-          atomicAdd(&gsm[2 * g_prev + 1], aa);
-          a = 0.f, aa = 0.f, g_prev = g;
-        }
-        a += s[j], aa += ss[j];
-      }
-      atomicAdd(&gsm[2 * g_prev], a);
-      atomicAdd(&gsm[2 * g_prev + 1], aa);
+      float4* dst = (float4*)(gsm + ((long long)p_lane * C + ch) * 2);
+      dst[0] = make_float4(s[0], ss[0], s[1], ss[1]);
+      dst[1] = make_float4(s[2], ss[2], s[3], ss[3]);
+      dst[2] = make_float4(s[4], ss[4], s[5], ss[5]);
+      dst[3] = make_float4(s[6], ss[6], s[7], ss[7]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&stats[(long long)n * groups * 2 + i], (double)gsm[i]);
+  // (group, stat) pair p is owned by `tpp` consecutive threads (tpp: power of two <= 32): strided partial sums, then an xor tree
+  const int pairs = groups * 2;
+  const int pair = (int)threadIdx.x / tpp, sub = (int)threadIdx.x % tpp;
+  const bool owner = pair < pairs;
+  const int g = owner ? pair >> 1 : 0, stat = pair & 1;
+  float acc = 0.f;
+  if (owner)
+    for (int idx = sub; idx < cpg * lanes; idx += tpp) acc += gsm[((long long)(idx / cpg) * C + g * cpg + idx % cpg) * 2 + stat];
+  for (int o = tpp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const int nblk = gridDim.x;
+  if (owner && sub == 0) partials[((long long)n * nblk + blockIdx.x) * pairs + pair] = acc;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(&tickets[n], 1u) == (unsigned)(nblk - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double tot = 0.0;
+  if (owner)
+    for (int b = sub; b < nblk; b += tpp) tot += (double)__ldcg(&partials[((long long)n * nblk + b) * pairs + pair]);
+  for (int o = tpp >> 1; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+  if (owner && sub == 0) stats[(long long)n * pairs + pair] = tot;
 }
 
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int hw, int groups,
                 const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float eps, int silu_act, __half* __restrict__ out, __half* __restrict__ raw_out, int pix_per_block) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float ssm[];  // scale[C], shift[C]
   const int n = blockIdx.y;
   const int C = c1 + c2;
@@ -365,10 +389,10 @@ extern "C" int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const fl
                       ((ldo * out_sz) % (4 * out_sz) == 0) && (!out2 || (uintptr_t)out2 % 16 == 0) && (!gamma || (uintptr_t)gamma % 16 == 0) &&
                       (!beta || (uintptr_t)beta % 16 == 0) && (!add || (uintptr_t)add % 16 == 0) && cols <= 8192;
 #define LN_VEC(TI, TO, TPR, NV)                                                                                              \
-  layernorm_vec_kernel<TI, TO, TPR, NV><<<(unsigned)((rows + (LN_THREADS / TPR) - 1) / (LN_THREADS / TPR)), LN_THREADS, 0, st>>>( \
+  launch_k(layernorm_vec_kernel<TI, TO, TPR, NV>, (unsigned)((rows + (LN_THREADS / TPR) - 1) / (LN_THREADS / TPR)), LN_THREADS, 0, st,  \
       (const TI*)x, ldx, gamma, beta, (TO*)out, ldo, (TO*)out2, add, (int)(add ? add_rows : 1), rows, (int)cols, eps, rms)
 #define LN_ROWS(TI, TO, NV)                                                                                                          \
-  layernorm_rows_kernel<TI, TO, NV><<<rows_grid, LN_THREADS, (size_t)cols * 8, st>>>((const TI*)x, ldx, gamma, beta, (TO*)out, ldo, (TO*)out2, \
+  launch_k(layernorm_rows_kernel<TI, TO, NV>, rows_grid, LN_THREADS, (size_t)cols * 8, st, (const TI*)x, ldx, gamma, beta, (TO*)out, ldo, (TO*)out2, \
                                                                                    add, (int)(add ? add_rows : 1), rows, (int)cols, eps, rms)
 #define LN_VEC_DISPATCH(TI, TO)                  \
   do {                                           \
@@ -390,7 +414,7 @@ extern "C" int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const fl
   const unsigned rows_grid = (unsigned)rg;
   dim3 grid((unsigned)rows);
 #define LN_LAUNCH(TI, TO)                                                                                                  \
-  layernorm_kernel<TI, TO><<<grid, LN_THREADS, 0, st>>>((const TI*)x, ldx, gamma, beta, (TO*)out, ldo, (TO*)out2, add, \
+  launch_k(layernorm_kernel<TI, TO>, grid, LN_THREADS, 0, st, (const TI*)x, ldx, gamma, beta, (TO*)out, ldo, (TO*)out2, add, \
                                                         (int)(add ? add_rows : 1), (int)cols, eps, rms)
 #define LN_BOTH(TI, TO)            \
   do {                             \
@@ -411,6 +435,21 @@ extern "C" int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const fl
   return check_cuda(cudaGetLastError(), "layernorm_kernel launch");
 }
 
+// CTAs per image of the statistics pass: ~4 waves of CTAs over the batch, >= 32 pixels each
+static int64_t gn_stat_blocks(int64_t n, int64_t hw, int64_t* pix_per_block) {
+  int64_t spb = (hw * n + 148 * 4 - 1) / (148 * 4);
+  if (spb < 32) spb = 32;
+  if (spb > hw) spb = hw;
+  if (pix_per_block) *pix_per_block = spb;
+  return (hw + spb - 1) / spb;
+}
+
+extern "C" int64_t seedx_groupnorm_ws_bytes(int64_t n, int groups) {
+  if (n <= 0 || groups <= 0) return 0;
+  const int64_t nblk = (148 * 4) / n + 2;   // >= gn_stat_blocks(n, hw) for every hw
+  return n * groups * 2 * (int64_t)sizeof(double) + n * nblk * groups * 2 * (int64_t)sizeof(float) + n * (int64_t)sizeof(unsigned);
+}
+
 extern "C" int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, int64_t c2, int64_t n, int64_t hw, int groups,
                                     const float* gamma, const float* beta, float eps, int silu_act, void* out, void* raw_out,
                                     void* stats_ws, void* stream) {
@@ -421,13 +460,21 @@ extern "C" int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, 
                 (long long)c1, (long long)c2);
   SEEDX_REQUIRE(n > 0 && n <= 65535 && hw > 0, "seedx_groupnorm_nhwc: bad n/hw");
   cudaStream_t st = (cudaStream_t)stream;
-  SEEDX_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * groups * n, st));
-  int64_t spb = (hw * n + 148 * 4 - 1) / (148 * 4);  // ~4 waves of CTAs; >= 32 pixels each so the register partials amortise the atomics
-  if (spb < 32) spb = 32;
-  if (spb > hw) spb = hw;
-  dim3 g1((unsigned)((hw + spb - 1) / spb), (unsigned)n);
-  gn_stats_kernel<<<g1, 256, groups * 2 * sizeof(float), st>>>((const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw, groups, (int)spb,
-                                                               (double*)stats_ws);
+  int64_t spb_out = 0;
+  SEEDX_REQUIRE(groups <= 128, "seedx_groupnorm_nhwc: at most 128 groups");
+  const int64_t nblk = gn_stat_blocks(n, hw, &spb_out);
+  const int64_t spb = spb_out;
+  double* stats = (double*)stats_ws;                                  // [n][groups][2] fp64, read by the apply pass
+  float* partials = (float*)(stats + n * groups * 2);                 // [n][nblk][groups][2]
+  unsigned* tickets = (unsigned*)(partials + n * nblk * groups * 2);  // [n]
+  SEEDX_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * n, st));
+  int tpp = 1;
+  while (tpp < 32 && tpp * 2 * groups * 2 <= 256) tpp *= 2;
+  const int64_t vpp = C / 8;
+  const int64_t lanes = vpp >= 256 ? 1 : 256 / vpp;
+  dim3 g1((unsigned)nblk, (unsigned)n);
+  launch_k(gn_stats_kernel, g1, 256, (size_t)(lanes * C * 2) * sizeof(float), st, (const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw,
+           groups, (int)spb, stats, partials, tickets, tpp);
   count_launch();
   SEEDX_CUDA(cudaGetLastError());
   // apply: aim for ~4 waves of 148 SMs, at least 16 pixels per block
@@ -436,7 +483,7 @@ extern "C" int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, 
   if (ppb > hw) ppb = hw;
   dim3 g2((unsigned)((hw + ppb - 1) / ppb), (unsigned)n);
   const size_t smem = (size_t)C * 2 * sizeof(float);
-  gn_apply_kernel<<<g2, 256, smem, st>>>((const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw, groups, (const double*)stats_ws,
+  launch_k(gn_apply_kernel, g2, 256, smem, st, (const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw, groups, (const double*)stats_ws,
                                          gamma, beta, eps, silu_act, (__half*)out, (__half*)raw_out, (int)ppb);
   count_launch();
   return check_cuda(cudaGetLastError(), "groupnorm kernels launch");

@@ -1,3 +1,4 @@
+#include <cstdlib>
 // seedx-b200: host-side runtime glue of libseedx.so (error string, SM count, tensor-map encoder, launch counter).
 #include <atomic>
 #include <cstdarg>
@@ -25,6 +26,17 @@ int check_cuda(cudaError_t e, const char* what) {
   return 1;
 }
 
+static std::atomic<int> g_pdl{-1};
+int pdl_enabled() {
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("SEEDX_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+    g_pdl.store(v);
+  }
+  return v;
+}
+void set_pdl(int on) { g_pdl.store(on ? 1 : 0); }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int num_sms() {
@@ -82,4 +94,8 @@ int encode_tmap(CUtensorMap* map, CUtensorMapDataType dt, uint32_t rank, const v
 
 extern "C" const char* seedx_last_error(void) { return seedx::g_err; }
 extern "C" int seedx_abi_version(void) { return SEEDX_ABI_VERSION; }
+extern "C" int seedx_set_pdl(int on) {
+  seedx::set_pdl(on);
+  return 0;
+}
 extern "C" int64_t seedx_launch_count(void) { return (int64_t)seedx::g_launches.load(); }

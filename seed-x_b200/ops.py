@@ -169,6 +169,12 @@ def layernorm(x, gamma, beta, eps, out=None, *, out_dtype=torch.float16, rms=Fal
     return (out, out2) if add is not None else out
 
 
+def groupnorm_ws(n, groups, device):
+    """Scratch for groupnorm_nhwc (final fp64 statistics + per-CTA partials + tickets); reusable across layers of one batch size."""
+    nbytes = lib().seedx_groupnorm_ws_bytes(C.c_int64(n), C.c_int(groups))
+    return torch.empty(((nbytes + 7) // 8,), device=device, dtype=torch.float64)
+
+
 def groupnorm_nhwc(x1, gamma, beta, eps, *, x2=None, silu=False, groups=32, out=None, raw_out=None, stats_ws=None):
     """GroupNorm(+SiLU) over NHWC fp16 [N,H,W,C1] (optionally channel-concatenated with x2 [N,H,W,C2])."""
     _require_cuda(x1, x2, out)
@@ -181,7 +187,8 @@ def groupnorm_nhwc(x1, gamma, beta, eps, *, x2=None, silu=False, groups=32, out=
     if out is None:
         out = torch.empty((n, h, w, c1 + c2), device=x1.device, dtype=torch.float16)
     if stats_ws is None:
-        stats_ws = torch.empty((n * groups * 2,), device=x1.device, dtype=torch.float64)
+        stats_ws = groupnorm_ws(n, groups, x1.device)
+    assert stats_ws.numel() * stats_ws.element_size() >= lib().seedx_groupnorm_ws_bytes(C.c_int64(n), C.c_int(groups))
     check(lib().seedx_groupnorm_nhwc(_ptr(x1), C.c_int64(c1), _ptr(x2), C.c_int64(c2), C.c_int64(n), C.c_int64(h * w), C.c_int(groups),
                                      _ptr(gamma), _ptr(beta), C.c_float(eps), C.c_int(int(silu)), _ptr(out), _ptr(raw_out), _ptr(stats_ws),
                                      _stream()), "seedx_groupnorm_nhwc")

@@ -51,7 +51,7 @@ class ResamplerXLV2:
         dev = self.device
         x16 = ops.unary_f16(x.reshape(B * n, E).to(dev).contiguous())
         xf = ops.gemm(x16, self.proj_in[0], bias=self.proj_in[1], out_dtype=torch.float32)              # [B*n, D]
-        lat = self.latents.unsqueeze(0).expand(B, Q, D).contiguous().view(B * Q, D)                     # learned latents, broadcast copy
+        lat = self.latents.unsqueeze(0).repeat(B, 1, 1).view(B * Q, D)      # a COPY of the learned latents (updated in place below), also for B=1
         kvin = torch.empty((B, n + Q, D), device=dev, dtype=torch.float16)
         lbuf = torch.empty((B * Q, D), device=dev, dtype=torch.float16)
         o = torch.empty((B * Q, inner), device=dev, dtype=torch.float16)

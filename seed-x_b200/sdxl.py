@@ -223,6 +223,9 @@ class UNet2DConditionModel:
         nb = len(boc)
         cin = sd["conv_in.weight"].shape[1]
         self.cfg["in_channels"] = cin
+        # widths the checkpoint itself fixes (diffusers: time_embed_dim = 4*block_out_channels[0], projection_class_embeddings_input_dim)
+        self.cfg["time_embed_dim"] = sd["time_embedding.linear_1.weight"].shape[0]
+        self.cfg["text_embed_dim"] = sd["add_embedding.linear_1.weight"].shape[1] - 6 * cfg["addition_time_embed_dim"]
         if cin > 8:
             raise SeedxError("conv_in with more than 8 input channels is not supported")
         self.conv_in = (pack_conv(sd["conv_in.weight"], dev), _f(sd["conv_in.bias"], dev))
@@ -290,7 +293,7 @@ class UNet2DConditionModel:
         G = cfg["groups"]
         Be = x_in.shape[0]
         nb = len(cfg["block_out_channels"])
-        ws = torch.empty((Be * G * 2,), device=self.device, dtype=torch.float64)
+        ws = ops.groupnorm_ws(Be, G, self.device)
         T = cond["n_ctx"]
         temb_in = torch.empty((Be, cfg["block_out_channels"][0]), device=self.device, dtype=torch.float16)
         ops.timestep_embedding(t_dev, cfg["block_out_channels"][0], temb_in)
@@ -454,7 +457,7 @@ class AutoencoderKL:
             raise SeedxError("AutoencoderKL: decoder weights not loaded")
         G = self.cfg["groups"]
         B, _, h, w = latents.shape
-        ws = torch.empty((B * G * 2,), device=self.device, dtype=torch.float64)
+        ws = ops.groupnorm_ws(B, G, self.device)
         z = ops.nchw_to_nhwc_f16(latents.to(self.device).float().contiguous(), 8, scale=scale)
         x = ops.gemm(z.view(B * h * w, 8), self.post_quant[0], bias=self.post_quant[1]).view(B, h, w, -1)
         x = ops.conv2d_nhwc(x, self.d_conv_in[0], bias=self.d_conv_in[1])
@@ -480,7 +483,7 @@ class AutoencoderKL:
             raise SeedxError("AutoencoderKL: encoder weights not loaded")
         G = self.cfg["groups"]
         B = image.shape[0]
-        ws = torch.empty((B * G * 2,), device=self.device, dtype=torch.float64)
+        ws = ops.groupnorm_ws(B, G, self.device)
         x = ops.nchw_to_nhwc_f16(image.to(self.device).float().contiguous(), 8)
         x = ops.conv2d_nhwc(x, self.e_conv_in[0], bias=self.e_conv_in[1])
         for res, ds in self.e_down:
