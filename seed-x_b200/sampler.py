@@ -12,6 +12,27 @@ from . import ops
 from ._lib import SeedxError
 
 
+def _same_layout(a, b):
+    if torch.is_tensor(a):
+        return torch.is_tensor(b) and a.shape == b.shape and a.dtype == b.dtype
+    if isinstance(a, dict):
+        return isinstance(b, dict) and a.keys() == b.keys() and all(_same_layout(a[k], b[k]) for k in a)
+    if isinstance(a, (list, tuple)):
+        return isinstance(b, (list, tuple)) and len(a) == len(b) and all(_same_layout(x, y) for x, y in zip(a, b))
+    return a == b
+
+
+def _copy_tree(dst, src):
+    if torch.is_tensor(dst):
+        dst.copy_(src)
+    elif isinstance(dst, dict):
+        for k in dst:
+            _copy_tree(dst[k], src[k])
+    elif isinstance(dst, (list, tuple)):
+        for x, y in zip(dst, src):
+            _copy_tree(x, y)
+
+
 class DenoiseLoop:
     """Owns the static buffers of one (batch, mode) sampling configuration and an optional CUDA graph of the UNet forward."""
 
@@ -32,7 +53,12 @@ class DenoiseLoop:
     def set_condition(self, ctx, text_embeds, time_ids, image_latents=None):
         """ctx [branches*B, T, ctx_dim], text_embeds [branches*B, 1280], time_ids [branches*B, 6] in the pipeline's branch order;
         image_latents: fp32 NCHW [B,4,h,w] for the edit mode (branches [img, img, 0], pipeline...edit.py:544-546)."""
-        self.cond = self.unet.prepare_cond(ctx, text_embeds, time_ids)
+        cond = self.unet.prepare_cond(ctx, text_embeds, time_ids)
+        if self.cond is not None and _same_layout(self.cond, cond):
+            _copy_tree(self.cond, cond)       # same buffers, new values: the captured graph stays valid across requests
+            keep_graph = True
+        else:
+            self.cond, keep_graph = cond, False
         if image_latents is not None:
             if self.branches != 3:
                 raise SeedxError("image latents only apply to the 3-branch edit loop")
@@ -40,7 +66,8 @@ class DenoiseLoop:
             B = self.B
             for br in range(2):
                 ops.unary_f16(il.view(-1, 4), out=self.unet_in[br * B:(br + 1) * B].view(-1, 8)[:, 4:8])
-        self.graph = None   # conditioning buffers changed -> recapture
+        if not keep_graph:
+            self.graph = None   # conditioning buffers were reallocated (first call / different context length) -> recapture
 
     def _forward(self):
         return self.unet.forward_nhwc(self.unet_in, self.t_dev, self.cond)
