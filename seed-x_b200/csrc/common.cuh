@@ -314,15 +314,26 @@ SEEDX_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\
 // ----------------------------------------------------------------------------------------------
 SEEDX_DEVINL float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // exact-GELU with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below the fp16 output rounding); ~3x cheaper than erff
-SEEDX_DEVINL float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, 1.0f + 0.3275911f * z);
-  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-  const float erf_abs = 1.0f - poly * __expf(-z * z);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+SEEDX_DEVINL float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
 }
-SEEDX_DEVINL float silu(float x) { return x / (1.0f + __expf(-x)); }
+// ~14 FP32 ops + 2 MUFU (rcp, ex2) per value: the GEGLU epilogue of the UNet feed-forward GEMMs is issue-bound on this function
+SEEDX_DEVINL float gelu_erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float z = ax * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float w = ax * 0.84932180028801904272f;          // sqrt(log2(e) / 2): exp(-z^2) = 2^(-w^2)
+  const float erf_abs = fmaf(-poly, fast_exp2(-w * w), 1.0f);
+  return fmaf(0.5f * ax, erf_abs, 0.5f * x);             // 0.5 x (1 + sign(x) erf|z|)
+}
+SEEDX_DEVINL float silu(float x) { return x * rcp_approx(1.0f + fast_exp2(-1.4426950408889634f * x)); }
 
 SEEDX_DEVINL float warp_sum(float v) {
 #pragma unroll

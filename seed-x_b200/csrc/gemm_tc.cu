@@ -31,6 +31,7 @@ struct GemmParams {
   float alpha;
   int act, gated, out_f32, res_f32, vec_ok, b_batched, bias_vec;
   int tma_epi, epi_row_bytes, r_batched;  // TMA epilogue: output (and residual) tiles of 32 rows x epi_row_bytes staged in shared memory
+  int epi_out_bytes, epi_res_bytes;       // per-warp staging split: output buffers | residual buffers (host policy, see seedx_gemm_f16)
   int stages, epi_warp_bytes;             // pipeline depth and per-epilogue-warp staging bytes, sized on the host to fill shared memory
   // conv
   int conv, taps_w, c_chunks, conv_w, conv_h, tile_w, tile_h, tiles_per_img, tiles_w, pad, imgs_per_tile;
@@ -256,13 +257,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int col_end = min(p.N, n0 + BN);   // columns of this tile that exist
       // ---- TMA epilogue state: tiles of 32 rows x RB bytes in this warp's staging area, XOR-swizzled like the tensor maps
       const int ew = warp - 2;
-      const uint32_t stg_out = epi_base + (uint32_t)(ew * p.epi_warp_bytes), stg_res = stg_out + (uint32_t)EPI_OUT_BYTES;
+      const uint32_t stg_out = epi_base + (uint32_t)(ew * p.epi_warp_bytes), stg_res = stg_out + (uint32_t)p.epi_out_bytes;
       const int RB = p.epi_row_bytes;
       const uint32_t tile_bytes = 32u * (uint32_t)RB;
-      const int nbuf = tile_bytes <= 2048u ? 2 : 1;                 // output buffers (EPI_OUT_BYTES)
-      int nres = (int)(EPI_RES_BYTES / tile_bytes);                 // residual buffers: 8/4/2 -> clamp to 4
+      const int nbuf = (uint32_t)p.epi_out_bytes >= 2u * tile_bytes ? 2 : 1;   // output buffers
+      int nres = (int)((uint32_t)p.epi_res_bytes / tile_bytes);     // residual buffers, at most 4 (barriers)
       nres = nres > 4 ? 4 : nres;
-      const uint32_t swz_mask = (uint32_t)(RB / 16 - 1);
       const int row_base = m_blk * BM + lane_grp * 32;
       const bool tma_res = p.tma_epi && p.residual != nullptr;
       int n_chunks = 0;
@@ -311,14 +311,96 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         int nvals = 32;
         int ocol0 = col0;
+        // activation chosen once per chunk (warp-uniform), not once per value
         if (p.gated) {
+          if (p.act == SEEDX_ACT_GELU_ERF) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) x[i] = x[2 * i] * apply_act(x[2 * i + 1], p.act);
+            for (int i = 0; i < 16; ++i) x[i] = x[2 * i] * gelu_erf_fast(x[2 * i + 1]);
+          } else if (p.act == SEEDX_ACT_SILU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = x[2 * i] * silu(x[2 * i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = x[2 * i] * x[2 * i + 1];
+          }
           nvals = 16;
           ocol0 = col0 >> 1;
-        } else if (p.act != SEEDX_ACT_NONE) {
+        } else if (p.act == SEEDX_ACT_GELU_ERF) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = apply_act(x[i], p.act);
+          for (int i = 0; i < 32; ++i) x[i] = gelu_erf_fast(x[i]);
+        } else if (p.act == SEEDX_ACT_SILU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = silu(x[i]);
+        }
+        if (p.tma_epi) {
+          // ---- shared-memory staged epilogue: residual tile arrives by TMA, output tile leaves by TMA (whole 32-row x RB-byte
+          // boxes; rows / columns outside the matrix are clipped by the tensor map).  Lane = row; the 16-byte chunk index is
+          // XOR-swizzled exactly like the tensor map's swizzle mode, which also makes the 128-bit accesses bank-conflict free.
+          const int k = kchunk++;
+          const uint32_t sw = RB == 128 ? (uint32_t)(lane & 7) : (RB == 64 ? (uint32_t)((lane >> 1) & 3) : (uint32_t)((lane >> 2) & 1));
+          if (tma_res) {
+            const int rb = k % nres;
+            mbar_wait(res_bar(ew, rb), (epi_res_phase >> rb) & 1u);
+            epi_res_phase ^= 1u << rb;
+            const uint32_t rrow_addr = stg_res + (uint32_t)rb * tile_bytes + (uint32_t)(lane * RB);
+            if (p.out_f32) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (4 * j < nvals) {
+                  const uint4 q = lds128(rrow_addr + (((uint32_t)j ^ sw) << 4));
+                  x[4 * j] += __uint_as_float(q.x), x[4 * j + 1] += __uint_as_float(q.y);
+                  x[4 * j + 2] += __uint_as_float(q.z), x[4 * j + 3] += __uint_as_float(q.w);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (8 * j < nvals) {
+                  const uint4 q = lds128(rrow_addr + (((uint32_t)j ^ sw) << 4));
+                  const __half2* h = (const __half2*)&q;
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __half22float2(h[e]);
+                    x[8 * j + 2 * e] += f.x, x[8 * j + 2 * e + 1] += f.y;
+                  }
+                }
+              }
+            }
+            __syncwarp();                                             // every lane has consumed buffer rb
+            if (lane == 0 && k + nres < n_chunks) issue_res(k + nres);
+          }
+          const int ob = k % nbuf;
+          if (lane == 0) {                                            // the store that last read this output buffer has drained it
+            if (nbuf == 2) bulk_wait_read<1>();
+            else bulk_wait_read<0>();
+          }
+          __syncwarp();
+          const uint32_t orow_addr = stg_out + (uint32_t)ob * tile_bytes + (uint32_t)(lane * RB);
+          if (p.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (4 * j < nvals)
+                sts128(orow_addr + (((uint32_t)j ^ sw) << 4), make_uint4(__float_as_uint(x[4 * j]), __float_as_uint(x[4 * j + 1]),
+                                                                         __float_as_uint(x[4 * j + 2]), __float_as_uint(x[4 * j + 3])));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (8 * j < nvals) {
+                uint4 q;
+                __half2* h = (__half2*)&q;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(x[8 * j + 2 * e], x[8 * j + 2 * e + 1]);
+                sts128(orow_addr + (((uint32_t)j ^ sw) << 4), q);
+              }
+            }
+          }
+          fence_proxy_async();                                        // generic-proxy writes -> visible to the TMA engine
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmD, stg_out + (uint32_t)ob * tile_bytes, ocol0, row_base, b);
+            bulk_commit();
+          }
+          continue;
         }
         const int n_out = p.gated ? (col_end >> 1) : col_end;  // output columns of this tile end here
         if (!row_ok) continue;
@@ -624,7 +706,15 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
   p.vec_ok = vec ? 1 : 0;
   p.bias_vec = (a->bias_n && (uintptr_t)a->bias_n % 16 == 0) ? 1 : 0;
   p.tma_epi = tma_epi ? 1 : 0;
-  p.epi_warp_bytes = tma_epi ? (EPI_OUT_BYTES + (a->residual ? EPI_RES_BYTES : 0)) : 0;
+  {
+    // Staging policy.  Short-K tiles are epilogue-bound: double-buffer the output box and keep up to four residual boxes in flight.
+    // Long-K tiles hide the epilogue behind the main loop anyway and want the shared memory for pipeline stages instead: one box each.
+    const int box_bytes = 32 * (a->gated ? 16 : 32) * out_es;
+    const bool short_k = p.k_blocks < 32;
+    p.epi_out_bytes = tma_epi ? (short_k ? (box_bytes > EPI_OUT_BYTES / 2 ? box_bytes : EPI_OUT_BYTES) : box_bytes) : 0;
+    p.epi_res_bytes = (tma_epi && a->residual) ? (short_k ? EPI_RES_BYTES : box_bytes) : 0;
+    p.epi_warp_bytes = p.epi_out_bytes + p.epi_res_bytes;
+  }
   td = ta, tr = ta;  // placeholders when the TMA epilogue is off (never dereferenced)
   if (tma_epi) {
     const int cols = a->gated ? 16 : 32;                    // output columns per 32-column accumulator chunk
