@@ -85,6 +85,8 @@ typedef struct seedx_gemm_args {
 int seedx_gemm_f16(const seedx_gemm_args* args, void* stream);
 /* A/B switch for the 2-CTA cluster (TMA multicast of the B tile) variant: 0 = off, 1 = auto (default), 2 = whenever legal */
 void seedx_gemm_set_cluster(int mode);
+/* developer aid: device buffer of 8 uint64 per CTA that receives %globaltimer phase stamps of the following GEMM launches (NULL = off) */
+void seedx_gemm_set_debug(void* device_buffer);
 /* A/B switch for the epilogue: 1 (default) = output/residual tiles staged in shared memory and moved by TMA, 0 = direct row-per-thread stores */
 void seedx_gemm_set_tma_epilogue(int on);
 

@@ -25,6 +25,24 @@ struct FaParams {
   int m_tiles, heads, items;   // work items = m_tiles * heads * batch, q-tile fastest
 };
 
+// one value in (2 * POLY_EVERY) takes the polynomial exp2; 0 = MUFU only
+#ifndef SEEDX_FA_POLY_EVERY
+#define SEEDX_FA_POLY_EVERY 2
+#endif
+constexpr int POLY_EVERY = SEEDX_FA_POLY_EVERY;
+
+// 2^x for x <= ~100 on the FMA/ALU pipes: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (Remez on
+// the relative error: 7.5e-5); 2^n by adding n to the exponent field.  Inputs below -126 (masked scores are -inf) give ~1e-38 -> 0 in fp16.
+SEEDX_DEVINL float exp2_poly3(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;          // 1.5 * 2^23: the low mantissa bits of t now hold round(x)
+  const float f = x - (t - 12582912.0f);
+  float q = fmaf(0.0551716685f, f, 0.2426111251f);
+  q = fmaf(q, f, 0.6932609677f);
+  q = fmaf(q, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
+}
+
 template <int D>
 struct FaCfg {
   static constexpr int BM = 128, BN = 128;
@@ -39,8 +57,10 @@ struct FaCfg {
 // Persistent: grid = min(items, SMs); CTA c walks items c, c+grid, ...  Q tiles and O accumulators are double-buffered so the
 // TMA loads, the first QK^T of the next item and the output store of the previous one overlap; the S/P buffers, the K/V rings and
 // their barrier phases run on one global tile counter `g` straight through item boundaries.
-template <int D>
-__global__ void __launch_bounds__(320, 1)
+// NS = softmax threads per query row (2 or 4): 4*NS softmax warps.  NS = 4 puts four warps on every scheduler, which is what lets
+// the MUFU (exp2), FMA and TMEM-load latencies of different warps overlap: with NS = 2 the kernel ran at ~45% issue utilisation.
+template <int D, int NS>
+__global__ void __launch_bounds__(64 + 128 * NS, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const FaParams p) {
   using Cfg = FaCfg<D>;
@@ -78,9 +98,9 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(q_full(s), 1);
       mbar_init(q_empty(s), 1);
       mbar_init(s_full(s), 1);
-      mbar_init(p_full(s), 256);
+      mbar_init(p_full(s), 128 * NS);
       mbar_init(pv_done(s), 1);
-      mbar_init(o_free(s), 256);
+      mbar_init(o_free(s), 128 * NS);
     }
     mbar_fence_init();
   }
@@ -192,14 +212,16 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     }
   } else {
     // ------------------------------------------------------------ softmax / correction / epilogue
-    // row = TMEM lane; warps 2..5 own score columns [0,64) and O columns [0,D/2), warps 6..9 the upper halves
-    __shared__ float xch_max[2][2][128];   // [tile parity][column half][row]
-    __shared__ float xch_sum[2][128];
+    // row = TMEM lane (warp % 4 selects the lane quarter); the NS threads of a row own CW = 128/NS score columns and D/NS O columns each
+    constexpr int CW = 128 / NS;            // score columns per thread
+    constexpr int OC = D / NS;              // O columns per thread
+    constexpr int OCH = OC >= 32 ? 32 : 16; // O columns per TMEM load
+    __shared__ float xch_max[2][NS][128];   // [tile parity][column slice][row]
+    __shared__ float xch_sum[NS][128];
     const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int slice = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    constexpr int OC = D / 2;              // O columns per thread
     uint32_t g = 0;
     int n = 0;
     for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
@@ -208,36 +230,45 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int m0 = mt * Cfg::BM;
       const int n_tiles = tiles_of(m0);
       const int qrow = m0 + row;
-      const uint32_t tO = tmem_base + lane_addr + ((n & 1) ? Cfg::O_COL1 : Cfg::O_COL0) + (uint32_t)(half * OC);
+      const uint32_t tO = tmem_base + lane_addr + ((n & 1) ? Cfg::O_COL1 : Cfg::O_COL0) + (uint32_t)(slice * OC);
       float m_run = -INFINITY, l_run = 0.f;
       for (int j = 0; j < n_tiles; ++j, ++g) {
         const uint32_t tSb = tmem_base + lane_addr + ((g & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
         mbar_wait(s_full(g & 1), (g >> 1) & 1u);
         tc_fence_after();
-        float s[64];
+        float s[CW];   // raw q.k scores: the softmax scale is folded into the exp2 FFMA below
+        {
+          uint32_t v[CW / 32][32];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tSb + (uint32_t)(half * 64 + c * 32), v);
+          for (int c = 0; c < CW / 32; ++c) tmem_ld32(tSb + (uint32_t)(slice * CW + c * 32), v[c]);   // all requested before the single wait
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(v[i]) * p.scale_log2;
+          for (int c = 0; c < CW / 32; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s[c * 32 + i] = __uint_as_float(v[c][i]);
         }
-        const int key0 = j * Cfg::BN + half * 64;
+        const int key0 = j * Cfg::BN + slice * CW;
         const bool need_mask = (j * Cfg::BN + Cfg::BN > p.sk) || (p.causal && (j * Cfg::BN + Cfg::BN - 1 > m0 + causal_off));
         if (need_mask) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) {
+          for (int i = 0; i < CW; ++i) {
             const int key = key0 + i;
             if (key >= p.sk || (p.causal && key > qrow + causal_off)) s[i] = -INFINITY;
           }
         }
-        float m_tile = s[0];
+        // four independent max chains
+        float mx[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-        for (int i = 1; i < 64; ++i) m_tile = fmaxf(m_tile, s[i]);
-        xch_max[g & 1][half][row] = m_tile;
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");                   // the 8 softmax warps only
-        m_tile = fmaxf(m_tile, xch_max[g & 1][half ^ 1][row]);
+        for (int i = 4; i < CW; i += 4) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) mx[k] = fmaxf(mx[k], s[i + k]);
+        }
+        float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        xch_max[g & 1][slice][row] = m_tile;
+        asm volatile("bar.sync 1, %0;\n" ::"n"(128 * NS) : "memory");        // the softmax warps only
+#pragma unroll
+        for (int k = 0; k < NS; ++k) m_tile = fmaxf(m_tile, xch_max[g & 1][k][row]);
+        m_tile *= p.scale_log2;                                              // scale > 0 (checked on the host): max commutes
         // Lazy rescaling: the reference maximum m_run only moves when some row of this warp exceeds it by more than 2^8 (P then stays
         // <= 256, exact in fp16 range; sums and O are fp32).  Only then does the softmax have to wait for PV_{j-1} and touch O, so in
         // the steady state softmax_j does not depend on the tensor pipe at all and the MMA -> softmax -> MMA round trip disappears.
@@ -251,68 +282,74 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             mbar_wait(pv_done((g - 1) & 1), ((g - 1) >> 1) & 1u);  // O is quiescent: PV_{j-1} retired
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < OC / 32; ++c) {
-              uint32_t v[32];
-              tmem_ld32(tO + (uint32_t)(c * 32), v);
+            for (int c = 0; c < OC / OCH; ++c) {
+              uint32_t v[OCH];
+              tmem_ld_n<OCH>(tO + (uint32_t)(c * OCH), v);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-              tmem_st32(tO + (uint32_t)(c * 32), v);
+              for (int i = 0; i < OCH; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st_n<OCH>(tO + (uint32_t)(c * OCH), v);
             }
           }
           m_run = m_new;
         }
         const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-        // P_j = exp2(S_j - m) as fp16 pairs: my 64 scores -> 32 packed columns at [half*32, half*32+32) of the S_j buffer.
-        // (the other half-row thread may still be reading S columns >= 64 only if it is `half`=1: its columns are never overwritten
-        //  by P (P occupies columns 0..63), and a `half`=0 thread has already pulled columns 0..63 into registers before the bar.sync.)
-        float rs = 0.f;
+        // P_j = exp2(scale * S_j - m) as fp16 pairs: my CW scores -> CW/2 packed columns at [slice*CW/2, +CW/2) of the S_j buffer.
+        // P occupies columns 0..63 of the buffer; every thread whose score columns lie below 64 has pulled them into registers before the
+        // bar.sync above, and the columns >= 64 are never overwritten.
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial row sums
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < CW / 32; ++c) {
           uint32_t v[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float a = fast_exp2(s[c * 32 + 2 * i] - m_use), c2 = fast_exp2(s[c * 32 + 2 * i + 1] - m_use);
-            rs += a + c2;
+            // exp2 is the bottleneck of d=64 attention (16 MUFU/clk/SM vs 8192 tensor FLOP/clk/SM): every POLY_EVERY-th pair evaluates
+            // one value on the FMA pipe instead (Cody-Waite split + degree-3 minimax, rel. error 7.5e-5, below the fp16 rounding of P)
+            const float x0 = fmaf(s[c * 32 + 2 * i], p.scale_log2, -m_use), x1 = fmaf(s[c * 32 + 2 * i + 1], p.scale_log2, -m_use);
+            const float a = fast_exp2(x0);
+            const float c2 = (POLY_EVERY > 0 && (i % POLY_EVERY) == POLY_EVERY - 1) ? exp2_poly3(x1) : fast_exp2(x1);
+            rs4[i & 3] += a + c2;
             __half2 hh = __floats2half2_rn(a, c2);
             v[i] = *(uint32_t*)&hh;
           }
-          tmem_st16(tSb + (uint32_t)(half * 32 + c * 16), v);
+          tmem_st16(tSb + (uint32_t)(slice * (CW / 2) + c * 16), v);
         }
         tmem_st_wait();
-        l_run = l_run * alpha + rs;
+        l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
         tc_fence_before();
         mbar_arrive(p_full(g & 1));
       }
-      // ---- epilogue: combine the two half-row sums, normalise and store my half of the output columns
-      xch_sum[half][row] = l_run;
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
-      const float l_tot = l_run + xch_sum[half ^ 1][row];
+      // ---- epilogue: combine the row's partial sums, normalise and store my slice of the output columns
+      xch_sum[slice][row] = l_run;
+      asm volatile("bar.sync 1, %0;\n" ::"n"(128 * NS) : "memory");
+      float l_tot = 0.f;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) l_tot += xch_sum[k][row];
       const uint32_t gl = g - 1;
       mbar_wait(pv_done(gl & 1), (gl >> 1) & 1u);
       tc_fence_after();
       const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-      __half* orow = p.o + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)qrow * p.o_ss + half * OC;
+      __half* orow = p.o + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)qrow * p.o_ss + slice * OC;
 #pragma unroll
-      for (int c = 0; c < OC / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tO + (uint32_t)(c * 32), v);
+      for (int c = 0; c < OC / OCH; ++c) {
+        uint32_t v[OCH];
+        tmem_ld_n<OCH>(tO + (uint32_t)(c * OCH), v);
         tmem_ld_wait();
-        if (c == OC / 32 - 1) {            // accumulator drained into registers: the MMA warp may start item n+2 on it
+        if (c == OC / OCH - 1) {            // accumulator drained into registers: the MMA warp may start item n+2 on it
           tc_fence_before();
           mbar_arrive(o_free(n & 1));
         }
         if (qrow < p.sq) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            const int col = half * OC + c * 32 + i;
+          for (int i = 0; i < OCH; i += 8) {
+            const int col = slice * OC + c * OCH + i;
             if (col + 8 <= p.d) {
               uint4 q;
               __half2* hh = (__half2*)&q;
 #pragma unroll
               for (int t = 0; t < 4; ++t)
                 hh[t] = __floats2half2_rn(__uint_as_float(v[i + 2 * t]) * inv, __uint_as_float(v[i + 2 * t + 1]) * inv);
-              *(uint4*)(orow + c * 32 + i) = q;
+              *(uint4*)(orow + c * OCH + i) = q;
             }
           }
         }
@@ -327,13 +364,16 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
 }
 
+#ifndef SEEDX_FA_NS
+#define SEEDX_FA_NS 4
+#endif
 template <int D>
 static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, FaParams p, int B, int H, cudaStream_t st) {
   using Cfg = FaCfg<D>;
   static bool attr = false;
   static int sms = 0;
   if (!attr) {
-    SEEDX_CUDA(cudaFuncSetAttribute(flash_attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    SEEDX_CUDA(cudaFuncSetAttribute(flash_attn_tc_kernel<D, SEEDX_FA_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     int dev = 0;
     SEEDX_CUDA(cudaGetDevice(&dev));
     SEEDX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -345,7 +385,7 @@ static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   if (items > 0x7fffffffLL) return -1;
   p.items = (int)items;
   const int grid = p.items < sms ? p.items : sms;
-  launch_k(flash_attn_tc_kernel<D>, grid, 320, Cfg::SMEM_BYTES, st, tq, tk, tv, p);
+  launch_k(flash_attn_tc_kernel<D, SEEDX_FA_NS>, grid, 64 + 128 * SEEDX_FA_NS, Cfg::SMEM_BYTES, st, tq, tk, tv, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "flash_attn_tc_kernel launch");
 }
@@ -360,7 +400,7 @@ static int make_map(CUtensorMap* m, const void* ptr, int d, int s, int H, int B,
 // returns -1 when the problem is not eligible for the tensor-memory kernel (caller falls back to the mma.sync kernel)
 int attention_tc_try(const seedx_attn_args* a, cudaStream_t st) {
   // short key sequences (UNet cross-attention over 64 context tokens) would fill under half of one 128-key tile: mma.sync kernel is faster
-  if (a->d > 128 || a->d % 8 != 0 || a->sq < 128 || a->sk < 96) return -1;
+  if (a->d > 128 || a->d % 8 != 0 || a->sq < 128 || a->sk < 96 || !(a->scale > 0.f)) return -1;
   if (a->o_stride_s % 8 || a->o_stride_h % 8 || a->o_stride_b % 8 || (uintptr_t)a->o % 16) return -1;
   const long long str[] = {a->q_stride_s, a->q_stride_h, a->q_stride_b, a->k_stride_s, a->k_stride_h, a->k_stride_b,
                            a->v_stride_s, a->v_stride_h, a->v_stride_b};

@@ -300,6 +300,28 @@ SEEDX_DEVINL void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
       "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+SEEDX_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+// N = 16 or 32 consecutive 32-bit columns of this thread's TMEM lane
+template <int N>
+SEEDX_DEVINL void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(N == 16 || N == 32, "tmem_ld_n: 16 or 32 columns");
+  if constexpr (N == 16) tmem_ld16(taddr, r);
+  else tmem_ld32(taddr, r);
+}
+template <int N>
+SEEDX_DEVINL void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]) {
+  static_assert(N == 16 || N == 32, "tmem_st_n: 16 or 32 columns");
+  if constexpr (N == 16) tmem_st16(taddr, r);
+  else tmem_st32(taddr, r);
+}
 SEEDX_DEVINL void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 SEEDX_DEVINL float fast_exp2(float x) {
   float y;

@@ -31,6 +31,7 @@ struct GemmParams {
   float alpha;
   int act, gated, out_f32, res_f32, vec_ok, b_batched, bias_vec;
   int tma_epi, epi_row_bytes, r_batched;  // TMA epilogue: output (and residual) tiles of 32 rows x epi_row_bytes staged in shared memory
+  unsigned long long* dbg;                // optional per-CTA phase timestamps (%globaltimer ns), 8 slots per CTA; NULL in production
   int epi_out_bytes, epi_res_bytes;       // per-warp staging split: output buffers | residual buffers (host policy, see seedx_gemm_f16)
   int stages, epi_warp_bytes;             // pipeline depth and per-epilogue-warp staging bytes, sized on the host to fill shared memory
   // conv
@@ -65,6 +66,13 @@ struct TileCfg {
   static constexpr int TMEM_COLS = pow2_cols(2 * BN + 16);
 };
 
+SEEDX_DEVINL unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+#define GEMM_STAMP(slot) do { if (p.dbg != nullptr) p.dbg[(size_t)blockIdx.x * 8 + (slot)] = gtime_ns(); } while (0)
+
 SEEDX_DEVINL float apply_act(float x, int act) {
   if (act == SEEDX_ACT_GELU_ERF) return gelu_erf_fast(x);
   if (act == SEEDX_ACT_SILU) return silu(x);
@@ -83,6 +91,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using Cfg = TileCfg<BN, CL>;
   const int STAGES = p.stages;
+  if (threadIdx.x == 0) GEMM_STAMP(0);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned
@@ -126,8 +135,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
   // everything above touched only this CTA's shared/tensor memory: under programmatic dependent launch it ran while the previous
   // kernel was still draining.  Operands, residual and output may be that kernel's data: wait for it here.
+  if (threadIdx.x == 0) GEMM_STAMP(1);
   pdl_wait();
   pdl_trigger();
+  if (threadIdx.x == 0) GEMM_STAMP(2);
 
   // tile space: (batch, n block, m group) with CL consecutive m blocks per group; a cluster walks groups, CTA `crank` takes m = group*CL + crank
   const int m_groups = (p.m_blocks + CL - 1) / CL;
@@ -209,6 +220,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if (t == tile0 && kb == 0) GEMM_STAMP(3);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t adesc = umma_desc_k_sw128(sa);
@@ -260,7 +272,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t stg_out = epi_base + (uint32_t)(ew * p.epi_warp_bytes), stg_res = stg_out + (uint32_t)p.epi_out_bytes;
       const int RB = p.epi_row_bytes;
       const uint32_t tile_bytes = 32u * (uint32_t)RB;
-      const int nbuf = (uint32_t)p.epi_out_bytes >= 2u * tile_bytes ? 2 : 1;   // output buffers
+      const int nbuf = (uint32_t)p.epi_out_bytes >= 4u * tile_bytes ? 4 : ((uint32_t)p.epi_out_bytes >= 2u * tile_bytes ? 2 : 1);   // output buffers
       int nres = (int)((uint32_t)p.epi_res_bytes / tile_bytes);     // residual buffers, at most 4 (barriers)
       nres = nres > 4 ? 4 : nres;
       const int row_base = m_blk * BM + lane_grp * 32;
@@ -278,6 +290,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int k = 0; k < nres && k < n_chunks; ++k) issue_res(k);  // in flight while the main loop of this tile is still running
       int kchunk = 0;
       mbar_wait_relaxed(tfull_bar(acc), acc_phase);   // accumulator of this tile complete
+      if (warp == 2 && lane == 0) {
+        if (t == tile0) GEMM_STAMP(4);
+        GEMM_STAMP(5);                                 // overwritten every tile: the last tile's value survives
+      }
       tc_fence_after();
 #pragma unroll 1
       for (int c = chunk0; c < BN; c += 64) {
@@ -371,7 +387,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           const int ob = k % nbuf;
           if (lane == 0) {                                            // the store that last read this output buffer has drained it
-            if (nbuf == 2) bulk_wait_read<1>();
+            if (nbuf == 4) bulk_wait_read<3>();
+            else if (nbuf == 2) bulk_wait_read<1>();
             else bulk_wait_read<0>();
           }
           __syncwarp();
@@ -484,6 +501,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (acc == 0) acc_phase ^= 1u;
     }
     if (p.tma_epi && lane == 0) bulk_wait_read<0>();  // shared memory stays alive until the last TMA store has read it
+    if (warp == 2 && lane == 0) GEMM_STAMP(6);
   }
 
   tc_fence_before();
@@ -493,6 +511,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     if (CL == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
     else tmem_dealloc_2sm<Cfg::TMEM_COLS>(tmem_base);
+    if (lane == 0) GEMM_STAMP(7);
   }
 }
 
@@ -545,6 +564,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return launch_gemm_cl<BN, 1>(ta, tb, td, tr, p, st);
 }
 
+static unsigned long long* g_gemm_dbg = nullptr;
 static int g_gemm_cluster = 1;  // 0 = never cluster, 1 = auto, 2 = always when legal
 static int g_gemm_tma_epi = 1;  // 0 = row-per-thread direct stores, 1 = TMA-store epilogue when eligible
 
@@ -582,6 +602,7 @@ static int choose_tile_n(int m_tiles, int N, int k_blocks, bool heavy_epilogue, 
 
 using namespace seedx;
 
+extern "C" void seedx_gemm_set_debug(void* device_buffer) { seedx::g_gemm_dbg = (unsigned long long*)device_buffer; }
 extern "C" void seedx_gemm_set_cluster(int mode) { seedx::g_gemm_cluster = mode; }
 extern "C" void seedx_gemm_set_tma_epilogue(int on) { seedx::g_gemm_tma_epi = on; }
 
@@ -683,6 +704,7 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
     p.b_batched = bb ? 1 : 0;
   }
   p.D = a->D;
+  p.dbg = g_gemm_dbg;
   p.bias_n = a->bias_n, p.bias_m = a->bias_m, p.bias_g = a->bias_g;
   p.bias_g_rows = a->bias_g ? (int)a->bias_g_rows : 1;
   SEEDX_REQUIRE(p.bias_g_rows > 0, "seedx_gemm_f16: bias_g_rows must be > 0");
@@ -711,7 +733,8 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
     // Long-K tiles hide the epilogue behind the main loop anyway and want the shared memory for pipeline stages instead: one box each.
     const int box_bytes = 32 * (a->gated ? 16 : 32) * out_es;
     const bool short_k = p.k_blocks < 32;
-    p.epi_out_bytes = tma_epi ? (short_k ? (box_bytes > EPI_OUT_BYTES / 2 ? box_bytes : EPI_OUT_BYTES) : box_bytes) : 0;
+    const int out_short = a->residual ? EPI_OUT_BYTES : 2 * EPI_OUT_BYTES;   // no residual staging: four output boxes in flight
+    p.epi_out_bytes = tma_epi ? (short_k ? (box_bytes > out_short / 2 ? box_bytes : out_short) : box_bytes) : 0;
     p.epi_res_bytes = (tma_epi && a->residual) ? (short_k ? EPI_RES_BYTES : box_bytes) : 0;
     p.epi_warp_bytes = p.epi_out_bytes + p.epi_res_bytes;
   }

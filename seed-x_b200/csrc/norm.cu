@@ -252,8 +252,8 @@ layernorm_kernel(const TI* __restrict__ x, long long ldx, const float* __restric
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int hw, int groups, int pix_per_block,
-                double* __restrict__ stats /*[n][groups][2]*/, float* __restrict__ partials /*[n][blocks][groups][2]*/,
-                unsigned* __restrict__ tickets /*[n], zeroed by the launcher*/, int tpp /*threads per (group, stat) pair*/) {
+                float2* __restrict__ stats /*[n][groups] (mean, rstd)*/, float* __restrict__ partials /*[n][blocks][groups][2]*/,
+                unsigned* __restrict__ tickets /*[n], zeroed by the launcher*/, int tpp /*threads per (group, stat) pair*/, float eps) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float gsm[];  // [lanes][C][2] per-channel partials of this CTA
@@ -318,13 +318,22 @@ gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
   if (owner)
     for (int b = sub; b < nblk; b += tpp) tot += (double)__ldcg(&partials[((long long)n * nblk + b) * pairs + pair]);
   for (int o = tpp >> 1; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-  if (owner && sub == 0) stats[(long long)n * pairs + pair] = tot;
+  __shared__ double fin[256];
+  if (owner && sub == 0) fin[pair] = tot;
+  __syncthreads();
+  if ((int)threadIdx.x < groups) {      // (mean, rstd) per group, computed once here instead of once per CTA of the apply pass
+    const double cnt = (double)hw * (double)cpg;
+    const double m = fin[2 * threadIdx.x] / cnt;
+    double var = fin[2 * threadIdx.x + 1] / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    stats[(long long)n * groups + threadIdx.x] = make_float2((float)m, (float)(1.0 / sqrt(var + (double)eps)));
+  }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(320)
 gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int hw, int groups,
-                const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
-                float eps, int silu_act, __half* __restrict__ out, __half* __restrict__ raw_out, int pix_per_block) {
+                const float2* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                int silu_act, __half* __restrict__ out, __half* __restrict__ raw_out, int pix_per_block, int lanes) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float ssm[];  // scale[C], shift[C]
@@ -333,28 +342,17 @@ gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
   const int cpg = C / groups;
   float* scale = ssm;
   float* shift = ssm + C;
-  const double cnt = (double)hw * (double)cpg;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const double m = stats[((long long)n * groups + g) * 2] / cnt;
-    double var = stats[((long long)n * groups + g) * 2 + 1] / cnt - m * m;
-    if (var < 0.0) var = 0.0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
-    scale[c] = rstd * ga;
-    shift[c] = be - (float)m * rstd * ga;
+    const float2 mr = stats[(long long)n * groups + c / cpg];
+    const float sc = mr.y * (gamma ? gamma[c] : 1.f);
+    scale[c] = sc;
+    shift[c] = (beta ? beta[c] : 0.f) - mr.x * sc;
   }
   __syncthreads();
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(p0 + pix_per_block, hw);
-  const int vec_per_pix = C >> 3;
-  const int total = (p1 - p0) * vec_per_pix;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int pix = p0 + idx / vec_per_pix;
-    const int cv = (idx % vec_per_pix) * 8;
-    const __half* src = (cv < c1) ? x1 + ((long long)n * hw + pix) * c1 + cv : x2 + ((long long)n * hw + pix) * c2 + (cv - c1);
-    const uint4 q = *(const uint4*)src;
-    const long long ooff = ((long long)n * hw + pix) * C + cv;
+  const int vpp = C >> 3;
+  auto norm_store = [&](const uint4& q, const float* sc, const float* sh, long long ooff) {
     if (raw_out) *(uint4*)(raw_out + ooff) = q;
     const __half2* h = (const __half2*)&q;
     uint4 o;
@@ -362,12 +360,42 @@ gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 t = __half22float2(h[j]);
-      float a = t.x * scale[cv + 2 * j] + shift[cv + 2 * j];
-      float b = t.y * scale[cv + 2 * j + 1] + shift[cv + 2 * j + 1];
+      float a = fmaf(t.x, sc[2 * j], sh[2 * j]);
+      float b = fmaf(t.y, sc[2 * j + 1], sh[2 * j + 1]);
       if (silu_act) a = silu(a), b = silu(b);
       oh[j] = __floats2half2_rn(a, b);
     }
     *(uint4*)(out + ooff) = o;
+  };
+  if (lanes > 0) {
+    // blockDim = lanes * vpp: a thread owns ONE channel vector (scale/shift in registers) and strides over pixels, four independent
+    // 16-byte loads in flight before the first is consumed
+    const int cv = ((int)threadIdx.x % vpp) * 8, pl = (int)threadIdx.x / vpp;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sc[j] = scale[cv + j], sh[j] = shift[cv + j];
+    const bool first = cv < c1;
+    const __half* base = first ? x1 + (long long)n * hw * c1 + cv : x2 + (long long)n * hw * c2 + (cv - c1);
+    const int cstride = first ? c1 : c2;
+    constexpr int U = 4;
+    for (int pix0 = p0 + pl; pix0 < p1; pix0 += lanes * U) {
+      uint4 q[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (pix0 + u * lanes < p1) q[u] = *(const uint4*)(base + (long long)(pix0 + u * lanes) * cstride);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (pix0 + u * lanes < p1) norm_store(q[u], sc, sh, ((long long)n * hw + pix0 + u * lanes) * C + cv);
+    }
+    return;
+  }
+  const int total = (p1 - p0) * vpp;   // generic mapping (more channel vectors than threads)
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int pix = p0 + idx / vpp;
+    const int cv = (idx % vpp) * 8;
+    const __half* src = (cv < c1) ? x1 + ((long long)n * hw + pix) * c1 + cv : x2 + ((long long)n * hw + pix) * c2 + (cv - c1);
+    const uint4 q = *(const uint4*)src;
+    norm_store(q, scale + cv, shift + cv, ((long long)n * hw + pix) * C + cv);
   }
 }
 
@@ -464,9 +492,9 @@ extern "C" int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, 
   SEEDX_REQUIRE(groups <= 128, "seedx_groupnorm_nhwc: at most 128 groups");
   const int64_t nblk = gn_stat_blocks(n, hw, &spb_out);
   const int64_t spb = spb_out;
-  double* stats = (double*)stats_ws;                                  // [n][groups][2] fp64, read by the apply pass
-  float* partials = (float*)(stats + n * groups * 2);                 // [n][nblk][groups][2]
-  unsigned* tickets = (unsigned*)(partials + n * nblk * groups * 2);  // [n]
+  float2* stats = (float2*)stats_ws;                                   // [n][groups] (mean, rstd), read by the apply pass
+  float* partials = (float*)((double*)stats_ws + n * groups * 2);      // [n][nblk][groups][2]
+  unsigned* tickets = (unsigned*)(partials + n * nblk * groups * 2);   // [n]
   SEEDX_CUDA(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * n, st));
   int tpp = 1;
   while (tpp < 32 && tpp * 2 * groups * 2 <= 256) tpp *= 2;
@@ -474,17 +502,19 @@ extern "C" int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, 
   const int64_t lanes = vpp >= 256 ? 1 : 256 / vpp;
   dim3 g1((unsigned)nblk, (unsigned)n);
   launch_k(gn_stats_kernel, g1, 256, (size_t)(lanes * C * 2) * sizeof(float), st, (const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw,
-           groups, (int)spb, stats, partials, tickets, tpp);
+           groups, (int)spb, stats, partials, tickets, tpp, eps);
   count_launch();
   SEEDX_CUDA(cudaGetLastError());
-  // apply: aim for ~4 waves of 148 SMs, at least 16 pixels per block
+  // apply: ~8 CTAs per SM in flight, at least 16 pixels per block; block = whole pixels (lanes * vpp threads) when a pixel fits
   int64_t ppb = (hw * n + 148 * 8 - 1) / (148 * 8);
   if (ppb < 16) ppb = 16;
   if (ppb > hw) ppb = hw;
   dim3 g2((unsigned)((hw + ppb - 1) / ppb), (unsigned)n);
   const size_t smem = (size_t)C * 2 * sizeof(float);
-  launch_k(gn_apply_kernel, g2, 256, smem, st, (const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw, groups, (const double*)stats_ws,
-                                         gamma, beta, eps, silu_act, (__half*)out, (__half*)raw_out, (int)ppb);
+  const int a_lanes = vpp <= 320 ? (int)(320 / vpp) : 0;
+  const int a_threads = a_lanes > 0 ? (int)(a_lanes * vpp) : 256;
+  launch_k(gn_apply_kernel, g2, a_threads, smem, st, (const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw, groups, (const float2*)stats,
+           gamma, beta, silu_act, (__half*)out, (__half*)raw_out, (int)ppb, a_lanes);
   count_launch();
   return check_cuda(cudaGetLastError(), "groupnorm kernels launch");
 }
