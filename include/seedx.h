@@ -111,9 +111,10 @@ typedef struct seedx_attn_args {
 } seedx_attn_args;
 
 int seedx_attention_f16(const seedx_attn_args* args, void* stream);
-/* implementation switch for A/B tests: 0 = auto (tcgen05/TMEM kernel when d <= 128 and sq >= 128, else mma.sync), 1 = always mma.sync */
+/* implementation switch for A/B tests: 0 = auto (two-query-tile tcgen05/TMEM kernel when d <= 128 and sq >= 256, one-tile tcgen05
+ * kernel when sq >= 128, else mma.sync), 1 = always mma.sync, 2 = never the two-tile kernel */
 void seedx_attention_set_impl(int impl);
-int seedx_attention_last_impl(void); /* 2 = tcgen05 kernel, 1 = mma.sync kernel (most recent call) */
+int seedx_attention_last_impl(void); /* most recent call: 3 = tcgen05 two-tile, 2 = tcgen05 one-tile, 1 = mma.sync */
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm (rms=0) / RMSNorm (rms=1) over the last dimension, fp32 statistics.

@@ -275,8 +275,9 @@ static int launch_attn(const AttnParams& p, int B, int H, cudaStream_t st) {
 
 namespace seedx {
 int attention_tc_try(const seedx_attn_args* a, cudaStream_t st);
-static int g_attn_impl = 0;  // 0 = auto (tcgen05 kernel when eligible), 1 = force the mma.sync kernel
-static int g_attn_last = 0;  // implementation used by the most recent call: 2 = tcgen05, 1 = mma.sync
+int attention_pp_try(const seedx_attn_args* a, cudaStream_t st);
+static int g_attn_impl = 0;  // 0 = auto (two-tile tcgen05 kernel, else one-tile tcgen05 kernel, else mma.sync), 1 = force mma.sync, 2 = skip the two-tile kernel
+static int g_attn_last = 0;  // implementation used by the most recent call: 3 = tcgen05 two-tile, 2 = tcgen05 one-tile, 1 = mma.sync
 }
 using namespace seedx;
 
@@ -305,6 +306,13 @@ extern "C" int seedx_attention_f16(const seedx_attn_args* a, void* stream) {
   p.causal = a->causal;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_attn_impl == 0) {
+    const int rc = attention_pp_try(a, st);
+    if (rc >= 0) {
+      g_attn_last = 3;
+      return rc;
+    }
+  }
+  if (g_attn_impl == 0 || g_attn_impl == 2) {
     const int rc = attention_tc_try(a, st);
     if (rc >= 0) {
       g_attn_last = 2;

@@ -1,0 +1,459 @@
+// seedx-b200: tcgen05 flash attention (forward), two-query-tile "ping-pong" schedule for sm_100a.
+//
+//   O[b,h,i,:] = softmax_j( scale * Q[b,h,i,:].K[b,h,j,:] (+causal) ) V[b,h,j,:]         fp16 in/out, fp32 softmax/accumulate
+//
+// One work item = 256 query rows (two 128-row tiles A and B) of one (batch, head); CTAs are persistent and walk the item list.
+//   warp 0      TMA producer: the Q pair of an item, then K/V tiles of 128 keys through two mbarrier rings (each K/V tile serves both
+//               query tiles: half the shared-memory fill traffic per FLOP of the one-tile kernel)
+//   warp 1      single-thread MMA issuer: S_X = Q_X K_j^T into TMEM (one 128-column buffer per query tile), O_X += P_X V_j with P_X read
+//               back as the TMEM A operand and V_j as an MN-major shared-memory B operand
+//   warps 2-5   softmax group A, warps 6-9 softmax group B: ONE thread per query row (no cross-thread row reductions, no block
+//               barriers).  While group A exponentiates tile j the tensor pipe runs PV_B(j-1) and QK_B(j), and vice versa, so the two
+//               warps that share a scheduler are always in different phases and their MUFU / FMA / TMEM latencies overlap.
+// P_j (fp16) overwrites the first 64 columns of S_X; O_X is rescaled only when a row maximum moved by more than 2^8 (lazy rescale).
+// A share of the exponentials is evaluated on the FMA pipe (exp2_poly3) because d=64 attention is bound by the 16 MUFU/clk/SM rate.
+//
+// Replaces the same reference call sites as seedx_attention_f16 (include/seedx.h) for head dims <= 128 and sequences >= 128.
+#include <cstdlib>
+#include "common.cuh"
+#include "../../include/seedx.h"
+
+namespace seedx {
+void count_launch();
+
+struct PpParams {
+  __half* o;
+  long long o_sb, o_sh, o_ss;
+  int sq, sk, d;
+  float scale_log2;
+  int causal, q_batched;
+  int m_pairs, heads, items;   // work items = m_pairs * heads * batch, q-pair fastest
+};
+
+#ifndef SEEDX_PP_POLY_EVERY
+#define SEEDX_PP_POLY_EVERY 4   // one value in (2 * POLY_EVERY) takes the polynomial exp2; 0 = MUFU only.  Measured (B200, S=4096, d=64):
+                                // none 573, 1/8 627, 1/4 570, 1/2 537 TF/s -> the MUFU and FMA pipes balance at one value in eight
+#endif
+
+// 2^x on the FMA/ALU pipes: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax polynomial (Remez on the relative
+// error: 7.5e-5, below the fp16 rounding of P); 2^n by adding n to the exponent field.  Inputs below -126 (masked scores) give ~1e-38.
+SEEDX_DEVINL float pp_exp2_poly3(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;          // 1.5 * 2^23: the low mantissa bits of t now hold round(x)
+  const float f = x - (t - 12582912.0f);
+  float q = fmaf(0.0551716685f, f, 0.2426111251f);
+  q = fmaf(q, f, 0.6932609677f);
+  q = fmaf(q, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
+}
+
+template <int D>
+struct PpCfg {
+  static constexpr int BM = 128, BN = 128;
+  static constexpr int HALVES = D / 64;
+  static constexpr int HALF_BYTES = 128 * 64 * 2;           // one [128 rows x 64 fp16] swizzled tile
+  static constexpr int TILE_BYTES = HALVES * HALF_BYTES;    // one Q, K or V tile
+  static constexpr int QBUF = (D == 64) ? 2 : 1;            // item-level buffering of the Q pair (shared memory permitting)
+  static constexpr int KV_STAGES = (D == 64) ? 3 : 2;
+  static constexpr int SMEM_BYTES = TILE_BYTES * (2 * QBUF + 2 * KV_STAGES) + 1024 + 512;
+  static constexpr uint32_t S_COL = 0, O_COL = 256;         // S_X at S_COL + 128 X, O_X at O_COL + D X
+};
+
+template <int D, int PE>
+__global__ void __launch_bounds__(320, 1)
+flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                     const PpParams p) {
+  using Cfg = PpCfg<D>;
+  constexpr int KS = Cfg::KV_STAGES, QB = Cfg::QBUF;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ0 = smem_base;                                  // [QB][2] tiles
+  const uint32_t sK0 = sQ0 + 2 * QB * Cfg::TILE_BYTES;
+  const uint32_t sV0 = sK0 + KS * Cfg::TILE_BYTES;
+  const uint32_t bar = sV0 + KS * Cfg::TILE_BYTES;
+  auto k_full = [&](int s) { return bar + 8u * (s); };
+  auto k_empty = [&](int s) { return bar + 8u * (KS + s); };
+  auto v_full = [&](int s) { return bar + 8u * (2 * KS + s); };
+  auto v_empty = [&](int s) { return bar + 8u * (3 * KS + s); };
+  auto q_full = [&](int s) { return bar + 8u * (4 * KS + s); };
+  auto q_empty = [&](int s) { return bar + 8u * (4 * KS + 2 + s); };
+  auto s_full = [&](int x) { return bar + 8u * (4 * KS + 4 + x); };    // per query tile X
+  auto p_full = [&](int x) { return bar + 8u * (4 * KS + 6 + x); };
+  auto pv_done = [&](int x) { return bar + 8u * (4 * KS + 8 + x); };
+  auto o_free = [&](int x) { return bar + 8u * (4 * KS + 10 + x); };
+  const uint32_t tmem_slot = bar + 8u * (4 * KS + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int s = 0; s < KS; ++s) {
+      mbar_init(k_full(s), 1), mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1), mbar_init(v_empty(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
+      mbar_init(s_full(s), 1);
+      mbar_init(p_full(s), 128);
+      mbar_init(pv_done(s), 1);
+      mbar_init(o_free(s), 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();      // prologue above overlapped the previous kernel's tail (programmatic dependent launch)
+  pdl_trigger();
+
+  const int causal_off = p.sk - p.sq;
+  const int kv_tiles = (p.sk + Cfg::BN - 1) / Cfg::BN;
+  auto tiles_of = [&](int m0) {   // KV tiles an item starting at query row m0 (256 rows) has to visit
+    int n = kv_tiles;
+    if (p.causal) {
+      const int lim = (m0 + 2 * Cfg::BM - 1 + causal_off) / Cfg::BN + 1;
+      if (lim < n) n = lim < 1 ? 1 : lim;
+    }
+    return n;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      int n = 0;
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+        const int mp = it % p.m_pairs, hb = it / p.m_pairs;
+        const int h = hb % p.heads, b = hb / p.heads;
+        const int m0 = mp * 2 * Cfg::BM;
+        const int qb = n % QB;
+        mbar_wait(q_empty(qb), (uint32_t)(((n / QB) & 1) ^ 1));
+        mbar_expect_tx(q_full(qb), 2 * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int x = 0; x < 2; ++x)
+#pragma unroll
+          for (int hf = 0; hf < Cfg::HALVES; ++hf)
+            tma_load_4d(sQ0 + (qb * 2 + x) * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmQ, q_full(qb), hf * 64, m0 + x * Cfg::BM, h,
+                        p.q_batched ? b : 0);
+        const int n_tiles = tiles_of(m0);
+        for (int j = 0; j < n_tiles; ++j) {
+          mbar_wait(k_empty(st), ph ^ 1u);
+          mbar_expect_tx(k_full(st), Cfg::TILE_BYTES);
+#pragma unroll
+          for (int hf = 0; hf < Cfg::HALVES; ++hf)
+            tma_load_4d(sK0 + st * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmK, k_full(st), hf * 64, j * Cfg::BN, h, b);
+          mbar_wait(v_empty(st), ph ^ 1u);
+          mbar_expect_tx(v_full(st), Cfg::TILE_BYTES);
+#pragma unroll
+          for (int hf = 0; hf < Cfg::HALVES; ++hf)
+            tma_load_4d(sV0 + st * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmV, v_full(st), hf * 64, j * Cfg::BN, h, b);
+          if (++st == KS) st = 0, ph ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, D) | (1u << 16);  // B operand MN-major
+      int kst = 0, vst = 0;
+      uint32_t kph = 0, vph = 0;
+      uint32_t g = 0;                 // tiles processed so far (same count for both query tiles)
+      auto issue_qk = [&](int x, uint32_t sQ, uint32_t kb) {
+        const uint32_t tS = tmem_base + Cfg::S_COL + (uint32_t)(x * 128);
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) {
+          const uint32_t off = (uint32_t)((ks >> 2) * Cfg::HALF_BYTES + (ks & 3) * 32);
+          umma_f16(tS, umma_desc_k_sw128(sQ + off), umma_desc_k_sw128(kb + off), idesc_qk, ks != 0);
+        }
+        umma_commit(s_full(x));
+      };
+      auto issue_pv = [&](int x, uint32_t vb, bool first) {
+        const uint32_t tP = tmem_base + Cfg::S_COL + (uint32_t)(x * 128);
+        const uint32_t tO = tmem_base + Cfg::O_COL + (uint32_t)(x * D);
+#pragma unroll
+        for (int kk = 0; kk < Cfg::BN / 16; ++kk)  // 16 keys per MMA: A advances 8 TMEM columns, B 16 rows of 128 B
+          umma_f16_ts(tO, tP + (uint32_t)(kk * 8), umma_desc_mn_sw128(vb + kk * 2048, Cfg::HALF_BYTES), idesc_pv, !(first && kk == 0));
+        umma_commit(pv_done(x));
+      };
+      int n = 0;
+      for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+        const int m0 = (it % p.m_pairs) * 2 * Cfg::BM;
+        const int n_tiles = tiles_of(m0);
+        const int qb = n % QB;
+        const uint32_t sQA = sQ0 + (qb * 2) * Cfg::TILE_BYTES, sQB = sQA + Cfg::TILE_BYTES;
+        mbar_wait(q_full(qb), (uint32_t)((n / QB) & 1));
+        // S_A / S_B of the previous item were last read by its final PV_A / PV_B, issued earlier on the in-order tensor pipe
+        mbar_wait(k_full(kst), kph);
+        tc_fence_after();
+        issue_qk(0, sQA, sK0 + kst * Cfg::TILE_BYTES);
+        issue_qk(1, sQB, sK0 + kst * Cfg::TILE_BYTES);
+        umma_commit(k_empty(kst));
+        if (n_tiles == 1) umma_commit(q_empty(qb));
+        if (++kst == KS) kst = 0, kph ^= 1u;
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          const bool more = j + 1 < n_tiles;
+          // ---- query tile A
+          mbar_wait(p_full(0), g & 1u);
+          mbar_wait(v_full(vst), vph);
+          if (j == 0) mbar_wait(o_free(0), (uint32_t)((n & 1) ^ 1));   // epilogue of the previous item has drained O_A
+          tc_fence_after();
+          issue_pv(0, sV0 + vst * Cfg::TILE_BYTES, j == 0);
+          if (more) {
+            mbar_wait(k_full(kst), kph);
+            tc_fence_after();
+            issue_qk(0, sQA, sK0 + kst * Cfg::TILE_BYTES);
+          }
+          // ---- query tile B
+          mbar_wait(p_full(1), g & 1u);
+          if (j == 0) mbar_wait(o_free(1), (uint32_t)((n & 1) ^ 1));
+          tc_fence_after();
+          issue_pv(1, sV0 + vst * Cfg::TILE_BYTES, j == 0);
+          umma_commit(v_empty(vst));
+          if (++vst == KS) vst = 0, vph ^= 1u;
+          if (more) {
+            issue_qk(1, sQB, sK0 + kst * Cfg::TILE_BYTES);
+            umma_commit(k_empty(kst));
+            if (j + 2 == n_tiles) umma_commit(q_empty(qb));   // last QK^T of this item issued: the Q pair may be overwritten
+            if (++kst == KS) kst = 0, kph ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax / correction / epilogue: one thread per query row
+    const int x = (warp - 2) >> 2;                 // query tile of this softmax group
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tS = tmem_base + lane_addr + Cfg::S_COL + (uint32_t)(x * 128);
+    const uint32_t tO = tmem_base + lane_addr + Cfg::O_COL + (uint32_t)(x * D);
+    uint32_t g = 0;
+    int n = 0;
+    for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
+      const int mp = it % p.m_pairs, hb = it / p.m_pairs;
+      const int h = hb % p.heads, b = hb / p.heads;
+      const int m0 = mp * 2 * Cfg::BM;
+      const int n_tiles = tiles_of(m0);
+      const int qrow = m0 + x * Cfg::BM + row;
+      float m_run = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++g) {
+        mbar_wait(s_full(x), g & 1u);
+        tc_fence_after();
+        const bool need_mask = (j * Cfg::BN + Cfg::BN > p.sk) || (p.causal && (j * Cfg::BN + Cfg::BN - 1 > m0 + x * Cfg::BM + causal_off));
+        auto masked = [&](int key) { return key >= p.sk || (p.causal && key > qrow + causal_off); };
+        // ---- pass 1: row maximum of the raw scores (the softmax scale is folded into the exp2 FFMA of pass 2)
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tS + (uint32_t)(c2 * 64), v0);
+          tmem_ld32(tS + (uint32_t)(c2 * 64 + 32), v1);
+          tmem_ld_wait();
+          if (need_mask) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (masked(j * Cfg::BN + c2 * 64 + i)) v0[i] = 0xff800000u;        // -inf
+              if (masked(j * Cfg::BN + c2 * 64 + 32 + i)) v1[i] = 0xff800000u;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mx[k] = fmaxf(mx[k], fmaxf(__uint_as_float(v0[i + k]), __uint_as_float(v1[i + k])));
+          }
+        }
+        const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;   // scale > 0 (host check): max commutes
+        // Lazy rescaling: the reference maximum only moves when some row of this warp exceeds it by more than 2^8 (P then stays <= 256,
+        // fine in fp16; sums and O are fp32).  Only then does the softmax wait for PV_{j-1} and touch O.
+        const bool grow = m_tile > m_run + 8.0f;       // also true for j == 0 (m_run = -inf) unless the whole row is masked
+        float alpha = 1.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = fmaxf(m_run, m_tile);
+          const float m_ref = (m_new == -INFINITY) ? 0.f : m_new;
+          alpha = (m_run == -INFINITY) ? 0.f : fast_exp2(m_run - m_ref);
+          if (j > 0) {
+            mbar_wait(pv_done(x), (g - 1) & 1u);       // O_X is quiescent: PV_X(j-1) retired
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t v[32];
+              tmem_ld32(tO + (uint32_t)(c * 32), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+              tmem_st32(tO + (uint32_t)(c * 32), v);
+            }
+          }
+          m_run = m_new;
+        }
+        const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+        // ---- pass 2: P = exp2(scale * S - m) as fp16 pairs.  Chunk c re-reads score columns [32c, 32c+32) and writes packed columns
+        // [16c, 16c+16): a chunk's P never lands on columns a later chunk still has to read.
+        float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          uint32_t v0[32], v1[32];
+          tmem_ld32(tS + (uint32_t)(c2 * 64), v0);
+          tmem_ld32(tS + (uint32_t)(c2 * 64 + 32), v1);
+          tmem_ld_wait();
+          if (need_mask) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (masked(j * Cfg::BN + c2 * 64 + i)) v0[i] = 0xff800000u;
+              if (masked(j * Cfg::BN + c2 * 64 + 32 + i)) v1[i] = 0xff800000u;
+            }
+          }
+          uint32_t pk0[16], pk1[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), p.scale_log2, -m_use));
+            const float xb0 = fmaf(__uint_as_float(v0[2 * i + 1]), p.scale_log2, -m_use);
+            const float b0 = (PE > 0 && (i % (PE > 0 ? PE : 1)) == PE - 1) ? pp_exp2_poly3(xb0) : fast_exp2(xb0);
+            const float a1 = fast_exp2(fmaf(__uint_as_float(v1[2 * i]), p.scale_log2, -m_use));
+            const float xb1 = fmaf(__uint_as_float(v1[2 * i + 1]), p.scale_log2, -m_use);
+            const float b1 = (PE > 0 && (i % (PE > 0 ? PE : 1)) == PE - 1) ? pp_exp2_poly3(xb1) : fast_exp2(xb1);
+            rs4[i & 3] += (a0 + b0) + (a1 + b1);
+            __half2 h0 = __floats2half2_rn(a0, b0), h1 = __floats2half2_rn(a1, b1);
+            pk0[i] = *(uint32_t*)&h0, pk1[i] = *(uint32_t*)&h1;
+          }
+          tmem_st16(tS + (uint32_t)(c2 * 32), pk0);
+          tmem_st16(tS + (uint32_t)(c2 * 32 + 16), pk1);
+        }
+        tmem_st_wait();
+        l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+        tc_fence_before();
+        mbar_arrive(p_full(x));
+      }
+      // ---- epilogue: normalise and store this row (D contiguous fp16)
+      const uint32_t gl = g - 1;
+      mbar_wait(pv_done(x), gl & 1u);
+      tc_fence_after();
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __half* orow = p.o + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)qrow * p.o_ss;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tO + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (c == D / 32 - 1) {              // accumulator drained into registers: the MMA warp may start the next item on it
+          tc_fence_before();
+          mbar_arrive(o_free(x));
+        }
+        if (qrow < p.sq) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            const int col = c * 32 + i;
+            if (col + 8 <= p.d) {
+              uint4 q;
+              __half2* hh = (__half2*)&q;
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                hh[t] = __floats2half2_rn(__uint_as_float(v[i + 2 * t]) * inv, __uint_as_float(v[i + 2 * t + 1]) * inv);
+              *(uint4*)(orow + col) = q;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int D, int PE>
+static int launch_pp_pe(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, PpParams p, int B, int H, cudaStream_t st) {
+  using Cfg = PpCfg<D>;
+  static bool attr = false;
+  static int sms = 0;
+  if (!attr) {
+    SEEDX_CUDA(cudaFuncSetAttribute(flash_attn_pp_kernel<D, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    int dev = 0;
+    SEEDX_CUDA(cudaGetDevice(&dev));
+    SEEDX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    attr = true;
+  }
+  p.m_pairs = (p.sq + 2 * Cfg::BM - 1) / (2 * Cfg::BM);
+  p.heads = H;
+  const long long items = (long long)p.m_pairs * H * B;
+  if (items > 0x7fffffffLL) return -1;
+  p.items = (int)items;
+  const int grid = p.items < sms ? p.items : sms;
+  const cudaError_t e = launch_k(flash_attn_pp_kernel<D, PE>, grid, 320, Cfg::SMEM_BYTES, st, tq, tk, tv, p);
+  count_launch();
+  return check_cuda(e != cudaSuccess ? e : cudaGetLastError(), "flash_attn_pp_kernel launch");
+}
+
+// share of exponentials on the FMA pipe: 1 / (2 * PE); env SEEDX_PP_POLY_EVERY (0 = none, 1, 2, 4) overrides the default for experiments
+template <int D>
+static int launch_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const PpParams& p, int B, int H, cudaStream_t st) {
+  static int pe = -1;
+  if (pe < 0) {
+    const char* e = getenv("SEEDX_PP_POLY_EVERY");
+    pe = e ? atoi(e) : SEEDX_PP_POLY_EVERY;
+  }
+  switch (pe) {
+    case 0: return launch_pp_pe<D, 0>(tq, tk, tv, p, B, H, st);
+    case 1: return launch_pp_pe<D, 1>(tq, tk, tv, p, B, H, st);
+    case 4: return launch_pp_pe<D, 4>(tq, tk, tv, p, B, H, st);
+    default: return launch_pp_pe<D, 2>(tq, tk, tv, p, B, H, st);
+  }
+}
+
+static int make_map_pp(CUtensorMap* m, const void* ptr, int d, int s, int H, int B, long long ss, long long sh, long long sb) {
+  uint64_t dims[4] = {(uint64_t)d, (uint64_t)s, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)ss * 2, (uint64_t)(H > 1 ? sh : ss * s) * 2, (uint64_t)(B > 1 ? sb : ss * s) * 2};
+  uint32_t box[4] = {64, 128, 1, 1};
+  return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// returns -1 when the problem is not eligible (the caller falls back to the one-tile tcgen05 kernel, then to the mma.sync kernel)
+int attention_pp_try(const seedx_attn_args* a, cudaStream_t st) {
+  if (a->d > 128 || a->d % 8 != 0 || a->sq < 256 || a->sk < 96 || !(a->scale > 0.f)) return -1;
+  // causal problems waste the masked upper tiles of the second query tile, and few items balance badly over the SMs at 256 rows per
+  // item: both cases are faster on the one-tile kernel (measured: causal S=2048 369 vs 485 TF/s; B=2 S=4096 432 vs 484 TF/s)
+  if (a->causal) return -1;
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long items = (long long)((a->sq + 255) / 256) * a->heads * a->batch;
+    if (items < 3LL * sms) return -1;
+  }
+  if (a->o_stride_s % 8 || a->o_stride_h % 8 || a->o_stride_b % 8 || (uintptr_t)a->o % 16) return -1;
+  const long long str[] = {a->q_stride_s, a->q_stride_h, a->q_stride_b, a->k_stride_s, a->k_stride_h, a->k_stride_b,
+                           a->v_stride_s, a->v_stride_h, a->v_stride_b};
+  for (long long s : str)
+    if (s % 8 != 0 || s < 0) return -1;
+  if (a->q_stride_s == 0 || a->k_stride_s == 0 || a->v_stride_s == 0) return -1;
+  if ((a->heads > 1 && (a->q_stride_h == 0 || a->k_stride_h == 0 || a->v_stride_h == 0)) ||
+      (a->batch > 1 && (a->k_stride_b == 0 || a->v_stride_b == 0)))
+    return -1;
+  const bool qb = !(a->batch > 1 && a->q_stride_b == 0);
+  CUtensorMap tq, tk, tv;
+  if (make_map_pp(&tq, a->q, a->d, a->sq, a->heads, qb ? a->batch : 1, a->q_stride_s, a->q_stride_h, a->q_stride_b)) return -1;
+  if (make_map_pp(&tk, a->k, a->d, a->sk, a->heads, a->batch, a->k_stride_s, a->k_stride_h, a->k_stride_b)) return -1;
+  if (make_map_pp(&tv, a->v, a->d, a->sk, a->heads, a->batch, a->v_stride_s, a->v_stride_h, a->v_stride_b)) return -1;
+  PpParams p;
+  p.o = (__half*)a->o;
+  p.o_sb = a->o_stride_b, p.o_sh = a->o_stride_h, p.o_ss = a->o_stride_s;
+  p.sq = a->sq, p.sk = a->sk, p.d = a->d;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.causal = a->causal;
+  p.q_batched = qb ? 1 : 0;
+  if (a->d <= 64) return launch_pp<64>(tq, tk, tv, p, a->batch, a->heads, st);
+  return launch_pp<128>(tq, tk, tv, p, a->batch, a->heads, st);
+}
+
+}  // namespace seedx

@@ -27,7 +27,7 @@ struct FaParams {
 
 // one value in (2 * POLY_EVERY) takes the polynomial exp2; 0 = MUFU only
 #ifndef SEEDX_FA_POLY_EVERY
-#define SEEDX_FA_POLY_EVERY 2
+#define SEEDX_FA_POLY_EVERY 4
 #endif
 constexpr int POLY_EVERY = SEEDX_FA_POLY_EVERY;
 
@@ -365,7 +365,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 }
 
 #ifndef SEEDX_FA_NS
-#define SEEDX_FA_NS 4
+#define SEEDX_FA_NS 2
 #endif
 template <int D>
 static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, FaParams p, int B, int H, cudaStream_t st) {

@@ -25,16 +25,18 @@ def mk(shape, seed, scale=1.0):
     (1, 40, 174, 174, 128, True),      # LLaMA prefill (causal, ragged)
     (1, 4, 370, 370, 128, True),
     (2, 10, 4096, 4096, 64, False),    # UNet self-attention 64x64
+    (8, 20, 1024, 1024, 64, False),    # UNet self-attention 32x32 at batch: enough items for the two-tile kernel
+    (5, 16, 1024, 1024, 104, False),   # ViT MHSA, 5 views: two-tile kernel, padded head dim
     (2, 20, 1024, 64, 64, False),      # UNet cross-attention
     (2, 16, 64, 128, 64, False),       # perceiver
     (2, 16, 1, 65, 64, False),         # AttentionPool2d (single query)
     (1, 3, 77, 33, 72, False),
 ])
-@pytest.mark.parametrize("impl", ["tcgen05", "mma_sync"])
+@pytest.mark.parametrize("impl", ["tcgen05", "tcgen05_one_tile", "mma_sync"])
 def test_attention(B, H, Sq, Sk, D, causal, impl):
     from seedx_b200 import ops
     from seedx_b200._lib import lib
-    lib().seedx_attention_set_impl(1 if impl == "mma_sync" else 0)
+    lib().seedx_attention_set_impl({"tcgen05": 0, "tcgen05_one_tile": 2, "mma_sync": 1}[impl])
     shared_q = (Sq == 256 and Sk == 1024)
     q = mk((1 if shared_q else B, Sq, H, D), 1).half()
     k = mk((B, Sk, H, D), 2).half()
@@ -47,8 +49,10 @@ def test_attention(B, H, Sq, Sk, D, causal, impl):
     lib().seedx_attention_set_impl(0)
     ref = F.scaled_dot_product_attention(qf, k.float().permute(0, 2, 1, 3), v.float().permute(0, 2, 1, 3), is_causal=causal, scale=scale)
     assert rel(o.permute(0, 2, 1, 3), ref) < 2e-3
-    if impl == "tcgen05" and Sq >= 128 and Sk >= 96 and D <= 128:
-        assert used == 2, "the tcgen05 kernel should have handled this shape"
+    if impl != "mma_sync" and Sq >= 128 and Sk >= 96 and D <= 128:
+        assert used in (2, 3), "a tcgen05 kernel should have handled this shape, got %d" % used
+        if impl == "tcgen05_one_tile":
+            assert used == 2
 
 
 def test_attention_strided_qkv():

@@ -9,7 +9,7 @@ for (B, H, Sq, Sk, D, causal) in [(2, 10, 4096, 4096, 64, False), (8, 10, 4096, 
     q = torch.randn(B, Sq, H, D, device="cuda").half(); k = torch.randn(B, Sk, H, D, device="cuda").half(); v = torch.randn(B, Sk, H, D, device="cuda").half()
     o = torch.empty(B, Sq, H, D, device="cuda", dtype=torch.float16)
     res = []
-    for impl in (0, 1):
+    for impl in (0, 2):
         lib().seedx_attention_set_impl(impl)
         f = lambda: ops.attention(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), o.permute(0, 2, 1, 3), scale=D ** -0.5, causal=causal)
         f(); f(); torch.cuda.synchronize()
@@ -19,6 +19,6 @@ for (B, H, Sq, Sk, D, causal) in [(2, 10, 4096, 4096, 64, False), (8, 10, 4096, 
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
         fl = 4.0 * B * H * Sq * Sk * D * (0.5 if causal else 1.0)
-        res.append(f"{'tc' if lib().seedx_attention_last_impl()==2 else 'mma'}: {ms*1e3:8.1f} us {fl/ms/1e9:7.1f} TF/s")
+        res.append(f"{ {3:'pp',2:'tc',1:'mma'}[lib().seedx_attention_last_impl()] }: {ms*1e3:8.1f} us {fl/ms/1e9:7.1f} TF/s")
     lib().seedx_attention_set_impl(0)
     print(f"B={B} H={H} Sq={Sq} Sk={Sk} D={D} causal={causal}: " + " | ".join(res), flush=True)
