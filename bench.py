@@ -271,9 +271,9 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "CUDA-graph launch of one UNet sample-forward (gemm_tc_kernel = 59% of its device time)",
+            "roofline": {"bound": "tensor", "kernel": "CUDA-graph launch of one UNet sample-forward: 960 kernels, gemm_tc_kernel (GEMM + implicit-GEMM conv) = 71% of its device time, tcgen05 attention 21% (profiles/r01_unet_forward_launches_final.md)",
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": (achieved / tensor_peak) if achieved else None,
-                         "traffic": None, "peak_source": peak_src, "flop_per_launch": UNET_TFLOP * 2 * B * 1e12,
+                         "traffic": None, "traffic_note": "per-kernel DRAM bytes of the dominant GEMM shape: profiles/r01_ncu_full_geglu_gemm_final.md (95.8 MB/launch vs 131 MB algorithmic)", "peak_source": peak_src, "flop_per_launch": UNET_TFLOP * 2 * B * 1e12,
                          "launch_ms": unet_ms, "work_per_image_tflop": work_per_image_tflop(),
                          "pipeline_frac": (value / world) * work_per_image_tflop() / tensor_peak},
             "cpu_baseline": cpu_base,

@@ -62,5 +62,15 @@ def check(rc, what):
         raise SeedxError(f"{what} failed (rc={rc}): {lib().seedx_last_error().decode()}")
 
 
+_replayed = 0
+
+
+def note_replay(kernels):
+    """A captured CUDA graph holding `kernels` library launches was replayed once (they do not pass through the C entry points again)."""
+    global _replayed
+    _replayed += int(kernels)
+
+
 def launch_count():
-    return int(lib().seedx_launch_count())
+    """Library kernels launched by this process: direct launches (counted inside libseedx.so) + kernels executed by graph replays."""
+    return int(lib().seedx_launch_count()) + _replayed

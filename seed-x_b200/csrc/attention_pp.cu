@@ -418,9 +418,19 @@ static int make_map_pp(CUtensorMap* m, const void* ptr, int d, int s, int H, int
   return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// shortest key sequence routed to the tcgen05 kernels (a 128-key tile is then partly padding); env SEEDX_FA_MIN_SK overrides for experiments
+static int fa_min_sk() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEEDX_FA_MIN_SK");
+    v = e ? atoi(e) : 96;
+  }
+  return v;
+}
+
 // returns -1 when the problem is not eligible (the caller falls back to the one-tile tcgen05 kernel, then to the mma.sync kernel)
 int attention_pp_try(const seedx_attn_args* a, cudaStream_t st) {
-  if (a->d > 128 || a->d % 8 != 0 || a->sq < 256 || a->sk < 96 || !(a->scale > 0.f)) return -1;
+  if (a->d > 128 || a->d % 8 != 0 || a->sq < 256 || a->sk < fa_min_sk() || !(a->scale > 0.f)) return -1;
   // causal problems waste the masked upper tiles of the second query tile, and few items balance badly over the SMs at 256 rows per
   // item: both cases are faster on the one-tile kernel (measured: causal S=2048 369 vs 485 TF/s; B=2 S=4096 432 vs 484 TF/s)
   if (a->causal) return -1;

@@ -10,6 +10,7 @@
 // maximum moved.  QK^T of tile j+1 overlaps the softmax of tile j.
 //
 // Replaces the same reference call sites as seedx_attention_f16 (include/seedx.h) for head dims <= 128 and long sequences.
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/seedx.h"
 
@@ -397,10 +398,20 @@ static int make_map(CUtensorMap* m, const void* ptr, int d, int s, int H, int B,
   return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+// shortest key sequence routed to the tcgen05 kernels (a 128-key tile is then partly padding); env SEEDX_FA_MIN_SK overrides for experiments
+static int fa_min_sk() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SEEDX_FA_MIN_SK");
+    v = e ? atoi(e) : 96;
+  }
+  return v;
+}
+
 // returns -1 when the problem is not eligible for the tensor-memory kernel (caller falls back to the mma.sync kernel)
 int attention_tc_try(const seedx_attn_args* a, cudaStream_t st) {
   // short key sequences (UNet cross-attention over 64 context tokens) would fill under half of one 128-key tile: mma.sync kernel is faster
-  if (a->d > 128 || a->d % 8 != 0 || a->sq < 128 || a->sk < 96 || !(a->scale > 0.f)) return -1;
+  if (a->d > 128 || a->d % 8 != 0 || a->sq < 128 || a->sk < fa_min_sk() || !(a->scale > 0.f)) return -1;
   if (a->o_stride_s % 8 || a->o_stride_h % 8 || a->o_stride_b % 8 || (uintptr_t)a->o % 16) return -1;
   const long long str[] = {a->q_stride_s, a->q_stride_h, a->q_stride_b, a->k_stride_s, a->k_stride_h, a->k_stride_b,
                            a->v_stride_s, a->v_stride_h, a->v_stride_b};

@@ -12,7 +12,7 @@ import os
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import SeedxError
 
 LLAMA_13B = dict(vocab=32330, hidden=5120, layers=40, heads=40, ffn=13824, eps=1e-5)
@@ -228,13 +228,16 @@ class LlamaForCausalLM:
                     s_ = torch.cuda.Stream()
                     s_.wait_stream(torch.cuda.current_stream())
                     g = torch.cuda.CUDAGraph()
+                    n0 = _lib.launch_count()
                     with torch.cuda.graph(g, stream=s_):
                         self._decode_step(hidden, img_dev, eos_id, suppress_eos)
+                    g.n_kernels = _lib.launch_count() - n0
                     torch.cuda.current_stream().wait_stream(s_)
                     self._graphs[gkey] = g
             for i in range(steps):
                 if g is not None:
                     g.replay()
+                    _lib.note_replay(g.n_kernels)
                 else:
                     self._decode_step(hidden, img_dev, eos_id, suppress_eos)
                 if eos_id is not None and not suppress_eos and (i + 1) % sync_every == 0:

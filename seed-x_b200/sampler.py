@@ -8,7 +8,7 @@ with the per-step host work reduced to: one timestep write, one CUDA-graph repla
 """
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import SeedxError
 
 
@@ -86,12 +86,15 @@ class DenoiseLoop:
                 self._forward()                      # warm-up outside capture (lazy one-time setup inside the library)
             torch.cuda.current_stream().wait_stream(s)
             self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
             with torch.cuda.graph(self.graph):
                 self.eps = self._forward()
+            self.graph_kernels = _lib.launch_count() - n0
         for i in range(steps):
             self.t_dev.fill_(sch.timesteps[i])
             if self.use_graph:
                 self.graph.replay()
+                _lib.note_replay(self.graph_kernels)
             else:
                 self.eps = self._forward()
             ops.cfg_euler_step(self.eps, self.x, self.unet_in, self.branches, guidance, image_guidance, sch.sigmas[i], sch.sigmas[i + 1])
