@@ -1,0 +1,95 @@
+"""Host-side logic and the closed-form approximations the kernels use, checked on the CPU (no GPU, no compute calls into the library)."""
+import json
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exp2_polynomial_of_the_attention_kernels():
+    """attention_pp.cu / attention_tc.cu `exp2_poly3`: x = n + f, 2^f by a degree-3 minimax polynomial, 2^n through the exponent field.
+    Restated in numpy float32 with the same operation order; relative error must stay below the fp16 rounding of P (4.9e-4)."""
+    src = open(os.path.join(ROOT, "seed-x_b200", "csrc", "attention_pp.cu")).read()
+    for c in ("0.0551716685f", "0.2426111251f", "0.6932609677f", "0.9999280572f", "12582912.0f"):
+        assert c in src, "coefficient %s changed in the kernel: update this restatement" % c
+    x = np.linspace(-30.0, 8.5, 200001).astype(np.float32)
+    t = (x + np.float32(12582912.0)).astype(np.float32)
+    f = (x - (t - np.float32(12582912.0))).astype(np.float32)
+    q = np.float32(0.0551716685) * f + np.float32(0.2426111251)
+    q = q * f + np.float32(0.6932609677)
+    q = q * f + np.float32(0.9999280572)
+    r = (q.view(np.int32) + (t.view(np.int32) << 23)).view(np.float32)
+    ref = np.exp2(x.astype(np.float64))
+    assert np.abs(r / ref - 1).max() < 1.0e-4
+    assert np.abs(f).max() <= 0.5 + 1e-6
+
+
+def test_gelu_and_silu_closed_forms_of_the_gemm_epilogue():
+    """common.cuh `gelu_erf_fast` (Abramowitz-Stegun 7.1.26 in FMA form) and `silu` vs torch, fp32."""
+    x = torch.linspace(-12, 12, 100001, dtype=torch.float32)
+    ax = x.abs()
+    z = ax * 0.70710678118654752440
+    t = 1.0 / (0.3275911 * z + 1.0)
+    poly = t * 1.061405429 - 1.453152027
+    poly = poly * t + 1.421413741
+    poly = poly * t - 0.284496736
+    poly = poly * t + 0.254829592
+    poly = poly * t
+    w = ax * 0.84932180028801904272
+    erf_abs = 1.0 - poly * torch.exp2(-w * w)
+    gelu = 0.5 * ax * erf_abs + 0.5 * x
+    assert (gelu - torch.nn.functional.gelu(x.double()).float()).abs().max() < 5e-7 * 12
+    silu = x / (1.0 + torch.exp2(-1.4426950408889634 * x))
+    assert (silu - torch.nn.functional.silu(x.double()).float()).abs().max() < 1e-5
+
+
+def test_static_condition_tree_helpers():
+    from seedx_b200.sampler import _copy_tree, _same_layout
+    a = dict(n_ctx=4, down=[[torch.zeros(2, 3)], [torch.zeros(5)]], aug=torch.zeros(2, 2))
+    b = dict(n_ctx=4, down=[[torch.ones(2, 3)], [torch.full((5,), 2.0)]], aug=torch.full((2, 2), 3.0))
+    assert _same_layout(a, b)
+    ptr = a["down"][0][0].data_ptr()
+    _copy_tree(a, b)
+    assert a["down"][0][0].data_ptr() == ptr and float(a["down"][0][0].sum()) == 6.0 and float(a["aug"][0, 0]) == 3.0
+    assert not _same_layout(a, dict(b, n_ctx=5))
+    assert not _same_layout(a, dict(b, aug=torch.zeros(2, 3)))
+    assert not _same_layout(a, dict(n_ctx=4, down=[[torch.ones(2, 3)]], aug=b["aug"]))
+
+
+def test_launch_accounting_counts_graph_replays():
+    from seedx_b200 import _lib
+    n0 = _lib.launch_count()
+    _lib.note_replay(960)
+    _lib.note_replay(205)
+    assert _lib.launch_count() - n0 == 1165
+
+
+def test_groupnorm_workspace_size_covers_every_resolution():
+    """seedx_groupnorm_ws_bytes(n, groups) must bound final stats + per-CTA partials + tickets for any hw (host arithmetic only)."""
+    import ctypes as C
+    from seedx_b200._lib import lib
+    f = lib().seedx_groupnorm_ws_bytes
+    for n in (1, 2, 8, 16, 64):
+        got = f(C.c_int64(n), C.c_int(32))
+        for hw in (64, 1024, 4096, 16384, 1 << 20):
+            spb = max(32, -(-hw * n // 592))
+            spb = min(spb, hw)
+            nblk = -(-hw // spb)
+            need = n * 32 * 2 * 8 + n * nblk * 32 * 2 * 4 + n * 4
+            assert got >= need, (n, hw, got, need)
+
+
+def test_reference_arm_prints_the_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] in ("port", "reference") and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and math.isfinite(line["value"])
