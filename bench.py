@@ -238,6 +238,12 @@ def main():
         ms_dev, launches, stages = timed(e2e=False)
         ms_e2e, _, _ = timed(e2e=True)
     clocks = cs.summary()
+    # one extra untimed step with section marks on (seedx_b200.trace): where the step goes, stage by stage
+    from seedx_b200 import trace
+    trace.enable(True)
+    step(e2e=False)
+    detail = trace.summary()
+    trace.enable(False)
 
     if rank == 0:
         imgs = world * B * args.steps
@@ -267,6 +273,7 @@ def main():
                        "l2": "working set (35 GB fp16 weights/GPU) exceeds the 126 MB L2; no explicit flush", "weights": "random-init, full sizes",
                        "small_debug_models": bool(args.small)},
             "stage_ms_per_step": stages,
+            "stage_detail_ms": detail,
             "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * 1024 * 1024 * 3,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,

@@ -6,11 +6,13 @@ Restates
       LlamaDecoderLayer.forward 261-313, LlamaModel.forward 477-609, LlamaForCausalLM.forward 643-746),
   /root/reference/src/models/mllm/generation.py:19-31 (AutoImageTokenGenerationProcessor.__call__),
   /root/reference/src/models/mllm/seed_x.py:130-223 (ContinuousLVLM.generate),
+  /root/reference/src/models/mllm/peft_models.py:62-82 + PEFT 0.4.0 (vendored: /root/reference/proj/peft) LoRA forward, lora.py:808-832,
   transformers==4.30.2 GenerationMixin.greedy_search as used at seed_x.py:184-189 (THIRD-PARTY, absent:
   the loop semantics are "parity unpinned" — the installed transformers 5.5 cannot drive the reference model).
 PINNED: forward logits / hidden states / KV and the logits processor against golden vectors produced by the reference
 modules themselves (tests/golden/llama_tiny.pt, make_golden.py); the greedy loop against the same loop run around the
-reference forward + the reference's own processor class.
+reference forward + the reference's own processor class; the LoRA / vocabulary-growth path against the reference's
+get_peft_model_with_resize_embedding over its vendored PEFT (tests/golden/llama_lora_tiny.pt).
 """
 import math
 
@@ -35,9 +37,33 @@ def rope(x, pos, base=10000.0):
     return x * cos + rot * sin
 
 
-def llama_forward(sd, cfg, x, pos0, cache):
+def resize_embeddings(sd, new_vocab):
+    """get_peft_model_with_resize_embedding's vocabulary growth (/root/reference/src/models/mllm/peft_models.py:62-82): appended input
+    rows = mean of the old input rows; appended output rows = 3 x the mean of the old output rows."""
+    sd = dict(sd)
+    for key, gain in (("model.embed_tokens.weight", 1.0), ("lm_head.weight", 3.0)):
+        w = sd[key].float()
+        extra = new_vocab - w.shape[0]
+        if extra > 0:
+            sd[key] = torch.cat([w, (w.mean(dim=0, keepdim=True) * gain).expand(extra, -1)], dim=0)
+    return sd
+
+
+def lora_linear(sd, lora, name, x):
+    """PEFT 0.4.0 ``Linear.forward`` un-merged, eval mode (/root/reference/proj/peft/src/peft/tuners/lora.py:808-832):
+    ``F.linear(x, W) + lora_B(lora_A(x)) * (lora_alpha / r)``.  lora = dict(scaling=, sd={'<name>.lora_A.weight', '<name>.lora_B.weight'})."""
+    y = x @ sd[name + ".weight"].float().t()
+    if lora is not None and name + ".lora_A.weight" in lora["sd"]:
+        a, b = lora["sd"][name + ".lora_A.weight"].float(), lora["sd"][name + ".lora_B.weight"].float()
+        y = y + ((x @ a.t()) @ b.t()) * lora["scaling"]
+    return y
+
+
+def llama_forward(sd, cfg, x, pos0, cache, lora=None):
     """x: [T, D] input embeddings of positions pos0..pos0+T-1; cache: list per layer of (K [t,H,d], V [t,H,d]) or None.
-    Returns (logits [T,V], last_hidden post-final-norm [T,D], new cache).  Causal within the new tokens, full over the past."""
+    Returns (logits [T,V], last_hidden post-final-norm [T,D], new cache).  Causal within the new tokens, full over the past.
+    lora: optional un-merged adapters (see lora_linear)."""
+    lin = lambda name, t: lora_linear(sd, lora, name, t)  # noqa: E731
     D, H = cfg["hidden"], cfg["heads"]
     d = D // H
     T = x.shape[0]
@@ -47,9 +73,9 @@ def llama_forward(sd, cfg, x, pos0, cache):
     for i in range(cfg["layers"]):
         p = f"model.layers.{i}."
         n = rms_norm(h, sd[p + "input_layernorm.weight"], cfg["eps"])
-        q = (n @ sd[p + "self_attn.q_proj.weight"].t()).reshape(T, H, d)
-        k = (n @ sd[p + "self_attn.k_proj.weight"].t()).reshape(T, H, d)
-        v = (n @ sd[p + "self_attn.v_proj.weight"].t()).reshape(T, H, d)
+        q = lin(p + "self_attn.q_proj", n).reshape(T, H, d)
+        k = lin(p + "self_attn.k_proj", n).reshape(T, H, d)
+        v = lin(p + "self_attn.v_proj", n).reshape(T, H, d)
         q, k = rope(q, pos), rope(k, pos)
         if cache is not None and cache[i] is not None:
             k = torch.cat([cache[i][0], k], dim=0)
@@ -60,10 +86,10 @@ def llama_forward(sd, cfg, x, pos0, cache):
         mask = torch.arange(S)[None, :] > (pos0 + torch.arange(T))[:, None]   # key s visible to query t iff s <= pos0 + t
         att = att.masked_fill(mask[None], float("-inf")).softmax(-1)
         o = torch.einsum("hts,shd->thd", att, v).reshape(T, D)
-        h = h + o @ sd[p + "self_attn.o_proj.weight"].t()
+        h = h + lin(p + "self_attn.o_proj", o)
         n = rms_norm(h, sd[p + "post_attention_layernorm.weight"], cfg["eps"])
-        g = F.silu(n @ sd[p + "mlp.gate_proj.weight"].t()) * (n @ sd[p + "mlp.up_proj.weight"].t())
-        h = h + g @ sd[p + "mlp.down_proj.weight"].t()
+        g = F.silu(lin(p + "mlp.gate_proj", n)) * lin(p + "mlp.up_proj", n)
+        h = h + lin(p + "mlp.down_proj", g)
     hn = rms_norm(h, sd["model.norm.weight"], cfg["eps"])
     return hn @ sd["lm_head.weight"].t(), hn, new_cache
 

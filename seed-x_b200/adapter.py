@@ -12,7 +12,7 @@ import numpy as np
 import torch
 from PIL import Image
 
-from . import ops
+from . import ops, trace
 from ._lib import SeedxError
 from .sampler import DenoiseLoop, decode_to_uint8
 
@@ -115,13 +115,17 @@ class SDXLAdapter:
         p, n, pp, npool = self.get_image_embeds(image_pil=image_pil, image_tensor=image_tensor, image_embeds=image_embeds,
                                                return_negative=True, image_size=input_image_size)
         B = p.shape[0]
+        trace.mark("detok.resampler_xl")
         loop = self._loop(B, height, width)
         tid = torch.tensor([[height, width, 0, 0, height, width]], dtype=torch.float32, device=self.device).repeat(2 * B, 1)
         loop.set_condition(torch.cat([n, p]), torch.cat([npool, pp]), tid)        # batch order [negative, positive]
+        trace.mark("detok.prepare_cond")
         lat = loop.run(self._noise(B, height, width, seed, latents), steps=num_inference_steps, guidance=guidance_scale)
+        trace.mark("detok.denoise_loop")
         if output_type == "latent":
             return lat.clone()
         u8 = decode_to_uint8(self.vae, lat)
+        trace.mark("detok.vae_decode")
         return u8 if output_type == "uint8" else self._to_pil(u8)
 
 

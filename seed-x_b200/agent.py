@@ -6,7 +6,7 @@ The training ``forward`` (losses, seed_x.py:48-128) is out of scope.
 """
 import torch
 
-from . import ops
+from . import ops, trace
 from ._lib import SeedxError
 from .vit import ResamplerWeights
 
@@ -55,8 +55,12 @@ class ContinuousLVLM:
             wt = torch.zeros((w.shape[1], 8), dtype=torch.float16, device=w.device)
             wt[:, :4] = w.t().to(torch.float16)
             self.patch_w = wt.to(dev)
+        # a fine-tuned agent checkpoint also carries the LLM's trained tensors under 'llm.' — LoRA pairs, modules_to_save norms,
+        # embeddings (README.md:150-160; the reference's load_state_dict(strict=False) loads them into the wrapped model, utils.py:25-42)
+        llm_sd = {k[len("llm."):]: v for k, v in sd.items() if k.startswith("llm.")}
+        unexpected = self.llm.apply_peft_state_dict(llm_sd) if llm_sd else []
         self._loaded = True
-        return [], []
+        return [], ["llm." + k for k in unexpected]
 
     def encode_images(self, image_embeds, patch_positions):
         """input_resampler(image_embeds) + patch-position embedding (seed_x.py:164-171): [N,256,4096] -> fp32 [N*64, D]."""
@@ -144,9 +148,11 @@ class ContinuousLVLM:
             chunk = requests[c0:c0 + 8]
             pairs = [self._embed_request(r.get("input_ids"), r.get("image_embeds"), r.get("embeds_cmp_mask"), r.get("ids_cmp_mask"),
                                          r.get("patch_positions")) for r in chunk]
+            trace.mark("llm.embed+input_resampler")
             outs = self.llm.generate_greedy_batch([p[0] for p in pairs], [p[1] for p in pairs], img_ids=img_ids, max_new_tokens=max_new_tokens,
                                                   eos_id=eos, suppress_eos=suppress_eos)
             results += [self._harvest(tokenizer, o, p[0].numel(), num_img_gen_tokens) for o, p in zip(outs, pairs)]
+            trace.mark("llm.harvest+output_resampler")
         return results
 
     def generate(self, tokenizer, prompt=None, input_ids=None, image_embeds=None, embeds_cmp_mask=None, ids_cmp_mask=None,

@@ -1,5 +1,5 @@
 """Minimal stand-ins for the third-party helpers the reference entry scripts import but this image does not ship
-(hydra, omegaconf, pyrootutils, diffusers; SURVEY.md §5 'Config / flag system', §8b).  ``install()`` registers them in
+(hydra, omegaconf, pyrootutils, diffusers, peft; SURVEY.md §5 'Config / flag system', §8b).  ``install()`` registers them in
 sys.modules only when the real package is missing, so `import hydra` / `from omegaconf import OmegaConf` /
 `from diffusers import AutoencoderKL, UNet2DConditionModel, EulerDiscreteScheduler` in src/inference/eval_*.py resolve.
 """
@@ -104,6 +104,11 @@ def install():
         p = types.ModuleType("pyrootutils")
         p.setup_root = setup_root
         sys.modules["pyrootutils"] = p
+    if _missing("peft"):
+        from . import lora
+        pm = types.ModuleType("peft")
+        pm.LoraConfig = lora.LoraConfig
+        sys.modules["peft"] = pm
     if _missing("diffusers"):
         from . import sdxl
         d = types.ModuleType("diffusers")

@@ -8,7 +8,7 @@ import time
 
 import torch
 
-from . import ops, synth
+from . import ops, synth, trace
 from .adapter import SDXLAdapter
 from .agent import ContinuousLVLM, Resampler
 from .llm import LLAMA_13B, LlamaForCausalLM
@@ -91,8 +91,10 @@ class SeedXEngine:
         Returns uint8 device tensor [B, 1024, 1024, 3] and per-stage CUDA-event times (ms)."""
         B = len(text_ids)
         e0 = self._ev()
+        trace.mark("start")
         feats = self.vit(views)                                                   # [B*n_views, 256, 4096] fp16
         e1 = self._ev()
+        trace.mark("vit")
         reqs = []
         for b in range(B):
             ids, mask = self.build_prompt(n_views, text_ids[b])

@@ -12,7 +12,7 @@ import os
 
 import torch
 
-from . import _lib, ops
+from . import _lib, ops, trace
 from ._lib import SeedxError
 
 LLAMA_13B = dict(vocab=32330, hidden=5120, layers=40, heads=40, ffn=13824, eps=1e-5)
@@ -102,11 +102,110 @@ class LlamaForCausalLM:
                 wdown=h(sd[p + "mlp.down_proj.weight"])))
         self.norm = f(sd["model.norm.weight"])
         self.lm_head = h(sd["lm_head.weight"])
+        if self.embed.shape[0] != cfg["vocab"] or self.lm_head.shape[0] != cfg["vocab"]:
+            raise SeedxError(f"checkpoint vocabulary {self.embed.shape[0]} != configured vocab_size {cfg['vocab']}")
         d = D // H
         self.inv_freq = (1.0 / (10000.0 ** (torch.arange(0, d, 2).float() / d))).to(dev)   # modeling_llama_xformer.py:101
         self._alloc_state()
         self._loaded = True
         return [], []
+
+    # ---- fine-tuned checkpoints: partial updates and LoRA adapters, folded into the packed weights in place ------------------
+    @property
+    def config(self):
+        """the two HF config fields the reference reads through the model object (peft_models.py:63, seed_x.py)"""
+        import types
+        return types.SimpleNamespace(vocab_size=self.cfg["vocab"], hidden_size=self.cfg["hidden"], tie_word_embeddings=False)
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def resize_token_embeddings(self, vocab_size):
+        """HF ``resize_token_embeddings`` + the reference's initialisation of the new rows (peft_models.py:62-82): input rows = mean of the
+        old input rows, output rows = 3 x the mean of the old output rows.  Shrinking truncates."""
+        if not self._loaded:
+            raise SeedxError("resize_token_embeddings: weights not loaded")
+        old = self.cfg["vocab"]
+        if vocab_size == old:
+            return self
+        def grow(w, gain):
+            new = torch.empty((vocab_size, w.shape[1]), device=w.device, dtype=w.dtype)
+            n = min(old, vocab_size)
+            new[:n] = w[:n]
+            if vocab_size > old:
+                new[old:] = (w.float().mean(dim=0, keepdim=True) * gain).to(w.dtype)
+            return new
+        self.embed, self.lm_head = grow(self.embed, 1.0), grow(self.lm_head, 3.0)
+        self.cfg["vocab"] = int(vocab_size)
+        self._alloc_state(self.slots)
+        return self
+
+    def update_weights(self, plain=None, lora=None, scaling=1.0):
+        """plain: {HF parameter name: tensor} replacements; lora: {HF module name: (A [r,in], B [out,r])} low-rank updates added as
+        ``W += scaling * B @ A`` (fp32 arithmetic at load time, result rounded to the fp16 storage format).  The packed device tensors
+        are updated IN PLACE, so captured decode graphs stay valid.  Returns the names that matched nothing."""
+        from .lora import lora_delta
+        if not self._loaded:
+            raise SeedxError("update_weights: load the base checkpoint first")
+        plain, lora = dict(plain or {}), dict(lora or {})
+        dev, cfg = self.device, self.cfg
+        D, Fh = cfg["hidden"], cfg["ffn"]
+
+        def fold(dst, name):
+            """dst: a (possibly strided) view into a packed fp16 weight; name: HF module name, e.g. model.layers.0.self_attn.q_proj"""
+            w = plain.pop(name + ".weight", None)
+            ab = lora.pop(name, None)
+            if w is None and ab is None:
+                return
+            cur = w.to(dev).float() if w is not None else dst.float()
+            if tuple(cur.shape) != tuple(dst.shape):
+                raise SeedxError(f"{name}.weight: shape {tuple(cur.shape)} != {tuple(dst.shape)}")
+            if ab is not None:
+                delta = lora_delta(ab[0].to(dev), ab[1].to(dev), scaling)
+                if tuple(delta.shape) != tuple(dst.shape):
+                    raise SeedxError(f"LoRA update of {name}: shape {tuple(delta.shape)} != {tuple(dst.shape)}")
+                cur = cur + delta
+            dst.copy_(cur.to(torch.float16))
+
+        def setf(dst, name):
+            v = plain.pop(name, None)
+            if v is not None:
+                if tuple(v.shape) != tuple(dst.shape):
+                    raise SeedxError(f"{name}: shape {tuple(v.shape)} != {tuple(dst.shape)}")
+                dst.copy_(v.to(dev).to(dst.dtype))
+
+        for i, L in enumerate(self.layers):
+            p = f"model.layers.{i}."
+            for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+                fold(L["wqkv"][j * D:(j + 1) * D], p + "self_attn." + n)
+            fold(L["wo"], p + "self_attn.o_proj")
+            gu = L["wgu"].view(Fh, 2, D)                                   # rows [up_0, gate_0, up_1, gate_1, ...]
+            fold(gu[:, 0], p + "mlp.up_proj")
+            fold(gu[:, 1], p + "mlp.gate_proj")
+            fold(L["wdown"], p + "mlp.down_proj")
+            setf(L["ln1"], p + "input_layernorm.weight")
+            setf(L["ln2"], p + "post_attention_layernorm.weight")
+        setf(self.norm, "model.norm.weight")
+        for attr, name in (("embed", "model.embed_tokens"), ("lm_head", "lm_head")):
+            w = plain.get(name + ".weight")
+            if w is not None and w.shape[0] != getattr(self, attr).shape[0]:
+                raise SeedxError(f"{name}.weight has {w.shape[0]} rows, the model {getattr(self, attr).shape[0]}: call resize_token_embeddings first")
+            fold(getattr(self, attr), name)
+        return [k for k in plain if "rotary_emb" not in k] + list(lora)
+
+    def apply_peft_state_dict(self, sd, adapter="default"):
+        """keys as saved from a PEFT-wrapped model (``base_model.model.…lora_A.default.weight`` …): LoRA pairs are merged with the
+        scaling of ``self.peft_config`` (set by get_peft_model_with_resize_embedding), modules_to_save / plain tensors replace."""
+        from .lora import split_peft_state_dict
+        base, lora, saved = split_peft_state_dict(sd, adapter)
+        if lora and getattr(self, "peft_config", None) is None:
+            raise SeedxError("the checkpoint holds LoRA adapters but the LLM was not built with a peft_config "
+                             "(use configs/clm_models/llm_seed_x_lora.yaml)")
+        sc = self.peft_config.scaling if lora else 1.0
+        for mod, (a, _) in lora.items():
+            if a.shape[0] != self.peft_config.r:
+                raise SeedxError(f"{mod}: adapter rank {a.shape[0]} != peft_config.r {self.peft_config.r}")
+        return self.update_weights({**base, **saved}, lora, sc)
 
     def _alloc_state(self, slots=1):
         cfg, dev = self.cfg, self.device
@@ -218,6 +317,7 @@ class LlamaForCausalLM:
             ops.gemv(self.lm_head, xs[P - 1], self.logits[s], rms_w=self.norm, eps=self.cfg["eps"])
         self.state.copy_(torch.tensor(st0, dtype=torch.int32))
         ops.logits_argmax(self.logits, img_dev, self.seq, self.state, eos_id, suppress_eos)
+        trace.mark("llm.prefill")
         steps = max_new_tokens - 1
         if steps > 0:
             g = None
@@ -243,6 +343,7 @@ class LlamaForCausalLM:
                 if eos_id is not None and not suppress_eos and (i + 1) % sync_every == 0:
                     if bool((self.state[:n_req, 1] != 0).all().item()):
                         break
+        trace.mark("llm.decode")
         st = self.state.cpu().tolist()
         seq_host = self.seq.cpu()
         outs = []

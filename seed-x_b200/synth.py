@@ -280,6 +280,20 @@ def llama_state_dict(cfg):
     return sd
 
 
+def lora_fixture(shapes):
+    """fine-tuned tensors of the LoRA fixture (tests/golden/llama_lora_tiny.pt): a pure function of the PEFT key and its shape —
+    lora_A ~ in^-0.5, lora_B ~ 0.5 r^-0.5 (a visible but not dominant update), modules_to_save norm weights ~ N(1, 0.2)."""
+    out = {}
+    for k, shp in shapes.items():
+        if ".lora_A." in k:
+            out[k] = randn("lora:" + k, shp, std=shp[1] ** -0.5)
+        elif ".lora_B." in k:
+            out[k] = randn("lora:" + k, shp, std=0.5 * shp[1] ** -0.5)
+        else:
+            out[k] = randn("lora:" + k, shp, std=0.2, mean=1.0)
+    return out
+
+
 def agent_state_dict(llm_hidden, vit_dim, sd=None):
     """ContinuousLVLM parameters besides the LLM (seed_x.py:22-45): input/output Resampler + patch_pos_embed."""
     sd = OrderedDict() if sd is None else sd

@@ -39,8 +39,19 @@ def install_stubs():
         sys.modules["xformers.ops"] = xo
     if REF not in sys.path:
         sys.path.insert(0, REF)
+    # the reference's `src` is a namespace package (no __init__.py) while this repo ships a regular `src` shim package, which would win
+    # the import regardless of sys.path order: bind `src` to the reference tree explicitly
+    cur = sys.modules.get("src")
+    if cur is None or list(getattr(cur, "__path__", [])) != [REF + "/src"]:
+        for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+            del sys.modules[k]
+        pkg = types.ModuleType("src")
+        pkg.__path__ = [REF + "/src"]
+        sys.modules["src"] = pkg
 
 
 def ref_module(dotted):
     install_stubs()
-    return importlib.import_module(dotted)
+    m = importlib.import_module(dotted)
+    assert m.__file__.startswith(REF + "/"), f"{dotted} resolved to {m.__file__}, not the reference"
+    return m

@@ -122,6 +122,63 @@ def golden_llama():
     print("llama_tiny: text", out["text_gen_ids"][:8], "img-span tail", out["img_gen_ids"][62:])
 
 
+def golden_llama_lora():
+    """Reference get_peft_model_with_resize_embedding (src/models/mllm/peft_models.py:27-106) over the reference LlamaForCausalLM with the
+    PEFT 0.4.0 vendored under /root/reference/proj/peft: vocabulary grown 1024 -> 1034 (mean-initialised rows), LoRA r=4 alpha=8 on
+    the seven projections, modules_to_save norms; UN-MERGED forward in fp32 = golden logits / hidden states."""
+    import contextlib
+    import types
+    import transformers  # noqa: F401  (must be imported before the accelerate stub)
+    from transformers import LlamaConfig
+    from _ref_import import install_stubs
+    install_stubs()
+
+    class _Any(types.ModuleType):
+        def __getattr__(self, n):
+            if n.startswith("__"):
+                raise AttributeError(n)
+            return lambda *a, **k: None
+    for name in ["accelerate", "accelerate.hooks", "accelerate.utils", "accelerate.utils.modeling", "accelerate.big_modeling"]:
+        sys.modules.setdefault(name, _Any(name))
+    sys.modules["deepspeed"].zero = types.SimpleNamespace(GatheredParameters=lambda *a, **k: contextlib.nullcontext())
+    sys.path.insert(0, "/root/reference/proj/peft/src")
+    import peft
+    from seedx_b200 import compat
+    compat.install()                                        # hydra / omegaconf stand-ins for the reference module's imports
+    assert peft.__version__ == "0.4.0" and "/root/reference" in peft.__file__
+    pm = ref_module("src.models.mllm.peft_models")
+    mod = ref_module("src.models.mllm.modeling_llama_xformer")
+    cfg = synth.TINY_LLAMA
+    hc = LlamaConfig(vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], intermediate_size=cfg["ffn"], num_hidden_layers=cfg["layers"],
+                     num_attention_heads=cfg["heads"], rms_norm_eps=cfg["eps"], max_position_embeddings=2048)
+    hc.pad_token_id = 0
+    hc.tie_word_embeddings = False
+    model = mod.LlamaForCausalLM(hc).eval()
+    missing, unexpected = model.load_state_dict(synth.llama_state_dict(cfg), strict=False)
+    assert not unexpected and all("rotary" in m for m in missing), (missing, unexpected)
+    new_vocab = cfg["vocab"] + 10
+    lcfg = peft.LoraConfig(r=4, lora_alpha=8, lora_dropout=0.05, task_type="CAUSAL_LM",
+                           target_modules=["q_proj", "v_proj", "k_proj", "o_proj", "gate_proj", "down_proj", "up_proj"],
+                           modules_to_save=["input_layernorm", "post_attention_layernorm", "norm"])
+    pmodel = pm.get_peft_model_with_resize_embedding(model, peft_config=lcfg, vocab_size=new_vocab, torch_dtype="fp32").eval()
+    sd = pmodel.state_dict()
+    shapes = {k: tuple(v.shape) for k, v in sd.items() if ".lora_" in k or ".modules_to_save." in k}
+    assert len(shapes) == 2 * 7 * cfg["layers"] + 2 * cfg["layers"] + 1, len(shapes)
+    pmodel.load_state_dict(synth.lora_fixture(shapes), strict=False)
+    out = {"peft_keys": list(sd.keys()), "shapes": shapes, "new_vocab": new_vocab, "r": 4, "lora_alpha": 8,
+           "embed_new_rows": sd["base_model.model.model.embed_tokens.weight"][cfg["vocab"]:].clone(),
+           "head_new_rows": sd["base_model.model.lm_head.weight"][cfg["vocab"]:].clone()}
+    P = 40
+    ids = [1] + [int(v) for v in (synth.randn("lora_ids", (P - 4,)).abs() * 1000).long() % (cfg["vocab"] - 3) + 3] + [new_vocab - 1, new_vocab - 7, 17]
+    out["ids"] = ids
+    with torch.no_grad():
+        o = pmodel(input_ids=torch.tensor([ids]), attention_mask=torch.ones(1, P, dtype=torch.long), position_ids=torch.arange(P)[None],
+                   output_hidden_states=True, return_dict=True, use_cache=False)
+    out["logits"], out["hidden"] = o.logits[0].float(), o.hidden_states[-1][0].float()
+    torch.save(out, os.path.join(HERE, "llama_lora_tiny.pt"))
+    print("llama_lora_tiny: logits", tuple(out["logits"].shape), "keys e.g.", [k for k in out["peft_keys"] if "layers.0.self_attn.q_proj" in k])
+
+
 def golden_resampler_xl():
     rs = ref_module("src.models.detokenizer.resampler")
     out = {}
@@ -161,13 +218,15 @@ def golden_preprocess():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["vit", "resamplers", "llama", "resampler_xl", "preprocess"]
+    which = sys.argv[1:] or ["vit", "resamplers", "llama", "llama_lora", "resampler_xl", "preprocess"]
     if "vit" in which:
         golden_vit()
     if "resamplers" in which:
         golden_resamplers()
     if "llama" in which:
         golden_llama()
+    if "llama_lora" in which:
+        golden_llama_lora()
     if "resampler_xl" in which:
         golden_resampler_xl()
     if "preprocess" in which:

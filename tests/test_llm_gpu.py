@@ -166,3 +166,52 @@ def test_agent_generate_vs_oracle():
     e = rel(out["img_gen_feat"], ref["img_gen_feat"])
     print(f"agent img_gen_feat rel = {e:.3e}")
     assert e < TOL
+
+
+def test_lora_checkpoint_through_the_yaml_factory_matches_reference_peft(tmp_path):
+    """"Inference with your own model" (reference README.md:144-167): configs/clm_models/llm_seed_x_lora.yaml ->
+    get_peft_model_with_resize_embedding (vocabulary grown, LoRA config attached) -> ContinuousLVLM.from_pretrained loads an agent
+    checkpoint whose 'llm.base_model.model.*' keys carry lora_A/lora_B/modules_to_save tensors -> merged in place on the device.
+    Golden = UN-MERGED fp32 forward of the reference model under its vendored PEFT 0.4.0 (tests/golden/llama_lora_tiny.pt)."""
+    import json
+    from safetensors.torch import save_file
+    from seedx_b200 import compat
+    compat.install()
+    import hydra
+    from omegaconf import OmegaConf
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = torch.load(os.path.join(GOLD, "llama_lora_tiny.pt"))
+    cfg = synth.TINY_LLAMA
+    d = tmp_path / "llm"
+    os.makedirs(d)
+    json.dump(dict(vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], num_hidden_layers=cfg["layers"], num_attention_heads=cfg["heads"],
+                   intermediate_size=cfg["ffn"], rms_norm_eps=cfg["eps"]), open(d / "config.json", "w"))
+    save_file({k: v.half().contiguous() for k, v in synth.llama_state_dict(cfg).items()}, str(d / "model.safetensors"))
+    y = OmegaConf.load(os.path.join(root, "configs", "clm_models", "llm_seed_x_lora.yaml"))
+    assert y["peft_config"]["r"] == 32 and y["peft_config"]["lora_alpha"] == 32 and y["vocab_size"] == 32330     # the shipped values
+    y["model"]["pretrained_model_name_or_path"] = str(d)
+    y["peft_config"].update(r=g["r"], lora_alpha=g["lora_alpha"])
+    y["vocab_size"] = g["new_vocab"]
+    llm = hydra.utils.instantiate(y)
+    assert llm.config.vocab_size == g["new_vocab"] and llm.peft_config.scaling == g["lora_alpha"] / g["r"]
+    assert rel(llm.embed[cfg["vocab"]:], g["embed_new_rows"]) < 1e-3 and rel(llm.lm_head[cfg["vocab"]:], g["head_new_rows"]) < 1e-3
+
+    from seedx_b200.agent import ContinuousLVLM, Resampler
+    vit_dim = 320
+    ckpt = dict(synth.agent_state_dict(cfg["hidden"], vit_dim))
+    ckpt.update({"llm." + k: v for k, v in synth.lora_fixture(g["shapes"]).items()})
+    torch.save(ckpt, tmp_path / "pytorch_model.bin")
+    ids = torch.tensor(g["ids"])
+    before, _ = llm.logits_all(llm.prefill(llm.get_input_embeddings()(ids)[0]))
+    agent = ContinuousLVLM.from_pretrained(llm=llm, input_resampler=Resampler(8, cfg["hidden"], 2, vit_dim),
+                                           output_resampler=Resampler(8, vit_dim, 2, cfg["hidden"]), add_patch_pos=True, vit_down=True,
+                                           pretrained_model_path=str(tmp_path / "pytorch_model.bin"))
+    logits, hid = agent.llm.logits_all(agent.llm.prefill(agent.llm.get_input_embeddings()(ids)[0]))
+    e0, e1, e2 = rel(before, g["logits"]), rel(logits, g["logits"]), rel(hid, g["hidden"])
+    print(f"LoRA merged: logits rel = {e1:.3e}, hidden rel = {e2:.3e} (without the adapters: {e0:.2f})")
+    assert e0 > 0.05 and e1 < TOL and e2 < TOL
+    # adapters without a peft_config are refused, rank mismatches too
+    from seedx_b200._lib import SeedxError
+    m2, _ = _llm()
+    with pytest.raises(SeedxError):
+        m2.apply_peft_state_dict(synth.lora_fixture(g["shapes"]))

@@ -62,6 +62,42 @@ def test_llama_oracle_matches_reference():
     assert gen == g["img_gen_ids"] and rel(h, g["img_hidden"]) < 2e-5
 
 
+def test_llama_lora_oracle_and_merge_match_reference_peft():
+    """un-merged LoRA forward restated in the oracle, the load-time merge of seedx_b200.lora and the vocabulary growth, all against the
+    reference's get_peft_model_with_resize_embedding run over its vendored PEFT 0.4.0 (golden = un-merged fp32 logits)."""
+    from oracle import llm
+    from seedx_b200 import lora
+    g = torch.load(os.path.join(GOLD, "llama_lora_tiny.pt"))
+    cfg = dict(synth.TINY_LLAMA)
+    base = llm.resize_embeddings(synth.llama_state_dict(cfg), g["new_vocab"])
+    assert torch.allclose(base["model.embed_tokens.weight"][cfg["vocab"]:], g["embed_new_rows"], atol=1e-6)
+    assert torch.allclose(base["lm_head.weight"][cfg["vocab"]:], g["head_new_rows"], atol=1e-6)
+    cfg["vocab"] = g["new_vocab"]
+    ft = synth.lora_fixture(g["shapes"])                                  # PEFT key names exactly as the reference model reports them
+    scaling = g["lora_alpha"] / g["r"]
+    # (1) oracle, un-merged
+    _, pairs, saved = lora.split_peft_state_dict(ft)
+    assert len(pairs) == 7 * cfg["layers"] and len(saved) == 2 * cfg["layers"] + 1
+    sd_u = {**base, **saved}
+    lsd = {}
+    for mod, (a, b) in pairs.items():
+        lsd[mod + ".lora_A.weight"], lsd[mod + ".lora_B.weight"] = a, b
+    x = sd_u["model.embed_tokens.weight"][torch.tensor(g["ids"])]
+    logits, hid, _ = llm.llama_forward(sd_u, cfg, x, 0, None, lora=dict(scaling=scaling, sd=lsd))
+    assert rel(logits, g["logits"]) < 2e-5 and rel(hid, g["hidden"]) < 2e-5
+    # (2) product merge: a PEFT-named state dict holding base + adapters -> plain HF names
+    full = {"base_model.model." + k: v for k, v in base.items() if "norm" not in k and "rotary_emb" not in k}   # PEFT wraps the saved norms: no plain key for them
+    full.update(ft)
+    assert set(full) == {k for k in g["peft_keys"] if ".original_module." not in k and "rotary_emb" not in k}
+    merged = lora.merge_lora_state_dict(full, scaling)
+    assert set(merged) == {k for k in base if "rotary_emb" not in k}
+    logits_m, hid_m, _ = llm.llama_forward(merged, cfg, x, 0, None)
+    assert rel(logits_m, g["logits"]) < 2e-5 and rel(hid_m, g["hidden"]) < 2e-5
+    # the adapters matter: without them the logits are far away
+    logits_0, _, _ = llm.llama_forward(base, cfg, x, 0, None)
+    assert rel(logits_0, g["logits"]) > 0.05
+
+
 def test_resampler_xl_oracle_matches_reference():
     from oracle import resampler_xl as orx
     g = torch.load(os.path.join(GOLD, "resampler_xl.pt"))
