@@ -136,6 +136,12 @@ class SDXLAdapterWithLatentImage(SDXLAdapter):
 
     def __init__(self, unet, resampler, full_ft=False, set_trainable_late=False, vit_down=False, **kw):
         super().__init__(unet, resampler, full_ft=full_ft, vit_down=vit_down)
+        # set_trainable() widens conv_in to 8 input channels at construction: the first 4 keep the SDXL weights, the 4 image-latent channels
+        # start at zero (adapter_modules.py:183-198).  The packed conv_in already pads its input channels to 64 with zeros and the sampler's
+        # UNet input buffer always carries 8 channels, so the widened layer is the one in memory: only the declared width changes.  A
+        # fine-tuned checkpoint ('unet.*' keys) then replaces the whole UNet in load_state_dict.
+        if getattr(unet, "_loaded", False) and unet.cfg.get("in_channels") == 4:
+            unet.cfg["in_channels"] = 8
 
     def init_pipe(self, vae, scheduler, visual_encoder, image_transform, dtype=torch.float16, device="cuda"):
         super().init_pipe(vae, scheduler, visual_encoder, image_transform, None, dtype, device)

@@ -37,6 +37,38 @@ class GreedyOutput:
         self.n_generated = n_generated
 
 
+class AutoImageTokenGenerationProcessor:
+    """Same constructor and ``img_ids_list`` as the reference logits processor (/root/reference/src/models/mllm/generation.py:9-31).
+    The rule itself — after ``<img>`` / ``<img_k>`` force the next id of the span (score = max + 10), otherwise set the scores of
+    ``<img_0..n-1>`` and ``</img>`` to 0.0 — runs inside ``logits_argmax_kernel`` on the device; ``__call__`` restates it for host tensors
+    so the object still works as a plain HF ``LogitsProcessor``."""
+
+    def __init__(self, tokenizer, num_img_gen_tokens=64):
+        s = "".join(["<img>"] + ["<img_{:05d}>".format(i) for i in range(num_img_gen_tokens)] + ["</img>"])
+        self.img_ids_list = tokenizer.encode(s, add_special_tokens=False)
+
+    def __call__(self, input_ids, scores):
+        for i in range(input_ids.shape[0]):
+            cur = int(input_ids[i, -1])
+            if cur in self.img_ids_list[:-1]:
+                scores[i, ..., self.img_ids_list[self.img_ids_list.index(cur) + 1]] = scores[i, ...].max() + 10.0
+            else:
+                scores[i, ..., torch.tensor(self.img_ids_list[1:], dtype=torch.long)] = 0.0
+        return scores
+
+
+class GreedySearchOutput(dict):
+    """``return_dict_in_generate=True`` result: ``.sequences`` [1, P+n] int64 and ``.hidden_states`` in the HF layout the reference
+    consumes at seed_x.py:196-197 — one tuple per generation step whose LAST element is the post-norm hidden state, [1, P, D] for the
+    first step and [1, 1, D] afterwards (the per-layer intermediate states are not materialised)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
 class LlamaForCausalLM:
     def __init__(self, cfg=None, max_len=2048, device="cuda"):
         self.cfg = dict(LLAMA_13B if cfg is None else cfg)
@@ -53,7 +85,7 @@ class LlamaForCausalLM:
         d = pretrained_model_name_or_path
         c = json.load(open(os.path.join(d, "config.json")))
         cfg = dict(vocab=c["vocab_size"], hidden=c["hidden_size"], layers=c["num_hidden_layers"], heads=c["num_attention_heads"],
-                   ffn=c["intermediate_size"], eps=c.get("rms_norm_eps", 1e-5))
+                   ffn=c["intermediate_size"], eps=c.get("rms_norm_eps", 1e-5), eos=c.get("eos_token_id", 2))
         m = cls(cfg)
         sd = {}
         idx = os.path.join(d, "pytorch_model.bin.index.json")
@@ -280,7 +312,7 @@ class LlamaForCausalLM:
         ops.logits_argmax(self.logits, img_ids, self.seq, self.state, eos_id, suppress_eos)
 
     def generate_greedy_batch(self, input_ids_list, inputs_embeds_list, img_ids=None, max_new_tokens=120, eos_id=None, suppress_eos=False,
-                              use_graph=True, sync_every=32):
+                              use_graph=True, sync_every=32, keep_prefill_hidden=False):
         """Greedy decoding of up to 8 independent requests in lock-step (HF greedy_search per request, seed_x.py:184-189):
         request r's inputs_embeds [P_r, D] feed its prefill, then its last id each step.  Returns a list of GreedyOutput."""
         if not self._loaded:
@@ -303,7 +335,7 @@ class LlamaForCausalLM:
             self._hidden = torch.zeros((slots, self.max_len, self.cfg["hidden"]), device=dev, dtype=torch.float32)
             self._graphs = {}
         hidden = self._hidden
-        st0, plens = [], []
+        st0, plens, pre_hidden = [], [], []
         for s in range(slots):
             r = min(s, n_req - 1)                       # padding slots replay the last request
             ids = torch.as_tensor(input_ids_list[r]).reshape(-1)
@@ -315,6 +347,8 @@ class LlamaForCausalLM:
             self.seq[s, :P].copy_(ids.to(dev, torch.int32))
             xs = self.prefill(inputs_embeds_list[r].reshape(P, -1).to(dev, torch.float32), slot=s)
             ops.gemv(self.lm_head, xs[P - 1], self.logits[s], rms_w=self.norm, eps=self.cfg["eps"])
+            if keep_prefill_hidden and s < n_req:      # post-norm states of the prompt positions (HF hidden_states[0][-1])
+                pre_hidden.append(ops.layernorm(xs, self.norm, None, self.cfg["eps"], out_dtype=torch.float32, rms=True))
         self.state.copy_(torch.tensor(st0, dtype=torch.int32))
         ops.logits_argmax(self.logits, img_dev, self.seq, self.state, eos_id, suppress_eos)
         trace.mark("llm.prefill")
@@ -350,7 +384,45 @@ class LlamaForCausalLM:
         for r in range(n_req):
             n_gen = st[r][1] if st[r][1] else st[r][2]   # stop at (and include) the first EOS, like HF greedy_search
             outs.append(GreedyOutput(seq_host[r, : plens[r] + n_gen].to(torch.int64).unsqueeze(0), hidden[r, : max(n_gen - 1, 0)].clone(), n_gen))
+            outs[-1].prefill_hidden = pre_hidden[r] if keep_prefill_hidden else None
         return outs
+
+    def generate(self, input_ids=None, inputs_embeds=None, output_hidden_states=False, return_dict_in_generate=False, logits_processor=None,
+                 max_new_tokens=20, do_sample=False, num_beams=1, temperature=None, top_p=None, eos_token_id="default", **kw):
+        """The slice of HF ``GenerationMixin.generate`` that the reference calls (seed_x.py:184-189; transformers==4.30.2 greedy_search,
+        SURVEY.md B.1): greedy decoding of ONE prompt whose first step consumes ``inputs_embeds`` [1,P,D] and later steps the embedding
+        of the last id; stops at EOS or after ``max_new_tokens``.  ``temperature`` / ``top_p`` are accepted and unused because
+        ``do_sample=False`` (the reference passes them the same way).  ``logits_processor``: an iterable holding at most one
+        AutoImageTokenGenerationProcessor (anything exposing ``img_ids_list``); its rule runs on the device."""
+        if do_sample or num_beams != 1:
+            raise SeedxError("only greedy search (do_sample=False, num_beams=1) is implemented: it is the only mode the reference uses")
+        if input_ids is None:
+            raise SeedxError("generate() needs input_ids (the returned sequences start with them)")
+        ids = torch.as_tensor(input_ids)
+        if ids.dim() == 1:
+            ids = ids.unsqueeze(0)
+        if ids.shape[0] != 1:
+            raise SeedxError("generate() decodes one prompt per call like the reference (seed_x.py:191 reads sequences[0]); "
+                             "use generate_greedy_batch for lock-step decoding of several requests")
+        P = ids.shape[1]
+        emb = inputs_embeds if inputs_embeds is not None else self.get_input_embeddings()(ids)
+        emb = emb.reshape(P, -1)
+        img_ids = None
+        for proc in (logits_processor or []):
+            if not hasattr(proc, "img_ids_list") or img_ids is not None:
+                raise SeedxError(f"unsupported logits processor {type(proc).__name__}: only one AutoImageTokenGenerationProcessor runs on the device")
+            img_ids = list(proc.img_ids_list)
+        eos = self.cfg.get("eos", 2) if isinstance(eos_token_id, str) else eos_token_id
+        out = self.generate_greedy_batch([ids[0]], [emb], img_ids=img_ids, max_new_tokens=max_new_tokens, eos_id=eos,
+                                         keep_prefill_hidden=bool(output_hidden_states))[0]
+        if not return_dict_in_generate:
+            return out.sequences
+        res = GreedySearchOutput(sequences=out.sequences)
+        if output_hidden_states:
+            steps = [(out.prefill_hidden.unsqueeze(0),)]
+            steps += [(out.last_hidden_states[j].view(1, 1, -1),) for j in range(out.last_hidden_states.shape[0])]
+            res["hidden_states"] = tuple(steps)
+        return res
 
     def generate_greedy(self, input_ids, inputs_embeds, img_ids=None, max_new_tokens=120, eos_id=None, suppress_eos=False, use_graph=True,
                         sync_every=32):

@@ -19,3 +19,17 @@ with torch.no_grad():
     out = agent.generate(tokenizer=tok, input_ids=input_ids, image_embeds=image_embeds, embeds_cmp_mask=torch.ones(views.shape[0], dtype=torch.bool),
                          patch_positions=patch_pos, ids_cmp_mask=ids_cmp_mask, max_new_tokens=512, num_img_gen_tokens=64)
 print(re.sub("<[^>]*>", "", out["text"]))
+
+# detection / grounding (reference flow: eval_img2text_seed_x_i.py:181-231): <box_start><loc-…>×4<box_end> spans -> boxes drawn on the image
+image = Image.open("demo_images/ground.png").convert("RGB")
+views, patch_pos = process_anyres_image(image, m["image_transform"], demo.grid_pinpoints(), demo.BASE_RES)
+input_ids, ids_cmp_mask = demo.image_prompt(tok, views.shape[0], "Is there anything in the image that can protect me from catching the flu virus "
+                                            "when I go out? Show me the location.")
+with torch.no_grad():
+    image_embeds = m["visual_encoder"](views.to("cuda"))
+    out = agent.generate(tokenizer=tok, input_ids=input_ids, image_embeds=image_embeds, embeds_cmp_mask=torch.ones(views.shape[0], dtype=torch.bool),
+                         patch_positions=patch_pos, ids_cmp_mask=ids_cmp_mask, max_new_tokens=512, num_img_gen_tokens=64)
+print(out["text"])
+bbox = demo.extract_box(out["text"])
+if bbox is not None:
+    demo.visualize_bbox(image, bbox, "vis/ground.png")

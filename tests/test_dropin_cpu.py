@@ -1,0 +1,179 @@
+"""Drop-in surface checked without a GPU: prompt layouts, grounding post-processing, the launcher for unmodified reference scripts, and
+(in the build container, where /root/reference exists) a static check that every keyword the reference's entry scripts pass to the
+factories / generate() / init_pipe() is a named parameter of the replacement."""
+import ast
+import glob
+import inspect
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from seedx_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+
+
+def test_chat_prompt_layout_single_and_multi_turn():
+    from seedx_b200 import demo
+    tok = synth.SynthTokenizer()
+    q = "What is in the image?"
+    a_ids, a_mask = demo.image_prompt(tok, 3, q)
+    b_ids, b_mask = demo.chat_prompt(tok, [q], views_per_image=[3])
+    assert torch.equal(a_ids, b_ids) and torch.equal(a_mask, b_mask)          # one turn, one image == the eval_img2text layout
+    assert int(a_mask.sum()) == 3 * 64
+    # the layout of eval_img2text_seed_x_i.py:142-147 spelled out
+    img = "".join("<img_{:05d}>".format(i) for i in range(64))
+    text = "[INST] " + ("<patch>" + img + "</patch>") * 2 + "<img>" + img + "</img>" + q + " [/INST]\n"
+    assert a_ids[0].tolist() == [tok.bos_token_id] + tok.encode(text)
+    # two images (2 + 1 views), three turns, system message
+    ids, mask = demo.chat_prompt(tok, ["q1", "a1", "q2"], views_per_image=[2, 1], system_message="sys")
+    assert int(mask.sum()) == 3 * 64
+    want = "sys\n[INST] " + "<patch>" + img + "</patch>" + "<img>" + img + "</img>" + "<img>" + img + "</img>" + "q1 [/INST]\na1\n[INST] q2 [/INST]\n"
+    assert ids[0].tolist() == [tok.bos_token_id] + tok.encode(want)
+    # masked rows are exactly the <img_k> ids, in order, once per view
+    first = tok.tok2id["<img_00000>"]
+    assert ids[0][mask[0]].tolist() == list(range(first, first + 64)) * 3
+    ids_f, _ = demo.chat_prompt(tok, ["draw a cat"], force_image=True)
+    assert ids_f[0, -1].item() == tok.tok2id["<img>"]
+    with pytest.raises(ValueError):
+        demo.chat_prompt(tok, ["q1", "a1"])
+
+
+def _ref_function(path, name):
+    """source of one top-level function of a reference script, executed in an empty namespace (no reference code is stored here)"""
+    tree = ast.parse(open(path).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {}
+    import re
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), {"re": re}, ns)
+    return ns[name]
+
+
+def test_extract_box_and_pixel_corners():
+    from seedx_b200 import demo
+    s = "The mask <box_start><loc-112><loc-56><loc-40><loc-20><box_end> and <box_start><loc-0><loc-223><loc-10><loc-5><box_end>."
+    assert demo.extract_box(s) == [[112, 56, 40, 20], [0, 223, 10, 5]]
+    assert demo.extract_box("no boxes here <loc-3>") is None
+    # (x_center, y_center, w, h) in 224 bins on a 448 x 896 image
+    assert demo.box_to_pixels([112, 56, 40, 20], 448, 896) == (184, 184, 264, 264)
+    assert demo.box_to_pixels([0, 223, 10, 5], 448, 896) == (-10, 882, 10, 902)
+    if os.path.isdir(REF):
+        ref = _ref_function(os.path.join(REF, "src/inference/eval_img2text_seed_x_i.py"), "extract_box")
+        for t in (s, "none", "<box_start><loc-7><box_end><box_start><box_end>", "<box_start>a<loc-1>b<loc-22>c<box_end>"):
+            assert demo.extract_box(t) == ref(t)
+
+
+def test_visualize_bbox_draws_the_rectangle(tmp_path):
+    import numpy as np
+    from PIL import Image
+    from seedx_b200 import demo
+    img = Image.new("RGB", (448, 224), (0, 0, 0))
+    out = demo.visualize_bbox(img, [[112, 112, 56, 56]], str(tmp_path / "vis" / "g.png"))
+    a = np.asarray(out)
+    x1, y1, x2, y2 = demo.box_to_pixels([112, 112, 56, 56], 448, 224)
+    assert (x1, y1, x2, y2) == (168, 84, 280, 140)
+    assert tuple(a[y1, x1]) == (0, 255, 0) and tuple(a[y2, x2]) == (0, 255, 0) and tuple(a[(y1 + y2) // 2, (x1 + x2) // 2]) == (0, 0, 0)
+    assert os.path.exists(tmp_path / "vis" / "g.png")
+
+
+def test_launcher_runs_a_reference_style_script(tmp_path):
+    """a script that begins like the reference's (top-level third-party imports, pyrootutils marker, sibling import, YAML `_target_`)
+    runs unmodified through `python -m seedx_b200.run` even though hydra / omegaconf / pyrootutils / diffusers are not installed"""
+    d = tmp_path / "proj" / "src" / "inference"
+    os.makedirs(d)
+    open(tmp_path / "proj" / ".project-root", "w").close()
+    (d / "any_res.py").write_text("def process_anyres_image(*a):\n    return 'sibling import ok'\n")
+    (d / "eval_demo.py").write_text(
+        "import hydra\nimport torch\nimport os\nimport pyrootutils\nfrom omegaconf import OmegaConf\n"
+        "from diffusers import AutoencoderKL, UNet2DConditionModel, EulerDiscreteScheduler\n"
+        "from any_res import process_anyres_image\n"
+        "root = pyrootutils.setup_root(__file__, indicator='.project-root', pythonpath=True)\n"
+        "import sys\nassert __name__ == '__main__' and sys.argv[1:] == ['--flag']\n"
+        "cfg = OmegaConf.load('configs/processer/qwen_448_transform.yaml')\n"
+        "t = hydra.utils.instantiate(cfg)\n"
+        "lc = OmegaConf.load('configs/clm_models/llm_seed_x_lora.yaml')\n"
+        "print('OK', callable(t), process_anyres_image(), os.path.basename(str(root)), lc.peft_config.r, lc['vocab_size'])\n")
+    r = subprocess.run([sys.executable, "-m", "seedx_b200.run", str(d / "eval_demo.py"), "--flag"], cwd=ROOT, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().endswith("OK True sibling import ok proj 32 32330"), r.stdout
+
+
+# ---- static call-surface check against the reference's own entry scripts ---------------------------------------------------------------
+def _calls(tree):
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute):
+            yield node
+
+
+def _named_params(fn):
+    return {p.name for p in inspect.signature(fn).parameters.values() if p.kind in (p.POSITIONAL_OR_KEYWORD, p.KEYWORD_ONLY)}
+
+
+@needs_ref
+def test_reference_scripts_only_use_keywords_the_replacement_names():
+    from seedx_b200 import compat
+    compat.install()
+    from seedx_b200.adapter import SDXLAdapter, SDXLAdapterWithLatentImage
+    from seedx_b200.agent import ContinuousLVLM
+    from seedx_b200.sdxl import AutoencoderKL, EulerDiscreteScheduler, UNet2DConditionModel
+    scripts = sorted(glob.glob(os.path.join(REF, "src/inference/eval_*.py")))
+    assert len(scripts) == 7
+    seen = 0
+    for path in scripts:
+        tree = ast.parse(open(path).read())
+        src = open(path).read()
+        edit = "with_latent_image" in src
+        adapter_cls = SDXLAdapterWithLatentImage if edit else SDXLAdapter
+        for c in _calls(tree):
+            kws = {k.arg for k in c.keywords if k.arg is not None}
+            owner = c.func.value.id if isinstance(c.func.value, ast.Name) else None
+            if c.func.attr == "generate" and owner == "agent_model":
+                target = ContinuousLVLM.generate
+            elif c.func.attr == "generate" and owner == "adapter":
+                target = adapter_cls.generate
+            elif c.func.attr == "init_pipe" and owner == "adapter":
+                target = adapter_cls.init_pipe
+            elif c.func.attr == "from_pretrained" and owner in ("AutoencoderKL", "UNet2DConditionModel", "EulerDiscreteScheduler"):
+                target = {"AutoencoderKL": AutoencoderKL, "UNet2DConditionModel": UNet2DConditionModel,
+                          "EulerDiscreteScheduler": EulerDiscreteScheduler}[owner].from_pretrained
+            else:
+                continue
+            missing = kws - _named_params(target)
+            assert not missing, f"{os.path.basename(path)}:{c.lineno} passes {sorted(missing)} which {target.__qualname__} does not name"
+            seen += 1
+    assert seen >= 20, seen
+
+
+@needs_ref
+def test_reference_yaml_targets_resolve_with_identical_keys():
+    """every inference YAML of the reference has a twin here with the same `_target_`s and keys (values may differ only in comments)"""
+    import yaml
+    from seedx_b200 import compat
+    names = ["visual_encoder/qwen_vitg_448.yaml", "processer/qwen_448_transform.yaml", "discrete_model/discrete_identity.yaml",
+             "tokenizer/clm_llama_tokenizer_224loc_anyres.yaml", "clm_models/llm_seed_x.yaml", "clm_models/llm_seed_x_i.yaml",
+             "clm_models/llm_seed_x_edit.yaml", "clm_models/llm_seed_x_lora.yaml", "clm_models/agent_seed_x.yaml", "clm_models/agent_seed_x_i.yaml",
+             "clm_models/agent_seed_x_edit.yaml", "sdxl_adapter/sdxl_qwen_vit_resampler_l4_q64_pretrain_no_normalize.yaml",
+             "sdxl_adapter/sdxl_qwen_vit_resampler_l4_q64_full_with_latent_image_pretrain_no_normalize.yaml"]
+
+    def targets(o, acc):
+        if isinstance(o, dict):
+            if "_target_" in o:
+                acc.append(o["_target_"])
+            for v in o.values():
+                targets(v, acc)
+        return acc
+
+    for n in names:
+        ours = yaml.safe_load(open(os.path.join(ROOT, "configs", n)))
+        ref = yaml.safe_load(open(os.path.join(REF, "configs", n)))
+        assert ours == ref, n
+        for t in targets(ours, []):
+            if t.startswith(("src.", "peft.")):
+                compat.install()
+                assert callable(compat._locate(t)), t

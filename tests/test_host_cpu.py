@@ -5,6 +5,7 @@ import os
 import subprocess
 import sys
 
+import pytest
 import numpy as np
 import torch
 
@@ -93,3 +94,49 @@ def test_reference_arm_prints_the_contract_line():
         assert k in line, k
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] in ("port", "reference") and line["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and math.isfinite(line["value"])
+
+
+def test_lora_merge_updates_the_packed_weights_in_place():
+    """LlamaForCausalLM.apply_peft_state_dict on host tensors (no kernel is involved at load time): the packed [q|k|v] / [up,gate]-interleaved
+    fp16 weights equal the fp16 rounding of W + (alpha/r) B A from seedx_b200.lora.merge_lora_state_dict, norms are replaced, storage
+    pointers are unchanged (captured decode graphs stay valid), and the vocabulary growth follows peft_models.py:62-82."""
+    import os
+    import torch
+    from seedx_b200 import lora, synth
+    from seedx_b200._lib import SeedxError
+    from seedx_b200.llm import LlamaForCausalLM
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "llama_lora_tiny.pt"))
+    cfg = dict(synth.TINY_LLAMA)
+    base = synth.llama_state_dict(cfg)
+    m = LlamaForCausalLM(cfg, max_len=64, device="cpu")
+    m.load_state_dict({k: v.clone() for k, v in base.items()})        # on the host .to() may alias the caller's tensors
+    m.resize_token_embeddings(g["new_vocab"])
+    assert m.config.vocab_size == g["new_vocab"] and m.logits.shape[1] == g["new_vocab"]
+    assert torch.allclose(m.embed[cfg["vocab"]:].float(), g["embed_new_rows"], atol=1e-3)
+    assert torch.allclose(m.lm_head[cfg["vocab"]:].float(), g["head_new_rows"], atol=1e-3)
+    ft = synth.lora_fixture(g["shapes"])
+    with pytest.raises(SeedxError):
+        m.apply_peft_state_dict(ft)                                     # no peft_config
+    m.peft_config = lora.LoraConfig(r=g["r"], lora_alpha=g["lora_alpha"])
+    ptrs = [L["wqkv"].data_ptr() for L in m.layers] + [L["wgu"].data_ptr() for L in m.layers]
+    extra = m.apply_peft_state_dict({**ft, "base_model.model.model.layers.0.self_attn.rotary_emb.inv_freq": torch.zeros(4),
+                                     "base_model.model.model.layers.9.mlp.up_proj.weight": torch.zeros(2, 2)})
+    assert extra == ["model.layers.9.mlp.up_proj.weight"]               # reported like load_state_dict(strict=False)'s unexpected keys
+    assert ptrs == [L["wqkv"].data_ptr() for L in m.layers] + [L["wgu"].data_ptr() for L in m.layers]
+    full = {"base_model.model." + k: v for k, v in base.items()}
+    full.update(ft)
+    merged = lora.merge_lora_state_dict(full, g["lora_alpha"] / g["r"])
+    D = cfg["hidden"]
+    for i, L in enumerate(m.layers):
+        p = f"model.layers.{i}."
+        for j, n in enumerate(("q_proj", "k_proj", "v_proj")):
+            assert torch.equal(L["wqkv"][j * D:(j + 1) * D], merged[p + f"self_attn.{n}.weight"].half())
+        assert torch.equal(L["wo"], merged[p + "self_attn.o_proj.weight"].half())
+        assert torch.equal(L["wgu"][0::2], merged[p + "mlp.up_proj.weight"].half())
+        assert torch.equal(L["wgu"][1::2], merged[p + "mlp.gate_proj.weight"].half())
+        assert torch.equal(L["wdown"], merged[p + "mlp.down_proj.weight"].half())
+        assert torch.equal(L["ln1"], merged[p + "input_layernorm.weight"]) and not torch.equal(L["ln1"], base[p + "input_layernorm.weight"])
+    assert torch.equal(m.norm, merged["model.norm.weight"])
+    with pytest.raises(SeedxError):                                     # rank mismatch vs the configured r
+        m.peft_config = lora.LoraConfig(r=8, lora_alpha=8)
+        m.apply_peft_state_dict(ft)

@@ -215,3 +215,38 @@ def test_lora_checkpoint_through_the_yaml_factory_matches_reference_peft(tmp_pat
     m2, _ = _llm()
     with pytest.raises(SeedxError):
         m2.apply_peft_state_dict(synth.lora_fixture(g["shapes"]))
+
+
+def test_hf_style_generate_surface_matches_reference_golden():
+    """LlamaForCausalLM.generate called exactly as seed_x.py:184-189 calls HF generate, and its result consumed exactly as
+    seed_x.py:191-197 consumes it (sequences[0][P:], cat of hidden_state[-1] over steps, rows P:)."""
+    from seedx_b200.llm import AutoImageTokenGenerationProcessor
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    m, cfg = _llm()
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    sd = synth.llama_state_dict(cfg)
+    ids_b = g["ids"] + [tok.encode("<img>")[0]]
+    emb_b = torch.cat([g["embeds"], sd["model.embed_tokens.weight"][ids_b[-1]][None]])
+    input_ids = torch.tensor([ids_b])
+    P = input_ids.shape[1]
+    output = m.generate(input_ids=input_ids, inputs_embeds=emb_b.cuda().unsqueeze(0), output_hidden_states=True, return_dict_in_generate=True,
+                        logits_processor=[AutoImageTokenGenerationProcessor(tokenizer=tok, num_img_gen_tokens=64)],
+                        temperature=0.7, num_beams=1, max_new_tokens=72, top_p=0.5, do_sample=False, eos_token_id=None)
+    generate_ids = output.sequences[0][P:]
+    assert generate_ids.tolist() == g["img_gen_ids"]
+    assert output.sequences[0][:P].tolist() == ids_b
+    assert len(output.hidden_states) == 72 and output["hidden_states"][0][-1].shape == (1, P, cfg["hidden"])
+    last_hidden_states = torch.cat([hidden_state[-1] for hidden_state in output.hidden_states], dim=1)[0, P:, :]
+    assert rel(last_hidden_states, g["img_hidden"]) < TOL
+    assert rel(output.hidden_states[0][-1][0, :P - 1], g["prefill_hidden"]) < TOL
+    # plain call: ids only, tensor result, EOS honoured (first generated id declared EOS -> exactly one new token)
+    seq = m.generate(input_ids=torch.tensor([g["ids"]]), max_new_tokens=16, eos_token_id=None)
+    assert tuple(seq.shape) == (1, len(g["ids"]) + 16)
+    first = int(seq[0, len(g["ids"])])
+    seq2 = m.generate(input_ids=torch.tensor([g["ids"]]), max_new_tokens=16, eos_token_id=first)
+    assert seq2[0].tolist() == g["ids"] + [first]
+    from seedx_b200._lib import SeedxError
+    with pytest.raises(SeedxError):
+        m.generate(input_ids=torch.tensor([g["ids"]]), do_sample=True)
+    with pytest.raises(SeedxError):
+        m.generate(input_ids=torch.tensor([g["ids"], g["ids"]]))

@@ -98,6 +98,17 @@ def test_llama_lora_oracle_and_merge_match_reference_peft():
     assert rel(logits_0, g["logits"]) > 0.05
 
 
+def test_product_logits_processor_class_matches_reference():
+    """seedx_b200.llm.AutoImageTokenGenerationProcessor (host form of the rule the device kernel applies) vs the reference class's outputs."""
+    from seedx_b200.llm import AutoImageTokenGenerationProcessor
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    tok = synth.SynthTokenizer(vocab=synth.TINY_LLAMA["vocab"])
+    proc = AutoImageTokenGenerationProcessor(tok, num_img_gen_tokens=64)
+    assert len(proc.img_ids_list) == 66
+    assert torch.equal(proc(torch.tensor([[5, 6, 7]]), g["proc_in"].clone()), g["proc_out_text"])
+    assert torch.equal(proc(torch.tensor([[5, tok.encode("<img_00010>")[0]]]), g["proc_in"].clone()), g["proc_out_img"])
+
+
 def test_resampler_xl_oracle_matches_reference():
     from oracle import resampler_xl as orx
     g = torch.load(os.path.join(GOLD, "resampler_xl.pt"))

@@ -1,0 +1,108 @@
+"""The entry points of src/inference/ executed end to end on the GPU, launched the way a user launches them
+(`python -m seedx_b200.run src/inference/<script>.py`, cwd = a project root holding .project-root, configs/, pretrained/, demo_images/),
+with tiny checkpoints written in the reference's on-disk layouts and the YAMLs' dimensions scaled down to match."""
+import contextlib
+import io
+import os
+import shutil
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from seedx_b200 import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VIT = dict(width=208, layers=2, heads=2, mlp_width=520, output_dim=256, n_queries=256, patch=14)
+
+
+def _project(root):
+    """tmp project root: configs/ (shipped YAMLs, dimensions overridden), pretrained/ (tiny checkpoints), demo_images/ (noise)."""
+    import json
+    from PIL import Image
+    from safetensors.torch import save_file
+    open(root / ".project-root", "w").close()
+    lc = synth.TINY_LLAMA
+    ucfg = dict(synth.TINY_UNET, cross_attention_dim=256, text_embed_dim=160)
+    vcfg, rcfg = synth.TINY_VAE, dict(synth.TINY_RESAMPLER_XL, embedding_dim=256)
+    # ---- configs ----
+    for dp, _, fs in os.walk(os.path.join(ROOT, "configs")):
+        for f in fs:
+            rel = os.path.relpath(os.path.join(dp, f), ROOT)
+            y = yaml.safe_load(open(os.path.join(ROOT, rel)))
+            if rel.endswith("qwen_vitg_448.yaml"):
+                y.update(width=VIT["width"], layers=VIT["layers"], heads=VIT["heads"], mlp_ratio=2.5, output_dim=VIT["output_dim"])
+            if "agent_seed_x" in rel:
+                y["input_resampler"].update(embed_dim=lc["hidden"], num_heads=2, kv_dim=256)
+                y["output_resampler"].update(embed_dim=256, num_heads=2, kv_dim=lc["hidden"])
+            if "sdxl_adapter" in rel:
+                y["resampler"].update(dim=rcfg["dim"], depth=rcfg["depth"], heads=rcfg["heads"], embedding_dim=256, output1_dim=rcfg["output1_dim"],
+                                      output2_dim=rcfg["output2_dim"])
+            if "tokenizer" in rel:        # no sentencepiece model offline: the synthetic id map with the reference's added tokens
+                y = {"_target_": "seedx_b200.synth.SynthTokenizer", "vocab": lc["vocab"]}
+            if rel.endswith("llm_seed_x_lora.yaml"):
+                continue
+            os.makedirs(root / os.path.dirname(rel), exist_ok=True)
+            yaml.safe_dump(y, open(root / rel, "w"))
+    # ---- pretrained ----
+    pre = root / "pretrained"
+    os.makedirs(pre / "QwenViT")
+    torch.save(synth.vit_state_dict(**VIT), pre / "QwenViT" / "qwen_vit_G.pt")
+    for variant in ("seed_x", "seed_x_i", "seed_x_edit"):
+        os.makedirs(pre / variant / "llm"), os.makedirs(pre / variant / "agent")
+        json.dump(dict(vocab_size=lc["vocab"], hidden_size=lc["hidden"], num_hidden_layers=lc["layers"], num_attention_heads=lc["heads"],
+                       intermediate_size=lc["ffn"], rms_norm_eps=lc["eps"]), open(pre / variant / "llm" / "config.json", "w"))
+        save_file({k: v.half().contiguous() for k, v in synth.llama_state_dict(lc).items()}, str(pre / variant / "llm" / "model.safetensors"))
+        torch.save(synth.agent_state_dict(lc["hidden"], 256), pre / variant / "agent" / "pytorch_model.bin")
+    sd_dir = pre / "stable-diffusion-xl-base-1.0"
+    os.makedirs(sd_dir / "unet"), os.makedirs(sd_dir / "vae"), os.makedirs(sd_dir / "scheduler")
+    json.dump(dict(in_channels=4, out_channels=4, block_out_channels=list(ucfg["block_out_channels"]), layers_per_block=2,
+                   transformer_layers_per_block=list(ucfg["transformer_layers"]), attention_head_dim=list(ucfg["heads"]),
+                   cross_attention_dim=256, addition_time_embed_dim=ucfg["addition_time_embed_dim"],
+                   down_block_types=["DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"]), open(sd_dir / "unet" / "config.json", "w"))
+    save_file({k: v.half().contiguous() for k, v in synth.unet_state_dict(ucfg).items()}, str(sd_dir / "unet" / "diffusion_pytorch_model.safetensors"))
+    json.dump(dict(block_out_channels=list(vcfg["block_out_channels"]), layers_per_block=vcfg["layers_per_block"], latent_channels=4,
+                   scaling_factor=0.13025), open(sd_dir / "vae" / "config.json", "w"))
+    torch.save(synth.vae_state_dict(vcfg), sd_dir / "vae" / "diffusion_pytorch_model.bin")
+    json.dump(dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, steps_offset=1), open(sd_dir / "scheduler" / "scheduler_config.json", "w"))
+    rs = {"resampler." + k: v for k, v in synth.resampler_xl_state_dict(rcfg).items()}
+    os.makedirs(pre / "seed_detokenizer" / "first_stage"), os.makedirs(pre / "seed_detokenizer" / "second_stage")
+    torch.save(rs, pre / "seed_detokenizer" / "first_stage" / "pytorch_model.bin")
+    edit = dict(rs)                                                  # full fine-tune checkpoint: resampler.* + unet.* with the 8-channel conv_in
+    edit.update({"unet." + k: v for k, v in synth.unet_state_dict(dict(ucfg, in_channels=8)).items()})
+    torch.save(edit, pre / "seed_detokenizer" / "second_stage" / "pytorch_model.bin")
+    # ---- demo images ----
+    os.makedirs(root / "demo_images")
+    rng = np.random.RandomState(0)
+    for name, (w, h) in dict(advisor=(700, 500), ground=(640, 480), car=(600, 600), man=(500, 640), bank=(512, 512)).items():
+        img = Image.fromarray(rng.randint(0, 255, (h, w, 3), dtype=np.uint8))
+        img.save(root / "demo_images" / (name + (".png" if name in ("advisor", "ground", "bank") else ".jpg")))
+
+
+def _run(script, root, monkeypatch):
+    from seedx_b200 import run
+    monkeypatch.chdir(root)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        run.main([os.path.join(ROOT, "src", "inference", script)])
+    return buf.getvalue()
+
+
+def test_entry_scripts_run_end_to_end(tmp_path, monkeypatch):
+    from PIL import Image
+    _project(tmp_path)
+    monkeypatch.syspath_prepend(ROOT)
+    out = _run("eval_img2text_seed_x_i.py", tmp_path, monkeypatch)
+    assert out.strip(), "comprehension script printed nothing"
+    _run("eval_text2img_seed_x_i.py", tmp_path, monkeypatch)
+    img = Image.open(tmp_path / "vis" / "text2img.jpg")
+    assert img.size == (1024, 1024) and np.asarray(img).std() > 1.0
+    _run("eval_seed_x_detokenizer.py", tmp_path, monkeypatch)
+    assert Image.open(tmp_path / "vis" / "men_recon.jpg").size == (1024, 1024)
+    _run("eval_img2edit_seed_x_edit.py", tmp_path, monkeypatch)
+    assert Image.open(tmp_path / "vis" / "car_edit.jpg").size == (1024, 1024)
+    _run("eval_seed_x_detokenizer_with_condition.py", tmp_path, monkeypatch)
+    assert Image.open(tmp_path / "vis" / "bank_recon.png").size == (1024, 1024)
+    shutil.rmtree(tmp_path / "pretrained")
