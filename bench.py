@@ -262,6 +262,27 @@ def main():
         torch.cuda.synchronize()
         unet_ms = e0.elapsed_time(e1) / reps
         achieved = UNET_TFLOP * 2 * B / (unet_ms / 1e3) if not args.small else None
+        # per-stage achieved rate against the roofline that bounds the stage, from the marked extra step
+        P = int(eng.build_prompt(n_views, text_ids[0])[0].numel())
+        new_tok = 66
+
+        def tens(tflop, ms):
+            return {"bound": "tensor", "achieved": tflop / (ms / 1e3), "unit": "TFLOP/s", "peak": tensor_peak, "frac": tflop / (ms / 1e3) / tensor_peak,
+                    "ms": ms}
+        stage_roof = None
+        if not args.small and detail:
+            dec_ms = detail.get("llm.decode", 0.0)
+            gb = 26.04 * (new_tok - 1)
+            stage_roof = {
+                "vit": tens(B * n_views * VIT_TFLOP_448, detail["vit"]),
+                "llm_prefill": dict(tens(B * P * LLM_GFLOP_TOK / 1e3, detail["llm.prefill"]), prompt_len=P,
+                                    note="P ~ 240 rows per prompt: near the tensor/HBM ridge; all prompts of a step share one pass over the weights"),
+                "llm_decode": {"bound": "hbm", "achieved": gb / (dec_ms / 1e3), "unit": "GB/s", "peak": hbm_peak, "frac": gb / (dec_ms / 1e3) / hbm_peak,
+                               "ms": dec_ms, "ms_per_token_step": dec_ms / (new_tok - 1), "sequences_in_lock_step": B,
+                               "bytes_per_step_gb": 26.04},
+                "unet_denoise_loop": tens(2 * B * args.denoise_steps * UNET_TFLOP, detail["detok.denoise_loop"]),
+                "vae_decode": tens(B * VAE_DEC_TFLOP, detail["detok.vae_decode"]),
+            }
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
@@ -274,6 +295,7 @@ def main():
                        "small_debug_models": bool(args.small)},
             "stage_ms_per_step": stages,
             "stage_detail_ms": detail,
+            "stage_roofline": stage_roof,
             "e2e": {"value": e2e_v, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * 1024 * 1024 * 3,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,

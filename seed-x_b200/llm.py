@@ -78,6 +78,7 @@ class LlamaForCausalLM:
         self._loaded = False
         self._graphs = {}
         self._hidden = None
+        self.batched_prefill = os.environ.get("SEEDX_BATCHED_PREFILL", "1") != "0"
 
     # ---- reference-compatible plumbing --------------------------------------------------------------------------------
     @classmethod
@@ -287,6 +288,42 @@ class LlamaForCausalLM:
             ops.gemm(gu, L["wdown"], out=x, residual=x)
         return x
 
+    def prefill_batch(self, xs, slots):
+        """Prefill several sequences in ONE pass over the weights: the rows of all prompts are concatenated for the four projection GEMMs of
+        a layer (each fp16 weight matrix is streamed once instead of once per prompt — at P ~ 240 a single prompt's GEMMs are weight-read
+        bound), while RoPE + KV append and the causal attention run per sequence on its row block.  xs: list of fp32 device [P_r, D];
+        slots: the KV-cache slot of each.  Returns the list of fp32 residual streams [P_r, D] (views of one buffer)."""
+        cfg = self.cfg
+        D, H = cfg["hidden"], cfg["heads"]
+        d = D // H
+        lens = [int(x.shape[0]) for x in xs]
+        if max(lens) > self.max_len:
+            raise SeedxError(f"sequence length {max(lens)} exceeds the KV cache ({self.max_len})")
+        offs = [0]
+        for n_ in lens:
+            offs.append(offs[-1] + n_)
+        T = offs[-1]
+        x = torch.cat([t.reshape(-1, D) for t in xs], dim=0).contiguous()
+        n = torch.empty((T, D), device=x.device, dtype=torch.float16)
+        qkv = torch.empty((T, 3 * D), device=x.device, dtype=torch.float16)
+        o = torch.empty((T, D), device=x.device, dtype=torch.float16)
+        gu = torch.empty((T, cfg["ffn"]), device=x.device, dtype=torch.float16)
+        for li, L in enumerate(self.layers):
+            ops.layernorm(x, L["ln1"], None, cfg["eps"], out=n, rms=True)
+            ops.gemm(n, L["wqkv"], out=qkv)
+            for r, slot in enumerate(slots):
+                a, P = offs[r], lens[r]
+                blk = qkv[a:a + P]
+                ops.rope_kv_prefill(blk, 0, H, d, self.inv_freq, self.kcache[li][slot], self.vcache[li][slot])
+                q4 = blk.view(1, P, 3, H, d)
+                qv, kv, vv = (q4[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+                ops.attention(qv, kv, vv, o[a:a + P].view(1, P, H, d).permute(0, 2, 1, 3), scale=d ** -0.5, causal=True)
+            ops.gemm(o, L["wo"], out=x, residual=x)
+            ops.layernorm(x, L["ln2"], None, cfg["eps"], out=n, rms=True)
+            ops.gemm(n, L["wgu"], out=gu, act=ops.ACT_SILU, gated=True)
+            ops.gemm(gu, L["wdown"], out=x, residual=x)
+        return [x[offs[r]:offs[r + 1]] for r in range(len(xs))]
+
     def logits_all(self, x):
         """final RMSNorm + lm_head over every row of the residual stream (parity checks; LlamaForCausalLM.forward :702-707)."""
         hn = ops.layernorm(x, self.norm, None, self.cfg["eps"], out_dtype=torch.float32, rms=True)
@@ -335,7 +372,7 @@ class LlamaForCausalLM:
             self._hidden = torch.zeros((slots, self.max_len, self.cfg["hidden"]), device=dev, dtype=torch.float32)
             self._graphs = {}
         hidden = self._hidden
-        st0, plens, pre_hidden = [], [], []
+        st0, plens, pre_hidden, embs = [], [], [], []
         for s in range(slots):
             r = min(s, n_req - 1)                       # padding slots replay the last request
             ids = torch.as_tensor(input_ids_list[r]).reshape(-1)
@@ -345,8 +382,13 @@ class LlamaForCausalLM:
             plens.append(P)
             st0.append([P, 0, 0, P])
             self.seq[s, :P].copy_(ids.to(dev, torch.int32))
-            xs = self.prefill(inputs_embeds_list[r].reshape(P, -1).to(dev, torch.float32), slot=s)
-            ops.gemv(self.lm_head, xs[P - 1], self.logits[s], rms_w=self.norm, eps=self.cfg["eps"])
+            embs.append(inputs_embeds_list[r].reshape(P, -1).to(dev, torch.float32))
+        if slots > 1 and self.batched_prefill:          # one pass over the weights for all prompts
+            streams = self.prefill_batch(embs, list(range(slots)))
+        else:
+            streams = [self.prefill(embs[s], slot=s) for s in range(slots)]
+        for s, xs in enumerate(streams):
+            ops.gemv(self.lm_head, xs[plens[s] - 1], self.logits[s], rms_w=self.norm, eps=self.cfg["eps"])
             if keep_prefill_hidden and s < n_req:      # post-norm states of the prompt positions (HF hidden_states[0][-1])
                 pre_hidden.append(ops.layernorm(xs, self.norm, None, self.cfg["eps"], out_dtype=torch.float32, rms=True))
         self.state.copy_(torch.tensor(st0, dtype=torch.int32))

@@ -250,3 +250,22 @@ def test_hf_style_generate_surface_matches_reference_golden():
         m.generate(input_ids=torch.tensor([g["ids"]]), do_sample=True)
     with pytest.raises(SeedxError):
         m.generate(input_ids=torch.tensor([g["ids"], g["ids"]]))
+
+
+def test_batched_prefill_matches_sequential():
+    """prefill_batch (one pass over the weights for several ragged prompts) == prefill per prompt: residual streams and KV caches"""
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    m, cfg = _llm()
+    m._alloc_state(4)
+    emb = g["embeds"].cuda()
+    xs = [emb, emb[:20].contiguous(), torch.cat([emb, emb[:1]]), emb[:33].contiguous()]
+    seq = [m.prefill(x, slot=i).clone() for i, x in enumerate(xs)]
+    kc = [m.kcache[1][i, :xs[i].shape[0]].clone() for i in range(4)]
+    for c in m.kcache + m.vcache:
+        c.zero_()
+    bat = m.prefill_batch(xs, [0, 1, 2, 3])
+    for i in range(4):
+        assert rel(bat[i], seq[i]) < 1e-6, i
+        assert rel(m.kcache[1][i, :xs[i].shape[0]], kc[i]) < 1e-6, i
+    logits, hid = m.logits_all(bat[0])
+    assert rel(logits, g["prefill_logits"]) < TOL and rel(hid, g["prefill_hidden"]) < TOL

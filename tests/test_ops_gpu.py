@@ -24,6 +24,7 @@ def mk(shape, seed, scale=1.0):
     (2, 32, 64, 256, 160, False),      # input resampler
     (1, 40, 174, 174, 128, True),      # LLaMA prefill (causal, ragged)
     (1, 4, 370, 370, 128, True),
+    (4, 40, 241, 241, 128, True),      # LLaMA prefill of 4 equal-length prompts as one batched call
     (2, 10, 4096, 4096, 64, False),    # UNet self-attention 64x64
     (8, 20, 1024, 1024, 64, False),    # UNet self-attention 32x32 at batch: enough items for the two-tile kernel
     (5, 16, 1024, 1024, 104, False),   # ViT MHSA, 5 views: two-tile kernel, padded head dim
