@@ -262,6 +262,34 @@ def main():
         torch.cuda.synchronize()
         unet_ms = e0.elapsed_time(e1) / reps
         achieved = UNET_TFLOP * 2 * B / (unet_ms / 1e3) if not args.small else None
+        # the dominant kernel's dominant shape, timed alone with CUDA events on the launching stream: gemm_tc_kernel<256,2> on the GEGLU
+        # projection of the UNet feed-forward (60 launches per forward = 16 % of it, the largest single line of the launch list); three
+        # operand sets (393 MB) rotate so that no launch finds its inputs in the 126 MB L2
+        dom = None
+        if not args.small:
+            from seedx_b200 import ops
+            Mg, Ng, Kg = 2 * B * 1024, 10240, 1280
+            As = [torch.randn(Mg, Kg, device="cuda").half() for _ in range(3)]
+            Ws = [(torch.randn(Ng, Kg, device="cuda") * 0.03).half() for _ in range(3)]
+            Os = [torch.empty(Mg, Ng // 2, device="cuda", dtype=torch.float16) for _ in range(3)]
+            gb = torch.randn(Ng, device="cuda")
+            for j in range(3):
+                ops.gemm(As[j], Ws[j], out=Os[j], bias=gb, act=ops.ACT_GELU, gated=True)
+            torch.cuda.synchronize()
+            n_l = 30
+            e0.record()
+            for j in range(n_l):
+                ops.gemm(As[j % 3], Ws[j % 3], out=Os[j % 3], bias=gb, act=ops.ACT_GELU, gated=True)
+            e1.record()
+            torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / n_l
+            fl = 2.0 * Mg * Ng * Kg
+            dom = {"kernel": "gemm_tc_kernel<256,2> (tcgen05 cta_group::2), GEGLU projection M=%d N=%d K=%d, bias + GELU gating fused" % (Mg, Ng, Kg),
+                   "launch_us": us, "achieved": fl / us / 1e6, "unit": "TFLOP/s", "peak": tensor_peak, "frac": fl / us / 1e6 / tensor_peak,
+                   "algorithmic_bytes": 2 * (Mg * Kg + Ng * Kg + Mg * Ng // 2),
+                   "traffic": 95.8e6 if B == 4 else None,
+                   "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch of this shape, ncu --set full: profiles/r01_ncu_full_geglu_gemm_final.md"}
+            del As, Ws, Os
         # per-stage achieved rate against the roofline that bounds the stage, from the marked extra step
         P = int(eng.build_prompt(n_views, text_ids[0])[0].numel())
         new_tok = 66
@@ -302,7 +330,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "CUDA-graph launch of one UNet sample-forward: 960 kernels, gemm_tc_kernel (GEMM + implicit-GEMM conv) = 71% of its device time, tcgen05 attention 21% (profiles/r01_unet_forward_launches_final.md)",
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": (achieved / tensor_peak) if achieved else None,
-                         "traffic": None, "traffic_note": "per-kernel DRAM bytes of the dominant GEMM shape: profiles/r01_ncu_full_geglu_gemm_final.md (95.8 MB/launch vs 131 MB algorithmic)", "peak_source": peak_src, "flop_per_launch": UNET_TFLOP * 2 * B * 1e12,
+                         "dominant_kernel": dom, "traffic": None, "traffic_note": "per-kernel DRAM bytes of the dominant GEMM shape: profiles/r01_ncu_full_geglu_gemm_final.md (95.8 MB/launch vs 131 MB algorithmic)", "peak_source": peak_src, "flop_per_launch": UNET_TFLOP * 2 * B * 1e12,
                          "launch_ms": unet_ms, "work_per_image_tflop": work_per_image_tflop(),
                          "pipeline_frac": (value / world) * work_per_image_tflop() / tensor_peak},
             "cpu_baseline": cpu_base,

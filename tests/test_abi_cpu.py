@@ -93,3 +93,16 @@ def test_synth_is_deterministic():
     a, b = synth.randn("x.y", (4, 5), 0.3), synth.randn("x.y", (4, 5), 0.3)
     assert torch.equal(a, b) and not torch.equal(a, synth.randn("x.z", (4, 5), 0.3))
     assert torch.equal(a, a.half().float())      # fp16-representable
+
+
+def test_scheduler_known_answers():
+    """Published constants of the Stable-Diffusion scaled-linear schedule (beta 0.00085..0.012, 1000 steps): sigma_min = 0.0292,
+    sigma_max = 14.6146 (k-diffusion / diffusers defaults); 'leading' spacing with steps_offset 1 visits t = 981, 961, ..., 1 at 50 steps
+    (SURVEY.md B.2).  Pins the scheduler tables independently of the in-repo oracle."""
+    from seedx_b200.sdxl import EulerDiscreteScheduler
+    s = EulerDiscreteScheduler()
+    assert abs(s._sig[0] - 0.0292) < 5e-5 and abs(s._sig[-1] - 14.6146) < 5e-5
+    a = s.set_timesteps(50)
+    assert a.timesteps == [float(t) for t in range(981, 0, -20)] and len(a.sigmas) == 51 and a.sigmas[-1] == 0.0
+    assert all(x > y for x, y in zip(a.sigmas, a.sigmas[1:]))
+    assert abs(a.init_noise_sigma - (a.sigmas[0] ** 2 + 1) ** 0.5) < 1e-12 and abs(a.sigmas[0] - s._sig[981]) < 1e-12
