@@ -234,10 +234,15 @@ def main():
               for i, k in enumerate(("vit_ms", "llm_ms", "detok_ms"))}
         return ms, _lib.launch_count() - n0, st
 
-    with ClockSampler(local) as cs:
+    if rank == 0:       # one nvidia-smi poller per job (8 of them would only add host noise); rank 0's GPU stands for the box
+        with ClockSampler(local) as cs:
+            ms_dev, launches, stages = timed(e2e=False)
+            ms_e2e, _, _ = timed(e2e=True)
+        clocks = cs.summary()
+    else:
         ms_dev, launches, stages = timed(e2e=False)
         ms_e2e, _, _ = timed(e2e=True)
-    clocks = cs.summary()
+        clocks = None
     # one extra untimed step with section marks on (seedx_b200.trace): where the step goes, stage by stage
     from seedx_b200 import trace
     trace.enable(True)
@@ -338,6 +343,7 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()          # rank 0 is still measuring the roofline launches: nobody tears the communicator down before it is done
         dist.destroy_process_group()
 
 
