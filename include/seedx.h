@@ -192,6 +192,14 @@ int seedx_decode_attention(const float* qkv, const int32_t* state, const float* 
 /* prefill: RoPE q,k in place on fp16 [tokens, 3*H*d] for positions pos0.., and copy k,v rows into the caches */
 int seedx_rope_kv_prefill(void* qkv, int64_t tokens, int64_t pos0, int heads, int head_dim, const float* inv_freq, void* kcache, void* vcache,
                           void* stream);
+/* Paged KV cache (vLLM-style): the cache of a layer is a pool of pages, fp16 [n_pages][page_size tokens][H*d]; sequence b reads / appends through
+ * its row of the page table (int32 [batch][table_stride]: physical page of logical page t / page_size; page_size a power of two).  Same arithmetic
+ * as the two calls above; replaces the per-step torch.cat growth of past_key_value (modeling_llama_xformer.py:215-218) without tying a sequence to
+ * one contiguous slab. */
+int seedx_decode_attention_paged(const float* qkv, const int32_t* state, const float* inv_freq, void* kpool, void* vpool, const int32_t* page_table,
+                                 int64_t table_stride, int64_t page_size, float* out, int batch, int heads, int head_dim, float scale, void* stream);
+int seedx_rope_kv_prefill_paged(void* qkv, int64_t tokens, int64_t pos0, int heads, int head_dim, const float* inv_freq, void* kpool, void* vpool,
+                                const int32_t* page_table_row, int64_t page_size, void* stream);
 /* embedding rows -> fp32 [n, dim]; ids == NULL: row b = last token of device sequence b (seq[b*seq_stride + state[b][0]-1]) */
 int seedx_embed_rows(const void* table, const int32_t* ids, const int32_t* state, const int32_t* seq, int64_t seq_stride, int64_t n, int64_t dim,
                      float* out, void* stream);

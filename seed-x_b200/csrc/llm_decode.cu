@@ -156,10 +156,16 @@ gemv_mma_kernel(const __half* __restrict__ W, const float* __restrict__ x, long 
 constexpr int DA_THREADS = 256;
 constexpr int DA_GROUPS = DA_THREADS / 16;  // half-warps
 
+// KV-cache row of logical position t of one sequence.  Paged mode (pt != NULL): the cache is a pool of pages of 2^shift tokens and
+// pt[] is the sequence's page table (physical page of logical page t >> shift); contiguous mode: the sequence owns one slab.
+__device__ __forceinline__ long long kv_row(const int* __restrict__ pt, int shift, int t) {
+  return pt ? ((((long long)__ldg(pt + (t >> shift))) << shift) | (long long)(t & ((1 << shift) - 1))) : (long long)t;
+}
+
 __global__ void __launch_bounds__(DA_THREADS)
 decode_attn_kernel(const float* __restrict__ qkv_all, const int* __restrict__ state_all, const float* __restrict__ inv_freq,
                    __half* __restrict__ kcache_all, __half* __restrict__ vcache_all, long long cache_stride, float* __restrict__ out_all, int H,
-                   float scale) {
+                   float scale, const int* __restrict__ page_table, int table_stride, int page_shift) {
   pdl_wait();
   pdl_trigger();
   constexpr int HD = 128;
@@ -171,11 +177,13 @@ decode_attn_kernel(const float* __restrict__ qkv_all, const int* __restrict__ st
   const int bidx = blockIdx.y;                    // sequence slot
   const float* qkv = qkv_all + (long long)bidx * 3 * D;
   const int* state = state_all + bidx * 4;
-  __half* kcache = kcache_all + (long long)bidx * cache_stride;
-  __half* vcache = vcache_all + (long long)bidx * cache_stride;
+  __half* kcache = kcache_all + (page_table ? 0ll : (long long)bidx * cache_stride);
+  __half* vcache = vcache_all + (page_table ? 0ll : (long long)bidx * cache_stride);
+  const int* pt = page_table ? page_table + (long long)bidx * table_stride : nullptr;
   float* out = out_all + (long long)bidx * D;
   const int pos = state[0] - 1;
   const int tid = threadIdx.x;
+  const long long prow = kv_row(pt, page_shift, pos) * D;      // cache row that receives this step's k, v
   if (tid < HD / 2) {
     const float ang = (float)pos * inv_freq[tid];
     const float c = cosf(ang), s = sinf(ang);
@@ -183,11 +191,11 @@ decode_attn_kernel(const float* __restrict__ qkv_all, const int* __restrict__ st
     const float k0 = qkv[D + h * HD + tid], k1 = qkv[D + h * HD + tid + HD / 2];
     qs[tid] = (q0 * c - q1 * s) * scale;
     qs[tid + HD / 2] = (q1 * c + q0 * s) * scale;
-    kcache[(long long)pos * D + h * HD + tid] = __float2half_rn(k0 * c - k1 * s);
-    kcache[(long long)pos * D + h * HD + tid + HD / 2] = __float2half_rn(k1 * c + k0 * s);
+    kcache[prow + h * HD + tid] = __float2half_rn(k0 * c - k1 * s);
+    kcache[prow + h * HD + tid + HD / 2] = __float2half_rn(k1 * c + k0 * s);
   } else if (tid < HD / 2 + HD) {
     const int i = tid - HD / 2;
-    vcache[(long long)pos * D + h * HD + i] = __float2half_rn(qkv[2 * D + h * HD + i]);
+    vcache[prow + h * HD + i] = __float2half_rn(qkv[2 * D + h * HD + i]);
   }
   __syncthreads();
 
@@ -202,9 +210,10 @@ decode_attn_kernel(const float* __restrict__ qkv_all, const int* __restrict__ st
     const int t = t0 + grp;
     const bool valid = t <= pos;
     uint4 kq = make_uint4(0, 0, 0, 0), vq = make_uint4(0, 0, 0, 0);
-    if (valid) {
-      kq = *(const uint4*)(kcache + (long long)t * D + h * HD + gl_lane * 8);
-      vq = *(const uint4*)(vcache + (long long)t * D + h * HD + gl_lane * 8);
+    if (valid) {   // one half-warp = one token: 16 lanes x 16 bytes = the head's 256 contiguous bytes of the row (two full 128 B lines)
+      const long long r = kv_row(pt, page_shift, t) * D + h * HD + gl_lane * 8;
+      kq = *(const uint4*)(kcache + r);
+      vq = *(const uint4*)(vcache + r);
     }
     const __half2* kh = (const __half2*)&kq;
     float s = 0.f;
@@ -251,7 +260,7 @@ decode_attn_kernel(const float* __restrict__ qkv_all, const int* __restrict__ st
 
 // RoPE on the prefill q/k (in place, fp16 [T, 3D] = [q | k | v]) + copy of k, v into the cache rows pos0..pos0+T-1
 __global__ void rope_kv_prefill_kernel(__half* __restrict__ qkv, int T, int pos0, int H, const float* __restrict__ inv_freq,
-                                       __half* __restrict__ kcache, __half* __restrict__ vcache) {
+                                       __half* __restrict__ kcache, __half* __restrict__ vcache, const int* __restrict__ pt, int page_shift) {
   pdl_wait();
   pdl_trigger();
   constexpr int HD = 128;
@@ -273,7 +282,7 @@ __global__ void rope_kv_prefill_kernel(__half* __restrict__ qkv, int T, int pos0
     const __half kr0 = __float2half_rn(k0 * c - k1 * s), kr1 = __float2half_rn(k1 * c + k0 * s);
     row[D + o] = kr0;
     row[D + o + HD / 2] = kr1;
-    const long long cr = (long long)(pos0 + t) * D;
+    const long long cr = kv_row(pt, page_shift, pos0 + t) * D;
     kcache[cr + o] = kr0;
     kcache[cr + o + HD / 2] = kr1;
     vcache[cr + o] = row[2 * D + o];
@@ -427,9 +436,28 @@ extern "C" int seedx_decode_attention(const float* qkv, const int32_t* state, co
   SEEDX_REQUIRE(qkv && state && inv_freq && kcache && vcache && out && batch >= 1, "seedx_decode_attention: bad arguments");
   SEEDX_REQUIRE(head_dim == 128, "seedx_decode_attention: head_dim must be 128 (LLaMA)");
   launch_k(decode_attn_kernel, dim3(heads, batch), DA_THREADS, 0, (cudaStream_t)stream, qkv, state, inv_freq, (__half*)kcache, (__half*)vcache,
-                                                                                  cache_stride, out, heads, scale);
+                                                                                  (long long)cache_stride, out, heads, scale, (const int*)nullptr, 0, 0);
   count_launch();
   return check_cuda(cudaGetLastError(), "decode_attention launch");
+}
+
+static int log2_exact(int64_t v) {
+  int s = 0;
+  while ((1ll << s) < v) ++s;
+  return (1ll << s) == v ? s : -1;
+}
+
+extern "C" int seedx_decode_attention_paged(const float* qkv, const int32_t* state, const float* inv_freq, void* kpool, void* vpool,
+                                            const int32_t* page_table, int64_t table_stride, int64_t page_size, float* out, int batch, int heads,
+                                            int head_dim, float scale, void* stream) {
+  SEEDX_REQUIRE(qkv && state && inv_freq && kpool && vpool && page_table && out && batch >= 1, "seedx_decode_attention_paged: bad arguments");
+  SEEDX_REQUIRE(head_dim == 128, "seedx_decode_attention_paged: head_dim must be 128 (LLaMA)");
+  const int shift = log2_exact(page_size);
+  SEEDX_REQUIRE(shift >= 0 && table_stride >= 1, "seedx_decode_attention_paged: page_size=%lld must be a power of two", (long long)page_size);
+  launch_k(decode_attn_kernel, dim3(heads, batch), DA_THREADS, 0, (cudaStream_t)stream, qkv, state, inv_freq, (__half*)kpool, (__half*)vpool, 0ll, out,
+                                                                                  heads, scale, (const int*)page_table, (int)table_stride, shift);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "decode_attention_paged launch");
 }
 
 extern "C" int seedx_rope_kv_prefill(void* qkv, int64_t tokens, int64_t pos0, int heads, int head_dim, const float* inv_freq, void* kcache,
@@ -437,9 +465,21 @@ extern "C" int seedx_rope_kv_prefill(void* qkv, int64_t tokens, int64_t pos0, in
   SEEDX_REQUIRE(qkv && inv_freq && kcache && vcache && tokens > 0, "seedx_rope_kv_prefill: bad arguments");
   SEEDX_REQUIRE(head_dim == 128, "seedx_rope_kv_prefill: head_dim must be 128 (LLaMA)");
   launch_k(rope_kv_prefill_kernel, ew_grid(tokens * heads * 64, 256), 256, 0, (cudaStream_t)stream, (__half*)qkv, (int)tokens, (int)pos0, heads, inv_freq,
-                                                                                             (__half*)kcache, (__half*)vcache);
+                                                                                             (__half*)kcache, (__half*)vcache, (const int*)nullptr, 0);
   count_launch();
   return check_cuda(cudaGetLastError(), "rope_kv_prefill launch");
+}
+
+extern "C" int seedx_rope_kv_prefill_paged(void* qkv, int64_t tokens, int64_t pos0, int heads, int head_dim, const float* inv_freq, void* kpool,
+                                           void* vpool, const int32_t* page_table_row, int64_t page_size, void* stream) {
+  SEEDX_REQUIRE(qkv && inv_freq && kpool && vpool && page_table_row && tokens > 0, "seedx_rope_kv_prefill_paged: bad arguments");
+  SEEDX_REQUIRE(head_dim == 128, "seedx_rope_kv_prefill_paged: head_dim must be 128 (LLaMA)");
+  const int shift = log2_exact(page_size);
+  SEEDX_REQUIRE(shift >= 0, "seedx_rope_kv_prefill_paged: page_size=%lld must be a power of two", (long long)page_size);
+  launch_k(rope_kv_prefill_kernel, ew_grid(tokens * heads * 64, 256), 256, 0, (cudaStream_t)stream, (__half*)qkv, (int)tokens, (int)pos0, heads, inv_freq,
+                                                                                             (__half*)kpool, (__half*)vpool, (const int*)page_table_row, shift);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "rope_kv_prefill_paged launch");
 }
 
 extern "C" int seedx_embed_rows(const void* table, const int32_t* ids, const int32_t* state, const int32_t* seq, int64_t seq_stride, int64_t n,

@@ -4,8 +4,9 @@ surface of the reference class ``src.models.mllm.modeling_llama_xformer.LlamaFor
 and a greedy ``generate`` that reproduces what seed_x.py:184-197 consumes (sequences + last-layer hidden states).
 
 HBM layout: weights fp16 ([q|k|v] fused, [up_j,gate_j] row-interleaved for the SwiGLU epilogue); residual stream fp32;
-KV cache fp16, one [max_len, H*d] slab per layer and tensor, appended in place (the reference re-copies it with
-torch.cat every step, :215-218); sampler state (sequence, length, EOS marker) device resident.
+KV cache fp16, PAGED: per layer and tensor a pool [n_pages, 64 tokens, H*d]; every sequence slot owns a row of a device page table,
+rows are appended in place (the reference re-copies the whole cache with torch.cat every step, :215-218); sampler state (sequence,
+length, EOS marker) device resident.
 """
 import json
 import os
@@ -28,6 +29,29 @@ class _Embedding:
         out = torch.empty((1, ids.numel(), self.llm.cfg["hidden"]), device=self.llm.device, dtype=torch.float32)
         ops.embed_rows(self.llm.embed, out, ids=ids)
         return out
+
+
+class KVPageAllocator:
+    """Host-side free list of KV-cache pages (the device side only ever sees the page table).  Pages are handed out from the END of the
+    list, so consecutive logical pages of a sequence are not physically consecutive even on a fresh pool — the indirection is always
+    exercised, not just after fragmentation."""
+
+    def __init__(self, n_pages):
+        self.n_pages = n_pages
+        self.free = list(range(n_pages))
+
+    def alloc(self, n):
+        if n > len(self.free):
+            raise SeedxError(f"KV cache exhausted: {n} pages requested, {len(self.free)} of {self.n_pages} free")
+        out = [self.free.pop() for _ in range(n)]
+        return out
+
+    def release(self, pages):
+        self.free.extend(pages)
+
+    def shuffle(self, seed=0):
+        import random
+        random.Random(seed).shuffle(self.free)
 
 
 class GreedyOutput:
@@ -70,10 +94,13 @@ class GreedySearchOutput(dict):
 
 
 class LlamaForCausalLM:
-    def __init__(self, cfg=None, max_len=2048, device="cuda"):
+    def __init__(self, cfg=None, max_len=2048, device="cuda", kv_page_size=64, kv_pages=None):
         self.cfg = dict(LLAMA_13B if cfg is None else cfg)
         self.device = torch.device(device)
         self.max_len = max_len
+        if kv_page_size < 1 or kv_page_size & (kv_page_size - 1):
+            raise SeedxError("kv_page_size must be a power of two")
+        self.page_size, self.kv_pages = kv_page_size, kv_pages
         self.dtype = torch.float16
         self._loaded = False
         self._graphs = {}
@@ -246,13 +273,43 @@ class LlamaForCausalLM:
         self.slots = slots
         self._graphs = {}          # captured decode graphs reference the state buffers below
         self._hidden = None
-        self.kcache = [torch.zeros((slots, self.max_len, D), device=dev, dtype=torch.float16) for _ in range(L)]
-        self.vcache = [torch.zeros((slots, self.max_len, D), device=dev, dtype=torch.float16) for _ in range(L)]
+        # paged KV cache: per layer and tensor one pool fp16 [n_pages, page_size, H*d]; a sequence slot reaches its rows through its row of
+        # the page table (shared by all layers).  Default pool = enough pages for every slot at max_len; `kv_pages` shrinks it (admission
+        # then fails with "KV cache exhausted" instead of over-committing).
+        PS = self.page_size
+        self.pages_per_slot = (self.max_len + PS - 1) // PS
+        n_pages = self.kv_pages if self.kv_pages is not None else slots * self.pages_per_slot
+        self.kv_alloc = KVPageAllocator(n_pages)
+        self.slot_pages = [[] for _ in range(slots)]
+        self.page_table = torch.zeros((slots, self.pages_per_slot), device=dev, dtype=torch.int32)
+        self.kcache = [torch.zeros((n_pages, PS, D), device=dev, dtype=torch.float16) for _ in range(L)]
+        self.vcache = [torch.zeros((n_pages, PS, D), device=dev, dtype=torch.float16) for _ in range(L)]
         self.seq = torch.zeros((slots, self.max_len), device=dev, dtype=torch.int32)
         self.state = torch.zeros((slots, 4), device=dev, dtype=torch.int32)
         z = lambda n: torch.zeros((slots, n), device=dev, dtype=torch.float32)  # noqa: E731
         self.xa, self.xb, self.qkv1, self.att1, self.g1, self.hn1 = z(D), z(D), z(3 * D), z(D), z(cfg["ffn"]), z(D)
         self.logits = z(cfg["vocab"])
+
+    # ---- KV pages --------------------------------------------------------------------------------------------------------------
+    def reserve_kv(self, slot, n_tokens, fresh=False):
+        """make sure sequence slot `slot` owns pages for positions [0, n_tokens); fresh=True first returns its old pages (new request)."""
+        if n_tokens > self.max_len:
+            raise SeedxError(f"sequence length {n_tokens} exceeds the KV cache ({self.max_len})")
+        if fresh and self.slot_pages[slot]:
+            self.kv_alloc.release(self.slot_pages[slot])
+            self.slot_pages[slot] = []
+        need = (n_tokens + self.page_size - 1) // self.page_size - len(self.slot_pages[slot])
+        if need > 0:
+            self.slot_pages[slot] += self.kv_alloc.alloc(need)
+            row = torch.zeros((self.pages_per_slot,), dtype=torch.int32)
+            row[:len(self.slot_pages[slot])] = torch.tensor(self.slot_pages[slot], dtype=torch.int32)
+            self.page_table[slot].copy_(row)          # same device buffer: captured decode graphs keep reading it
+
+    def kv_rows(self, li, slot, n):
+        """contiguous copies [n, H*d] of the first n cached K and V rows of a slot (page gather; chunked prefill and tests)"""
+        pages = torch.tensor(self.slot_pages[slot][:(n + self.page_size - 1) // self.page_size], dtype=torch.long, device=self.device)
+        D = self.cfg["hidden"]
+        return self.kcache[li][pages].reshape(-1, D)[:n], self.vcache[li][pages].reshape(-1, D)[:n]
 
     # ---- prefill: tensor-core path ---------------------------------------------------------------------------------------
     def prefill(self, x, pos0=0, slot=0):
@@ -262,8 +319,7 @@ class LlamaForCausalLM:
         D, H = cfg["hidden"], cfg["heads"]
         d = D // H
         P = x.shape[0]
-        if pos0 + P > self.max_len:
-            raise SeedxError(f"sequence length {pos0 + P} exceeds the KV cache ({self.max_len})")
+        self.reserve_kv(slot, pos0 + P, fresh=(pos0 == 0))
         x = x.contiguous().clone()
         n = torch.empty((P, D), device=x.device, dtype=torch.float16)
         qkv = torch.empty((P, 3 * D), device=x.device, dtype=torch.float16)
@@ -275,13 +331,14 @@ class LlamaForCausalLM:
         for li, L in enumerate(self.layers):
             ops.layernorm(x, L["ln1"], None, cfg["eps"], out=n, rms=True)
             ops.gemm(n, L["wqkv"], out=qkv)
-            ops.rope_kv_prefill(qkv, pos0, H, d, self.inv_freq, self.kcache[li][slot], self.vcache[li][slot])
+            ops.rope_kv_prefill(qkv, pos0, H, d, self.inv_freq, self.kcache[li], self.vcache[li], page_table_row=self.page_table[slot],
+                                page_size=self.page_size)
             if pos0 == 0:
                 ops.attention(qv, kv, vv, ov, scale=d ** -0.5, causal=True)
-            else:   # chunked prefill: keys/values come from the cache (positions 0..pos0+P-1)
-                kc = self.kcache[li][slot, : pos0 + P].view(1, pos0 + P, H, d).permute(0, 2, 1, 3)
-                vc = self.vcache[li][slot, : pos0 + P].view(1, pos0 + P, H, d).permute(0, 2, 1, 3)
-                ops.attention(qv, kc, vc, ov, scale=d ** -0.5, causal=True)
+            else:   # chunked prefill: keys/values come from the cache (positions 0..pos0+P-1), gathered from their pages
+                kc, vc = self.kv_rows(li, slot, pos0 + P)
+                ops.attention(qv, kc.view(1, pos0 + P, H, d).permute(0, 2, 1, 3), vc.view(1, pos0 + P, H, d).permute(0, 2, 1, 3), ov,
+                              scale=d ** -0.5, causal=True)
             ops.gemm(o, L["wo"], out=x, residual=x)
             ops.layernorm(x, L["ln2"], None, cfg["eps"], out=n, rms=True)
             ops.gemm(n, L["wgu"], out=gu, act=ops.ACT_SILU, gated=True)
@@ -297,8 +354,8 @@ class LlamaForCausalLM:
         D, H = cfg["hidden"], cfg["heads"]
         d = D // H
         lens = [int(x.shape[0]) for x in xs]
-        if max(lens) > self.max_len:
-            raise SeedxError(f"sequence length {max(lens)} exceeds the KV cache ({self.max_len})")
+        for n_, slot in zip(lens, slots):
+            self.reserve_kv(slot, n_, fresh=True)
         offs = [0]
         for n_ in lens:
             offs.append(offs[-1] + n_)
@@ -314,7 +371,8 @@ class LlamaForCausalLM:
             for r, slot in enumerate(slots):
                 a, P = offs[r], lens[r]
                 blk = qkv[a:a + P]
-                ops.rope_kv_prefill(blk, 0, H, d, self.inv_freq, self.kcache[li][slot], self.vcache[li][slot])
+                ops.rope_kv_prefill(blk, 0, H, d, self.inv_freq, self.kcache[li], self.vcache[li], page_table_row=self.page_table[slot],
+                                    page_size=self.page_size)
                 q4 = blk.view(1, P, 3, H, d)
                 qv, kv, vv = (q4[:, :, i].permute(0, 2, 1, 3) for i in range(3))
                 ops.attention(qv, kv, vv, o[a:a + P].view(1, P, H, d).permute(0, 2, 1, 3), scale=d ** -0.5, causal=True)
@@ -339,7 +397,8 @@ class LlamaForCausalLM:
         ops.embed_rows(self.embed, self.xa, state=self.state, seq=self.seq)
         for li, L in enumerate(self.layers):
             ops.gemv(L["wqkv"], self.xa, self.qkv1, rms_w=L["ln1"], eps=cfg["eps"])
-            ops.decode_attention(self.qkv1, self.state, self.inv_freq, self.kcache[li], self.vcache[li], self.att1, H, d)
+            ops.decode_attention(self.qkv1, self.state, self.inv_freq, self.kcache[li], self.vcache[li], self.att1, H, d,
+                                 page_table=self.page_table, page_size=self.page_size)
             ops.gemv(L["wo"], self.att1, self.xb, residual=self.xa)
             ops.gemv(L["wgu"], self.xb, self.g1, rms_w=L["ln2"], eps=cfg["eps"], gated=True)
             ops.gemv(L["wdown"], self.g1, self.xa, residual=self.xb)
@@ -387,6 +446,8 @@ class LlamaForCausalLM:
             streams = self.prefill_batch(embs, list(range(slots)))
         else:
             streams = [self.prefill(embs[s], slot=s) for s in range(slots)]
+        for s in range(slots):                           # pages for the tokens the loop will append
+            self.reserve_kv(s, plens[s] + max_new_tokens)
         for s, xs in enumerate(streams):
             ops.gemv(self.lm_head, xs[plens[s] - 1], self.logits[s], rms_w=self.norm, eps=self.cfg["eps"])
             if keep_prefill_hidden and s < n_req:      # post-norm states of the prompt positions (HF hidden_states[0][-1])

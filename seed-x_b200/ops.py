@@ -336,17 +336,30 @@ def gemv(W, x, out, *, rms_w=None, eps=1e-5, residual=None, gated=False):
     return out
 
 
-def decode_attention(qkv, state, inv_freq, kcache, vcache, out, heads, head_dim):
-    """qkv fp32 [B, 3*H*d]; kcache/vcache fp16 [B, max_len, H*d]; state int32 [B,4]; out fp32 [B, H*d]."""
+def decode_attention(qkv, state, inv_freq, kcache, vcache, out, heads, head_dim, page_table=None, page_size=0):
+    """qkv fp32 [B, 3*H*d]; state int32 [B,4]; out fp32 [B, H*d].  Contiguous caches: kcache/vcache fp16 [B, max_len, H*d].  Paged:
+    kcache/vcache = page pools fp16 [n_pages, page_size, H*d] and page_table int32 [B, pages_per_seq]."""
     B = qkv.shape[0]
+    if page_table is not None:
+        assert page_table.dtype == torch.int32 and page_table.is_contiguous() and page_table.shape[0] == B and kcache.shape[1] == page_size
+        check(lib().seedx_decode_attention_paged(_ptr(qkv), _ptr(state), _ptr(inv_freq), _ptr(kcache), _ptr(vcache), _ptr(page_table),
+                                                 _i64(page_table.stride(0)), _i64(page_size), _ptr(out), C.c_int(B), C.c_int(heads),
+                                                 C.c_int(head_dim), C.c_float(head_dim ** -0.5), _stream()), "seedx_decode_attention_paged")
+        return out
     check(lib().seedx_decode_attention(_ptr(qkv), _ptr(state), _ptr(inv_freq), _ptr(kcache), _ptr(vcache), _i64(kcache.stride(0)), _ptr(out),
                                        C.c_int(B), C.c_int(heads), C.c_int(head_dim), C.c_float(head_dim ** -0.5), _stream()),
           "seedx_decode_attention")
     return out
 
 
-def rope_kv_prefill(qkv, pos0, heads, head_dim, inv_freq, kcache, vcache):
+def rope_kv_prefill(qkv, pos0, heads, head_dim, inv_freq, kcache, vcache, page_table_row=None, page_size=0):
     assert qkv.dtype == torch.float16 and qkv.is_contiguous()
+    if page_table_row is not None:
+        assert page_table_row.dtype == torch.int32 and page_table_row.is_contiguous() and kcache.shape[1] == page_size
+        check(lib().seedx_rope_kv_prefill_paged(_ptr(qkv), _i64(qkv.shape[0]), _i64(pos0), C.c_int(heads), C.c_int(head_dim), _ptr(inv_freq),
+                                                _ptr(kcache), _ptr(vcache), _ptr(page_table_row), _i64(page_size), _stream()),
+              "seedx_rope_kv_prefill_paged")
+        return
     check(lib().seedx_rope_kv_prefill(_ptr(qkv), _i64(qkv.shape[0]), _i64(pos0), C.c_int(heads), C.c_int(head_dim), _ptr(inv_freq), _ptr(kcache),
                                       _ptr(vcache), _stream()), "seedx_rope_kv_prefill")
 

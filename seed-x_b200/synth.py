@@ -282,15 +282,16 @@ def llama_state_dict(cfg):
 
 def lora_fixture(shapes):
     """fine-tuned tensors of the LoRA fixture (tests/golden/llama_lora_tiny.pt): a pure function of the PEFT key and its shape —
-    lora_A ~ in^-0.5, lora_B ~ 0.5 r^-0.5 (a visible but not dominant update), modules_to_save norm weights ~ N(1, 0.2)."""
+    lora_A ~ in^-0.5, lora_B ~ 0.15 r^-0.5 (with alpha/r = 2 the dense update is ~0.3 of the base weight's scale: clearly visible in the
+    logits, yet a fine-tune, not a new network), modules_to_save norm weights ~ N(1, 0.1) like the base norms."""
     out = {}
     for k, shp in shapes.items():
         if ".lora_A." in k:
             out[k] = randn("lora:" + k, shp, std=shp[1] ** -0.5)
         elif ".lora_B." in k:
-            out[k] = randn("lora:" + k, shp, std=0.5 * shp[1] ** -0.5)
+            out[k] = randn("lora:" + k, shp, std=0.15 * shp[1] ** -0.5)
         else:
-            out[k] = randn("lora:" + k, shp, std=0.2, mean=1.0)
+            out[k] = randn("lora:" + k, shp, std=0.1, mean=1.0)
     return out
 
 

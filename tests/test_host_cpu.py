@@ -140,3 +140,36 @@ def test_lora_merge_updates_the_packed_weights_in_place():
     with pytest.raises(SeedxError):                                     # rank mismatch vs the configured r
         m.peft_config = lora.LoraConfig(r=8, lora_alpha=8)
         m.apply_peft_state_dict(ft)
+
+
+def test_kv_page_allocator_and_page_table_rows():
+    """host half of the paged KV cache: free-list accounting, growth of a slot's reservation, release on a fresh request, exhaustion"""
+    import torch
+    from seedx_b200 import synth
+    from seedx_b200._lib import SeedxError
+    from seedx_b200.llm import KVPageAllocator, LlamaForCausalLM
+    a = KVPageAllocator(5)
+    p = a.alloc(3)
+    assert len(set(p)) == 3 and len(a.free) == 2
+    with pytest.raises(SeedxError, match="KV cache exhausted"):
+        a.alloc(3)
+    a.release(p)
+    assert sorted(a.free) == [0, 1, 2, 3, 4]
+    cfg = dict(synth.TINY_LLAMA)
+    m = LlamaForCausalLM(cfg, max_len=100, device="cpu", kv_page_size=16)
+    m.load_state_dict(synth.llama_state_dict(cfg))
+    m._alloc_state(2)
+    assert m.pages_per_slot == 7 and m.kv_alloc.n_pages == 14 and tuple(m.kcache[0].shape) == (14, 16, cfg["hidden"])
+    m.reserve_kv(0, 17, fresh=True)
+    first = list(m.slot_pages[0])
+    assert len(first) == 2 and m.page_table[0, :2].tolist() == first
+    m.reserve_kv(1, 40, fresh=True)
+    m.reserve_kv(0, 60)                                    # grows, keeps the pages (and cached rows) it already has
+    assert m.slot_pages[0][:2] == first and len(m.slot_pages[0]) == 4 and m.page_table[0, :4].tolist() == m.slot_pages[0]
+    assert not set(m.slot_pages[0]) & set(m.slot_pages[1])
+    m.reserve_kv(0, 5, fresh=True)                         # new request in the slot: old pages returned first
+    assert len(m.slot_pages[0]) == 1 and len(m.kv_alloc.free) + 1 + len(m.slot_pages[1]) == 14
+    with pytest.raises(SeedxError, match="exceeds the KV cache"):
+        m.reserve_kv(0, 101)
+    with pytest.raises(SeedxError):
+        LlamaForCausalLM(cfg, kv_page_size=48)

@@ -277,12 +277,61 @@ def test_batched_prefill_matches_sequential():
     emb = g["embeds"].cuda()
     xs = [emb, emb[:20].contiguous(), torch.cat([emb, emb[:1]]), emb[:33].contiguous()]
     seq = [m.prefill(x, slot=i).clone() for i, x in enumerate(xs)]
-    kc = [m.kcache[1][i, :xs[i].shape[0]].clone() for i in range(4)]
+    kc = [m.kv_rows(1, i, xs[i].shape[0])[0].clone() for i in range(4)]
     for c in m.kcache + m.vcache:
         c.zero_()
     bat = m.prefill_batch(xs, [0, 1, 2, 3])
     for i in range(4):
         assert rel(bat[i], seq[i]) < 1e-6, i
-        assert rel(m.kcache[1][i, :xs[i].shape[0]], kc[i]) < 1e-6, i
+        assert rel(m.kv_rows(1, i, xs[i].shape[0])[0], kc[i]) < 1e-6, i
     logits, hid = m.logits_all(bat[0])
     assert rel(logits, g["prefill_logits"]) < TOL and rel(hid, g["prefill_hidden"]) < TOL
+
+
+def test_paged_kv_cache_with_scattered_pages_matches_reference_golden():
+    """The KV cache is a pool of pages reached through a device page table: with 16-token pages handed out in shuffled order (every
+    sequence's pages scattered over the pool, interleaved with the other slots') lock-step decoding still reproduces the reference's
+    greedy ids and hidden states, bitwise identical to the run with the default 64-token pages; pages return to the pool."""
+    from seedx_b200._lib import SeedxError
+    from seedx_b200.llm import LlamaForCausalLM
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    cfg = synth.TINY_LLAMA
+    sd = synth.llama_state_dict(cfg)
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    img_ids = tok.encode("".join(["<img>"] + ["<img_{:05d}>".format(i) for i in range(64)] + ["</img>"]))
+    ids_a, emb_a = g["ids"], g["embeds"]
+    ids_b = g["ids"] + [tok.encode("<img>")[0]]
+    emb_b = torch.cat([g["embeds"], sd["model.embed_tokens.weight"][ids_b[-1]][None]])
+    ids_c, emb_c = g["ids"][:20], g["embeds"][:20]
+
+    def run(page, shuffle):
+        m = LlamaForCausalLM(cfg, max_len=512, kv_page_size=page)
+        m.load_state_dict(sd)
+        m._alloc_state(4)
+        if shuffle:
+            m.kv_alloc.shuffle(3)
+        n_free = len(m.kv_alloc.free)
+        outs = m.generate_greedy_batch([ids_a, ids_b, ids_c], [emb_a.cuda(), emb_b.cuda(), emb_c.cuda()], img_ids=img_ids, max_new_tokens=72)
+        return m, outs, n_free
+
+    m16, o16, n_free = run(16, True)
+    assert o16[0].sequences[0][len(ids_a):len(ids_a) + 16].tolist() == g["text_gen_ids"]
+    assert o16[1].sequences[0][len(ids_b):].tolist() == g["img_gen_ids"]
+    assert rel(o16[1].last_hidden_states, g["img_hidden"]) < TOL
+    pt = m16.page_table.cpu()
+    used = (len(ids_b) + 72 + 15) // 16
+    row = pt[1, :used].tolist()
+    assert len(set(row)) == used and row != sorted(row) and row != sorted(row, reverse=True), row      # really scattered
+    owned = [p for pages in m16.slot_pages for p in pages]
+    assert len(owned) == len(set(owned)) and len(owned) + len(m16.kv_alloc.free) == n_free            # no page owned twice, none lost
+    m64, o64, _ = run(64, False)
+    for a, b in zip(o16, o64):
+        assert a.sequences.tolist() == b.sequences.tolist() and torch.equal(a.last_hidden_states, b.last_hidden_states)
+    # a second batch of requests re-uses the slots: their old pages go back to the pool first
+    m16.generate_greedy_batch([ids_c], [emb_c.cuda()], img_ids=img_ids, max_new_tokens=8)
+    assert sum(len(p) for p in m16.slot_pages) + len(m16.kv_alloc.free) == m16.kv_alloc.n_pages
+    # admission control: a pool that cannot hold the prompt refuses it
+    small = LlamaForCausalLM(cfg, max_len=512, kv_page_size=16, kv_pages=2)
+    small.load_state_dict(sd)
+    with pytest.raises(SeedxError, match="KV cache exhausted"):
+        small.prefill(emb_a.cuda())
