@@ -223,10 +223,9 @@ def test_lora_checkpoint_through_the_yaml_factory_matches_reference_peft(tmp_pat
     print(f"LoRA merged: vs oracle on the fp16-stored merged weights logits {k1:.3e} hidden {k2:.3e}; vs the reference's un-merged fp32 "
           f"forward logits {e1:.3e} hidden {e2:.3e} (without the adapters: {e0:.2f})")
     assert k1 < TOL and k2 < TOL
-    # Against the reference's UN-MERGED fp32 forward the merged weights add one fp16 rounding per weight (2^-11 relative, ~2.8e-4 per GEMM
-    # output, 15 GEMMs deep here -> ~1.1e-3) on top of the kernel error: the fp16 reference itself rounds lora_A/lora_B and every
-    # intermediate the same way.  Bound: 2.5e-3.
-    assert e0 > 0.05 and e1 < 2.5e-3 and e2 < 2.5e-3
+    # Against the reference's UN-MERGED fp32 forward the merged weights add one fp16 rounding per weight (2^-11 relative; 4.3e-4 on these
+    # logits, measured with the oracle) on top of the kernel error — still inside the north_star tolerance (measured on B200: 7.1e-4).
+    assert e0 > 0.05 and e1 < TOL and e2 < TOL
     # adapters without a peft_config are refused, rank mismatches too
     from seedx_b200._lib import SeedxError
     m2, _ = _llm()
