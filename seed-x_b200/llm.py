@@ -106,6 +106,7 @@ class LlamaForCausalLM:
         self._graphs = {}
         self._hidden = None
         self.batched_prefill = os.environ.get("SEEDX_BATCHED_PREFILL", "1") != "0"
+        self.jump_forward = os.environ.get("SEEDX_JUMP_FORWARD", "1") != "0"     # forced image spans ride in the prefill pass
 
     # ---- reference-compatible plumbing --------------------------------------------------------------------------------
     @classmethod
@@ -431,7 +432,7 @@ class LlamaForCausalLM:
             self._hidden = torch.zeros((slots, self.max_len, self.cfg["hidden"]), device=dev, dtype=torch.float32)
             self._graphs = {}
         hidden = self._hidden
-        st0, plens, pre_hidden, embs = [], [], [], []
+        st0, plens, pre_hidden, embs, ids_all, ahead = [], [], [], [], [], []
         for s in range(slots):
             r = min(s, n_req - 1)                       # padding slots replay the last request
             ids = torch.as_tensor(input_ids_list[r]).reshape(-1)
@@ -439,23 +440,46 @@ class LlamaForCausalLM:
             if P + max_new_tokens > self.max_len:
                 raise SeedxError("prompt + max_new_tokens exceeds the KV cache")
             plens.append(P)
-            st0.append([P, 0, 0, P])
-            self.seq[s, :P].copy_(ids.to(dev, torch.int32))
+            ids_all.append(ids)
             embs.append(inputs_embeds_list[r].reshape(P, -1).to(dev, torch.float32))
+            # Jump-forward over a forced image span.  The reference's logits processor makes the continuation of a prompt that ends inside
+            # "<img><img_00000>...<img_00063></img>" independent of the logits (generation.py:23-26: score[next id of the span] = max + 10),
+            # so those tokens are known before the model runs.  All but (at least) the last generated token are appended to the prompt
+            # and ride through the prefill pass as teacher-forced rows on the tensor cores — same positions, same causal attention, same
+            # hidden states as feeding them one by one, but the 26 GB of weights are streamed once instead of once per forced token.
+            last = int(ids[-1])
+            a = []
+            if self.jump_forward and ikey is not None and last in ikey[:-1]:
+                a = list(ikey[ikey.index(last) + 1:])[: max(max_new_tokens - 1, 0)]
+            ahead.append(a)
+        over = max(len(a) for a in ahead) - min(len(a) for a in ahead)     # slots with a longer span run `over` surplus steps (dropped below)
+        if any(plens[s] + max_new_tokens + over > self.max_len for s in range(slots)):
+            ahead, over = [[] for _ in range(slots)], 0
+        for s in range(slots):
+            P, a = plens[s], ahead[s]
+            self.seq[s, :P].copy_(ids_all[s].to(dev, torch.int32))
+            if a:
+                a_t = torch.tensor(a, dtype=torch.int32, device=dev)
+                self.seq[s, P:P + len(a)].copy_(a_t)
+                embs[s] = torch.cat([embs[s], self.get_input_embeddings()(a_t)[0]], dim=0)
+            st0.append([P + len(a), 0, len(a), P])
         if slots > 1 and self.batched_prefill:          # one pass over the weights for all prompts
             streams = self.prefill_batch(embs, list(range(slots)))
         else:
             streams = [self.prefill(embs[s], slot=s) for s in range(slots)]
         for s in range(slots):                           # pages for the tokens the loop will append
-            self.reserve_kv(s, plens[s] + max_new_tokens)
+            self.reserve_kv(s, plens[s] + max_new_tokens + over)
         for s, xs in enumerate(streams):
-            ops.gemv(self.lm_head, xs[plens[s] - 1], self.logits[s], rms_w=self.norm, eps=self.cfg["eps"])
+            P, na = plens[s], len(ahead[s])
+            ops.gemv(self.lm_head, xs[P + na - 1], self.logits[s], rms_w=self.norm, eps=self.cfg["eps"])
+            if na:   # post-norm states of the positions that consumed the pre-appended tokens = rows 0..na-1 of the harvest buffer
+                ops.layernorm(xs[P:P + na], self.norm, None, self.cfg["eps"], out=hidden[s, :na], rms=True)
             if keep_prefill_hidden and s < n_req:      # post-norm states of the prompt positions (HF hidden_states[0][-1])
-                pre_hidden.append(ops.layernorm(xs, self.norm, None, self.cfg["eps"], out_dtype=torch.float32, rms=True))
+                pre_hidden.append(ops.layernorm(xs[:P], self.norm, None, self.cfg["eps"], out_dtype=torch.float32, rms=True))
         self.state.copy_(torch.tensor(st0, dtype=torch.int32))
         ops.logits_argmax(self.logits, img_dev, self.seq, self.state, eos_id, suppress_eos)
         trace.mark("llm.prefill")
-        steps = max_new_tokens - 1
+        steps = max_new_tokens - 1 - min(len(a) for a in ahead)
         if steps > 0:
             g = None
             if use_graph:
@@ -486,6 +510,7 @@ class LlamaForCausalLM:
         outs = []
         for r in range(n_req):
             n_gen = st[r][1] if st[r][1] else st[r][2]   # stop at (and include) the first EOS, like HF greedy_search
+            n_gen = min(n_gen, max_new_tokens)           # surplus lock-step tokens of a slot that jumped further ahead are dropped
             outs.append(GreedyOutput(seq_host[r, : plens[r] + n_gen].to(torch.int64).unsqueeze(0), hidden[r, : max(n_gen - 1, 0)].clone(), n_gen))
             outs[-1].prefill_hidden = pre_hidden[r] if keep_prefill_hidden else None
         return outs

@@ -334,3 +334,44 @@ def test_paged_kv_cache_with_scattered_pages_matches_reference_golden():
     small.load_state_dict(sd)
     with pytest.raises(SeedxError, match="KV cache exhausted"):
         small.prefill(emb_a.cuda())
+
+
+def test_jump_forward_over_forced_image_span_equals_token_by_token():
+    """A prompt that ends inside "<img>...</img>" has a continuation the logits cannot change (generation.py:23-26); by default those tokens
+    ride through the prefill pass as teacher-forced rows.  Result == feeding them one by one (SEEDX_JUMP_FORWARD=0 behaviour): ids exact,
+    hidden states <= 1e-3 — for the full span, for a span cut by max_new_tokens, and for a lock-step batch where only one request jumps."""
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    m, cfg = _llm()
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    sd = synth.llama_state_dict(cfg)
+    img_ids = tok.encode("".join(["<img>"] + ["<img_{:05d}>".format(i) for i in range(64)] + ["</img>"]))
+    ids_a, emb_a = g["ids"], g["embeds"].cuda()
+    mid = tok.encode("<img><img_00000><img_00001><img_00002>")                      # prompt that stops in the middle of a span
+    ids_b = g["ids"] + mid
+    emb_b = torch.cat([g["embeds"], sd["model.embed_tokens.weight"][torch.tensor(mid)]]).cuda()
+    ids_c = g["ids"] + [tok.encode("<img>")[0]]
+    emb_c = torch.cat([g["embeds"], sd["model.embed_tokens.weight"][ids_c[-1]][None]]).cuda()
+
+    def both(ids_list, emb_list, n_new):
+        res = []
+        for jf in (True, False):
+            m.jump_forward = jf
+            res.append(m.generate_greedy_batch(ids_list, emb_list, img_ids=img_ids, max_new_tokens=n_new))
+        m.jump_forward = True
+        for a, b in zip(*res):
+            assert a.sequences.tolist() == b.sequences.tolist()
+            assert a.n_generated == b.n_generated == n_new and a.last_hidden_states.shape == b.last_hidden_states.shape
+            if a.last_hidden_states.numel():
+                assert rel(a.last_hidden_states, b.last_hidden_states) < TOL
+        return res[0]
+
+    out = both([ids_c], [emb_c], 72)[0]
+    assert out.sequences[0][len(ids_c):].tolist() == g["img_gen_ids"] and rel(out.last_hidden_states, g["img_hidden"]) < TOL
+    out = both([ids_b], [emb_b], 72)[0]
+    assert out.sequences[0][len(ids_b):len(ids_b) + 62].tolist() == img_ids[4:]     # the rest of the span, then free text
+    out = both([ids_c], [emb_c], 10)[0]                                             # budget ends inside the span
+    assert out.sequences[0][len(ids_c):].tolist() == img_ids[1:11]
+    both([ids_c], [emb_c], 1)
+    outs = both([ids_a, ids_c, ids_b], [emb_a, emb_c, emb_b], 72)                    # ragged: slot 0 does not jump, slots 1-3 do
+    assert outs[0].sequences[0][len(ids_a):len(ids_a) + 16].tolist() == g["text_gen_ids"]
+    assert outs[1].sequences[0][len(ids_c):].tolist() == g["img_gen_ids"]
