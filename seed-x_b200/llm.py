@@ -542,7 +542,7 @@ class LlamaForCausalLM:
             img_ids = list(proc.img_ids_list)
         eos = self.cfg.get("eos", 2) if isinstance(eos_token_id, str) else eos_token_id
         out = self.generate_greedy_batch([ids[0]], [emb], img_ids=img_ids, max_new_tokens=max_new_tokens, eos_id=eos,
-                                         keep_prefill_hidden=bool(output_hidden_states))[0]
+                                         keep_prefill_hidden=bool(output_hidden_states), use_graph=kw.get("use_graph", True))[0]
         if not return_dict_in_generate:
             return out.sequences
         res = GreedySearchOutput(sequences=out.sequences)

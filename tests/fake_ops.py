@@ -1,0 +1,160 @@
+"""TEST DOUBLE — not product code.  Plain-torch CPU restatements of the `seedx_b200.ops` entry points that `seedx_b200.llm.LlamaForCausalLM`
+calls, with the semantics documented in include/seedx.h (fp16 storage / operand rounding where the kernels round, fp32 accumulation).
+
+Purpose: the HOST logic of the stage-2 engine — paged KV bookkeeping, lock-step batching, jump-forward over forced image spans, the
+HF-style `generate` surface — can then run in the `-m "not gpu"` suite against the reference goldens, without a GPU and without the
+library.  The product never imports this module (it lives under tests/); on a GPU the same host code runs over libseedx.so and is checked by
+tests/test_llm_gpu.py.
+"""
+import torch
+import torch.nn.functional as F
+
+ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
+
+
+def _f16(t):
+    return t.to(torch.float16).float()
+
+
+def cast(x, dtype):
+    return x.to(dtype)
+
+
+def gemm(a, w, out=None, *, bias=None, residual=None, act=ACT_NONE, gated=False, alpha=1.0, out_dtype=torch.float16, **kw):
+    assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 2 and not any(v is not None and v is not False and v != 0 for v in kw.values())
+    acc = alpha * (a.float() @ w.float().t())
+    if bias is not None:
+        acc = acc + bias
+    if gated:                                                    # interleaved rows [value_j, gate_j]
+        g = acc[:, 1::2]
+        acc = acc[:, 0::2] * (F.silu(g) if act == ACT_SILU else F.gelu(g))
+    elif act == ACT_SILU:
+        acc = F.silu(acc)
+    elif act == ACT_GELU:
+        acc = F.gelu(acc)
+    if residual is not None:
+        acc = acc + residual.float()
+    if out is None:
+        out = torch.empty(acc.shape, dtype=out_dtype)
+    out.copy_(acc.to(out.dtype))
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out=None, *, out_dtype=torch.float16, rms=False, add=None, out2=None):
+    assert add is None and out2 is None
+    x2 = x.reshape(-1, x.shape[-1]).float()
+    if rms:
+        y = x2 * torch.rsqrt(x2.pow(2).mean(-1, keepdim=True) + eps) * gamma
+    else:
+        y = F.layer_norm(x2, (x2.shape[-1],), gamma, beta, eps)
+    if out is None:
+        out = torch.empty(x2.shape, dtype=out_dtype)
+    out.reshape(-1, x2.shape[-1]).copy_(y.to(out.dtype))
+    return out
+
+
+def attention(q, k, v, out, *, scale, causal=False):
+    """[batch, head, seq, d] fp16 views; fp32 softmax; causal = bottom-right aligned like the kernels (query i sees keys <= i + Sk - Sq)"""
+    Sq, Sk = q.shape[2], k.shape[2]
+    s = torch.einsum("bhqd,bhkd->bhqk", q.float(), k.float()) * scale
+    if causal:
+        mask = torch.arange(Sk)[None, :] > (torch.arange(Sq)[:, None] + (Sk - Sq))
+        s = s.masked_fill(mask, float("-inf"))
+    o = torch.einsum("bhqk,bhkd->bhqd", s.softmax(-1), v.float())
+    out.copy_(o.to(out.dtype))
+    return out
+
+
+def _rows(pt_row, page_size, positions):
+    p = torch.as_tensor(positions, dtype=torch.long)
+    return pt_row.long()[p // page_size] * page_size + p % page_size
+
+
+def _rope(x, pos, inv_freq):
+    """x [..., H, d]; rotate-half RoPE at integer positions pos [...]"""
+    d = x.shape[-1]
+    ang = pos.float()[..., None] * inv_freq                      # [..., d/2]
+    c, s = ang.cos()[..., None, :], ang.sin()[..., None, :]
+    x0, x1 = x[..., : d // 2], x[..., d // 2:]
+    return torch.cat([x0 * c - x1 * s, x1 * c + x0 * s], dim=-1)
+
+
+def rope_kv_prefill(qkv, pos0, heads, head_dim, inv_freq, kcache, vcache, page_table_row=None, page_size=0):
+    T, D = qkv.shape[0], heads * head_dim
+    pos = torch.arange(pos0, pos0 + T)
+    q = _rope(qkv[:, :D].float().view(T, heads, head_dim), pos, inv_freq).reshape(T, D).half()
+    k = _rope(qkv[:, D:2 * D].float().view(T, heads, head_dim), pos, inv_freq).reshape(T, D).half()
+    qkv[:, :D] = q
+    qkv[:, D:2 * D] = k
+    assert page_table_row is not None
+    rows = _rows(page_table_row, page_size, pos)
+    kcache.view(-1, D)[rows] = k
+    vcache.view(-1, D)[rows] = qkv[:, 2 * D:]
+
+
+def embed_rows(table, out, *, ids=None, state=None, seq=None):
+    if ids is None:
+        ids = torch.stack([seq[b, state[b, 0] - 1] for b in range(state.shape[0])])
+    out.reshape(-1, out.shape[-1]).copy_(table[ids.long()].float())
+    return out
+
+
+def gemv(W, x, out, *, rms_w=None, eps=1e-5, residual=None, gated=False):
+    x2 = x.reshape(-1, W.shape[1]).float()
+    if rms_w is not None:
+        x2 = x2 * torch.rsqrt(x2.pow(2).mean(-1, keepdim=True) + eps) * rms_w
+    r = _f16(x2) @ W.float().t()                                 # activations are staged as fp16
+    if gated:
+        r = r[:, 0::2] * F.silu(r[:, 1::2])
+    if residual is not None:
+        r = r + residual.reshape(r.shape)
+    out.reshape(r.shape).copy_(r)
+    return out
+
+
+def decode_attention(qkv, state, inv_freq, kcache, vcache, out, heads, head_dim, page_table=None, page_size=0):
+    B, D = qkv.shape[0], heads * head_dim
+    assert page_table is not None
+    for b in range(B):
+        pos = int(state[b, 0]) - 1
+        p = torch.tensor(pos)
+        q = _rope(qkv[b, :D].view(heads, head_dim), p, inv_freq)
+        k = _rope(qkv[b, D:2 * D].view(heads, head_dim), p, inv_freq)
+        row = _rows(page_table[b], page_size, [pos])
+        kcache.view(-1, D)[row] = k.reshape(1, D).half()
+        vcache.view(-1, D)[row] = qkv[b, 2 * D:].reshape(1, D).half()
+        rows = _rows(page_table[b], page_size, list(range(pos + 1)))
+        K = kcache.view(-1, D)[rows].float().view(pos + 1, heads, head_dim)
+        V = vcache.view(-1, D)[rows].float().view(pos + 1, heads, head_dim)
+        s = torch.einsum("hd,thd->ht", q, K) * head_dim ** -0.5
+        out[b] = torch.einsum("ht,thd->hd", s.softmax(-1), V).reshape(D)
+    return out
+
+
+def store_hidden(x, state, hidden):
+    for b in range(hidden.shape[0]):
+        row = int(state[b, 0]) - int(state[b, 3]) - 1
+        if 0 <= row < hidden.shape[1]:
+            hidden[b, row] = x[b]
+
+
+def logits_argmax(logits, img_ids, seq, state, eos_id, suppress_eos):
+    """generation.py:19-31 + greedy argmax + append (restates logits_argmax_kernel; lowest index wins ties)"""
+    ids = img_ids.tolist() if img_ids is not None else []
+    for b in range(logits.shape[0]):
+        n = int(state[b, 0])
+        last = int(seq[b, n - 1])
+        if last in ids[:-1]:
+            nxt = ids[ids.index(last) + 1]
+        else:
+            if ids:
+                logits[b, torch.tensor(ids[1:])] = 0.0
+            if suppress_eos and eos_id is not None and 0 <= eos_id < logits.shape[1]:
+                logits[b, eos_id] = float("-inf")
+            nxt = int(torch.argmax(logits[b]))
+        if n < seq.shape[1]:
+            seq[b, n] = nxt
+            state[b, 0] = n + 1
+            state[b, 2] += 1
+            if eos_id is not None and nxt == eos_id and not suppress_eos and int(state[b, 1]) == 0:
+                state[b, 1] = state[b, 2]

@@ -1,0 +1,128 @@
+"""Host logic of the stage-2 engine on the CPU: `seedx_b200.llm.LlamaForCausalLM` runs unchanged, but its `ops` module is replaced by
+tests/fake_ops.py (plain-torch restatements of the C entry points — a test double, see its header).  What is checked here is everything the
+Python host decides: paged-KV bookkeeping, lock-step batching of ragged prompts, jump-forward over forced image spans, budget / EOS handling and
+the HF-style generate surface — against the goldens produced by the reference's own modules (tests/golden/llama_tiny.pt)."""
+import os
+
+import pytest
+import torch
+
+import fake_ops
+from seedx_b200 import llm as llm_mod
+from seedx_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+
+@pytest.fixture
+def host(monkeypatch):
+    monkeypatch.setattr(llm_mod, "ops", fake_ops)
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    cfg = synth.TINY_LLAMA
+    sd = synth.llama_state_dict(cfg)
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    img_ids = tok.encode("".join(["<img>"] + ["<img_{:05d}>".format(i) for i in range(64)] + ["</img>"]))
+
+    def make(**kw):
+        m = llm_mod.LlamaForCausalLM(cfg, max_len=256, device="cpu", **kw)
+        m.load_state_dict({k: v.clone() for k, v in sd.items()})
+        return m
+
+    ids_b = g["ids"] + [tok.encode("<img>")[0]]
+    emb_b = torch.cat([g["embeds"], sd["model.embed_tokens.weight"][ids_b[-1]][None]])
+    return dict(g=g, cfg=cfg, sd=sd, tok=tok, img_ids=img_ids, make=make, ids_b=ids_b, emb_b=emb_b)
+
+
+def test_prefill_and_chunked_prefill_through_pages(host):
+    g, m = host["g"], host["make"](kv_page_size=16)
+    m.kv_alloc.shuffle(1)
+    xs = m.prefill(g["embeds"])
+    logits, hid = m.logits_all(xs)
+    assert rel(logits, g["prefill_logits"]) < TOL and rel(hid, g["prefill_hidden"]) < TOL
+    m.prefill(g["embeds"][:-8])
+    tail, _ = m.logits_all(m.prefill(g["embeds"][-8:], pos0=g["embeds"].shape[0] - 8))      # keys / values gathered from scattered pages
+    assert rel(tail, logits[-8:]) < TOL
+
+
+@pytest.mark.parametrize("jump", [True, False])
+def test_greedy_loop_matches_reference_golden(host, jump):
+    g, m = host["g"], host["make"](kv_page_size=16)
+    m.jump_forward = jump
+    m.kv_alloc.shuffle(2)
+    out = m.generate_greedy(g["ids"], g["embeds"], img_ids=host["img_ids"], max_new_tokens=16, use_graph=False)
+    assert out.sequences[0][len(g["ids"]):].tolist() == g["text_gen_ids"] and rel(out.last_hidden_states, g["text_hidden"]) < TOL
+    out = m.generate_greedy(host["ids_b"], host["emb_b"], img_ids=host["img_ids"], max_new_tokens=72, use_graph=False)
+    assert out.sequences[0][len(host["ids_b"]):].tolist() == g["img_gen_ids"]
+    assert out.n_generated == 72 and rel(out.last_hidden_states, g["img_hidden"]) < TOL
+    assert sum(len(p) for p in m.slot_pages) + len(m.kv_alloc.free) == m.kv_alloc.n_pages
+
+
+def test_jump_forward_bookkeeping(host):
+    """how many token-loop steps remain, what lands in the sequence / harvest buffers, budget cut inside the span, surplus tokens dropped"""
+    g, img_ids = host["g"], host["img_ids"]
+    m = host["make"]()
+    calls = {"n": 0}
+    real = m._decode_step
+
+    def counting(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+    m._decode_step = counting
+    out = m.generate_greedy(host["ids_b"], host["emb_b"], img_ids=img_ids, max_new_tokens=72, use_graph=False)
+    assert calls["n"] == 72 - 1 - 65                        # the 65 forced tokens rode in the prefill pass
+    assert out.sequences[0][len(host["ids_b"]):].tolist() == g["img_gen_ids"]
+    calls["n"] = 0
+    out = m.generate_greedy(host["ids_b"], host["emb_b"], img_ids=img_ids, max_new_tokens=10, use_graph=False)     # budget ends inside the span
+    assert calls["n"] == 0 and out.sequences[0][len(host["ids_b"]):].tolist() == img_ids[1:11] and out.last_hidden_states.shape[0] == 9
+    assert rel(out.last_hidden_states, g["img_hidden"][:9]) < TOL
+    out = m.generate_greedy(host["ids_b"], host["emb_b"], img_ids=img_ids, max_new_tokens=1, use_graph=False)
+    assert out.sequences[0][len(host["ids_b"]):].tolist() == img_ids[1:2] and out.last_hidden_states.shape[0] == 0
+    # lock-step batch where only one request jumps: the jumping slot runs surplus steps that are dropped again
+    calls["n"] = 0
+    outs = m.generate_greedy_batch([g["ids"], host["ids_b"]], [g["embeds"], host["emb_b"]], img_ids=img_ids, max_new_tokens=72, use_graph=False)
+    assert calls["n"] == 71
+    assert outs[0].sequences[0][len(g["ids"]):len(g["ids"]) + 16].tolist() == g["text_gen_ids"] and outs[0].n_generated == 72
+    assert outs[1].sequences[0][len(host["ids_b"]):].tolist() == g["img_gen_ids"] and outs[1].n_generated == 72
+    assert rel(outs[1].last_hidden_states, g["img_hidden"]) < TOL
+    # without room for the surplus steps the shortcut is not taken (same result)
+    tight = host["make"]()
+    tight.max_len = len(host["ids_b"]) + 72 + 10
+    tight._alloc_state(2)
+    outs2 = tight.generate_greedy_batch([g["ids"], host["ids_b"]], [g["embeds"], host["emb_b"]], img_ids=img_ids, max_new_tokens=72, use_graph=False)
+    assert [o.sequences.tolist() for o in outs2] == [o.sequences.tolist() for o in outs]
+
+
+def test_lock_step_batch_of_ragged_prompts(host):
+    g, img_ids = host["g"], host["img_ids"]
+    m = host["make"](kv_page_size=16)
+    outs = m.generate_greedy_batch([g["ids"], host["ids_b"], g["ids"][:20]], [g["embeds"], host["emb_b"], g["embeds"][:20]], img_ids=img_ids,
+                                   max_new_tokens=72, use_graph=False)
+    assert m.slots == 4
+    assert outs[0].sequences[0][len(g["ids"]):len(g["ids"]) + 16].tolist() == g["text_gen_ids"]
+    assert outs[1].sequences[0][len(host["ids_b"]):].tolist() == g["img_gen_ids"]
+    single = m.generate_greedy(g["ids"][:20], g["embeds"][:20], img_ids=img_ids, max_new_tokens=72, use_graph=False)
+    assert outs[2].sequences.tolist() == single.sequences.tolist()
+    owned = [p for pages in m.slot_pages for p in pages]
+    assert len(owned) == len(set(owned))
+
+
+def test_eos_stops_a_sequence_and_hf_generate_surface(host):
+    g, tok = host["g"], host["tok"]
+    m = host["make"]()
+    first = g["text_gen_ids"][0]
+    seq = m.generate(input_ids=torch.tensor([g["ids"]]), inputs_embeds=g["embeds"][None], max_new_tokens=16, eos_token_id=g["text_gen_ids"][3], use_graph=False)
+    assert seq[0].tolist() == g["ids"] + g["text_gen_ids"][:4]                   # stops at, and includes, the EOS (HF greedy_search)
+    proc = llm_mod.AutoImageTokenGenerationProcessor(tok, num_img_gen_tokens=64)
+    out = m.generate(input_ids=torch.tensor([host["ids_b"]]), inputs_embeds=host["emb_b"][None], output_hidden_states=True, return_dict_in_generate=True,
+                     logits_processor=[proc], temperature=0.7, num_beams=1, max_new_tokens=72, top_p=0.5, do_sample=False, eos_token_id=None, use_graph=False)
+    P = len(host["ids_b"])
+    assert out.sequences[0][P:].tolist() == g["img_gen_ids"] and len(out.hidden_states) == 72
+    last_hidden_states = torch.cat([h[-1] for h in out.hidden_states], dim=1)[0, P:, :]          # exactly seed_x.py:196-197
+    assert rel(last_hidden_states, g["img_hidden"]) < TOL
+    assert rel(out.hidden_states[0][-1][0, :P - 1], g["prefill_hidden"]) < TOL
+    assert first == int(m.generate(input_ids=torch.tensor([g["ids"]]), inputs_embeds=g["embeds"][None], max_new_tokens=1, eos_token_id=None, use_graph=False)[0, -1])
