@@ -20,11 +20,27 @@ def cast(x, dtype):
     return x.to(dtype)
 
 
-def gemm(a, w, out=None, *, bias=None, residual=None, act=ACT_NONE, gated=False, alpha=1.0, out_dtype=torch.float16, **kw):
+def unary_f16(x, out=None, act=ACT_NONE):
+    assert act == ACT_NONE
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float16)
+    out.copy_(x.to(torch.float16))
+    return out
+
+
+def scatter_rows(src, idx, dst, src_idx=None):
+    rows = src if src_idx is None else src[src_idx.long()]
+    dst[idx.long()] = rows.float()
+    return dst
+
+
+def gemm(a, w, out=None, *, bias=None, bias_g=None, bias_g_rows=0, residual=None, act=ACT_NONE, gated=False, alpha=1.0, out_dtype=torch.float16, **kw):
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 2 and not any(v is not None and v is not False and v != 0 for v in kw.values())
     acc = alpha * (a.float() @ w.float().t())
     if bias is not None:
         acc = acc + bias
+    if bias_g is not None:                                       # one additive row per group of bias_g_rows output rows
+        acc = acc + bias_g.repeat_interleave(bias_g_rows, dim=0)
     if gated:                                                    # interleaved rows [value_j, gate_j]
         g = acc[:, 1::2]
         acc = acc[:, 0::2] * (F.silu(g) if act == ACT_SILU else F.gelu(g))
@@ -41,7 +57,6 @@ def gemm(a, w, out=None, *, bias=None, residual=None, act=ACT_NONE, gated=False,
 
 
 def layernorm(x, gamma, beta, eps, out=None, *, out_dtype=torch.float16, rms=False, add=None, out2=None):
-    assert add is None and out2 is None
     x2 = x.reshape(-1, x.shape[-1]).float()
     if rms:
         y = x2 * torch.rsqrt(x2.pow(2).mean(-1, keepdim=True) + eps) * gamma
@@ -50,12 +65,18 @@ def layernorm(x, gamma, beta, eps, out=None, *, out_dtype=torch.float16, rms=Fal
     if out is None:
         out = torch.empty(x2.shape, dtype=out_dtype)
     out.reshape(-1, x2.shape[-1]).copy_(y.to(out.dtype))
+    if add is not None:                                          # second output y + add[row % add_rows]
+        y2 = y + add.repeat(x2.shape[0] // add.shape[0], 1)
+        out2 = torch.empty(x2.shape, dtype=out.dtype) if out2 is None else out2
+        out2.copy_(y2.to(out2.dtype))
+        return out, out2
     return out
 
 
 def attention(q, k, v, out, *, scale, causal=False):
     """[batch, head, seq, d] fp16 views; fp32 softmax; causal = bottom-right aligned like the kernels (query i sees keys <= i + Sk - Sq)"""
     Sq, Sk = q.shape[2], k.shape[2]
+    q = q.expand(k.shape[0], -1, -1, -1)                         # shared queries (attention pooling): q batch 1
     s = torch.einsum("bhqd,bhkd->bhqk", q.float(), k.float()) * scale
     if causal:
         mask = torch.arange(Sk)[None, :] > (torch.arange(Sq)[:, None] + (Sk - Sq))

@@ -28,8 +28,8 @@ def host(monkeypatch):
     tok = synth.SynthTokenizer(vocab=cfg["vocab"])
     img_ids = tok.encode("".join(["<img>"] + ["<img_{:05d}>".format(i) for i in range(64)] + ["</img>"]))
 
-    def make(**kw):
-        m = llm_mod.LlamaForCausalLM(cfg, max_len=256, device="cpu", **kw)
+    def make(max_len=256, **kw):
+        m = llm_mod.LlamaForCausalLM(cfg, max_len=max_len, device="cpu", **kw)
         m.load_state_dict({k: v.clone() for k, v in sd.items()})
         return m
 
@@ -126,3 +126,35 @@ def test_eos_stops_a_sequence_and_hf_generate_surface(host):
     assert rel(last_hidden_states, g["img_hidden"]) < TOL
     assert rel(out.hidden_states[0][-1][0, :P - 1], g["prefill_hidden"]) < TOL
     assert first == int(m.generate(input_ids=torch.tensor([g["ids"]]), inputs_embeds=g["embeds"][None], max_new_tokens=1, eos_token_id=None, use_graph=False)[0, -1])
+
+
+def test_agent_generate_host_logic_vs_oracle(monkeypatch, host):
+    """ContinuousLVLM.generate on the CPU double: input resampler + patch-position row, mask scatter, forced image span, hidden-state harvest,
+    output resampler — ids / text exact and img_gen_feat <= 1e-3 against oracle/llm.py::lvlm_generate (multi-image prompt: 2 + 1 views)."""
+    from oracle import llm as ollm
+    from seedx_b200 import agent as agent_mod
+    from seedx_b200 import demo
+    from seedx_b200 import vit as vit_mod
+    monkeypatch.setattr(agent_mod, "ops", fake_ops)
+    monkeypatch.setattr(vit_mod, "ops", fake_ops)
+    cfg, tok = host["cfg"], host["tok"]
+    m = host["make"](max_len=512)
+    vit_dim = 320
+    agent_sd = synth.agent_state_dict(cfg["hidden"], vit_dim)
+    agent = agent_mod.ContinuousLVLM.from_pretrained(llm=m, input_resampler=agent_mod.Resampler(8, cfg["hidden"], 2, vit_dim),
+                                                     output_resampler=agent_mod.Resampler(8, vit_dim, 2, cfg["hidden"]), add_patch_pos=True, vit_down=True)
+    agent.load_state_dict(agent_sd)
+    N = 3
+    image_embeds = synth.randn("agent_img_cpu", (N, 256, vit_dim))
+    patch_pos = torch.tensor([[0.25, 0.5], [0.5, 0.5], [0.5, 0.5]])
+    input_ids, ids_cmp_mask = demo.chat_prompt(tok, ["what changed?", "the sky", "draw it again"], views_per_image=[2, 1], force_image=True)
+    assert int(ids_cmp_mask.sum()) == N * 64
+    embeds_cmp_mask = torch.ones((N, 64), dtype=torch.bool)
+    ref = ollm.lvlm_generate(host["sd"], agent_sd, cfg, tok, input_ids[0].tolist(), image_embeds, ids_cmp_mask[0], embeds_cmp_mask, patch_pos, 70)
+    real = m.generate_greedy_batch
+    monkeypatch.setattr(m, "generate_greedy_batch", lambda *a, **k: real(*a, **dict(k, use_graph=False)))
+    out = agent.generate(tokenizer=tok, input_ids=input_ids, image_embeds=image_embeds, embeds_cmp_mask=embeds_cmp_mask, ids_cmp_mask=ids_cmp_mask,
+                         patch_positions=patch_pos, max_new_tokens=70)
+    assert out["ids"] == ref["ids"] and out["text"] == ref["text"]
+    assert out["has_img_output"] and out["num_gen_imgs"] == 1 and tuple(out["img_gen_feat"].shape) == (1, 64, vit_dim)
+    assert rel(out["img_gen_feat"], ref["img_gen_feat"]) < TOL
