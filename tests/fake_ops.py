@@ -179,3 +179,35 @@ def logits_argmax(logits, img_ids, seq, state, eos_id, suppress_eos):
             state[b, 2] += 1
             if eos_id is not None and nxt == eos_id and not suppress_eos and int(state[b, 1]) == 0:
                 state[b, 1] = state[b, 2]
+
+
+def nchw_to_nhwc_f16(x, cpad, scale=1.0, out=None):
+    """fp32 NCHW [B,C,H,W] -> fp16 NHWC [B,H,W,cpad] (channels C..cpad-1 zero), values scaled"""
+    B, C, H, W = x.shape
+    if out is None:
+        out = torch.zeros((B, H, W, cpad), dtype=torch.float16)
+    out[..., :C] = (x.float() * scale).permute(0, 2, 3, 1).to(torch.float16)
+    return out
+
+
+def cfg_euler_step(eps, x, unet_in, branches, guidance, image_guidance, sigma, sigma_next, init_sigma=1.0):
+    """restates cfg_euler_kernel: classifier-free-guidance combine (2-way, or 3-way in sigma space: pipeline_stable_diffusion_xl_t2i_edit.py:
+    928-950) + Euler step (EulerDiscreteScheduler.step) + scale_model_input for the next step written into channels 0..3 of every branch"""
+    B = x.shape[0]
+    if eps is None:
+        xn = x * init_sigma
+    else:
+        e = eps.reshape(branches, B, x.shape[2], x.shape[3], 4).permute(0, 1, 4, 2, 3)          # [branch, B, 4, h, w]
+        if branches == 2:
+            comb = e[0] + guidance * (e[1] - e[0])
+        else:
+            et, ei, eu = (x - sigma * e[i] for i in range(3))
+            c = eu + guidance * (et - ei) + image_guidance * (ei - eu)
+            comb = (c - x) / (-sigma)
+        x0 = x - sigma * comb
+        xn = x + (x - x0) / sigma * (sigma_next - sigma)
+    x.copy_(xn)
+    s = (xn * (sigma_next ** 2 + 1.0) ** -0.5).permute(0, 2, 3, 1).to(torch.float16)
+    for br in range(branches):
+        unet_in[br * B:(br + 1) * B, ..., :4] = s
+    return x
