@@ -8,7 +8,7 @@ import time
 
 import torch
 
-from . import ops, synth, trace
+from . import synth, trace
 from .adapter import SDXLAdapter
 from .agent import ContinuousLVLM, Resampler
 from .llm import LLAMA_13B, LlamaForCausalLM
@@ -65,7 +65,6 @@ class SeedXEngine:
         finally:
             synth.set_device("cpu")
         self.tok = synth.SynthTokenizer(vocab=llm_cfg["vocab"])
-        self.timers = {}
         log(f"engine ready {time.time() - t0:.1f}s")
 
     # ---- prompt layout (eval_img2text_seed_x_i.py:142-162) ---------------------------------------------------

@@ -1,6 +1,4 @@
 """Parity of the non-GEMM kernels against torch fp32 references of the same op (CUDA path through the C ABI)."""
-import math
-
 import pytest
 import torch
 import torch.nn.functional as F
