@@ -107,6 +107,7 @@ class LlamaForCausalLM:
         self._hidden = None
         self.batched_prefill = os.environ.get("SEEDX_BATCHED_PREFILL", "1") != "0"
         self.jump_forward = os.environ.get("SEEDX_JUMP_FORWARD", "1") != "0"     # forced image spans ride in the prefill pass
+        self.jump_forward_mid = os.environ.get("SEEDX_JUMP_FORWARD_MID", "0") == "1"   # experimental: also spans opened mid-generation
 
     # ---- reference-compatible plumbing --------------------------------------------------------------------------------
     @classmethod
@@ -495,15 +496,21 @@ class LlamaForCausalLM:
                     g.n_kernels = _lib.launch_count() - n0
                     torch.cuda.current_stream().wait_stream(s_)
                     self._graphs[gkey] = g
-            for i in range(steps):
+            def run_step():
                 if g is not None:
                     g.replay()
                     _lib.note_replay(g.n_kernels)
                 else:
                     self._decode_step(hidden, img_dev, eos_id, suppress_eos)
-                if eos_id is not None and not suppress_eos and (i + 1) % sync_every == 0:
-                    if bool((self.state[:n_req, 1] != 0).all().item()):
-                        break
+
+            if self.jump_forward_mid and ikey is not None:
+                self._decode_with_span_jumps(run_step, hidden, ikey, slots, n_req, plens, max_new_tokens, suppress_eos)
+            else:
+                for i in range(steps):
+                    run_step()
+                    if eos_id is not None and not suppress_eos and (i + 1) % sync_every == 0:
+                        if bool((self.state[:n_req, 1] != 0).all().item()):
+                            break
         trace.mark("llm.decode")
         st = self.state.cpu().tolist()
         seq_host = self.seq.cpu()
@@ -514,6 +521,40 @@ class LlamaForCausalLM:
             outs.append(GreedyOutput(seq_host[r, : plens[r] + n_gen].to(torch.int64).unsqueeze(0), hidden[r, : max(n_gen - 1, 0)].clone(), n_gen))
             outs[-1].prefill_hidden = pre_hidden[r] if keep_prefill_hidden else None
         return outs
+
+    def _decode_with_span_jumps(self, run_step, hidden, ikey, slots, n_req, plens, max_new_tokens, suppress_eos):
+        """EXPERIMENTAL (SEEDX_JUMP_FORWARD_MID=1, off by default): token loop that also jumps over image spans the model opens by itself
+        ("... here it is: <img>" in the middle of an answer).  The decision needs the last generated id on the host, so every step pays one
+        device sync; in exchange the rest of a span is computed as ONE chunked prefill over the cached keys (tensor-core GEMMs) instead of
+        up to 64 weight-streaming steps.  Slots then progress unevenly: the loop runs until every request has its `max_new_tokens` (or
+        EOS); a slot that is already done keeps stepping in lock-step and its surplus tokens are dropped by the caller."""
+        dev = self.device
+        for _ in range(4 * max_new_tokens + 16):
+            st = self.state.cpu().tolist()
+            gen = [st[s][2] for s in range(slots)]
+            done = [(st[s][1] != 0 and not suppress_eos) or gen[s] >= max_new_tokens for s in range(slots)]
+            if all(done[:n_req]):
+                return
+            lens = [st[s][0] for s in range(slots)]
+            last = self.seq[torch.arange(slots, device=dev), torch.tensor(lens, device=dev) - 1].cpu().tolist()
+            for s in range(slots):
+                if done[s] or last[s] not in ikey[:-1]:
+                    continue
+                forced = list(ikey[ikey.index(last[s]) + 1:])[: max_new_tokens - 1 - gen[s]]      # keep one token for the step below
+                L, P, a = lens[s], plens[s], len(forced)
+                if a < 2 or L + a + 1 > self.max_len:
+                    continue
+                # consume [last, forced[:-1]] at positions L-1 .. L+a-2 in one pass; forced[-1] is consumed by the regular step
+                chunk = torch.tensor([last[s]] + forced[:-1], dtype=torch.int32, device=dev)
+                xs = self.prefill(self.get_input_embeddings()(chunk)[0], pos0=L - 1, slot=s)
+                ops.layernorm(xs, self.norm, None, self.cfg["eps"], out=hidden[s, L - 1 - P:L - 1 - P + a], rms=True)
+                self.seq[s, L:L + a].copy_(torch.tensor(forced, dtype=torch.int32, device=dev))
+                self.state[s].copy_(torch.tensor([L + a, st[s][1], gen[s] + a, P], dtype=torch.int32))
+                lens[s] = L + a
+            for s in range(slots):
+                self.reserve_kv(s, min(lens[s], self.max_len))
+            run_step()
+        raise SeedxError("decode loop did not terminate")
 
     def generate(self, input_ids=None, inputs_embeds=None, output_hidden_states=False, return_dict_in_generate=False, logits_processor=None,
                  max_new_tokens=20, do_sample=False, num_beams=1, temperature=None, top_p=None, eos_token_id="default", **kw):

@@ -375,3 +375,27 @@ def test_jump_forward_over_forced_image_span_equals_token_by_token():
     outs = both([ids_a, ids_c, ids_b], [emb_a, emb_c, emb_b], 72)                    # ragged: slot 0 does not jump, slots 1-3 do
     assert outs[0].sequences[0][len(ids_a):len(ids_a) + 16].tolist() == g["text_gen_ids"]
     assert outs[1].sequences[0][len(ids_c):].tolist() == g["img_gen_ids"]
+
+
+@pytest.mark.skipif(os.environ.get("SEEDX_EXPERIMENTAL") != "1", reason="experimental mode, validated on the CPU double only so far (SEEDX_EXPERIMENTAL=1 to run)")
+def test_mid_generation_span_jump_experimental_gpu():
+    """GPU twin of tests/test_llm_host_cpu.py::test_mid_generation_span_jump_experimental (SEEDX_JUMP_FORWARD_MID, off by default)."""
+    from seedx_b200.llm import LlamaForCausalLM
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    cfg = synth.TINY_LLAMA
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    img_ids = tok.encode("".join(["<img>"] + ["<img_{:05d}>".format(i) for i in range(64)] + ["</img>"]))
+    sd = dict(synth.llama_state_dict(cfg))
+    m0, _ = _llm()
+    h = m0.generate_greedy(g["ids"], g["embeds"].cuda(), img_ids=img_ids, max_new_tokens=24).last_hidden_states[4].cpu()
+    sd["lm_head.weight"] = sd["lm_head.weight"].clone()
+    sd["lm_head.weight"][tok.tok2id["<img>"]] = (40.0 * h / h.pow(2).sum()).half().float()
+    outs = []
+    for mid in (False, True):
+        m = LlamaForCausalLM(cfg, max_len=512)
+        m.load_state_dict(sd)
+        m.jump_forward_mid = mid
+        outs.append(m.generate_greedy_batch([g["ids"], g["ids"][:20]], [g["embeds"].cuda(), g["embeds"][:20].cuda()], img_ids=img_ids, max_new_tokens=100))
+    assert tok.tok2id["</img>"] in outs[0][0].sequences[0].tolist()
+    for a, b in zip(outs[1], outs[0]):
+        assert a.sequences.tolist() == b.sequences.tolist() and rel(a.last_hidden_states, b.last_hidden_states) < TOL

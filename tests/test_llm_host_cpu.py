@@ -158,3 +158,42 @@ def test_agent_generate_host_logic_vs_oracle(monkeypatch, host):
     assert out["ids"] == ref["ids"] and out["text"] == ref["text"]
     assert out["has_img_output"] and out["num_gen_imgs"] == 1 and tuple(out["img_gen_feat"].shape) == (1, 64, vit_dim)
     assert rel(out["img_gen_feat"], ref["img_gen_feat"]) < TOL
+
+
+def test_mid_generation_span_jump_experimental(host):
+    """SEEDX_JUMP_FORWARD_MID (off by default): a span the model opens by itself in the middle of its answer is finished by one chunked prefill.
+    The tiny model is nudged to emit <img> (its lm_head row is aligned with one of its own hidden states); mode on == mode off."""
+    g, tok, img_ids, sd = host["g"], host["tok"], host["img_ids"], dict(host["sd"])
+    base = host["make"]()
+    ref0 = base.generate_greedy(g["ids"], g["embeds"], img_ids=img_ids, max_new_tokens=24, use_graph=False)
+    h = ref0.last_hidden_states[4]
+    sd["lm_head.weight"] = sd["lm_head.weight"].clone()
+    sd["lm_head.weight"][tok.tok2id["<img>"]] = (40.0 * h / h.pow(2).sum()).half().float()          # logit ~ 40 where the state is h
+
+    def run(mid, ids_list, emb_list, n_new):
+        m = llm_mod.LlamaForCausalLM(host["cfg"], max_len=256, device="cpu", kv_page_size=16)
+        m.load_state_dict({k: v.clone() for k, v in sd.items()})
+        m.jump_forward_mid = mid
+        calls = {"n": 0}
+        real = m._decode_step
+
+        def counting(*a, **k):
+            calls["n"] += 1
+            return real(*a, **k)
+        m._decode_step = counting
+        return m.generate_greedy_batch(ids_list, emb_list, img_ids=img_ids, max_new_tokens=n_new, use_graph=False), calls["n"]
+
+    off, n_off = run(False, [g["ids"]], [g["embeds"]], 100)
+    on, n_on = run(True, [g["ids"]], [g["embeds"]], 100)
+    gen = off[0].sequences[0][len(g["ids"]):].tolist()
+    assert tok.tok2id["<img>"] in gen and tok.tok2id["</img>"] in gen, "the nudged model did not open an image span"
+    assert on[0].sequences.tolist() == off[0].sequences.tolist() and on[0].n_generated == off[0].n_generated == 100
+    assert rel(on[0].last_hidden_states, off[0].last_hidden_states) < TOL
+    assert n_off == 99 and n_on <= 99 - 60                                  # at least one 64-token span left the token loop
+    # lock-step pair: one request opens a span, the other (shorter prompt) does not necessarily; budget cut inside a span
+    for n_new in (100, 12):
+        off2, _ = run(False, [g["ids"], g["ids"][:20]], [g["embeds"], g["embeds"][:20]], n_new)
+        on2, _ = run(True, [g["ids"], g["ids"][:20]], [g["embeds"], g["embeds"][:20]], n_new)
+        for a, b in zip(on2, off2):
+            assert a.sequences.tolist() == b.sequences.tolist() and a.n_generated == b.n_generated
+            assert rel(a.last_hidden_states, b.last_hidden_states) < TOL
