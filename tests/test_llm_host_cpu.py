@@ -197,3 +197,26 @@ def test_mid_generation_span_jump_experimental(host):
         for a, b in zip(on2, off2):
             assert a.sequences.tolist() == b.sequences.tolist() and a.n_generated == b.n_generated
             assert rel(a.last_hidden_states, b.last_hidden_states) < TOL
+
+
+@pytest.mark.parametrize("page", [1, 16, 512])
+def test_boundaries_exact_fit_page_sizes_and_eight_slots(host, page):
+    """sequence that fills the cache to the last row, pages of one token / one page per sequence, 5 requests padded to 8 lock-step slots"""
+    g, img_ids = host["g"], host["img_ids"]
+    P = len(host["ids_b"])
+    m = host["make"](max_len=P + 72, kv_page_size=page)                   # prompt + max_new_tokens == max_len exactly
+    out = m.generate_greedy(host["ids_b"], host["emb_b"], img_ids=img_ids, max_new_tokens=72, use_graph=False)
+    assert out.sequences[0][P:].tolist() == g["img_gen_ids"] and rel(out.last_hidden_states, g["img_hidden"]) < TOL
+    from seedx_b200._lib import SeedxError
+    with pytest.raises(SeedxError, match="exceeds the KV cache"):
+        m.generate_greedy(host["ids_b"], host["emb_b"], img_ids=img_ids, max_new_tokens=73, use_graph=False)
+    if page == 16:
+        m8 = host["make"](max_len=160, kv_page_size=page)
+        reqs = [g["ids"][:n] for n in (45, 7, 1, 33, 20)]
+        embs = [g["embeds"][:n] for n in (45, 7, 1, 33, 20)]
+        outs = m8.generate_greedy_batch(reqs, embs, img_ids=img_ids, max_new_tokens=16, use_graph=False)
+        assert m8.slots == 8 and len(outs) == 5
+        assert outs[0].sequences[0][45:].tolist() == g["text_gen_ids"]
+        for r, e, o in zip(reqs, embs, outs):
+            single = host["make"](max_len=160).generate_greedy(r, e, img_ids=img_ids, max_new_tokens=16, use_graph=False)
+            assert o.sequences.tolist() == single.sequences.tolist()
