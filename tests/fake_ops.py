@@ -34,8 +34,19 @@ def scatter_rows(src, idx, dst, src_idx=None):
     return dst
 
 
-def gemm(a, w, out=None, *, bias=None, bias_g=None, bias_g_rows=0, residual=None, act=ACT_NONE, gated=False, alpha=1.0, out_dtype=torch.float16, **kw):
+def patchify(x, patch, kpad):
+    """NCHW image -> fp16 [N*S, kpad] rows of flattened (c, ph, pw) patches, zero padded from 3*patch^2 to kpad (the patch-embed GEMM's A)"""
+    cols = F.unfold(x.float(), kernel_size=patch, stride=patch).transpose(1, 2).reshape(-1, 3 * patch * patch)
+    out = torch.zeros((cols.shape[0], kpad), dtype=torch.float16)
+    out[:, : cols.shape[1]] = cols.to(torch.float16)
+    return out
+
+
+def gemm(a, w, out=None, *, bias=None, bias_g=None, bias_g_rows=0, residual=None, res_row_mod=0, act=ACT_NONE, gated=False, alpha=1.0,
+         out_dtype=torch.float16, **kw):
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 2 and not any(v is not None and v is not False and v != 0 for v in kw.values())
+    if residual is not None and res_row_mod:                     # residual row = output row % res_row_mod (position tables)
+        residual = residual.repeat(a.shape[0] // res_row_mod, 1)
     acc = alpha * (a.float() @ w.float().t())
     if bias is not None:
         acc = acc + bias
