@@ -222,3 +222,17 @@ def cfg_euler_step(eps, x, unet_in, branches, guidance, image_guidance, sigma, s
     for br in range(branches):
         unet_in[br * B:(br + 1) * B, ..., :4] = s
     return x
+
+
+def avgpool_tokens(x, k):
+    n, t, c = x.shape
+    return x.float().view(n, t // k, k, c).mean(2).to(x.dtype)
+
+
+def add_bcast_f16(a, b, out=None):
+    a2 = a.reshape(-1, a.shape[-1]).float()
+    r = (a2 + b.repeat(a2.shape[0] // b.shape[0], 1)).to(torch.float16)
+    if out is None:
+        return r
+    out.copy_(r)
+    return out
