@@ -21,10 +21,11 @@ def cast(x, dtype):
 
 
 def unary_f16(x, out=None, act=ACT_NONE):
-    assert act == ACT_NONE
+    v = x.float()
+    v = F.silu(v) if act == ACT_SILU else F.gelu(v) if act == ACT_GELU else v
     if out is None:
         out = torch.empty(x.shape, dtype=torch.float16)
-    out.copy_(x.to(torch.float16))
+    out.copy_(v.to(torch.float16))
     return out
 
 
@@ -42,7 +43,7 @@ def patchify(x, patch, kpad):
     return out
 
 
-def gemm(a, w, out=None, *, bias=None, bias_g=None, bias_g_rows=0, residual=None, res_row_mod=0, act=ACT_NONE, gated=False, alpha=1.0,
+def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, residual=None, res_row_mod=0, act=ACT_NONE, gated=False, alpha=1.0,
          out_dtype=torch.float16, **kw):
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 2 and not any(v is not None and v is not False and v != 0 for v in kw.values())
     if residual is not None and res_row_mod:                     # residual row = output row % res_row_mod (position tables)
@@ -50,6 +51,8 @@ def gemm(a, w, out=None, *, bias=None, bias_g=None, bias_g_rows=0, residual=None
     acc = alpha * (a.float() @ w.float().t())
     if bias is not None:
         acc = acc + bias
+    if bias_m is not None:                                       # one bias per output ROW (transposed products)
+        acc = acc + bias_m[:, None]
     if bias_g is not None:                                       # one additive row per group of bias_g_rows output rows
         acc = acc + bias_g.repeat_interleave(bias_g_rows, dim=0)
     if gated:                                                    # interleaved rows [value_j, gate_j]
@@ -236,3 +239,83 @@ def add_bcast_f16(a, b, out=None):
         return r
     out.copy_(r)
     return out
+
+
+# ---- stage 3 (NHWC fp16 feature maps) ---------------------------------------------------------------------------------------------------
+def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None, act=ACT_NONE, out_dtype=torch.float16, tile_n=0):
+    """stride-1 'same' conv; w packed [Cout, taps*taps*Cpad] with k = (kh*taps + kw)*Cpad + c, Cpad = roundup(Cin, 64); bias_g fp32 [N, Cout] per image"""
+    n, h, wd, c = x.shape
+    cout = w.shape[0]
+    cpad = w.shape[1] // (taps * taps)
+    w4 = w.float().view(cout, taps, taps, cpad)[..., :c].permute(0, 3, 1, 2)                 # [Cout, Cin, kh, kw]
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), w4, bias=bias, padding=taps // 2)
+    if bias_g is not None:
+        y = y + bias_g[:, :, None, None]
+    y = y.permute(0, 2, 3, 1)
+    if act == ACT_SILU:
+        y = F.silu(y)
+    if residual is not None:
+        y = y + residual.float()
+    if out is None:
+        out = torch.empty((n, h, wd, cout), dtype=out_dtype)
+    out.copy_(y.to(out.dtype))
+    return out
+
+
+def groupnorm_ws(n, groups, device):
+    return torch.empty((1,), dtype=torch.float64)
+
+
+def groupnorm_nhwc(x1, gamma, beta, eps, *, x2=None, silu=False, groups=32, out=None, raw_out=None, stats_ws=None):
+    x = torch.cat([x1, x2], dim=3) if x2 is not None else x1
+    if raw_out is not None:
+        raw_out.copy_(x)
+    y = F.group_norm(x.float().permute(0, 3, 1, 2), groups, gamma, beta, eps)
+    if silu:
+        y = F.silu(y)
+    y = y.permute(0, 2, 3, 1).to(torch.float16)
+    if out is None:
+        return y.contiguous()
+    out.copy_(y)
+    return out
+
+
+def im2col_nhwc(x, k, stride, pad_before, ho, wo):
+    """rows = output pixels, columns ordered (kh, kw, c); zero fill outside the image"""
+    n, h, w, c = x.shape
+    pad_after_h = max((ho - 1) * stride + k - pad_before - h, 0)
+    pad_after_w = max((wo - 1) * stride + k - pad_before - w, 0)
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (pad_before, pad_after_w, pad_before, pad_after_h))
+    cols = F.unfold(xp, kernel_size=k, stride=stride)                                         # [n, c*k*k, ho*wo], (c, kh, kw) order
+    cols = cols.view(n, c, k * k, ho * wo).permute(0, 3, 2, 1).reshape(n * ho * wo, k * k * c)
+    return cols.to(torch.float16)
+
+
+def upsample2x_nhwc(x):
+    return x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
+
+
+def timestep_embedding(t, dim, out):
+    half = dim // 2
+    f = torch.exp(-9.210340371976184 * torch.arange(half, dtype=torch.float32) / half)
+    a = t.float().reshape(-1, 1) * f
+    out[:, :half] = torch.cos(a).to(torch.float16)
+    out[:, half:dim] = torch.sin(a).to(torch.float16)
+    return out
+
+
+def softmax_rows(x, scale, out=None):
+    y = (x.float() * scale).softmax(-1).to(torch.float16)
+    if out is None:
+        return y
+    out.copy_(y)
+    return out
+
+
+def nhwc_to_nchw_f32(x, c, scale=1.0):
+    return (x[..., :c].float() * scale).permute(0, 3, 1, 2).contiguous()
+
+
+def image_to_u8(x):
+    v = (x[..., :3].float() * 0.5 + 0.5).clamp(0, 1)
+    return torch.round(v * 255.0).to(torch.uint8)
