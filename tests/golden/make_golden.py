@@ -16,6 +16,8 @@ sys.path.insert(0, HERE)
 from _ref_import import ref_module  # noqa: E402
 from seedx_b200 import synth  # noqa: E402
 
+OUT = os.environ.get("SEEDX_GOLDEN_OUT", HERE)          # tests regenerate into a scratch directory and compare with the committed files
+
 VIT_SMALL = dict(width=208, layers=2, heads=2, mlp_width=520, output_dim=256, n_queries=256, patch=14)
 
 
@@ -38,7 +40,7 @@ def golden_vit():
             out[f"out_{size}"] = model(x).float()
     out["attn_pool_pos_embed"] = ref_pos
     out["cfg"] = cfg
-    torch.save(out, os.path.join(HERE, "vit_small.pt"))
+    torch.save(out, os.path.join(OUT, "vit_small.pt"))
     print("vit_small", {k: tuple(v.shape) for k, v in out.items() if hasattr(v, "shape")})
 
 
@@ -54,7 +56,7 @@ def golden_resamplers():
         x = synth.randn(f"res_{name}_x", (3, nkv, kv_dim))
         with torch.no_grad():
             out[name] = m(x).float()
-    torch.save(out, os.path.join(HERE, "resamplers.pt"))
+    torch.save(out, os.path.join(OUT, "resamplers.pt"))
     print("resamplers", {k: tuple(v.shape) for k, v in out.items()})
 
 
@@ -118,7 +120,7 @@ def golden_llama():
     out["proc_in"] = s.clone()
     out["proc_out_text"] = proc(torch.tensor([[5, 6, 7]]), s.clone())
     out["proc_out_img"] = proc(torch.tensor([[5, tok.encode("<img_00010>")[0]]]), s.clone())
-    torch.save(out, os.path.join(HERE, "llama_tiny.pt"))
+    torch.save(out, os.path.join(OUT, "llama_tiny.pt"))
     print("llama_tiny: text", out["text_gen_ids"][:8], "img-span tail", out["img_gen_ids"][62:])
 
 
@@ -175,7 +177,7 @@ def golden_llama_lora():
         o = pmodel(input_ids=torch.tensor([ids]), attention_mask=torch.ones(1, P, dtype=torch.long), position_ids=torch.arange(P)[None],
                    output_hidden_states=True, return_dict=True, use_cache=False)
     out["logits"], out["hidden"] = o.logits[0].float(), o.hidden_states[-1][0].float()
-    torch.save(out, os.path.join(HERE, "llama_lora_tiny.pt"))
+    torch.save(out, os.path.join(OUT, "llama_lora_tiny.pt"))
     print("llama_lora_tiny: logits", tuple(out["logits"].shape), "keys e.g.", [k for k in out["peft_keys"] if "layers.0.self_attn.q_proj" in k])
 
 
@@ -190,7 +192,7 @@ def golden_resampler_xl():
             with torch.no_grad():
                 p, pooled = m(x)
             out[f"{name}_{n_tok}_prompt"], out[f"{name}_{n_tok}_pooled"] = p.float().half(), pooled.float()
-    torch.save(out, os.path.join(HERE, "resampler_xl.pt"))
+    torch.save(out, os.path.join(OUT, "resampler_xl.pt"))
     print("resampler_xl", {k: tuple(v.shape) for k, v in out.items()})
 
 
@@ -213,7 +215,7 @@ def golden_preprocess():
         out["cases"].append(dict(size=(w, h), shape=tuple(views.shape), pos=pos.clone(), sum=float(views.double().sum()),
                                  abssum=float(views.double().abs().sum()), first=views[0, :, :4, :4].clone(), last=views[-1, :, -4:, -4:].clone(),
                                  keep_sum=float(tk.double().sum())))
-    torch.save(out, os.path.join(HERE, "preprocess.pt"))
+    torch.save(out, os.path.join(OUT, "preprocess.pt"))
     print("preprocess", [c["shape"] for c in out["cases"]])
 
 

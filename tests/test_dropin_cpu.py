@@ -177,3 +177,31 @@ def test_reference_yaml_targets_resolve_with_identical_keys():
             if t.startswith(("src.", "peft.")):
                 compat.install()
                 assert callable(compat._locate(t)), t
+
+
+@needs_ref
+def test_goldens_regenerate_bit_identically_from_the_reference(tmp_path):
+    """tests/golden/*.pt ARE the outputs of the reference's own modules: running the generator again (imports /root/reference, binds `src` to it
+    explicitly) reproduces every committed tensor exactly"""
+    env = dict(os.environ, SEEDX_GOLDEN_OUT=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "make_golden.py")], cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+    def same(a, b, path):
+        if torch.is_tensor(a):
+            assert torch.is_tensor(b) and a.shape == b.shape and torch.equal(a, b), path
+        elif isinstance(a, dict):
+            assert a.keys() == b.keys(), path
+            for k in a:
+                same(a[k], b[k], f"{path}/{k}")
+        elif isinstance(a, (list, tuple)):
+            assert len(a) == len(b), path
+            for i, (x, y) in enumerate(zip(a, b)):
+                same(x, y, f"{path}[{i}]")
+        else:
+            assert a == b, path
+
+    names = sorted(f for f in os.listdir(os.path.join(ROOT, "tests", "golden")) if f.endswith(".pt"))
+    assert names == sorted(f for f in os.listdir(tmp_path) if f.endswith(".pt")) and len(names) == 6
+    for f in names:
+        same(torch.load(os.path.join(ROOT, "tests", "golden", f)), torch.load(tmp_path / f), f)
