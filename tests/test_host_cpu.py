@@ -96,6 +96,24 @@ def test_reference_arm_prints_the_contract_line():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and math.isfinite(line["value"])
 
 
+def test_reference_arm_under_torchrun_prints_once():
+    """launched the way the driver launches N>1 (torch.distributed.run, one process per rank): rank 0 alone times and prints the line,
+    the other ranks exit 0 without output"""
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+
+
 def test_lora_merge_updates_the_packed_weights_in_place():
     """LlamaForCausalLM.apply_peft_state_dict on host tensors (no kernel is involved at load time): the packed [q|k|v] / [up,gate]-interleaved
     fp16 weights equal the fp16 rounding of W + (alpha/r) B A from seedx_b200.lora.merge_lora_state_dict, norms are replaced, storage
