@@ -205,3 +205,37 @@ def test_goldens_regenerate_bit_identically_from_the_reference(tmp_path):
     assert names == sorted(f for f in os.listdir(tmp_path) if f.endswith(".pt")) and len(names) == 6
     for f in names:
         same(torch.load(os.path.join(ROOT, "tests", "golden", f)), torch.load(tmp_path / f), f)
+
+
+@needs_ref
+def test_anyres_preprocessing_equals_the_reference_on_random_sizes():
+    """seedx_b200.preprocess vs the reference's own functions (imported in a subprocess so its `src` package cannot shadow this repo's shims):
+    grid choice, tile order, patch positions and pixel values, bit for bit, on 60 random image sizes and both transform modes"""
+    code = r'''
+import sys, numpy as np, torch
+from PIL import Image
+sys.path.insert(0, "%s"); sys.path.insert(0, "%s/tests/golden")
+from _ref_import import ref_module
+ar, tr = ref_module("src.inference.any_res"), ref_module("src.processer.transforms")
+from seedx_b200 import preprocess as pp
+base = 448
+grids = [[base * int(g[0]), base * int(g[2])] for g in ["1x1", "1x2", "1x3", "2x1", "3x1", "1x4", "4x1", "2x2"]]
+rng = np.random.RandomState(7)
+n = 0
+for i in range(60):
+    w, h = int(rng.randint(40, 2600)), int(rng.randint(40, 2600))
+    img = Image.fromarray(rng.randint(0, 255, (h, w, 3), dtype=np.uint8))
+    use = grids if i %% 3 else grids[:1]
+    v0, p0 = ar.process_anyres_image(img, tr.get_transform("clip", keep_ratio=False, image_size=base), use, base)
+    v1, p1 = pp.process_anyres_image(img, pp.get_transform("clip", keep_ratio=False, image_size=base), use, base)
+    assert v0.shape == v1.shape and torch.equal(p0, p1) and torch.equal(v0, v1), (w, h)
+    if i %% 10 == 0:
+        k0 = tr.get_transform("clip", keep_ratio=True, image_size=base)(img)
+        k1 = pp.get_transform("clip", keep_ratio=True, image_size=base)(img)
+        assert torch.equal(k0, k1), (w, h)
+    n += 1
+print("checked", n)
+''' % (ROOT, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert r.stdout.strip().endswith("checked 60")
