@@ -181,6 +181,79 @@ def golden_llama_lora():
     print("llama_lora_tiny: logits", tuple(out["logits"].shape), "keys e.g.", [k for k in out["peft_keys"] if "layers.0.self_attn.q_proj" in k])
 
 
+def agent_fixture(tok):
+    """the request of the agent golden: 2 images (2 + 1 views), three chat turns, prompt forced to open an image span"""
+    img = "".join("<img_{:05d}>".format(i) for i in range(64))
+    text = "[INST] " + "<patch>" + img + "</patch>" + "<img>" + img + "</img>" + "<img>" + img + "</img>" + "what changed? [/INST]\nthe sky\n[INST] draw it again [/INST]\n<img>"
+    ids = torch.tensor([tok.bos_token_id] + tok.encode(text))
+    first = tok.tok2id["<img_00000>"]
+    lst = ids.tolist()
+    starts = [i for i, t in enumerate(lst) if t in (tok.tok2id["<img>"], tok.tok2id["<patch>"])]
+    ends = [i for i, t in enumerate(lst) if t in (tok.tok2id["</img>"], tok.tok2id["</patch>"])]
+    mask = torch.zeros_like(ids, dtype=torch.bool)
+    for a, b in zip(starts, ends):
+        mask[a + 1:b] = True
+    assert int(mask.sum()) == 3 * 64 and lst[int(mask.nonzero()[0])] == first
+    return ids.unsqueeze(0), mask.unsqueeze(0), synth.randn("agent_golden_img", (3, 256, 320)), torch.tensor([[0.25, 0.5], [0.5, 0.5], [0.5, 0.5]])
+
+
+def golden_agent():
+    """The reference's OWN ContinuousLVLM.generate (src/models/mllm/seed_x.py:130-223: input resampler + patch-position row, mask scatter, logits
+    processor, hidden-state harvest, output resampler, text assembly) over the reference LlamaForCausalLM and Resamplers.  Only `llm.generate` is
+    substituted: the installed transformers (5.x) cannot drive the reference model, so a greedy loop with HF-4.30 `greedy_search` semantics
+     runs the reference forward and the reference's logits processor list, and returns `.sequences` / `.hidden_states` in HF's layout."""
+    import types
+    from transformers import LlamaConfig
+    mod = ref_module("src.models.mllm.modeling_llama_xformer")
+    sx = ref_module("src.models.mllm.seed_x")
+    qv = ref_module("src.models.tokenizer.qwen_visual")
+    cfg, vit_dim = synth.TINY_LLAMA, 320
+    hc = LlamaConfig(vocab_size=cfg["vocab"], hidden_size=cfg["hidden"], intermediate_size=cfg["ffn"], num_hidden_layers=cfg["layers"],
+                     num_attention_heads=cfg["heads"], rms_norm_eps=cfg["eps"], max_position_embeddings=2048)
+    hc.pad_token_id = 0
+    llm = mod.LlamaForCausalLM(hc).eval()
+    missing, unexpected = llm.load_state_dict(synth.llama_state_dict(cfg), strict=False)
+    assert not unexpected and all("rotary" in m for m in missing), (missing, unexpected)
+    agent = sx.ContinuousLVLM(llm=llm, input_resampler=qv.Resampler(grid_size=8, embed_dim=cfg["hidden"], num_heads=2, kv_dim=vit_dim),
+                              output_resampler=qv.Resampler(grid_size=8, embed_dim=vit_dim, num_heads=2, kv_dim=cfg["hidden"]),
+                              add_patch_pos=True, vit_down=True, mse=True).eval()
+    missing, unexpected = agent.load_state_dict(synth.agent_state_dict(cfg["hidden"], vit_dim), strict=False)
+    assert not unexpected and all(m.startswith("llm.") for m in missing), (missing, unexpected)
+
+    def fwd(**kw):
+        with torch.no_grad():
+            return llm(use_cache=True, output_hidden_states=True, return_dict=True, **kw)
+
+    def hf_generate(input_ids=None, inputs_embeds=None, logits_processor=None, max_new_tokens=20, **kw):
+        assert kw.get("output_hidden_states") and kw.get("return_dict_in_generate") and kw.get("do_sample") is False and kw.get("num_beams") == 1
+        P = input_ids.shape[1]
+        o = fwd(inputs_embeds=inputs_embeds, attention_mask=torch.ones(1, P, dtype=torch.long), position_ids=torch.arange(P)[None])
+        seq, past, logits = input_ids[0].tolist(), o.past_key_values, o.logits[:, -1, :]
+        hidden = [(o.hidden_states[-1],)]
+        for step in range(max_new_tokens):
+            nxt = int(logits_processor(torch.tensor([seq]), logits.clone().float()).argmax(-1))
+            seq.append(nxt)
+            if nxt == 2 or step == max_new_tokens - 1:              # eos_token_id of the LLaMA generation config
+                break
+            o = fwd(input_ids=torch.tensor([[nxt]]), past_key_values=past, attention_mask=torch.ones(1, len(seq), dtype=torch.long),
+                    position_ids=torch.tensor([[len(seq) - 1]]))
+            past, logits = o.past_key_values, o.logits[:, -1, :]
+            hidden.append((o.hidden_states[-1],))
+        return types.SimpleNamespace(sequences=torch.tensor([seq]), hidden_states=tuple(hidden))
+
+    llm.generate = hf_generate
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    input_ids, ids_cmp_mask, image_embeds, patch_pos = agent_fixture(tok)
+    with torch.no_grad():
+        res = agent.generate(tokenizer=tok, input_ids=input_ids, image_embeds=image_embeds, embeds_cmp_mask=torch.ones((3, 64), dtype=torch.bool),
+                             ids_cmp_mask=ids_cmp_mask, patch_positions=patch_pos, max_new_tokens=70, num_img_gen_tokens=64, device="cpu", dtype=torch.float32)
+    assert res["has_img_output"] and res["num_gen_imgs"] == 1
+    out = dict(text=res["text"], has_img_output=res["has_img_output"], num_gen_imgs=res["num_gen_imgs"], img_gen_feat=res["img_gen_feat"].float(),
+               input_ids=input_ids, ids_cmp_mask=ids_cmp_mask, patch_pos=patch_pos)
+    torch.save(out, os.path.join(OUT, "agent_tiny.pt"))
+    print("agent_tiny: text", repr(res["text"]), "feat", tuple(out["img_gen_feat"].shape))
+
+
 def golden_resampler_xl():
     rs = ref_module("src.models.detokenizer.resampler")
     out = {}
@@ -220,7 +293,7 @@ def golden_preprocess():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["vit", "resamplers", "llama", "llama_lora", "resampler_xl", "preprocess"]
+    which = sys.argv[1:] or ["vit", "resamplers", "llama", "llama_lora", "agent", "resampler_xl", "preprocess"]
     if "vit" in which:
         golden_vit()
     if "resamplers" in which:
@@ -229,6 +302,8 @@ if __name__ == "__main__":
         golden_llama()
     if "llama_lora" in which:
         golden_llama_lora()
+    if "agent" in which:
+        golden_agent()
     if "resampler_xl" in which:
         golden_resampler_xl()
     if "preprocess" in which:

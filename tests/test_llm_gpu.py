@@ -399,3 +399,22 @@ def test_mid_generation_span_jump_experimental_gpu():
     assert tok.tok2id["</img>"] in outs[0][0].sequences[0].tolist()
     for a, b in zip(outs[1], outs[0]):
         assert a.sequences.tolist() == b.sequences.tolist() and rel(a.last_hidden_states, b.last_hidden_states) < TOL
+
+
+def test_agent_generate_matches_the_reference_generate_golden():
+    """ContinuousLVLM.generate on the GPU vs the output of the reference's OWN ContinuousLVLM.generate (tests/golden/agent_tiny.pt, produced by
+    /root/reference/src/models/mllm/seed_x.py:130-223 with only `llm.generate` substituted): 2 images (2 + 1 views), 3 chat turns, forced image span."""
+    from seedx_b200.agent import ContinuousLVLM, Resampler
+    g = torch.load(os.path.join(GOLD, "agent_tiny.pt"))
+    m, cfg = _llm()
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    agent = ContinuousLVLM.from_pretrained(llm=m, input_resampler=Resampler(8, cfg["hidden"], 2, 320), output_resampler=Resampler(8, 320, 2, cfg["hidden"]),
+                                           add_patch_pos=True, vit_down=True)
+    agent.load_state_dict(synth.agent_state_dict(cfg["hidden"], 320))
+    out = agent.generate(tokenizer=tok, input_ids=g["input_ids"], image_embeds=synth.randn("agent_golden_img", (3, 256, 320)).cuda(),
+                         embeds_cmp_mask=torch.ones((3, 64), dtype=torch.bool), ids_cmp_mask=g["ids_cmp_mask"], patch_positions=g["patch_pos"],
+                         max_new_tokens=70, num_img_gen_tokens=64)
+    assert out["text"] == g["text"] and out["has_img_output"] and out["num_gen_imgs"] == 1
+    e = rel(out["img_gen_feat"], g["img_gen_feat"])
+    print(f"agent vs the reference's own generate: img_gen_feat rel = {e:.3e}")
+    assert e < TOL

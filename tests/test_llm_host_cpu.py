@@ -220,3 +220,24 @@ def test_boundaries_exact_fit_page_sizes_and_eight_slots(host, page):
         for r, e, o in zip(reqs, embs, outs):
             single = host["make"](max_len=160).generate_greedy(r, e, img_ids=img_ids, max_new_tokens=16, use_graph=False)
             assert o.sequences.tolist() == single.sequences.tolist()
+
+
+def test_agent_generate_matches_the_reference_generate(monkeypatch, host):
+    """product ContinuousLVLM.generate (CPU double) vs the reference's OWN ContinuousLVLM.generate output (tests/golden/agent_tiny.pt)"""
+    from seedx_b200 import agent as agent_mod
+    from seedx_b200 import vit as vit_mod
+    monkeypatch.setattr(agent_mod, "ops", fake_ops)
+    monkeypatch.setattr(vit_mod, "ops", fake_ops)
+    g = torch.load(os.path.join(GOLD, "agent_tiny.pt"))
+    cfg, tok = host["cfg"], host["tok"]
+    m = host["make"](max_len=512)
+    agent = agent_mod.ContinuousLVLM.from_pretrained(llm=m, input_resampler=agent_mod.Resampler(8, cfg["hidden"], 2, 320),
+                                                     output_resampler=agent_mod.Resampler(8, 320, 2, cfg["hidden"]), add_patch_pos=True, vit_down=True)
+    agent.load_state_dict(synth.agent_state_dict(cfg["hidden"], 320))
+    real = m.generate_greedy_batch
+    monkeypatch.setattr(m, "generate_greedy_batch", lambda *a, **k: real(*a, **dict(k, use_graph=False)))
+    out = agent.generate(tokenizer=tok, input_ids=g["input_ids"], image_embeds=synth.randn("agent_golden_img", (3, 256, 320)),
+                         embeds_cmp_mask=torch.ones((3, 64), dtype=torch.bool), ids_cmp_mask=g["ids_cmp_mask"], patch_positions=g["patch_pos"],
+                         max_new_tokens=70, num_img_gen_tokens=64)
+    assert out["text"] == g["text"] and out["has_img_output"] and out["num_gen_imgs"] == 1
+    assert rel(out["img_gen_feat"], g["img_gen_feat"]) < TOL

@@ -109,6 +109,20 @@ def test_product_logits_processor_class_matches_reference():
     assert torch.equal(proc(torch.tensor([[5, tok.encode("<img_00010>")[0]]]), g["proc_in"].clone()), g["proc_out_img"])
 
 
+def test_lvlm_generate_oracle_matches_the_reference_generate():
+    """oracle/llm.py::lvlm_generate vs the reference's OWN ContinuousLVLM.generate (tests/golden/agent_tiny.pt: only `llm.generate` was substituted by
+    the restated greedy loop): generated text, image-span detection and the output-resampler features of a 2-image, 3-turn prompt"""
+    from oracle import llm
+    g = torch.load(os.path.join(GOLD, "agent_tiny.pt"))
+    cfg = synth.TINY_LLAMA
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    image_embeds = synth.randn("agent_golden_img", (3, 256, 320))
+    out = llm.lvlm_generate(synth.llama_state_dict(cfg), synth.agent_state_dict(cfg["hidden"], 320), cfg, tok, g["input_ids"][0].tolist(), image_embeds,
+                            g["ids_cmp_mask"][0], torch.ones((3, 64), dtype=torch.bool), g["patch_pos"], 70, eos_id=2)
+    assert out["text"] == g["text"] and out["has_img_output"] == g["has_img_output"] and out["num_gen_imgs"] == g["num_gen_imgs"] == 1
+    assert rel(out["img_gen_feat"], g["img_gen_feat"]) < 2e-5
+
+
 def test_resampler_xl_oracle_matches_reference():
     from oracle import resampler_xl as orx
     g = torch.load(os.path.join(GOLD, "resampler_xl.pt"))
