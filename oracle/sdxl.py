@@ -8,6 +8,11 @@ anchored on the reference's own call sites:
   src/models/detokenizer/pipeline_stable_diffusion_xl_t2i_edit.py:474-566, 823-994 (edit loop)
   src/models/detokenizer/adapter_modules.py:132-169 (t2i call into StableDiffusionXLPipeline)
 State-dict keys are the diffusers names, so real checkpoints load unchanged.
+
+PINNED around that gap: `edit_sample` (3-way CFG order, un-scaled image latents, sigma-space combine, Euler walk, time ids) reproduces at 2e-5 the
+latents and image of the reference's OWN SDXLAdapterWithLatentImage.generate + StableDiffusionXLText2ImageAndEditPipeline.__call__ when those are
+handed UNet / VAE / scheduler objects backed by this file (tests/golden/edit_adapter_tiny.pt, make_golden.py::golden_edit_adapter).  What stays
+unpinned is the arithmetic INSIDE those three diffusers objects and the stock 2-way t2i pipeline.
 """
 import math
 

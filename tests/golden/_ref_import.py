@@ -55,3 +55,81 @@ def ref_module(dotted):
     m = importlib.import_module(dotted)
     assert m.__file__.startswith(REF + "/"), f"{dotted} resolved to {m.__file__}, not the reference"
     return m
+
+
+def install_diffusers_stub():
+    """diffusers (==0.25.0, requirements.txt:4) is not installable offline.  The reference's OWN pipeline file
+    (src/models/detokenizer/pipeline_stable_diffusion_xl_t2i_edit.py) and adapter file only need a handful of names from it at import time and a
+    tiny `DiffusionPipeline` base (module registry, progress bar, execution device).  These stand-ins carry NO arithmetic: UNet / VAE / scheduler
+    objects are passed in by the caller (make_golden.py backs them with oracle/sdxl.py)."""
+    import contextlib
+    if "diffusers" in sys.modules and getattr(sys.modules["diffusers"], "_seedx_stub", False):
+        return
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class _Any:
+        def __init__(self, *a, **k):
+            pass
+
+    class VaeImageProcessor:
+        def __init__(self, vae_scale_factor=8, **k):
+            self.vae_scale_factor = vae_scale_factor
+
+        def preprocess(self, image):          # diffusers: latents (4 channels) and tensors already in [-1, 1] pass through unchanged
+            assert torch.is_tensor(image)
+            return image
+
+        def postprocess(self, image, output_type="pil"):
+            return image
+
+    class DiffusionPipeline:
+        def register_modules(self, **kw):
+            for k, v in kw.items():
+                setattr(self, k, v)
+
+        def register_to_config(self, **kw):
+            self.config = types.SimpleNamespace(**kw)
+
+        @property
+        def _execution_device(self):
+            return torch.device("cpu")
+
+        def to(self, *a, **k):
+            return self
+
+        def maybe_free_model_hooks(self):
+            pass
+
+        @contextlib.contextmanager
+        def progress_bar(self, total=None):
+            yield types.SimpleNamespace(update=lambda *a: None)
+
+    class Output:
+        def __init__(self, images):
+            self.images = images
+
+    def randn_tensor(shape, generator=None, device=None, dtype=None):
+        return torch.randn(shape, generator=generator, dtype=dtype)
+
+    logging = types.SimpleNamespace(get_logger=lambda name: types.SimpleNamespace(warning=lambda *a, **k: None, info=lambda *a, **k: None))
+    d = mod("diffusers", StableDiffusionXLPipeline=_Any, _seedx_stub=True)
+    mod("diffusers.image_processor", PipelineImageInput=object, VaeImageProcessor=VaeImageProcessor)
+    mod("diffusers.loaders", FromSingleFileMixin=type("FromSingleFileMixin", (), {}), StableDiffusionXLLoraLoaderMixin=type("L", (), {}),
+        TextualInversionLoaderMixin=type("T", (), {}))
+    mod("diffusers.models", AutoencoderKL=_Any, UNet2DConditionModel=_Any)
+    mod("diffusers.models.attention_processor", AttnProcessor2_0=_Any, LoRAAttnProcessor2_0=_Any, LoRAXFormersAttnProcessor=_Any, XFormersAttnProcessor=_Any)
+    mod("diffusers.models.lora", adjust_lora_scale_text_encoder=lambda *a, **k: None)
+    mod("diffusers.schedulers", KarrasDiffusionSchedulers=_Any)
+    mod("diffusers.utils", USE_PEFT_BACKEND=False, deprecate=lambda *a, **k: None, is_invisible_watermark_available=lambda: False,
+        is_torch_xla_available=lambda: False, logging=logging, replace_example_docstring=lambda doc: (lambda f: f), scale_lora_layers=lambda *a, **k: None)
+    mod("diffusers.utils.torch_utils", randn_tensor=randn_tensor)
+    mod("diffusers.pipelines")
+    mod("diffusers.pipelines.pipeline_utils", DiffusionPipeline=DiffusionPipeline)
+    mod("diffusers.pipelines.stable_diffusion_xl")
+    mod("diffusers.pipelines.stable_diffusion_xl.pipeline_output", StableDiffusionXLPipelineOutput=Output)
+    return d

@@ -254,6 +254,91 @@ def golden_agent():
     print("agent_tiny: text", repr(res["text"]), "feat", tuple(out["img_gen_feat"].shape))
 
 
+def golden_edit_adapter():
+    """The reference's OWN SDXLAdapterWithLatentImage.generate (src/models/detokenizer/adapter_modules.py:172-287) driving the reference's OWN
+    StableDiffusionXLText2ImageAndEditPipeline.__call__ (pipeline_stable_diffusion_xl_t2i_edit.py:618-994) with the reference's OWN ViT and
+    ResamplerXLV2 — negative conditioning, [text, image, uncond] batch, time ids, VAE-encoded source latents, sigma-space 3-way CFG, Euler steps.
+    diffusers itself is absent: import-time names come from tests/golden/_ref_import.install_diffusers_stub (no arithmetic), and the three objects
+    diffusers would provide (UNet, VAE, scheduler) are thin adapters over oracle/sdxl.py — so this pins everything in the de-tokenizer EXCEPT the
+    diffusers-internal UNet / VAE / Euler arithmetic."""
+    import types
+    from _ref_import import install_diffusers_stub
+    from oracle import sdxl as osd
+    install_diffusers_stub()
+    am = ref_module("src.models.detokenizer.adapter_modules")
+    rs = ref_module("src.models.detokenizer.resampler")
+    qv = ref_module("src.models.tokenizer.qwen_visual")
+    vcfg = dict(VIT_SMALL)
+    rcfg = dict(synth.TINY_RESAMPLER_XL, embedding_dim=256)
+    ucfg = dict(synth.TINY_UNET, cross_attention_dim=256, text_embed_dim=160, in_channels=8)
+    u_sd, v_sd = synth.unet_state_dict(ucfg), synth.vae_state_dict(synth.TINY_VAE)
+    vit = qv.VisionTransformerWithAttnPool(image_size=448, patch_size=14, width=vcfg["width"], layers=vcfg["layers"], heads=vcfg["heads"],
+                                           mlp_ratio=vcfg["mlp_width"] / vcfg["width"], n_queries=256, output_dim=vcfg["output_dim"]).eval()
+    vit.load_state_dict({k: v for k, v in synth.vit_state_dict(**vcfg).items() if k != "attn_pool.pos_embed"}, strict=False)
+    rx = rs.ResamplerXLV2(normalize=False, **rcfg).eval()
+    rx.load_state_dict(synth.resampler_xl_state_dict(rcfg), strict=True)
+
+    class Sched:                                            # diffusers EulerDiscreteScheduler surface over oracle.Euler
+        order = 1
+        config = types.SimpleNamespace(num_train_timesteps=1000)
+
+        def __init__(self):
+            self.e = osd.Euler()
+
+        def set_timesteps(self, n, device=None):
+            self.e.set_timesteps(n)
+            self.timesteps, self.sigmas, self.init_noise_sigma = self.e.timesteps, self.e.sigmas, self.e.init_noise_sigma
+
+        def _i(self, t):
+            return int((self.timesteps == t).nonzero()[0])
+
+        def scale_model_input(self, sample, t):
+            return self.e.scale_model_input(sample, self._i(t))
+
+        def step(self, model_output, t, sample, return_dict=False):
+            return (self.e.step(model_output, self._i(t), sample),)
+
+    class UNet:                                             # diffusers UNet2DConditionModel surface over oracle.unet_forward
+        dtype = torch.float32
+        config = types.SimpleNamespace(sample_size=16, addition_time_embed_dim=ucfg["addition_time_embed_dim"], in_channels=8)
+        add_embedding = types.SimpleNamespace(linear_1=types.SimpleNamespace(in_features=u_sd["add_embedding.linear_1.weight"].shape[1]))
+        calls = []
+
+        def __call__(self, x, t, encoder_hidden_states=None, cross_attention_kwargs=None, added_cond_kwargs=None, return_dict=False):
+            self.calls.append(float(t))
+            return (osd.unet_forward(u_sd, ucfg, x, float(t), encoder_hidden_states, added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"]),)
+
+    class VAE:                                              # diffusers AutoencoderKL surface over oracle.vae_*
+        dtype = torch.float32
+        config = types.SimpleNamespace(block_out_channels=synth.TINY_VAE["block_out_channels"], latent_channels=4,
+                                       scaling_factor=synth.TINY_VAE["scaling_factor"], force_upcast=False)
+
+        def encode(self, x):
+            mode = osd.vae_encode_mode(v_sd, synth.TINY_VAE, x)
+            return types.SimpleNamespace(latent_dist=types.SimpleNamespace(mode=lambda: mode))
+
+        def decode(self, z, return_dict=False):
+            return (osd.vae_decode(v_sd, synth.TINY_VAE, z),)
+
+    unet = UNet()
+    ad = am.SDXLAdapterWithLatentImage(unet=unet, resampler=rx, full_ft=True, set_trainable_late=True, vit_down=True).eval()
+    ad.init_pipe(vae=VAE(), scheduler=Sched(), visual_encoder=vit, image_transform=None, dtype=torch.float32, device="cpu")
+    B, hw, steps = 1, 8, 3
+    feats = synth.randn("edit_golden_feats", (B, 64, 256))
+    noise = synth.randn("edit_golden_noise", (B, 4, hw, hw))
+    src = synth.randn("edit_golden_src", (B, 3, hw * 8, hw * 8)).clamp(-1, 1)
+    out = {}
+    with torch.no_grad():
+        out["latents"] = ad.generate(image_embeds=feats, latent_image=src, num_inference_steps=steps, height=hw * 8, width=hw * 8, latents=noise.clone(),
+                                     input_image_size=224, guidance_scale=7.5, image_guidance_scale=1.5, output_type="latent").float()
+        out["image"] = ad.generate(image_embeds=feats, latent_image=src, num_inference_steps=steps, height=hw * 8, width=hw * 8, latents=noise.clone(),
+                                   input_image_size=224, guidance_scale=7.5, image_guidance_scale=1.5, output_type="pt").float()
+        p, n, pp, npool = ad.get_image_embeds(image_embeds=feats, return_negative=True, image_size=224)
+    out.update(prompt=p.float(), neg_prompt=n.float(), pooled=pp.float(), neg_pooled=npool.float(), steps=steps, unet_timesteps=unet.calls[:steps])
+    torch.save(out, os.path.join(OUT, "edit_adapter_tiny.pt"))
+    print("edit_adapter_tiny: latents", tuple(out["latents"].shape), "image", tuple(out["image"].shape), "timesteps", out["unet_timesteps"])
+
+
 def golden_resampler_xl():
     rs = ref_module("src.models.detokenizer.resampler")
     out = {}
@@ -293,7 +378,7 @@ def golden_preprocess():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["vit", "resamplers", "llama", "llama_lora", "agent", "resampler_xl", "preprocess"]
+    which = sys.argv[1:] or ["vit", "resamplers", "llama", "llama_lora", "agent", "resampler_xl", "preprocess", "edit_adapter"]
     if "vit" in which:
         golden_vit()
     if "resamplers" in which:
@@ -306,5 +391,7 @@ if __name__ == "__main__":
         golden_agent()
     if "resampler_xl" in which:
         golden_resampler_xl()
+    if "edit_adapter" in which:
+        golden_edit_adapter()
     if "preprocess" in which:
         golden_preprocess()

@@ -89,3 +89,24 @@ def test_edit_adapter_composition(parts):
     il = osd.vae_encode_mode(parts["v_sd"], synth.TINY_VAE, src)                                       # latent_dist.mode(), NOT x 0.13025
     ref = osd.edit_sample(u_sd, dict(ucfg, in_channels=8), noise, il, prompt[:B], pooled[:B], prompt[B:], pooled[B:], steps=steps, size=hw * 8)
     assert rel(lat, ref) < 1e-2
+
+
+def test_edit_adapter_matches_the_reference_adapter_and_pipeline(parts):
+    """product SDXLAdapterWithLatentImage.generate (CPU double) vs the reference's OWN adapter + pipeline output (tests/golden/edit_adapter_tiny.pt)"""
+    import os
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "edit_adapter_tiny.pt"))
+    ucfg = dict(synth.TINY_UNET, cross_attention_dim=256, text_embed_dim=160, in_channels=8)
+    B, hw = 1, 8
+    ad, _ = _adapter(adapter_mod.SDXLAdapterWithLatentImage, parts, ucfg, B, hw, 3)
+    feats = synth.randn("edit_golden_feats", (B, 64, 256))
+    noise = synth.randn("edit_golden_noise", (B, 4, hw, hw))
+    src = synth.randn("edit_golden_src", (B, 3, hw * 8, hw * 8)).clamp(-1, 1)
+    p, n, pp, npool = ad.get_image_embeds(image_embeds=feats, return_negative=True, image_size=224)
+    assert rel(p, g["prompt"]) < 2e-3 and rel(n, g["neg_prompt"]) < 2e-3 and rel(pp, g["pooled"]) < 2e-3 and rel(npool, g["neg_pooled"]) < 2e-3
+    lat = ad.generate(image_embeds=feats, latent_image=src, num_inference_steps=g["steps"], height=hw * 8, width=hw * 8, latents=noise, input_image_size=224,
+                      guidance_scale=7.5, image_guidance_scale=1.5, output_type="latent")
+    assert rel(lat, g["latents"]) < 1e-2
+    u8 = ad.generate(image_embeds=feats, latent_image=src, num_inference_steps=g["steps"], height=hw * 8, width=hw * 8, latents=noise, input_image_size=224,
+                     guidance_scale=7.5, image_guidance_scale=1.5, output_type="uint8")
+    want = ((g["image"] / 2 + 0.5).clamp(0, 1) * 255).round().permute(0, 2, 3, 1)
+    assert (u8.float() - want).abs().mean() < 2.0

@@ -202,7 +202,7 @@ def test_goldens_regenerate_bit_identically_from_the_reference(tmp_path):
             assert a == b, path
 
     names = sorted(f for f in os.listdir(os.path.join(ROOT, "tests", "golden")) if f.endswith(".pt"))
-    assert names == sorted(f for f in os.listdir(tmp_path) if f.endswith(".pt")) and len(names) == 7
+    assert names == sorted(f for f in os.listdir(tmp_path) if f.endswith(".pt")) and len(names) == 8
     for f in names:
         same(torch.load(os.path.join(ROOT, "tests", "golden", f)), torch.load(tmp_path / f), f)
 

@@ -123,6 +123,33 @@ def test_lvlm_generate_oracle_matches_the_reference_generate():
     assert rel(out["img_gen_feat"], g["img_gen_feat"]) < 2e-5
 
 
+def test_edit_pipeline_oracle_matches_the_reference_adapter_and_pipeline():
+    """oracle composition (ViT(zeros) pooled negative -> ResamplerXLV2 -> VAE-encoded source latents -> oracle.edit_sample) vs the output of the
+    reference's OWN SDXLAdapterWithLatentImage.generate + StableDiffusionXLText2ImageAndEditPipeline.__call__ (tests/golden/edit_adapter_tiny.pt; the
+    UNet / VAE / scheduler objects handed to the reference code were backed by this same oracle, so what is pinned is everything around them: conditioning,
+    branch order [text, image, uncond], time ids, un-scaled image latents, sigma-space 3-way CFG, the Euler walk)"""
+    from oracle import resampler_xl as orx, sdxl as osd, vit as ovit
+    g = torch.load(os.path.join(GOLD, "edit_adapter_tiny.pt"))
+    vcfg = dict(width=208, layers=2, heads=2, mlp_width=520, output_dim=256, n_queries=256, patch=14)
+    rcfg = dict(synth.TINY_RESAMPLER_XL, embedding_dim=256)
+    ucfg = dict(synth.TINY_UNET, cross_attention_dim=256, text_embed_dim=160, in_channels=8)
+    B, hw = 1, 8
+    feats = synth.randn("edit_golden_feats", (B, 64, 256))
+    noise = synth.randn("edit_golden_noise", (B, 4, hw, hw))
+    src = synth.randn("edit_golden_src", (B, 3, hw * 8, hw * 8)).clamp(-1, 1)
+    neg = ovit.vit_down(ovit.vit_forward(synth.vit_state_dict(**vcfg), torch.zeros(1, 3, 224, 224), 2))
+    prompt, pooled = orx.resampler_xl(synth.resampler_xl_state_dict(rcfg), rcfg, torch.cat([feats, neg.expand(B, -1, -1)]))
+    assert rel(prompt[:B], g["prompt"]) < 2e-5 and rel(prompt[B:], g["neg_prompt"]) < 2e-5
+    assert rel(pooled[:B], g["pooled"]) < 2e-5 and rel(pooled[B:], g["neg_pooled"]) < 2e-5
+    assert osd.Euler().set_timesteps(g["steps"]).timesteps.tolist() == g["unet_timesteps"]
+    v_sd = synth.vae_state_dict(synth.TINY_VAE)
+    il = osd.vae_encode_mode(v_sd, synth.TINY_VAE, src)
+    lat = osd.edit_sample(synth.unet_state_dict(ucfg), ucfg, noise, il, prompt[:B], pooled[:B], prompt[B:], pooled[B:], steps=g["steps"], size=hw * 8)
+    assert rel(lat, g["latents"]) < 2e-5
+    img = osd.vae_decode(v_sd, synth.TINY_VAE, lat / synth.TINY_VAE["scaling_factor"])
+    assert rel(img, g["image"]) < 2e-5
+
+
 def test_resampler_xl_oracle_matches_reference():
     from oracle import resampler_xl as orx
     g = torch.load(os.path.join(GOLD, "resampler_xl.pt"))
