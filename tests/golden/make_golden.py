@@ -334,7 +334,11 @@ def golden_edit_adapter():
         out["image"] = ad.generate(image_embeds=feats, latent_image=src, num_inference_steps=steps, height=hw * 8, width=hw * 8, latents=noise.clone(),
                                    input_image_size=224, guidance_scale=7.5, image_guidance_scale=1.5, output_type="pt").float()
         p, n, pp, npool = ad.get_image_embeds(image_embeds=feats, return_negative=True, image_size=224)
-    out.update(prompt=p.float(), neg_prompt=n.float(), pooled=pp.float(), neg_pooled=npool.float(), steps=steps, unet_timesteps=unet.calls[:steps])
+        # reconstruction path (eval_seed_x_detokenizer.py): an image tensor in -> un-pooled 256-token conditioning, negative = ViT(zeros) un-pooled too
+        it = synth.image("edit_golden_img224", 1, 224)
+        tp, tn, tpp, tnp = ad.get_image_embeds(image_tensor=it, return_negative=True)
+    out.update(prompt=p.float(), neg_prompt=n.float(), pooled=pp.float(), neg_pooled=npool.float(), steps=steps, unet_timesteps=unet.calls[:steps],
+               tensor_prompt=tp.float(), tensor_neg_prompt=tn.float(), tensor_pooled=tpp.float(), tensor_neg_pooled=tnp.float())
     torch.save(out, os.path.join(OUT, "edit_adapter_tiny.pt"))
     print("edit_adapter_tiny: latents", tuple(out["latents"].shape), "image", tuple(out["image"].shape), "timesteps", out["unet_timesteps"])
 

@@ -103,6 +103,9 @@ def test_edit_adapter_matches_the_reference_adapter_and_pipeline(parts):
     src = synth.randn("edit_golden_src", (B, 3, hw * 8, hw * 8)).clamp(-1, 1)
     p, n, pp, npool = ad.get_image_embeds(image_embeds=feats, return_negative=True, image_size=224)
     assert rel(p, g["prompt"]) < 2e-3 and rel(n, g["neg_prompt"]) < 2e-3 and rel(pp, g["pooled"]) < 2e-3 and rel(npool, g["neg_pooled"]) < 2e-3
+    tp, tn, tpp, tnp = ad.get_image_embeds(image_tensor=synth.image("edit_golden_img224", 1, 224), return_negative=True)     # un-pooled 256-token path
+    assert rel(tp, g["tensor_prompt"]) < 2e-3 and rel(tn, g["tensor_neg_prompt"]) < 2e-3
+    assert rel(tpp, g["tensor_pooled"]) < 2e-3 and rel(tnp, g["tensor_neg_pooled"]) < 2e-3
     lat = ad.generate(image_embeds=feats, latent_image=src, num_inference_steps=g["steps"], height=hw * 8, width=hw * 8, latents=noise, input_image_size=224,
                       guidance_scale=7.5, image_guidance_scale=1.5, output_type="latent")
     assert rel(lat, g["latents"]) < 1e-2

@@ -141,6 +141,12 @@ def test_edit_pipeline_oracle_matches_the_reference_adapter_and_pipeline():
     prompt, pooled = orx.resampler_xl(synth.resampler_xl_state_dict(rcfg), rcfg, torch.cat([feats, neg.expand(B, -1, -1)]))
     assert rel(prompt[:B], g["prompt"]) < 2e-5 and rel(prompt[B:], g["neg_prompt"]) < 2e-5
     assert rel(pooled[:B], g["pooled"]) < 2e-5 and rel(pooled[B:], g["neg_pooled"]) < 2e-5
+    # image-tensor path (adapter_modules.py:100-108): positive and negative are both the un-pooled 256 tokens
+    it = synth.image("edit_golden_img224", 1, 224)
+    f2 = ovit.vit_forward(synth.vit_state_dict(**vcfg), torch.cat([it, torch.zeros_like(it)]), 2)
+    p2, pool2 = orx.resampler_xl(synth.resampler_xl_state_dict(rcfg), rcfg, f2)
+    assert rel(p2[:1], g["tensor_prompt"]) < 2e-5 and rel(p2[1:], g["tensor_neg_prompt"]) < 2e-5
+    assert rel(pool2[:1], g["tensor_pooled"]) < 2e-5 and rel(pool2[1:], g["tensor_neg_pooled"]) < 2e-5
     assert osd.Euler().set_timesteps(g["steps"]).timesteps.tolist() == g["unet_timesteps"]
     v_sd = synth.vae_state_dict(synth.TINY_VAE)
     il = osd.vae_encode_mode(v_sd, synth.TINY_VAE, src)
