@@ -79,11 +79,12 @@ typedef struct seedx_gemm_args {
   /* conv mode */
   int32_t conv_taps_h, conv_taps_w; /* 0,0 = plain GEMM; 3,3 or 1,1 */
   int64_t conv_n, conv_h, conv_w, conv_c;
-  int32_t tile_n;    /* 0 = auto; else 64/128/256 */
+  int32_t tile_n;    /* 0 = auto (wave/cycle model); else one of 64/96/128/144/160/192/208/224/240/256 accumulator columns */
 } seedx_gemm_args;
 
 int seedx_gemm_f16(const seedx_gemm_args* args, void* stream);
-/* A/B switch for the 2-CTA cluster (TMA multicast of the B tile) variant: 0 = off, 1 = auto (default), 2 = whenever legal */
+/* A/B switch for the CTA-pair variant (tcgen05 cta_group::2: one 256 x tile_n accumulator tile over two SMs, each CTA staging its own
+ * 128 rows of A and half of the B tile): 0 = off, 1 = auto (default), 2 = whenever legal */
 void seedx_gemm_set_cluster(int mode);
 /* developer aid: device buffer of 8 uint64 per CTA that receives %globaltimer phase stamps of the following GEMM launches (NULL = off) */
 void seedx_gemm_set_debug(void* device_buffer);

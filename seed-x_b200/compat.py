@@ -1,7 +1,7 @@
 """Minimal stand-ins for the third-party helpers the reference entry scripts import but this image does not ship
 (hydra, omegaconf, pyrootutils, diffusers, peft; SURVEY.md §5 'Config / flag system', §8b).  ``install()`` registers them in
 sys.modules only when the real package is missing, so `import hydra` / `from omegaconf import OmegaConf` /
-`from diffusers import AutoencoderKL, UNet2DConditionModel, EulerDiscreteScheduler` in src/inference/eval_*.py resolve.
+`from diffusers import AutoencoderKL, UNet2DConditionModel, EulerDiscreteScheduler[, Transformer2DModel]` in src/inference/eval_*.py resolve.
 """
 import importlib
 import os
@@ -113,4 +113,6 @@ def install():
         from . import sdxl
         d = types.ModuleType("diffusers")
         d.AutoencoderKL, d.UNet2DConditionModel, d.EulerDiscreteScheduler = sdxl.AutoencoderKL, sdxl.UNet2DConditionModel, sdxl.EulerDiscreteScheduler
+        # eval_img2edit_seed_x_edit.py:8 imports the name without ever instantiating it
+        d.Transformer2DModel = sdxl.Transformer2DModel
         sys.modules["diffusers"] = d

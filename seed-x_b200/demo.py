@@ -13,7 +13,11 @@ from omegaconf import OmegaConf  # noqa: E402
 
 BOI_TOKEN, EOI_TOKEN, IMG_TOKEN = "<img>", "</img>", "<img_{:05d}>"
 BOP_TOKEN, EOP_TOKEN = "<patch>", "</patch>"
-INSTRUCTION = "[INST] {instruction} [/INST]\n"
+INSTRUCTION = "[INST] {instruction} [/INST]\n"          # instruction-tuned checkpoints (eval_*_seed_x_i.py:23, eval_img2edit_seed_x_edit.py:27)
+# pre-trained (base) checkpoint templates: eval_text2img_seed_x.py:23, eval_img2text_seed_x.py:55-56
+BASE_GEN_PROMPT = "{instruction}" + BOI_TOKEN
+BASE_QUESTION_PROMPT = "Question: {instruction}\nAnswer:"
+BASE_BBOX_PROMPT = "{instruction} [[ <box_start>"
 RESOLUTION_GRIDS = ["1x1", "1x2", "1x3", "2x1", "3x1", "1x4", "4x1", "2x2"]
 BASE_RES = 448
 DIFFUSION_PATH = "pretrained/stable-diffusion-xl-base-1.0"
@@ -50,11 +54,13 @@ def load(variant="seed_x_i", adapter="sdxl_qwen_vit_resampler_l4_q64_pretrain_no
     return out
 
 
-def image_prompt(tokenizer, n_views, question, n_tokens=64, force_image=False):
-    """token layout of SURVEY.md A.2 / eval_img2text_seed_x_i.py:142-162 -> (input_ids [1,P], ids_cmp_mask [1,P])."""
+def image_prompt(tokenizer, n_views, question, n_tokens=64, force_image=False, template=INSTRUCTION):
+    """token layout of SURVEY.md A.2 / eval_img2text_seed_x_i.py:142-162 -> (input_ids [1,P], ids_cmp_mask [1,P]).  `template` holds one
+    ``{instruction}`` slot that receives the image tokens followed by the text: INSTRUCTION for the instruction-tuned checkpoints, one of the
+    BASE_* templates for the pre-trained one."""
     img = "".join(IMG_TOKEN.format(i) for i in range(n_tokens))
     image_tokens = (BOP_TOKEN + img + EOP_TOKEN) * (n_views - 1) + BOI_TOKEN + img + EOI_TOKEN if n_views else ""
-    prompt = INSTRUCTION.format_map({"instruction": image_tokens + question}) + (BOI_TOKEN if force_image else "")
+    prompt = template.format_map({"instruction": image_tokens + question}) + (BOI_TOKEN if force_image else "")
     ids = torch.tensor([tokenizer.bos_token_id] + tokenizer.encode(prompt, add_special_tokens=False))
     mask = span_mask(tokenizer, ids)
     return ids.unsqueeze(0), mask.unsqueeze(0)

@@ -169,6 +169,10 @@ class _Transformer:
         return ops.gemm(h16, self.w_out, bias=self.b_out, residual=x.view(M, c)).view(n, h, w, c)
 
 
+# diffusers name of the block above: src/inference/eval_img2edit_seed_x_edit.py:8 imports it (and never instantiates it)
+Transformer2DModel = _Transformer
+
+
 def _conv_s2(x, w, b, pad_before):
     """3x3 stride-2 conv = patch gather + GEMM (UNet Downsample2D pad 1; VAE encoder asymmetric pad (0,1))."""
     n, h, wd, c = x.shape

@@ -15,11 +15,11 @@ tok, agent = m["tokenizer"], m["agent_model"]
 image = Image.open("demo_images/car.jpg").convert("RGB")
 source = image.resize((1024, 1024))
 views, patch_pos = process_anyres_image(image, m["image_transform"], demo.grid_pinpoints(["1x1"]), demo.BASE_RES)
-input_ids, ids_cmp_mask = demo.image_prompt(tok, views.shape[0], "Make it a red sports car.", force_image=True)
+input_ids, ids_cmp_mask = demo.image_prompt(tok, views.shape[0], "Make it under the sunset")   # no forced <img>: reference :27,117
 with torch.no_grad():
     image_embeds = m["visual_encoder"](views.to("cuda"))
     out = agent.generate(tokenizer=tok, input_ids=input_ids, image_embeds=image_embeds, embeds_cmp_mask=torch.ones(views.shape[0], dtype=torch.bool),
-                         patch_positions=patch_pos, ids_cmp_mask=ids_cmp_mask, max_new_tokens=120, num_img_gen_tokens=64)
+                         patch_positions=patch_pos, ids_cmp_mask=ids_cmp_mask, max_new_tokens=512, num_img_gen_tokens=64)
     if out["has_img_output"]:
         images = m["adapter"].generate(image_embeds=out["img_gen_feat"], latent_image=source, num_inference_steps=50)
         demo.save(images, "vis/car_edit.jpg")

@@ -11,9 +11,9 @@ from any_res import process_anyres_image
 
 m = demo.load(variant="seed_x")
 tok, agent = m["tokenizer"], m["agent_model"]
-image = Image.open("demo_images/advisor.png").convert("RGB")
+image = Image.open("demo_images/cat_dog.jpeg").convert("RGB")
 views, patch_pos = process_anyres_image(image, m["image_transform"], demo.grid_pinpoints(), demo.BASE_RES)
-input_ids, ids_cmp_mask = demo.image_prompt(tok, views.shape[0], "Can I conntect with an advisor on Sunday?")
+input_ids, ids_cmp_mask = demo.image_prompt(tok, views.shape[0], "Describe this image briefly.", template=demo.BASE_QUESTION_PROMPT)  # reference :55,149-150
 with torch.no_grad():
     image_embeds = m["visual_encoder"](views.to("cuda"))
     out = agent.generate(tokenizer=tok, input_ids=input_ids, image_embeds=image_embeds, embeds_cmp_mask=torch.ones(views.shape[0], dtype=torch.bool),

@@ -12,9 +12,9 @@ from any_res import process_anyres_image
 m = demo.load(variant="seed_x")
 tok, agent = m["tokenizer"], m["agent_model"]
 caption = "A photo of an astronaut riding a horse on the moon."
-input_ids, _ = demo.image_prompt(tok, 0, "Generate an image: " + caption, force_image=True)
+input_ids, _ = demo.image_prompt(tok, 0, caption, template=demo.BASE_GEN_PROMPT)      # '{caption}<img>' (reference :23)
 with torch.no_grad():
-    out = agent.generate(tokenizer=tok, input_ids=input_ids, max_new_tokens=120, num_img_gen_tokens=64)
+    out = agent.generate(tokenizer=tok, input_ids=input_ids, num_img_gen_tokens=64)
     if out["has_img_output"]:
         images = m["adapter"].generate(image_embeds=out["img_gen_feat"], num_inference_steps=50)
         demo.save(images, "vis/text2img.jpg")

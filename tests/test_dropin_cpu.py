@@ -151,6 +151,40 @@ def test_reference_scripts_only_use_keywords_the_replacement_names():
 
 
 @needs_ref
+def test_import_block_of_every_reference_entry_script_executes_under_the_stand_ins():
+    """the statements every reference entry script runs before touching a model — its top-level imports (incl. `from diffusers import …,
+    Transformer2DModel` and the sibling `from any_res import …`) and `pyrootutils.setup_root` — execute against this repo exactly as
+    `python -m seedx_b200.run <script>` would run them (compat.install() + script directory on sys.path); a missing name fails here, not on a GPU box"""
+    scripts = sorted(glob.glob(os.path.join(REF, "src/inference/eval_*.py")))
+    assert len(scripts) == 7
+    code = r'''
+import ast, os, sys
+sys.path.insert(0, %r)
+from seedx_b200 import compat
+compat.install()
+sys.path.insert(0, os.path.join(%r, "src", "inference"))      # what seedx_b200.run does for the sibling import
+for path in %r:
+    tree = ast.parse(open(path).read())
+    block = []
+    for node in tree.body:
+        is_setup = isinstance(node, ast.Expr) and isinstance(node.value, ast.Call) and getattr(node.value.func, "attr", "") == "setup_root"
+        if isinstance(node, (ast.Import, ast.ImportFrom)) or is_setup:
+            block.append(node)
+    assert len(block) >= 7, path
+    # __file__ of the script as the launcher sees it: the same relative location inside THIS repo
+    ns = {"__name__": "not_main", "__file__": os.path.join(%r, "src", "inference", os.path.basename(path))}
+    exec(compile(ast.Module(body=block, type_ignores=[]), path, "exec"), ns)
+    import diffusers
+    for n in ("AutoencoderKL", "UNet2DConditionModel", "EulerDiscreteScheduler"):
+        assert ns[n] is getattr(diffusers, n)
+    print("ok", os.path.basename(path))
+''' % (ROOT, ROOT, scripts, ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert r.stdout.count("ok eval_") == 7, r.stdout
+
+
+@needs_ref
 def test_reference_yaml_targets_resolve_with_identical_keys():
     """every inference YAML of the reference has a twin here with the same `_target_`s and keys (values may differ only in comments)"""
     import yaml
