@@ -263,7 +263,8 @@ class LlamaForCausalLM:
         if lora and getattr(self, "peft_config", None) is None:
             raise SeedxError("the checkpoint holds LoRA adapters but the LLM was not built with a peft_config "
                              "(use configs/clm_models/llm_seed_x_lora.yaml)")
-        sc = self.peft_config.scaling if lora else 1.0
+        # alpha / r spelled out: the real peft.LoraConfig dataclass (when the package is installed) has no `.scaling` property
+        sc = float(self.peft_config.lora_alpha) / float(self.peft_config.r) if lora else 1.0
         for mod, (a, _) in lora.items():
             if a.shape[0] != self.peft_config.r:
                 raise SeedxError(f"{mod}: adapter rank {a.shape[0]} != peft_config.r {self.peft_config.r}")

@@ -67,8 +67,33 @@ def pad_rows(w, b, nmin=8):
     return wp, bp
 
 
+class _ParamRegistry:
+    """checkpoint key -> (packed device tensor or slice of one, packing function): lets a later (partial) state dict overwrite the packed
+    parameters IN PLACE (the reference loads adapter checkpoints with strict=False: only `to_k` / `to_v` (+ `conv_in`) of the UNet are present
+    when full_ft is false, adapter_modules.py:20-33,59-65), so captured CUDA graphs and cached loops keep pointing at live storage."""
+
+    def __init__(self):
+        self.slots = {}
+
+    def add(self, key, dest, fn):
+        self.slots[key] = (dest, fn)
+
+    def update(self, key, value):
+        dest, fn = self.slots[key]
+        new = fn(value)
+        if new.shape != dest.shape:
+            raise SeedxError(f"{key}: shape {tuple(value.shape)} does not match the loaded model")
+        dest.copy_(new)
+
+
+def _interleave_rows(w):
+    """GEGLU / SwiGLU weight [2*inner, ...] -> rows [hidden_0, gate_0, hidden_1, gate_1, ...] (gate beside its value in one accumulator tile)"""
+    inner = w.shape[0] // 2
+    return torch.stack([w[:inner], w[inner:]], dim=1).reshape((2 * inner,) + tuple(w.shape[1:]))
+
+
 class _Resnet:
-    def __init__(self, sd, p, dev, eps):
+    def __init__(self, sd, p, dev, eps, reg=None):
         self.eps = eps
         self.n1 = (_f(sd[p + ".norm1.weight"], dev), _f(sd[p + ".norm1.bias"], dev))
         self.n2 = (_f(sd[p + ".norm2.weight"], dev), _f(sd[p + ".norm2.bias"], dev))
@@ -81,6 +106,17 @@ class _Resnet:
         if (p + ".conv_shortcut.weight") in sd:
             w = sd[p + ".conv_shortcut.weight"]
             self.wsc, self.bsc = _h(w.reshape(w.shape[0], w.shape[1]), dev), _f(sd[p + ".conv_shortcut.bias"], dev)
+        if reg is not None:
+            hh, ff = (lambda t: _h(t, dev)), (lambda t: _f(t, dev))
+            for nm, pair in (("norm1", self.n1), ("norm2", self.n2)):
+                reg.add(f"{p}.{nm}.weight", pair[0], ff), reg.add(f"{p}.{nm}.bias", pair[1], ff)
+            for nm, w_, b_ in (("conv1", self.w1, self.b1), ("conv2", self.w2, self.b2)):
+                reg.add(f"{p}.{nm}.weight", w_, lambda t: pack_conv(t, dev)), reg.add(f"{p}.{nm}.bias", b_, ff)
+            if self.wt is not None:
+                reg.add(p + ".time_emb_proj.weight", self.wt, hh), reg.add(p + ".time_emb_proj.bias", self.bt, ff)
+            if self.wsc is not None:
+                reg.add(p + ".conv_shortcut.weight", self.wsc, lambda t: _h(t.reshape(t.shape[0], t.shape[1]), dev))
+                reg.add(p + ".conv_shortcut.bias", self.bsc, ff)
 
     def __call__(self, x, skip, semb, groups, ws):
         """ResnetBlock2D on NHWC fp16; `skip` (optional) is channel-concatenated behind x (UNet up blocks)."""
@@ -105,21 +141,24 @@ class _Transformer:
     # halves the HBM traffic of the residual epilogues and LayerNorm reads; fp32 is available for parity experiments.
     stream_dtype = torch.float16
 
-    def __init__(self, sd, p, dev, depth, heads):
+    def __init__(self, sd, p, dev, depth, heads, reg=None):
         self.heads = heads
         self.norm = (_f(sd[p + ".norm.weight"], dev), _f(sd[p + ".norm.bias"], dev))
         self.w_in, self.b_in = _h(sd[p + ".proj_in.weight"], dev), _f(sd[p + ".proj_in.bias"], dev)
         self.w_out, self.b_out = _h(sd[p + ".proj_out.weight"], dev), _f(sd[p + ".proj_out.bias"], dev)
+        hh, ff = (lambda t: _h(t, dev)), (lambda t: _f(t, dev))
+        if reg is not None:
+            reg.add(p + ".norm.weight", self.norm[0], ff), reg.add(p + ".norm.bias", self.norm[1], ff)
+            reg.add(p + ".proj_in.weight", self.w_in, hh), reg.add(p + ".proj_in.bias", self.b_in, ff)
+            reg.add(p + ".proj_out.weight", self.w_out, hh), reg.add(p + ".proj_out.bias", self.b_out, ff)
         self.blocks = []
         for k in range(depth):
             b = f"{p}.transformer_blocks.{k}"
             g = lambda s: sd[f"{b}.{s}"]  # noqa: E731
             w_ff = g("ff.net.0.proj.weight")
             b_ff = g("ff.net.0.proj.bias")
-            inner = w_ff.shape[0] // 2
             # GEGLU: interleave [hidden_j, gate_j] rows so the gate sits beside its value in one accumulator tile
-            w_il = torch.stack([w_ff[:inner], w_ff[inner:]], dim=1).reshape(2 * inner, -1)
-            b_il = torch.stack([b_ff[:inner], b_ff[inner:]], dim=1).reshape(2 * inner)
+            w_il, b_il = _interleave_rows(w_ff), _interleave_rows(b_ff)
             self.blocks.append(dict(
                 n1=(_f(g("norm1.weight"), dev), _f(g("norm1.bias"), dev)),
                 n2=(_f(g("norm2.weight"), dev), _f(g("norm2.bias"), dev)),
@@ -131,6 +170,20 @@ class _Transformer:
                 w_o2=_h(g("attn2.to_out.0.weight"), dev), b_o2=_f(g("attn2.to_out.0.bias"), dev),
                 w_ff1=_h(w_il, dev), b_ff1=_f(b_il, dev),
                 w_ff2=_h(g("ff.net.2.weight"), dev), b_ff2=_f(g("ff.net.2.bias"), dev)))
+            if reg is not None:
+                blk = self.blocks[-1]
+                c = blk["w_o1"].shape[0]
+                for i, nm in enumerate(("n1", "n2", "n3")):
+                    reg.add(f"{b}.norm{i + 1}.weight", blk[nm][0], ff), reg.add(f"{b}.norm{i + 1}.bias", blk[nm][1], ff)
+                for i, nm in enumerate(("to_q", "to_k", "to_v")):
+                    reg.add(f"{b}.attn1.{nm}.weight", blk["w_qkv"][i * c:(i + 1) * c], hh)
+                reg.add(f"{b}.attn2.to_q.weight", blk["w_q2"], hh)
+                reg.add(f"{b}.attn2.to_k.weight", blk["w_kv2"][:c], hh), reg.add(f"{b}.attn2.to_v.weight", blk["w_kv2"][c:], hh)
+                for a_, wn, bn in (("attn1", "w_o1", "b_o1"), ("attn2", "w_o2", "b_o2")):
+                    reg.add(f"{b}.{a_}.to_out.0.weight", blk[wn], hh), reg.add(f"{b}.{a_}.to_out.0.bias", blk[bn], ff)
+                reg.add(f"{b}.ff.net.0.proj.weight", blk["w_ff1"], lambda t: _h(_interleave_rows(t), dev))
+                reg.add(f"{b}.ff.net.0.proj.bias", blk["b_ff1"], lambda t: _f(_interleave_rows(t), dev))
+                reg.add(f"{b}.ff.net.2.weight", blk["w_ff2"], hh), reg.add(f"{b}.ff.net.2.bias", blk["b_ff2"], ff)
 
     def context_kv(self, ctx16):
         """cross-attention K/V of every block for a step-invariant context [B*T, ctx_dim] (hoisted out of the sampler loop)."""
@@ -195,6 +248,7 @@ class UNet2DConditionModel:
         self.device = torch.device(device)
         self.dtype = torch.float16
         self._loaded = False
+        self._reg = _ParamRegistry()
 
     @classmethod
     def from_pretrained(cls, path, subfolder=None, **kw):
@@ -221,10 +275,29 @@ class UNet2DConditionModel:
     def state_shape_in_channels(self):
         return self.cfg["in_channels"]
 
+    def update_state_dict(self, sd):
+        """overwrite the packed parameters named in `sd` in place (a partial checkpoint, `load_state_dict(..., strict=False)` in the
+        reference: adapter_modules.py:59-65).  Returns the keys this model does not have (the 'unexpected' list)."""
+        unexpected = []
+        for k, v in sd.items():
+            if k not in self._reg.slots:
+                unexpected.append(k)
+                continue
+            if k == "conv_in.weight":
+                if v.shape[1] > 8:
+                    raise SeedxError("conv_in with more than 8 input channels is not supported")
+                self.cfg["in_channels"] = v.shape[1]
+            self._reg.update(k, v)
+        return unexpected
+
     def load_state_dict(self, sd, strict=False):
+        if self._loaded:
+            # a second checkpoint on top of the loaded base model (possibly partial): in place, storage pointers unchanged
+            return [k for k in self._reg.slots if k not in sd], self.update_state_dict(sd)
         cfg, dev = self.cfg, self.device
         boc = cfg["block_out_channels"]
         nb = len(boc)
+        reg = self._reg = _ParamRegistry()
         cin = sd["conv_in.weight"].shape[1]
         self.cfg["in_channels"] = cin
         # widths the checkpoint itself fixes (diffusers: time_embed_dim = 4*block_out_channels[0], projection_class_embeddings_input_dim)
@@ -232,37 +305,47 @@ class UNet2DConditionModel:
         self.cfg["text_embed_dim"] = sd["add_embedding.linear_1.weight"].shape[1] - 6 * cfg["addition_time_embed_dim"]
         if cin > 8:
             raise SeedxError("conv_in with more than 8 input channels is not supported")
+        hh, ff = (lambda t: _h(t, dev)), (lambda t: _f(t, dev))
         self.conv_in = (pack_conv(sd["conv_in.weight"], dev), _f(sd["conv_in.bias"], dev))
-        lin = lambda p: (_h(sd[p + ".weight"], dev), _f(sd[p + ".bias"], dev))  # noqa: E731
+        reg.add("conv_in.weight", self.conv_in[0], lambda t: pack_conv(t, dev)), reg.add("conv_in.bias", self.conv_in[1], ff)
+
+        def lin(p):
+            w, b = _h(sd[p + ".weight"], dev), _f(sd[p + ".bias"], dev)
+            reg.add(p + ".weight", w, hh), reg.add(p + ".bias", b, ff)
+            return w, b
         self.t1, self.t2 = lin("time_embedding.linear_1"), lin("time_embedding.linear_2")
         self.a1, self.a2 = lin("add_embedding.linear_1"), lin("add_embedding.linear_2")
         self.down, self.up = [], []
         for i in range(nb):
             blk = dict(res=[], att=[], ds=None)
             for j in range(cfg["layers_per_block"]):
-                blk["res"].append(_Resnet(sd, f"down_blocks.{i}.resnets.{j}", dev, 1e-5))
+                blk["res"].append(_Resnet(sd, f"down_blocks.{i}.resnets.{j}", dev, 1e-5, reg))
                 if cfg["down_attn"][i]:
-                    blk["att"].append(_Transformer(sd, f"down_blocks.{i}.attentions.{j}", dev, cfg["transformer_layers"][i], cfg["heads"][i]))
+                    blk["att"].append(_Transformer(sd, f"down_blocks.{i}.attentions.{j}", dev, cfg["transformer_layers"][i], cfg["heads"][i], reg))
             if i < nb - 1:
                 p = f"down_blocks.{i}.downsamplers.0.conv"
                 blk["ds"] = (pack_conv_dense(sd[p + ".weight"], dev), _f(sd[p + ".bias"], dev))
+                reg.add(p + ".weight", blk["ds"][0], lambda t: pack_conv_dense(t, dev)), reg.add(p + ".bias", blk["ds"][1], ff)
             self.down.append(blk)
-        self.mid = dict(r0=_Resnet(sd, "mid_block.resnets.0", dev, 1e-5),
-                        att=_Transformer(sd, "mid_block.attentions.0", dev, cfg["transformer_layers"][-1], cfg["heads"][-1]),
-                        r1=_Resnet(sd, "mid_block.resnets.1", dev, 1e-5))
+        self.mid = dict(r0=_Resnet(sd, "mid_block.resnets.0", dev, 1e-5, reg),
+                        att=_Transformer(sd, "mid_block.attentions.0", dev, cfg["transformer_layers"][-1], cfg["heads"][-1], reg),
+                        r1=_Resnet(sd, "mid_block.resnets.1", dev, 1e-5, reg))
         for i in range(nb):
             r = nb - 1 - i
             blk = dict(res=[], att=[], us=None)
             for j in range(cfg["layers_per_block"] + 1):
-                blk["res"].append(_Resnet(sd, f"up_blocks.{i}.resnets.{j}", dev, 1e-5))
+                blk["res"].append(_Resnet(sd, f"up_blocks.{i}.resnets.{j}", dev, 1e-5, reg))
                 if cfg["down_attn"][r]:
-                    blk["att"].append(_Transformer(sd, f"up_blocks.{i}.attentions.{j}", dev, cfg["transformer_layers"][r], cfg["heads"][r]))
+                    blk["att"].append(_Transformer(sd, f"up_blocks.{i}.attentions.{j}", dev, cfg["transformer_layers"][r], cfg["heads"][r], reg))
             if i < nb - 1:
                 p = f"up_blocks.{i}.upsamplers.0.conv"
                 blk["us"] = (pack_conv(sd[p + ".weight"], dev), _f(sd[p + ".bias"], dev))
+                reg.add(p + ".weight", blk["us"][0], lambda t: pack_conv(t, dev)), reg.add(p + ".bias", blk["us"][1], ff)
             self.up.append(blk)
         self.norm_out = (_f(sd["conv_norm_out.weight"], dev), _f(sd["conv_norm_out.bias"], dev))
         self.conv_out = (pack_conv(sd["conv_out.weight"], dev), _f(sd["conv_out.bias"], dev))
+        reg.add("conv_norm_out.weight", self.norm_out[0], ff), reg.add("conv_norm_out.bias", self.norm_out[1], ff)
+        reg.add("conv_out.weight", self.conv_out[0], lambda t: pack_conv(t, dev)), reg.add("conv_out.bias", self.conv_out[1], ff)
         self._loaded = True
         return [], []
 
@@ -529,8 +612,22 @@ class EulerDiscreteScheduler:
         cj = os.path.join(d, "scheduler_config.json")
         if os.path.exists(cj):
             c = json.load(open(cj))
+            cls.check_config(c)
             return cls(c.get("num_train_timesteps", 1000), c.get("beta_start", 0.00085), c.get("beta_end", 0.012), c.get("steps_offset", 1))
         return cls()
+
+    # what the sampler implements = the SDXL-base scheduler_config.json the reference loads (eval_*.py:97); anything else would sample with
+    # the wrong sigmas / init_noise_sigma without an error, so it is refused instead
+    SUPPORTED = dict(beta_schedule="scaled_linear", timestep_spacing="leading", prediction_type="epsilon", interpolation_type="linear",
+                     use_karras_sigmas=False, rescale_betas_zero_snr=False, timestep_type="discrete")
+
+    @classmethod
+    def check_config(cls, c):
+        for k, want in cls.SUPPORTED.items():
+            if k in c and c[k] is not None and c[k] != want:
+                raise SeedxError(f"EulerDiscreteScheduler: {k}={c[k]!r} is not implemented (only {want!r}, the SDXL-base scheduler config)")
+        if c.get("trained_betas") is not None:
+            raise SeedxError("EulerDiscreteScheduler: trained_betas is not implemented")
 
     def set_timesteps(self, n, device=None):
         ratio = self.num_train // n

@@ -135,7 +135,9 @@ def test_lora_merge_updates_the_packed_weights_in_place():
     ft = synth.lora_fixture(g["shapes"])
     with pytest.raises(SeedxError):
         m.apply_peft_state_dict(ft)                                     # no peft_config
-    m.peft_config = lora.LoraConfig(r=g["r"], lora_alpha=g["lora_alpha"])
+    # the real peft.LoraConfig is a dataclass with r / lora_alpha and NO `.scaling` property (peft 0.4.0 config.py): a plain object stands for it
+    import types
+    m.peft_config = types.SimpleNamespace(r=g["r"], lora_alpha=g["lora_alpha"])
     ptrs = [L["wqkv"].data_ptr() for L in m.layers] + [L["wgu"].data_ptr() for L in m.layers]
     extra = m.apply_peft_state_dict({**ft, "base_model.model.model.layers.0.self_attn.rotary_emb.inv_freq": torch.zeros(4),
                                      "base_model.model.model.layers.9.mlp.up_proj.weight": torch.zeros(2, 2)})

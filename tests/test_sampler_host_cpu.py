@@ -88,3 +88,24 @@ def test_edit_loop_host_logic(patched):
     from seedx_b200._lib import SeedxError
     with pytest.raises(SeedxError):
         sampler_mod.DenoiseLoop(unet, EulerDiscreteScheduler(), B, (hw, hw), 4)
+
+
+def test_scheduler_from_pretrained_refuses_configs_it_does_not_implement(tmp_path):
+    """the SDXL-base scheduler_config.json loads; a config that asks for another spacing / prediction type / Karras sigmas would sample with the
+    wrong sigmas without any error, so from_pretrained raises instead of silently assuming the SDXL defaults"""
+    import json
+    from seedx_b200._lib import SeedxError
+    base = dict(_class_name="EulerDiscreteScheduler", beta_end=0.012, beta_schedule="scaled_linear", beta_start=0.00085, clip_sample=False,
+                interpolation_type="linear", num_train_timesteps=1000, prediction_type="epsilon", sample_max_value=1.0, set_alpha_to_one=False,
+                skip_prk_steps=True, steps_offset=1, timestep_spacing="leading", trained_betas=None, use_karras_sigmas=False)
+    d = tmp_path / "scheduler"
+    d.mkdir()
+    json.dump(base, open(d / "scheduler_config.json", "w"))
+    s = EulerDiscreteScheduler.from_pretrained(str(tmp_path), subfolder="scheduler").set_timesteps(50)
+    o = osd.Euler().set_timesteps(50)
+    assert torch.allclose(torch.tensor(s.sigmas), o.sigmas, rtol=1e-6) and abs(s.init_noise_sigma - o.init_noise_sigma) < 1e-5
+    for bad in (dict(timestep_spacing="trailing"), dict(prediction_type="v_prediction"), dict(use_karras_sigmas=True), dict(beta_schedule="linear"),
+                dict(trained_betas=[0.1, 0.2])):
+        json.dump({**base, **bad}, open(d / "scheduler_config.json", "w"))
+        with pytest.raises(SeedxError):
+            EulerDiscreteScheduler.from_pretrained(str(tmp_path), subfolder="scheduler")

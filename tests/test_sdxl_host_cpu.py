@@ -37,6 +37,42 @@ def test_unet_host_wiring_vs_oracle(patched, in_ch):
     assert out.shape == ref.shape and rel(out, ref) < 5e-3
 
 
+def test_partial_adapter_checkpoint_updates_the_unet_in_place(patched):
+    """adapter checkpoints saved with full_ft=False hold only the UNet's `to_k` / `to_v` (+ the widened `conv_in` of the edit variant),
+    loaded with strict=False in the reference (adapter_modules.py:20-33,59-65): they merge into the loaded base UNet, the packed device tensors
+    keep their storage (captured graphs / cached loops stay valid), every other parameter keeps its base value, unknown keys are reported."""
+    from seedx_b200.adapter import SDXLAdapterWithLatentImage
+    cfg = dict(synth.TINY_UNET, in_channels=4)
+    base = synth.unet_state_dict(cfg)
+    m = sdxl_mod.UNet2DConditionModel(cfg, device="cpu")
+    m.load_state_dict({k: v.clone() for k, v in base.items()})
+    ptrs = {k: d.data_ptr() for k, (d, _) in m._reg.slots.items()}
+    assert set(m._reg.slots) == set(base)                             # every checkpoint key has a packed destination
+    part = {k: synth.randn("ft:" + k, v.shape, v.shape[-1] ** -0.5) for k, v in base.items() if k.endswith(("to_k.weight", "to_v.weight"))}
+    assert len(part) >= 8
+    part["conv_in.weight"] = torch.cat([base["conv_in.weight"], synth.randn("ft:conv_in", base["conv_in.weight"].shape, 0.05)], dim=1)
+    ad = SDXLAdapterWithLatentImage.__new__(SDXLAdapterWithLatentImage)
+    ad.unet, ad.resampler = m, None
+    ad.load_state_dict({**{"unet." + k: v for k, v in part.items()}, "unet.not_a_parameter": torch.zeros(1)})
+    assert m.cfg["in_channels"] == 8
+    assert ptrs == {k: d.data_ptr() for k, (d, _) in m._reg.slots.items()}
+    merged = {**base, **part}
+    cfg8 = dict(cfg, in_channels=8)
+    B, hw = 1, 16
+    x = synth.randn("cpu_unet_x8", (B, 8, hw, hw))
+    ctx = synth.randn("cpu_unet_ctx", (B, 16, cfg["cross_attention_dim"]))
+    te = synth.randn("cpu_unet_te", (B, cfg["text_embed_dim"]))
+    tid = torch.tensor([[1024.0, 1024.0, 0.0, 0.0, 1024.0, 1024.0]])
+    ref = osd.unet_forward(merged, cfg8, x, 301.0, ctx, te, tid)
+    out = m(x, 301.0, ctx, added_cond_kwargs=dict(text_embeds=te, time_ids=tid))
+    assert rel(out, ref) < 5e-3
+    assert rel(out, osd.unet_forward({**base, "conv_in.weight": part["conv_in.weight"]}, cfg8, x, 301.0, ctx, te, tid)) > 5e-2   # the update took effect
+    missing, unexpected = m.load_state_dict({"mid_block.resnets.0.conv1.bias": base["mid_block.resnets.0.conv1.bias"], "bogus": torch.zeros(1)})
+    assert unexpected == ["bogus"] and len(missing) == len(base) - 1
+    with pytest.raises(sdxl_mod.SeedxError):
+        m.load_state_dict({"conv_out.weight": torch.zeros(5, 7, 3, 3)})
+
+
 def test_vae_host_wiring_vs_oracle(patched):
     cfg = synth.TINY_VAE
     sd = synth.vae_state_dict(cfg)
