@@ -79,7 +79,7 @@ def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, 
 
 
 def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None, act=ACT_NONE,
-                out_dtype=torch.float16, tile_n=0):
+                out_dtype=torch.float16, tile_n=0, alpha=1.0):
     """Stride-1 'same' convolution as an implicit GEMM.  x: fp16 NHWC [N,H,W,C]; w: fp16 [Cout, taps*taps*roundup(C,64)]
     (k = (kh*taps+kw)*Cpad + c); out: NHWC [N,H,W,Cout].  bias_g: fp32 [N, Cout] added per image."""
     _require_cuda(x, w, out, bias, residual)
@@ -93,7 +93,7 @@ def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None
     g.A, g.B, g.D = x.data_ptr(), w.data_ptr(), out.data_ptr()
     g.M, g.N, g.K, g.batch = n * h * wd, cout, K, 1
     g.lda, g.ldb, g.ldd = c, K, cout
-    g.alpha = 1.0
+    g.alpha = alpha
     if bias is not None:
         assert bias.dtype == torch.float32
         g.bias_n = bias.data_ptr()

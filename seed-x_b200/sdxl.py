@@ -95,6 +95,7 @@ def _interleave_rows(w):
 class _Resnet:
     def __init__(self, sd, p, dev, eps, reg=None):
         self.eps = eps
+        self._sb = {}
         self.n1 = (_f(sd[p + ".norm1.weight"], dev), _f(sd[p + ".norm1.bias"], dev))
         self.n2 = (_f(sd[p + ".norm2.weight"], dev), _f(sd[p + ".norm2.bias"], dev))
         self.w1, self.b1 = pack_conv(sd[p + ".conv1.weight"], dev), _f(sd[p + ".conv1.bias"], dev)
@@ -118,22 +119,35 @@ class _Resnet:
                 reg.add(p + ".conv_shortcut.weight", self.wsc, lambda t: _h(t.reshape(t.shape[0], t.shape[1]), dev))
                 reg.add(p + ".conv_shortcut.bias", self.bsc, ff)
 
-    def __call__(self, x, skip, semb, groups, ws):
-        """ResnetBlock2D on NHWC fp16; `skip` (optional) is channel-concatenated behind x (UNet up blocks)."""
+    def _scaled(self, alpha):
+        """biases of the convs that write the scaled stream, multiplied by alpha once (the GEMM epilogue computes alpha*acc + bias)"""
+        if alpha not in self._sb:
+            self._sb[alpha] = tuple(None if b is None else (b * alpha).contiguous() for b in (self.b1, self.b2, self.bsc))
+        return self._sb[alpha]
+
+    def __call__(self, x, skip, semb, groups, ws, alpha=1.0):
+        """ResnetBlock2D on NHWC fp16; `skip` (optional) is channel-concatenated behind x (UNet up blocks).
+        alpha != 1 (VAE `force_upcast` mode, AutoencoderKL.stream_scale): x, the conv1 output and the result are alpha * their true
+        values.  GroupNorm is scale invariant once eps is scaled by alpha^2, so the normalised operands of both convs are unchanged and
+        only the conv epilogues carry the factor — exact in fp32, and the stored fp16 stream stays 1/alpha below the overflow limit."""
         n, h, w, _ = x.shape
         raw = None
         if skip is not None:
             raw = torch.empty((n, h, w, x.shape[3] + skip.shape[3]), device=x.device, dtype=torch.float16)
-        a = ops.groupnorm_nhwc(x, self.n1[0], self.n1[1], self.eps, x2=skip, silu=True, groups=groups, raw_out=raw, stats_ws=ws)
+        b1, b2, bsc = (self.b1, self.b2, self.bsc) if alpha == 1.0 else self._scaled(alpha)
+        eps = self.eps * alpha * alpha
+        a = ops.groupnorm_nhwc(x, self.n1[0], self.n1[1], eps, x2=skip, silu=True, groups=groups, raw_out=raw, stats_ws=ws)
         tb = ops.gemm(semb, self.wt, bias=self.bt, out_dtype=torch.float32) if self.wt is not None else None
-        a = ops.conv2d_nhwc(a, self.w1, bias=self.b1, bias_g=tb)
-        a = ops.groupnorm_nhwc(a, self.n2[0], self.n2[1], self.eps, silu=True, groups=groups, stats_ws=ws)
+        if tb is not None and alpha != 1.0:
+            raise SeedxError("scaled-stream ResnetBlock2D with a time embedding is not used by any model")
+        a = ops.conv2d_nhwc(a, self.w1, bias=b1, bias_g=tb, alpha=alpha)
+        a = ops.groupnorm_nhwc(a, self.n2[0], self.n2[1], eps, silu=True, groups=groups, stats_ws=ws)
         xin = raw if raw is not None else x
         if self.wsc is not None:
-            sc = ops.gemm(xin.view(n * h * w, xin.shape[3]), self.wsc, bias=self.bsc).view(n, h, w, -1)
+            sc = ops.gemm(xin.view(n * h * w, xin.shape[3]), self.wsc, bias=bsc).view(n, h, w, -1)     # linear in the scaled input
         else:
             sc = xin
-        return ops.conv2d_nhwc(a, self.w2, bias=self.b2, residual=sc)
+        return ops.conv2d_nhwc(a, self.w2, bias=b2, residual=sc, alpha=alpha)
 
 
 class _Transformer:
@@ -262,7 +276,7 @@ class UNet2DConditionModel:
                        transformer_layers=tuple(c["transformer_layers_per_block"]), heads=tuple(c["attention_head_dim"]),
                        cross_attention_dim=c["cross_attention_dim"], addition_time_embed_dim=c["addition_time_embed_dim"],
                        down_attn=tuple("CrossAttn" in t for t in c["down_block_types"]))
-        m = cls(cfg)
+        m = cls(cfg, device=kw.get("device", "cuda"))
         m.load_state_dict(_load_weights_dir(d))
         return m
 
@@ -434,11 +448,12 @@ class _VaeAttention:
         self.wv, self.bv = _h(sd[p + ".to_v.weight"], dev), _f(sd[p + ".to_v.bias"], dev)
         self.wo, self.bo = _h(sd[p + ".to_out.0.weight"], dev), _f(sd[p + ".to_out.0.bias"], dev)
 
-    def __call__(self, x, groups, ws):
-        """single-head attention over H*W tokens, head dim = C (512): scores are materialised per image (C > 160)."""
+    def __call__(self, x, groups, ws, alpha=1.0):
+        """single-head attention over H*W tokens, head dim = C (512): scores are materialised per image (C > 160).
+        alpha: scale of the residual stream x (see _Resnet.__call__); q/k/v come from the scale-invariant GroupNorm output."""
         n, h, w, c = x.shape
         S = h * w
-        hn = ops.groupnorm_nhwc(x, self.norm[0], self.norm[1], 1e-6, silu=False, groups=groups, stats_ws=ws).view(n, S, c)
+        hn = ops.groupnorm_nhwc(x, self.norm[0], self.norm[1], 1e-6 * alpha * alpha, silu=False, groups=groups, stats_ws=ws).view(n, S, c)
         q = ops.gemm(hn.view(n * S, c), self.wq, bias=self.bq).view(n, S, c)
         k = ops.gemm(hn.view(n * S, c), self.wk, bias=self.bk).view(n, S, c)
         out = torch.empty((n, S, c), device=x.device, dtype=torch.float16)
@@ -451,18 +466,37 @@ class _VaeAttention:
             ops.softmax_rows(scores, 1.0, out=probs)
             ops.gemm(probs, vt, out=out[i])
         xr = x.view(n * S, c)
-        return ops.gemm(out.view(n * S, c), self.wo, bias=self.bo, residual=xr).view(n, h, w, c)
+        bo = self.bo if alpha == 1.0 else (self.bo * alpha)
+        return ops.gemm(out.view(n * S, c), self.wo, bias=bo, residual=xr, alpha=alpha).view(n, h, w, c)
 
 
 class AutoencoderKL:
-    """SDXL VAE (encode -> latent mode, decode).  The reference up-casts the VAE to fp32 (pipeline...edit.py:569-586);
-    here operands are fp16 with fp32 accumulation (DESIGN.md 'precision')."""
+    """SDXL VAE (encode -> latent mode, decode).
+
+    Precision: the reference up-casts the VAE to fp32 when its config says `force_upcast` (pipeline_stable_diffusion_xl_t2i_edit.py:569-586,
+    965-975) because the activations of the stock stabilityai SDXL VAE exceed the fp16 range (NaN / black images); the `sdxl-vae-fp16-fix`
+    checkpoint sets force_upcast=false.  This engine keeps fp16 tensor-core operands with fp32 accumulation in both cases and honours
+    `force_upcast` by storing the un-normalised activations — the residual stream and the conv1 outputs, everything a GroupNorm reads —
+    multiplied by `stream_scale` = 2^-7: GroupNorm is invariant to that factor (its eps is scaled by stream_scale^2), the normalised conv /
+    attention operands are unchanged, and only epilogue constants (alpha, biases) carry it, which is exact in fp32.  Activations up to
+    65504 * 128 = 8.4e6 are then representable; fp16 keeps 11 mantissa bits (bf16 would keep 8).  With force_upcast=false the stream is
+    stored unscaled (stream_scale = 1), identical to round 1."""
+
+    UPCAST_STREAM_SCALE = 2.0 ** -7
 
     def __init__(self, cfg=None, device="cuda"):
         self.cfg = dict(SDXL_VAE if cfg is None else cfg)
+        self.cfg.setdefault("force_upcast", False)
         self.device = torch.device(device)
         self.dtype = torch.float16
         self._loaded = False
+
+    @property
+    def stream_scale(self):
+        env = os.environ.get("SEEDX_VAE_STREAM_SCALE")
+        if env:
+            return float(env)
+        return self.UPCAST_STREAM_SCALE if self.cfg.get("force_upcast") else 1.0
 
     class _Config:
         pass
@@ -471,6 +505,8 @@ class AutoencoderKL:
     def config(self):
         c = AutoencoderKL._Config()
         c.scaling_factor = self.cfg["scaling_factor"]
+        # False towards the caller: the pipeline's `upcast_vae()` branch (pipeline...edit.py:965-975) would cast modules this class does not
+        # have; the range problem it exists for is handled inside (cfg["force_upcast"] -> stream_scale)
         c.force_upcast = False
         c.block_out_channels = list(self.cfg["block_out_channels"])
         return c
@@ -483,8 +519,9 @@ class AutoencoderKL:
         if os.path.exists(cj):
             c = json.load(open(cj))
             cfg.update(block_out_channels=tuple(c["block_out_channels"]), layers_per_block=c["layers_per_block"],
-                       latent_channels=c["latent_channels"], scaling_factor=c.get("scaling_factor", 0.13025))
-        m = cls(cfg)
+                       latent_channels=c["latent_channels"], scaling_factor=c.get("scaling_factor", 0.13025),
+                       force_upcast=bool(c.get("force_upcast", True)))      # diffusers' AutoencoderKL default is True
+        m = cls(cfg, device=kw.get("device", "cuda"))
         m.load_state_dict(_load_weights_dir(d))
         return m
 
@@ -544,19 +581,21 @@ class AutoencoderKL:
             raise SeedxError("AutoencoderKL: decoder weights not loaded")
         G = self.cfg["groups"]
         B, _, h, w = latents.shape
+        al = self.stream_scale
+        sb = (lambda b: b) if al == 1.0 else (lambda b: b * al)       # bias of a conv that writes the scaled stream
         ws = ops.groupnorm_ws(B, G, self.device)
         z = ops.nchw_to_nhwc_f16(latents.to(self.device).float().contiguous(), 8, scale=scale)
         x = ops.gemm(z.view(B * h * w, 8), self.post_quant[0], bias=self.post_quant[1]).view(B, h, w, -1)
-        x = ops.conv2d_nhwc(x, self.d_conv_in[0], bias=self.d_conv_in[1])
-        x = self.d_mid[0](x, None, None, G, ws)
-        x = self.d_mid[1](x, G, ws)
-        x = self.d_mid[2](x, None, None, G, ws)
+        x = ops.conv2d_nhwc(x, self.d_conv_in[0], bias=sb(self.d_conv_in[1]), alpha=al)
+        x = self.d_mid[0](x, None, None, G, ws, al)
+        x = self.d_mid[1](x, G, ws, al)
+        x = self.d_mid[2](x, None, None, G, ws, al)
         for res, us in self.d_up:
             for r in res:
-                x = r(x, None, None, G, ws)
+                x = r(x, None, None, G, ws, al)
             if us is not None:
-                x = ops.conv2d_nhwc(ops.upsample2x_nhwc(x), us[0], bias=us[1])
-        a = ops.groupnorm_nhwc(x, self.d_norm_out[0], self.d_norm_out[1], 1e-6, silu=True, groups=G, stats_ws=ws)
+                x = ops.conv2d_nhwc(ops.upsample2x_nhwc(x), us[0], bias=sb(us[1]))     # linear in the scaled stream
+        a = ops.groupnorm_nhwc(x, self.d_norm_out[0], self.d_norm_out[1], 1e-6 * al * al, silu=True, groups=G, stats_ws=ws)
         return ops.conv2d_nhwc(a, self.d_conv_out[0], bias=self.d_conv_out[1], tile_n=64, out_dtype=torch.float32)
 
     def decode(self, latents, scale=1.0):
@@ -570,18 +609,20 @@ class AutoencoderKL:
             raise SeedxError("AutoencoderKL: encoder weights not loaded")
         G = self.cfg["groups"]
         B = image.shape[0]
+        al = self.stream_scale
+        sb = (lambda b: b) if al == 1.0 else (lambda b: b * al)
         ws = ops.groupnorm_ws(B, G, self.device)
         x = ops.nchw_to_nhwc_f16(image.to(self.device).float().contiguous(), 8)
-        x = ops.conv2d_nhwc(x, self.e_conv_in[0], bias=self.e_conv_in[1])
+        x = ops.conv2d_nhwc(x, self.e_conv_in[0], bias=sb(self.e_conv_in[1]), alpha=al)
         for res, ds in self.e_down:
             for r in res:
-                x = r(x, None, None, G, ws)
+                x = r(x, None, None, G, ws, al)
             if ds is not None:
-                x = _conv_s2(x, ds[0], ds[1], 0)
-        x = self.e_mid[0](x, None, None, G, ws)
-        x = self.e_mid[1](x, G, ws)
-        x = self.e_mid[2](x, None, None, G, ws)
-        a = ops.groupnorm_nhwc(x, self.e_norm_out[0], self.e_norm_out[1], 1e-6, silu=True, groups=G, stats_ws=ws)
+                x = _conv_s2(x, ds[0], sb(ds[1]), 0)
+        x = self.e_mid[0](x, None, None, G, ws, al)
+        x = self.e_mid[1](x, G, ws, al)
+        x = self.e_mid[2](x, None, None, G, ws, al)
+        a = ops.groupnorm_nhwc(x, self.e_norm_out[0], self.e_norm_out[1], 1e-6 * al * al, silu=True, groups=G, stats_ws=ws)
         m = ops.conv2d_nhwc(a, self.e_conv_out[0], bias=self.e_conv_out[1], tile_n=64)
         n, h, w, c = m.shape
         mo = ops.gemm(m.view(n * h * w, c), self.quant[0], bias=self.quant[1], out_dtype=torch.float32).view(n, h, w, -1)

@@ -242,13 +242,15 @@ def add_bcast_f16(a, b, out=None):
 
 
 # ---- stage 3 (NHWC fp16 feature maps) ---------------------------------------------------------------------------------------------------
-def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None, act=ACT_NONE, out_dtype=torch.float16, tile_n=0):
+def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None, act=ACT_NONE, out_dtype=torch.float16, tile_n=0, alpha=1.0):
     """stride-1 'same' conv; w packed [Cout, taps*taps*Cpad] with k = (kh*taps + kw)*Cpad + c, Cpad = roundup(Cin, 64); bias_g fp32 [N, Cout] per image"""
     n, h, wd, c = x.shape
     cout = w.shape[0]
     cpad = w.shape[1] // (taps * taps)
     w4 = w.float().view(cout, taps, taps, cpad)[..., :c].permute(0, 3, 1, 2)                 # [Cout, Cin, kh, kw]
-    y = F.conv2d(x.float().permute(0, 3, 1, 2), w4, bias=bias, padding=taps // 2)
+    y = alpha * F.conv2d(x.float().permute(0, 3, 1, 2), w4, padding=taps // 2)       # epilogue order of seedx_gemm_f16: alpha*acc, then the biases
+    if bias is not None:
+        y = y + bias[None, :, None, None]
     if bias_g is not None:
         y = y + bias_g[:, :, None, None]
     y = y.permute(0, 2, 3, 1)

@@ -98,6 +98,36 @@ def test_vae_tiny_decode_encode():
     assert e < 5e-3, e
 
 
+def test_vae_force_upcast_scaled_stream_on_overflowing_weights():
+    """the stock SDXL VAE (config force_upcast=true) overflows fp16 activations; the reference then computes the VAE in fp32
+    (pipeline_stable_diffusion_xl_t2i_edit.py:569-586,965-975).  Synthetic weights with the same property: the plain fp16 stream gives inf/NaN,
+    the scaled stream (AutoencoderKL.stream_scale = 2^-7 when cfg['force_upcast']) decodes to >= 40 dB PSNR of the fp32 oracle."""
+    from oracle import sdxl as osd
+    from seedx_b200.sdxl import AutoencoderKL
+    cfg = dict(synth.TINY_VAE)
+    sd = synth.vae_state_dict(cfg)
+    hot = ("conv2.weight", "conv2.bias", "conv_shortcut.weight", "conv_shortcut.bias", "conv_in.weight", "conv_in.bias")
+    big = {k: (v * 300 if k.endswith(hot) and "quant" not in k else v) for k, v in sd.items()}
+    z = synth.randn("vae_z", (2, 4, 32, 32))
+    img = synth.randn("vae_img", (1, 3, 256, 256), 0.5)
+    ref, refm = osd.vae_decode(big, cfg, z), osd.vae_encode_mode(big, cfg, img)
+    plain = AutoencoderKL(dict(cfg, force_upcast=False))
+    plain.load_state_dict(big)
+    assert not torch.isfinite(plain.decode(z.cuda())).all()
+    up = AutoencoderKL(dict(cfg, force_upcast=True))
+    up.load_state_dict(big)
+    out, m = up.decode(z.cuda()), up.encode_mode(img.cuda())
+    p, e = psnr(out, ref), rel(m, refm)
+    print(f"force_upcast vae: decode PSNR = {p:.1f} dB (rel {rel(out, ref):.3e}), encode rel = {e:.3e}")
+    assert torch.isfinite(out).all() and p >= 40.0 and e < 5e-3, (p, e)
+    # and on ordinary weights the scaled stream costs nothing in accuracy
+    v2 = AutoencoderKL(dict(cfg, force_upcast=True))
+    v2.load_state_dict(sd)
+    p2 = psnr(v2.decode(z.cuda()), osd.vae_decode(sd, cfg, z))
+    print(f"force_upcast vae on ordinary weights: PSNR = {p2:.1f} dB")
+    assert p2 >= 40.0, p2
+
+
 def _cond(cfg, B, tag):
     T = 16
     return (synth.randn(tag + "p", (B, T, cfg["cross_attention_dim"])), synth.randn(tag + "pp", (B, cfg["text_embed_dim"])),

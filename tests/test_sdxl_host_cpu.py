@@ -87,3 +87,39 @@ def test_vae_host_wiring_vs_oracle(patched):
     x = synth.randn("cpu_vae_img", (1, 3, 64, 64)).clamp(-1, 1)
     lat = m.encode_mode(x)
     assert lat.shape == (1, 4, 8, 8) and rel(lat, osd.vae_encode_mode(sd, cfg, x)) < 5e-3
+
+
+def _overflowing_vae(cfg):
+    """synthetic VAE whose un-normalised activations leave the fp16 range (like the stock SDXL VAE): the layers that write the residual stream
+    are scaled up; every GroupNorm input is then O(1e4..1e6)"""
+    sd = synth.vae_state_dict(cfg)
+    hot = ("conv2.weight", "conv2.bias", "conv_shortcut.weight", "conv_shortcut.bias", "conv_in.weight", "conv_in.bias")
+    return {k: (v * 300 if k.endswith(hot) and "quant" not in k else v) for k, v in sd.items()}
+
+
+def test_vae_force_upcast_keeps_the_stream_in_fp16_range(patched, tmp_path):
+    """`force_upcast` (the stock SDXL VAE config; the reference then runs the VAE in fp32, pipeline...edit.py:569-586,965-975): the plain fp16
+    stream overflows on such weights, the scaled stream (stream_scale 2^-7, exact in fp32) matches the fp32 oracle; config.json is honoured."""
+    import json
+    cfg = dict(synth.TINY_VAE)
+    big = _overflowing_vae(cfg)
+    z = synth.randn("cpu_vae_z", (1, 4, 8, 8))
+    x = synth.randn("cpu_vae_img", (1, 3, 64, 64)).clamp(-1, 1)
+    ref_img, ref_lat = osd.vae_decode(big, cfg, z / cfg["scaling_factor"]), osd.vae_encode_mode(big, cfg, x)
+    plain = sdxl_mod.AutoencoderKL(dict(cfg, force_upcast=False), device="cpu")
+    plain.load_state_dict(big)
+    assert plain.stream_scale == 1.0 and not torch.isfinite(plain.decode(z, scale=1.0 / cfg["scaling_factor"])).all()     # what the upcast is for
+    json.dump(dict(block_out_channels=list(cfg["block_out_channels"]), layers_per_block=cfg["layers_per_block"], latent_channels=4,
+                   scaling_factor=cfg["scaling_factor"], force_upcast=True), open(tmp_path / "config.json", "w"))
+    torch.save(big, tmp_path / "diffusion_pytorch_model.bin")
+    m = sdxl_mod.AutoencoderKL.from_pretrained(str(tmp_path), device="cpu")
+    assert m.cfg["force_upcast"] is True and m.stream_scale == 2.0 ** -7 and m.config.force_upcast is False
+    img, lat = m.decode(z, scale=1.0 / cfg["scaling_factor"]), m.encode_mode(x)
+    assert torch.isfinite(img).all() and rel(img, ref_img) < 5e-3 and rel(lat, ref_lat) < 5e-3
+    # on weights that do not overflow both modes agree with the oracle equally well
+    sd = synth.vae_state_dict(cfg)
+    ref = osd.vae_decode(sd, cfg, z / cfg["scaling_factor"])
+    for fu in (False, True):
+        v = sdxl_mod.AutoencoderKL(dict(cfg, force_upcast=fu), device="cpu")
+        v.load_state_dict(sd)
+        assert rel(v.decode(z, scale=1.0 / cfg["scaling_factor"]), ref) < 5e-3
