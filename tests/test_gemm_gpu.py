@@ -114,3 +114,46 @@ def test_conv_nhwc(n, h, w, c, cout, taps, cluster_mode):
     res = mk((n, h, w, cout), 25).half()
     o = ops.conv2d_nhwc(xn, wp, taps=taps, bias=bias, bias_g=temb, residual=res, out_dtype=torch.float16)
     assert rel(o, ref + res.float()) < 2e-3
+
+
+# ---- the bench's hot shapes: long-K 3x3 convs with C >= 640 in pair mode with the TMA-residual epilogue, and the
+# M = 8192 x N = 10240 gated GEGLU projection, each with the tile the auto picker chooses --------------------------------------------------
+@pytest.mark.parametrize("n,h,w,c,cout", [(2, 32, 32, 1280, 1280), (2, 64, 64, 640, 640), (1, 32, 32, 2560, 1280), (1, 64, 64, 1920, 640),
+                                          (1, 128, 128, 960, 320)])
+def test_conv_nhwc_unet_hot_shapes(n, h, w, c, cout):
+    """3x3 convs of the SDXL UNet at their real widths (K = 9*C up to 23 040: >= 90 k-blocks through the stage ring, CTA pairs, bias + per-image
+    time-embedding add + fp16 residual through the TMA epilogue), fp32 torch reference on the device"""
+    from seedx_b200 import ops
+    x = mk((n, c, h, w), 31).half()
+    wt = mk((cout, c, 3, 3), 32, (c * 9) ** -0.5).half()
+    bias, temb = mk((cout,), 33), mk((n, cout), 34)
+    ref = (F.conv2d(x.float(), wt.float(), bias=bias, padding=1) + temb[:, :, None, None]).permute(0, 2, 3, 1).contiguous()
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * c).contiguous()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    res = mk((n, h, w, cout), 35).half()
+    o = ops.conv2d_nhwc(xn, wp, taps=3, bias=bias, bias_g=temb, residual=res, out_dtype=torch.float16)
+    assert rel(o, ref + res.float()) < 2e-3
+    o32 = ops.conv2d_nhwc(xn, wp, taps=3, bias=bias, bias_g=temb, out_dtype=torch.float32)
+    assert rel(o32, ref) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,kind", [(8192, 10240, 1280, "geglu"), (32768, 5120, 640, "geglu"), (8192, 1280, 5120, "residual"),
+                                        (8192, 1280, 1280, "residual"), (32768, 640, 2560, "residual"), (8192, 3840, 1280, "plain")])
+def test_gemm_unet_hot_shapes(M, N, K, kind):
+    """the transformer GEMMs of the UNet forward at bench size (8 samples): GEGLU projection with bias + gating, attention-out / feed-forward-down
+    with bias + in-place fp16 residual, fused QKV"""
+    from seedx_b200 import ops
+    a = mk((M, K), 41).half()
+    w = mk((N, K), 42, K ** -0.5).half()
+    bias = mk((N,), 43)
+    acc = a.float() @ w.float().t() + bias
+    if kind == "geglu":
+        o = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, gated=True)
+        assert rel(o, acc[:, 0::2] * F.gelu(acc[:, 1::2])) < 2e-3
+    elif kind == "residual":
+        r = mk((M, N), 44).half()
+        want = acc + r.float()
+        ops.gemm(a, w, out=r, bias=bias, residual=r)
+        assert rel(r, want) < 2e-3
+    else:
+        assert rel(ops.gemm(a, w, bias=bias), acc) < 2e-3

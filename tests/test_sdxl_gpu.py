@@ -168,8 +168,10 @@ def test_t2i_sampler_tiny(graph):
         assert rel(loop.run(noise2.cuda(), steps=steps, guidance=7.5), ref2) < 1e-2
 
 
-def test_edit_sampler_tiny():
-    """3-way CFG (text 7.5 / image 1.5) in sigma space with 8-channel conv_in, 6 steps."""
+@pytest.mark.parametrize("graph", [False, True])
+def test_edit_sampler_tiny(graph):
+    """3-way CFG (text 7.5 / image 1.5) in sigma space with 8-channel conv_in, 6 steps; eager and under the CUDA graph (the mode
+    adapter.generate(latent_image=...) runs), a second request with another source image replayed through the same captured graph."""
     from oracle import sdxl as osd
     from seedx_b200.sampler import DenoiseLoop
     from seedx_b200.sdxl import EulerDiscreteScheduler, UNet2DConditionModel
@@ -182,13 +184,22 @@ def test_edit_sampler_tiny():
     ref = osd.edit_sample(sd, cfg, noise, il, p, pp, n, npool, steps=steps)
     unet = UNet2DConditionModel(cfg)
     unet.load_state_dict(sd)
-    loop = DenoiseLoop(unet, EulerDiscreteScheduler(), B, (hw, hw), 3, use_graph=False)
+    loop = DenoiseLoop(unet, EulerDiscreteScheduler(), B, (hw, hw), 3, use_graph=graph)
     tid = torch.tensor([[1024.0, 1024.0, 0.0, 0.0, 1024.0, 1024.0]]).repeat(3 * B, 1)
     loop.set_condition(torch.cat([p, n, n]).cuda(), torch.cat([pp, npool, npool]).cuda(), tid.cuda(), image_latents=il.cuda())
     lat = loop.run(noise.cuda(), steps=steps, guidance=7.5, image_guidance=1.5)
     e = rel(lat, ref)
-    print(f"edit tiny: latents rel = {e:.3e}")
+    print(f"edit tiny (graph={graph}): latents rel = {e:.3e}")
     assert e < 1e-2, e
+    if graph:
+        assert loop.graph is not None
+        g0 = loop.graph
+        il2 = synth.randn("edit_il2", (B, 4, hw, hw), 0.7)
+        p2, pp2, n2, np2 = _cond(cfg, B, "edit2")
+        ref2 = osd.edit_sample(sd, cfg, noise, il2, p2, pp2, n2, np2, steps=steps)
+        loop.set_condition(torch.cat([p2, n2, n2]).cuda(), torch.cat([pp2, np2, np2]).cuda(), tid.cuda(), image_latents=il2.cuda())
+        assert loop.graph is g0                                  # static conditioning buffers: no recapture for a new request
+        assert rel(loop.run(noise.cuda(), steps=steps, guidance=7.5, image_guidance=1.5), ref2) < 1e-2
 
 
 def test_scheduler_tables_match_oracle():
