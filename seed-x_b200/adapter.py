@@ -169,18 +169,23 @@ class SDXLAdapterWithLatentImage(SDXLAdapter):
         p, n, pp, npool = self.get_image_embeds(image_pil=image_pil, image_tensor=image_tensor, image_embeds=image_embeds,
                                                return_negative=True, image_size=input_image_size)
         B = p.shape[0]
+        trace.mark("detok.resampler_xl")
         loop = self._loop(B, height, width)
         tid = torch.tensor([[height, width, 0, 0, height, width]], dtype=torch.float32, device=self.device).repeat(3 * B, 1)
         il = self._image_latents(latent_image, height, width) if latent_image is not None else \
             torch.zeros((B, 4, height // 8, width // 8), device=self.device)
         if il.shape[0] == 1 and B > 1:
             il = il.expand(B, -1, -1, -1).contiguous()
+        trace.mark("detok.vae_encode")
         loop.set_condition(torch.cat([p, n, n]), torch.cat([pp, npool, npool]), tid, image_latents=il)   # [text, image, uncond] (:884-886)
+        trace.mark("detok.prepare_cond")
         lat = loop.run(self._noise(B, height, width, seed, latents), steps=num_inference_steps, guidance=guidance_scale,
                        image_guidance=image_guidance_scale)
+        trace.mark("detok.denoise_loop")
         if output_type == "latent":
             return lat.clone()
         u8 = decode_to_uint8(self.vae, lat)
+        trace.mark("detok.vae_decode")
         return u8 if output_type == "uint8" else self._to_pil(u8)
 
 
