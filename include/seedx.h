@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SEEDX_ABI_VERSION 1
+#define SEEDX_ABI_VERSION 2
 
 /* dtype tags */
 enum { SEEDX_F16 = 1, SEEDX_F32 = 2 };
@@ -80,6 +80,16 @@ typedef struct seedx_gemm_args {
   int32_t conv_taps_h, conv_taps_w; /* 0,0 = plain GEMM; 3,3 or 1,1 */
   int64_t conv_n, conv_h, conv_w, conv_c;
   int32_t tile_n;    /* 0 = auto (wave/cycle model); else one of 64/96/128/144/160/192/208/224/240/256 accumulator columns */
+  /* ABI 2 --------------------------------------------------------------------------------------------------------------------------
+   * LayerNorm folded into the GEMM (diffusers BasicTransformerBlock.norm{1,2,3} -> to_q/to_k/to_v / ff.net.0.proj, reached from
+   * pipeline_stable_diffusion_xl_t2i_edit.py:915-922): with A = the UN-normalised rows x, B = W * gamma (per input column, folded at load
+   * time) and bias_n = W . beta (+ the layer's bias),  LN(x) . W^T = rstd[m] * (x . B^T - mean[m] * colsum[n]) + bias_n,  colsum[n] = sum_k B[n][k].
+   * ln_stats = fp32 [M][2] (mean, rstd) from seedx_row_stats; applied right after alpha*acc, before the biases.  NULL = off. */
+  const float* ln_stats;
+  const float* ln_colsum; /* fp32 [N] */
+  /* B is produced by the kernel launched just before this one on the same stream (activation x activation products).  Default 0: B holds
+   * weights, whose first tiles are requested before the programmatic-dependent-launch wait. */
+  int32_t b_dynamic;
 } seedx_gemm_args;
 
 int seedx_gemm_f16(const seedx_gemm_args* args, void* stream);
@@ -126,6 +136,10 @@ int seedx_attention_last_impl(void); /* most recent call: 3 = tcgen05 two-tile, 
 int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const float* gamma, const float* beta, void* out, int out_dtype,
                     int64_t ldo, void* out2, const float* add, int64_t add_rows, int64_t rows, int64_t cols, float eps,
                     int rms, void* stream);
+
+/* per-row LayerNorm statistics of an fp16 matrix: stats[r] = (mean, 1/sqrt(var + eps)) over cols columns, fp32, two-pass on the cached row.
+ * Feeds the folded-LayerNorm epilogue of seedx_gemm_f16 (ln_stats): the normalised activations are never written to memory. */
+int seedx_row_stats(const void* x, int x_dtype, int64_t ldx, int64_t rows, int64_t cols, float eps, float* stats, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ optional SiLU) on NHWC fp16 images; the input may be the channel-concatenation [x1 | x2] (UNet skip

@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("conv_taps_h", C.c_int32), ("conv_taps_w", C.c_int32),
         ("conv_n", C.c_int64), ("conv_h", C.c_int64), ("conv_w", C.c_int64), ("conv_c", C.c_int64),
         ("tile_n", C.c_int32),
+        ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("b_dynamic", C.c_int32),
     ]
 
 

@@ -44,14 +44,18 @@ SEEDX_DEVINL float exp2_poly3(float x) {
   return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
 }
 
-template <int D>
+// BN_ = keys per K/V tile: 128 for long key sequences; 64 for the UNet cross-attention, whose 64 context tokens are ONE tile (one QK^T MMA
+// group and one PV group per work item, no online-softmax loop), so nothing of the tile is padding.
+template <int D, int BN_ = 128>
 struct FaCfg {
-  static constexpr int BM = 128, BN = 128;
+  static constexpr int BM = 128, BN = BN_;
   static constexpr int HALVES = D / 64;
-  static constexpr int HALF_BYTES = 128 * 64 * 2;           // one [128 rows x 64 fp16] swizzled tile
-  static constexpr int TILE_BYTES = HALVES * HALF_BYTES;    // Q, K or V tile
-  static constexpr int KV_STAGES = (D == 64) ? 3 : 2;
-  static constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256;
+  static constexpr int HALF_BYTES = 128 * 64 * 2;           // one [128 rows x 64 fp16] swizzled tile (Q)
+  static constexpr int TILE_BYTES = HALVES * HALF_BYTES;    // Q tile
+  static constexpr int KV_HALF_BYTES = BN * 64 * 2;         // one [BN keys x 64 fp16] swizzled tile
+  static constexpr int KV_TILE_BYTES = HALVES * KV_HALF_BYTES;
+  static constexpr int KV_STAGES = (BN == 64) ? 4 : ((D == 64) ? 3 : 2);
+  static constexpr int SMEM_BYTES = TILE_BYTES * 2 + KV_TILE_BYTES * 2 * KV_STAGES + 1024 + 256;
   static constexpr uint32_t S_COL0 = 0, S_COL1 = 128, O_COL0 = 256, O_COL1 = 256 + D;
 };
 
@@ -60,18 +64,18 @@ struct FaCfg {
 // their barrier phases run on one global tile counter `g` straight through item boundaries.
 // NS = softmax threads per query row (2 or 4): 4*NS softmax warps.  NS = 4 puts four warps on every scheduler, which is what lets
 // the MUFU (exp2), FMA and TMEM-load latencies of different warps overlap: with NS = 2 the kernel ran at ~45% issue utilisation.
-template <int D, int NS>
+template <int D, int NS, int BN_>
 __global__ void __launch_bounds__(64 + 128 * NS, 1)
 flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                      const FaParams p) {
-  using Cfg = FaCfg<D>;
+  using Cfg = FaCfg<D, BN_>;
   constexpr int KS = Cfg::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ0 = smem_base;
   const uint32_t sK0 = sQ0 + 2 * Cfg::TILE_BYTES;
-  const uint32_t sV0 = sK0 + KS * Cfg::TILE_BYTES;
-  const uint32_t bar = sV0 + KS * Cfg::TILE_BYTES;
+  const uint32_t sV0 = sK0 + KS * Cfg::KV_TILE_BYTES;
+  const uint32_t bar = sV0 + KS * Cfg::KV_TILE_BYTES;
   // barriers: k_full[KS], k_empty[KS], v_full[KS], v_empty[KS], then pairs: q_full, q_empty, s_full, p_full, pv_done, o_free
   auto k_full = [&](int s) { return bar + 8u * (s); };
   auto k_empty = [&](int s) { return bar + 8u * (KS + s); };
@@ -144,15 +148,15 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int n_tiles = tiles_of(m0);
         for (int j = 0; j < n_tiles; ++j) {
           mbar_wait(k_empty(st), ph ^ 1u);
-          mbar_expect_tx(k_full(st), Cfg::TILE_BYTES);
+          mbar_expect_tx(k_full(st), Cfg::KV_TILE_BYTES);
 #pragma unroll
           for (int hf = 0; hf < Cfg::HALVES; ++hf)
-            tma_load_4d(sK0 + st * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmK, k_full(st), hf * 64, j * Cfg::BN, h, b);
+            tma_load_4d(sK0 + st * Cfg::KV_TILE_BYTES + hf * Cfg::KV_HALF_BYTES, &tmK, k_full(st), hf * 64, j * Cfg::BN, h, b);
           mbar_wait(v_empty(st), ph ^ 1u);
-          mbar_expect_tx(v_full(st), Cfg::TILE_BYTES);
+          mbar_expect_tx(v_full(st), Cfg::KV_TILE_BYTES);
 #pragma unroll
           for (int hf = 0; hf < Cfg::HALVES; ++hf)
-            tma_load_4d(sV0 + st * Cfg::TILE_BYTES + hf * Cfg::HALF_BYTES, &tmV, v_full(st), hf * 64, j * Cfg::BN, h, b);
+            tma_load_4d(sV0 + st * Cfg::KV_TILE_BYTES + hf * Cfg::KV_HALF_BYTES, &tmV, v_full(st), hf * 64, j * Cfg::BN, h, b);
           if (++st == KS) st = 0, ph ^= 1u;
         }
       }
@@ -160,7 +164,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128);
+      constexpr uint32_t idesc_qk = umma_idesc_f16(128, Cfg::BN);
       constexpr uint32_t idesc_pv = umma_idesc_f16(128, D) | (1u << 16);  // B operand MN-major
       int kst = 0, vst = 0;
       uint32_t kph = 0, vph = 0;
@@ -173,10 +177,10 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(v_full(vst), vph);
         tc_fence_after();
         const uint32_t tP = tmem_base + ((pend_g & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
-        const uint32_t vb = sV0 + vst * Cfg::TILE_BYTES;
+        const uint32_t vb = sV0 + vst * Cfg::KV_TILE_BYTES;
 #pragma unroll
         for (int kk = 0; kk < Cfg::BN / 16; ++kk)  // 16 keys per MMA: A advances 8 TMEM columns, B 16 rows of 128 B
-          umma_f16_ts(pend_tO, tP + (uint32_t)(kk * 8), umma_desc_mn_sw128(vb + kk * 2048, Cfg::HALF_BYTES), idesc_pv,
+          umma_f16_ts(pend_tO, tP + (uint32_t)(kk * 8), umma_desc_mn_sw128(vb + kk * 2048, Cfg::KV_HALF_BYTES), idesc_pv,
                       !(pend_first && kk == 0));
         umma_commit(v_empty(vst));
         umma_commit(pv_done(pend_g & 1));
@@ -194,11 +198,12 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mbar_wait(k_full(kst), kph);
           tc_fence_after();
           const uint32_t tS = tmem_base + ((g & 1) ? Cfg::S_COL1 : Cfg::S_COL0);
-          const uint32_t kb = sK0 + kst * Cfg::TILE_BYTES;
+          const uint32_t kb = sK0 + kst * Cfg::KV_TILE_BYTES;
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
-            const uint32_t off = (uint32_t)((ks >> 2) * Cfg::HALF_BYTES + (ks & 3) * 32);
-            umma_f16(tS, umma_desc_k_sw128(sQ + off), umma_desc_k_sw128(kb + off), idesc_qk, ks != 0);
+            const uint32_t qoff = (uint32_t)((ks >> 2) * Cfg::HALF_BYTES + (ks & 3) * 32);
+            const uint32_t koff = (uint32_t)((ks >> 2) * Cfg::KV_HALF_BYTES + (ks & 3) * 32);
+            umma_f16(tS, umma_desc_k_sw128(sQ + qoff), umma_desc_k_sw128(kb + koff), idesc_qk, ks != 0);
           }
           umma_commit(k_empty(kst));
           if (j == n_tiles - 1) umma_commit(q_empty(qi));
@@ -214,7 +219,7 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   } else {
     // ------------------------------------------------------------ softmax / correction / epilogue
     // row = TMEM lane (warp % 4 selects the lane quarter); the NS threads of a row own CW = 128/NS score columns and D/NS O columns each
-    constexpr int CW = 128 / NS;            // score columns per thread
+    constexpr int CW = Cfg::BN / NS;        // score columns per thread
     constexpr int OC = D / NS;              // O columns per thread
     constexpr int OCH = OC >= 32 ? 32 : 16; // O columns per TMEM load
     __shared__ float xch_max[2][NS][128];   // [tile parity][column slice][row]
@@ -368,13 +373,13 @@ flash_attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #ifndef SEEDX_FA_NS
 #define SEEDX_FA_NS 2
 #endif
-template <int D>
+template <int D, int BN = 128>
 static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, FaParams p, int B, int H, cudaStream_t st) {
-  using Cfg = FaCfg<D>;
+  using Cfg = FaCfg<D, BN>;
   static bool attr = false;
   static int sms = 0;
   if (!attr) {
-    SEEDX_CUDA(cudaFuncSetAttribute(flash_attn_tc_kernel<D, SEEDX_FA_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    SEEDX_CUDA(cudaFuncSetAttribute(flash_attn_tc_kernel<D, SEEDX_FA_NS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     int dev = 0;
     SEEDX_CUDA(cudaGetDevice(&dev));
     SEEDX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -386,15 +391,15 @@ static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   if (items > 0x7fffffffLL) return -1;
   p.items = (int)items;
   const int grid = p.items < sms ? p.items : sms;
-  launch_k(flash_attn_tc_kernel<D, SEEDX_FA_NS>, grid, 64 + 128 * SEEDX_FA_NS, Cfg::SMEM_BYTES, st, tq, tk, tv, p);
+  launch_k(flash_attn_tc_kernel<D, SEEDX_FA_NS, BN>, grid, 64 + 128 * SEEDX_FA_NS, Cfg::SMEM_BYTES, st, tq, tk, tv, p);
   count_launch();
   return check_cuda(cudaGetLastError(), "flash_attn_tc_kernel launch");
 }
 
-static int make_map(CUtensorMap* m, const void* ptr, int d, int s, int H, int B, long long ss, long long sh, long long sb) {
+static int make_map(CUtensorMap* m, const void* ptr, int d, int s, int H, int B, long long ss, long long sh, long long sb, int box_rows = 128) {
   uint64_t dims[4] = {(uint64_t)d, (uint64_t)s, (uint64_t)H, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)ss * 2, (uint64_t)(H > 1 ? sh : ss * s) * 2, (uint64_t)(B > 1 ? sb : ss * s) * 2};
-  uint32_t box[4] = {64, 128, 1, 1};
+  uint32_t box[4] = {64, (uint32_t)box_rows, 1, 1};
   return encode_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, ptr, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
@@ -410,8 +415,10 @@ static int fa_min_sk() {
 
 // returns -1 when the problem is not eligible for the tensor-memory kernel (caller falls back to the mma.sync kernel)
 int attention_tc_try(const seedx_attn_args* a, cudaStream_t st) {
-  // short key sequences (UNet cross-attention over 64 context tokens) would fill under half of one 128-key tile: mma.sync kernel is faster
-  if (a->d > 128 || a->d % 8 != 0 || a->sq < 128 || a->sk < fa_min_sk() || !(a->scale > 0.f)) return -1;
+  // key sequences of at most 64 tokens with d <= 64 (UNet cross-attention over the 64 context tokens): one 64-key tile per work item;
+  // 65..95 keys would fill under three quarters of a 128-key tile: the mma.sync kernel is faster there
+  const bool short_kv = a->sk <= 64 && a->sk >= 16 && a->d <= 64 && !a->causal;
+  if (a->d > 128 || a->d % 8 != 0 || a->sq < 128 || (a->sk < fa_min_sk() && !short_kv) || !(a->scale > 0.f)) return -1;
   if (a->o_stride_s % 8 || a->o_stride_h % 8 || a->o_stride_b % 8 || (uintptr_t)a->o % 16) return -1;
   const long long str[] = {a->q_stride_s, a->q_stride_h, a->q_stride_b, a->k_stride_s, a->k_stride_h, a->k_stride_b,
                            a->v_stride_s, a->v_stride_h, a->v_stride_b};
@@ -424,8 +431,9 @@ int attention_tc_try(const seedx_attn_args* a, cudaStream_t st) {
   const bool qb = !(a->batch > 1 && a->q_stride_b == 0);
   CUtensorMap tq, tk, tv;
   if (make_map(&tq, a->q, a->d, a->sq, a->heads, qb ? a->batch : 1, a->q_stride_s, a->q_stride_h, a->q_stride_b)) return -1;
-  if (make_map(&tk, a->k, a->d, a->sk, a->heads, a->batch, a->k_stride_s, a->k_stride_h, a->k_stride_b)) return -1;
-  if (make_map(&tv, a->v, a->d, a->sk, a->heads, a->batch, a->v_stride_s, a->v_stride_h, a->v_stride_b)) return -1;
+  const int kv_rows = short_kv ? 64 : 128;
+  if (make_map(&tk, a->k, a->d, a->sk, a->heads, a->batch, a->k_stride_s, a->k_stride_h, a->k_stride_b, kv_rows)) return -1;
+  if (make_map(&tv, a->v, a->d, a->sk, a->heads, a->batch, a->v_stride_s, a->v_stride_h, a->v_stride_b, kv_rows)) return -1;
   FaParams p;
   p.o = (__half*)a->o;
   p.o_sb = a->o_stride_b, p.o_sh = a->o_stride_h, p.o_ss = a->o_stride_s;
@@ -433,6 +441,7 @@ int attention_tc_try(const seedx_attn_args* a, cudaStream_t st) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.causal = a->causal;
   p.q_batched = qb ? 1 : 0;
+  if (short_kv) return launch_fa<64, 64>(tq, tk, tv, p, a->batch, a->heads, st);
   if (a->d <= 64) return launch_fa<64>(tq, tk, tv, p, a->batch, a->heads, st);
   return launch_fa<128>(tq, tk, tv, p, a->batch, a->heads, st);
 }

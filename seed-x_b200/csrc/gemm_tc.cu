@@ -34,6 +34,10 @@ struct GemmParams {
   unsigned long long* dbg;                // optional per-CTA phase timestamps (%globaltimer ns), 8 slots per CTA; NULL in production
   int epi_out_bytes, epi_res_bytes;       // per-warp staging split: output buffers | residual buffers (host policy, see seedx_gemm_f16)
   int stages, epi_warp_bytes;             // pipeline depth and per-epilogue-warp staging bytes, sized on the host to fill shared memory
+  // LayerNorm folded into the epilogue (A = the un-normalised rows, B = gamma-scaled weights): x = rstd[m] * (acc - mean[m] * colsum[n])
+  const float2* ln_stats;                 // [M] (mean, rstd) or NULL
+  const float* ln_colsum;                 // [N] sum_k B[n][k]
+  int b_static;                           // B does not depend on the preceding kernel (weights): its first tiles are requested before the PDL wait
   // conv
   int conv, taps_w, c_chunks, conv_w, conv_h, tile_w, tile_h, tiles_per_img, tiles_w, pad, imgs_per_tile;
 };
@@ -136,15 +140,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // everything above touched only this CTA's shared/tensor memory: under programmatic dependent launch it ran while the previous
   // kernel was still draining.  Operands, residual and output may be that kernel's data: wait for it here.
   if (threadIdx.x == 0) GEMM_STAMP(1);
-  pdl_wait();
-  pdl_trigger();
-  if (threadIdx.x == 0) GEMM_STAMP(2);
-
   // tile space: (batch, n block, m group) with CL consecutive m blocks per group; a cluster walks groups, CTA `crank` takes m = group*CL + crank
   const int m_groups = (p.m_blocks + CL - 1) / CL;
   const int tiles_per_batch = m_groups * p.n_blocks;
   const int num_tiles = tiles_per_batch * p.batch;
   const int tile0 = (int)blockIdx.x / CL, tile_step = (int)gridDim.x / CL;
+  // Weights never depend on the kernel before this one: the B halves of the first stages of this CTA's first tile are requested BEFORE the
+  // dependency wait (their bytes are already counted on the `full` barriers; the A halves follow after the wait).
+  int b_pre = 0;
+  if (p.b_static && tile0 < num_tiles) b_pre = p.k_blocks < STAGES ? p.k_blocks : STAGES;
+  if (warp == 0 && lane == 0 && b_pre > 0) {
+    const int b = tile0 / tiles_per_batch;
+    const int n_blk = (tile0 - b * tiles_per_batch) / m_groups;
+    for (int kb = 0; kb < b_pre; ++kb) {
+      const uint32_t sb = smem_base + kb * Cfg::STAGE_BYTES + A_STAGE_BYTES;
+      if (CL == 1) {
+        mbar_expect_tx(full_bar(kb), Cfg::STAGE_BYTES);
+        tma_load_3d(sb, &tmB, full_bar(kb), kb * BK, n_blk * BN, p.b_batched ? b : 0);
+      } else {
+        if (crank == 0) mbar_expect_tx(full_bar(kb), CL * Cfg::STAGE_BYTES);
+        tma_load_3d_2sm(sb, &tmB, mapa_cluster(full_bar(kb), 0), kb * BK, n_blk * BN + crank * (BN / CL), p.b_batched ? b : 0);
+      }
+    }
+  }
+  pdl_wait();
+  pdl_trigger();
+  if (threadIdx.x == 0) GEMM_STAMP(2);
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -172,8 +193,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
+          const bool b_done = (t == tile0) && (kb < b_pre);   // this stage's barrier is armed and its B half is in flight already
           if (CL == 1) {
-            mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+            if (!b_done) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
             if (p.conv) {
               const int tap = kb / p.c_chunks;
               const int cc = kb - tap * p.c_chunks;
@@ -183,11 +205,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               tma_load_3d(sa, &tmA, full_bar(stage), kb * BK, m_blk * BM, b);
             }
-            tma_load_3d(sb, &tmB, full_bar(stage), kb * BK, n_blk * BN, p.b_batched ? b : 0);
+            if (!b_done) tma_load_3d(sb, &tmB, full_bar(stage), kb * BK, n_blk * BN, p.b_batched ? b : 0);
           } else {
             // pair mode: the leader arms its barrier for the bytes of BOTH CTAs; every load names the leader's barrier
             const uint32_t lbar = mapa_cluster(full_bar(stage), 0);
-            if (crank == 0) mbar_expect_tx(full_bar(stage), CL * Cfg::STAGE_BYTES);
+            if (crank == 0 && !b_done) mbar_expect_tx(full_bar(stage), CL * Cfg::STAGE_BYTES);
             if (p.conv) {
               const int tap = kb / p.c_chunks;
               const int cc = kb - tap * p.c_chunks;
@@ -197,7 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
               tma_load_3d_2sm(sa, &tmA, lbar, kb * BK, m_blk * BM, b);
             }
-            tma_load_3d_2sm(sb, &tmB, lbar, kb * BK, n_blk * BN + crank * (BN / CL), p.b_batched ? b : 0);   // my half of the B tile
+            if (!b_done) tma_load_3d_2sm(sb, &tmB, lbar, kb * BK, n_blk * BN + crank * (BN / CL), p.b_batched ? b : 0);   // my half of the B tile
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -263,6 +285,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
 
       const float bm = (p.bias_m != nullptr && row_ok) ? p.bias_m[row] : 0.f;
+      float ln_rstd = 1.f, ln_nmr = 0.f;       // folded LayerNorm: x = rstd * acc + (-mean * rstd) * colsum[n]
+      if (p.ln_stats != nullptr && row_ok) {
+        const float2 mr = __ldg(p.ln_stats + row);
+        ln_rstd = mr.y, ln_nmr = -mr.x * mr.y;
+      }
       const float* bg = (p.bias_g != nullptr && row_ok) ? p.bias_g + (long long)(row / p.bias_g_rows) * p.N : nullptr;
       const int rrow = p.res_row_mod ? (row % p.res_row_mod) : row;
 
@@ -307,6 +334,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) * p.alpha + bm;
         const int col0 = n0 + c;
         const bool chunk_full = col0 + 32 <= col_end;
+        if (p.ln_stats != nullptr) {
+          if (chunk_full) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 q = __ldg((const float4*)(p.ln_colsum + col0 + i));
+              x[i] = fmaf(x[i], ln_rstd, ln_nmr * q.x), x[i + 1] = fmaf(x[i + 1], ln_rstd, ln_nmr * q.y);
+              x[i + 2] = fmaf(x[i + 2], ln_rstd, ln_nmr * q.z), x[i + 3] = fmaf(x[i + 3], ln_rstd, ln_nmr * q.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < col_end) x[i] = fmaf(x[i], ln_rstd, ln_nmr * __ldg(p.ln_colsum + col0 + i));
+          }
+        }
         if (p.bias_n != nullptr) {
           if (chunk_full && p.bias_vec) {
 #pragma unroll
@@ -705,6 +746,13 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
   }
   p.D = a->D;
   p.dbg = g_gemm_dbg;
+  if (a->ln_stats || a->ln_colsum) {
+    SEEDX_REQUIRE(a->ln_stats && a->ln_colsum, "seedx_gemm_f16: ln_stats and ln_colsum go together");
+    SEEDX_REQUIRE(a->batch == 1 && !conv && ((uintptr_t)a->ln_colsum % 16 == 0) && ((uintptr_t)a->ln_stats % 8 == 0) && a->N % 4 == 0,
+                  "seedx_gemm_f16: folded LayerNorm needs a plain un-batched GEMM, N %% 4 == 0 and aligned statistics");
+  }
+  p.ln_stats = (const float2*)a->ln_stats, p.ln_colsum = a->ln_colsum;
+  p.b_static = a->b_dynamic ? 0 : 1;
   p.bias_n = a->bias_n, p.bias_m = a->bias_m, p.bias_g = a->bias_g;
   p.bias_g_rows = a->bias_g ? (int)a->bias_g_rows : 1;
   SEEDX_REQUIRE(p.bias_g_rows > 0, "seedx_gemm_f16: bias_g_rows must be > 0");

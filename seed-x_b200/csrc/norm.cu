@@ -198,6 +198,61 @@ layernorm_rows_kernel(const TI* __restrict__ x, long long ldx, const float* __re
   }
 }
 
+// Statistics only: (mean, rstd) per row of an fp16 matrix, same warp-persistent walk and two-pass arithmetic as layernorm_rows_kernel but
+// nothing normalised is written — the consumer GEMM applies the normalisation in its epilogue (seedx_gemm_args.ln_stats).
+template <int NV>
+__global__ void __launch_bounds__(LN_THREADS)
+row_stats_kernel(const __half* __restrict__ x, long long ldx, long long rows, int cols, float eps, float2* __restrict__ stats) {
+  pdl_wait();
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  const int nvec = cols >> 3;                       // 16-byte vectors of 8 fp16
+  const long long wstride = (long long)gridDim.x * (LN_THREADS / 32);
+  long long row = (long long)blockIdx.x * (LN_THREADS / 32) + (threadIdx.x >> 5);
+  uint4 cur[NV], nxt[NV];
+  auto load_row = [&](uint4 (&dst)[NV], long long r) {
+    const __half* xr = x + r * ldx;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + i * 32;
+      dst[i] = (c < nvec) ? *(const uint4*)(xr + c * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  if (row < rows) load_row(cur, row);
+  for (; row < rows; row += wstride) {
+    const long long rn = row + wstride;
+    if (rn < rows) load_row(nxt, rn);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const __half2* h = (const __half2*)&cur[i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = __half22float2(h[j]);
+        s += t.x + t.y;
+      }
+    }
+    const float mean = warp_sum(s) / (float)cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nvec) {
+        const __half2* h = (const __half2*)&cur[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = __half22float2(h[j]);
+          const float a = t.x - mean, b = t.y - mean;
+          q += a * a + b * b;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
+    if (lane == 0) stats[row] = make_float2(mean, rstd);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) cur[i] = nxt[i];
+  }
+}
+
 // scalar fallback (cols not a multiple of 4 or unaligned rows): one CTA per row
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(LN_THREADS)
@@ -461,6 +516,24 @@ extern "C" int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const fl
 #undef LN_BOTH
   count_launch();
   return check_cuda(cudaGetLastError(), "layernorm_kernel launch");
+}
+
+extern "C" int seedx_row_stats(const void* x, int x_dtype, int64_t ldx, int64_t rows, int64_t cols, float eps, float* stats, void* stream) {
+  SEEDX_REQUIRE(x && stats, "seedx_row_stats: null pointer");
+  SEEDX_REQUIRE(x_dtype == SEEDX_F16, "seedx_row_stats: fp16 rows only (the rows are the A operand of the consumer GEMM)");
+  SEEDX_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 2048 && ldx % 8 == 0 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)stats % 8 == 0),
+                "seedx_row_stats: cols=%lld must be a multiple of 8 and <= 2048, rows 16-byte aligned", (long long)cols);
+  cudaStream_t st = (cudaStream_t)stream;
+  long long rg = (rows + (LN_THREADS / 32) - 1) / (LN_THREADS / 32);
+  if (rg > (long long)num_sms() * 8) rg = (long long)num_sms() * 8;
+  const unsigned grid = (unsigned)rg;
+  cudaError_t e;
+  if (cols <= 512) e = launch_k(row_stats_kernel<2>, grid, LN_THREADS, 0, st, (const __half*)x, (long long)ldx, (long long)rows, (int)cols, eps, (float2*)stats);
+  else if (cols <= 1024) e = launch_k(row_stats_kernel<4>, grid, LN_THREADS, 0, st, (const __half*)x, (long long)ldx, (long long)rows, (int)cols, eps, (float2*)stats);
+  else if (cols <= 1536) e = launch_k(row_stats_kernel<6>, grid, LN_THREADS, 0, st, (const __half*)x, (long long)ldx, (long long)rows, (int)cols, eps, (float2*)stats);
+  else e = launch_k(row_stats_kernel<8>, grid, LN_THREADS, 0, st, (const __half*)x, (long long)ldx, (long long)rows, (int)cols, eps, (float2*)stats);
+  count_launch();
+  return check_cuda(e != cudaSuccess ? e : cudaGetLastError(), "row_stats_kernel launch");
 }
 
 // CTAs per image of the statistics pass: ~4 waves of CTAs over the batch, >= 32 pixels each

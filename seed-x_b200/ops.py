@@ -34,10 +34,12 @@ def _require_cuda(*ts):
 
 
 def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, residual=None, res_row_mod=0,
-         act=ACT_NONE, gated=False, alpha=1.0, out_dtype=torch.float16, tile_n=0):
+         act=ACT_NONE, gated=False, alpha=1.0, out_dtype=torch.float16, tile_n=0, ln=None, dynamic_b=False):
     """out[b,m,n] = epi(alpha * a[b,m,:] . w[(b,)n,:]).
 
     a: fp16 [M,K] or [B,M,K] (last dim contiguous); w: fp16 [N,K] or [B,N,K]; returns/updates out [.., M, N_out].
+    ln = (row_stats fp32 [M,2], colsum fp32 [N]): LayerNorm of `a` folded into the epilogue (w = gamma-scaled weights, bias = W.beta + b).
+    dynamic_b: w is an activation written by the kernel launched just before (default: weights, prefetched before the PDL wait).
     """
     _require_cuda(a, w, out, bias, residual)
     assert a.dtype == torch.float16 and w.dtype == torch.float16
@@ -74,7 +76,23 @@ def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, 
         g.res_row_mod = res_row_mod
     g.act, g.gated, g.out_dtype = act, int(gated), _dt(out)
     g.tile_n = tile_n
+    if ln is not None:
+        st, cs = ln
+        assert st.dtype == torch.float32 and st.is_contiguous() and st.numel() == 2 * M and cs.dtype == torch.float32 and cs.is_contiguous() and cs.numel() == N
+        g.ln_stats, g.ln_colsum = st.data_ptr(), cs.data_ptr()
+    g.b_dynamic = int(dynamic_b)
     check(lib().seedx_gemm_f16(C.byref(g), _stream()), "seedx_gemm_f16")
+    return out
+
+
+def row_stats(x, eps, out=None):
+    """(mean, rstd) per row of an fp16 matrix [rows, cols] -> fp32 [rows, 2] (LayerNorm statistics for gemm(..., ln=...))."""
+    _require_cuda(x, out)
+    assert x.dtype == torch.float16 and x.dim() == 2 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty((x.shape[0], 2), device=x.device, dtype=torch.float32)
+    check(lib().seedx_row_stats(_ptr(x), _dt(x), C.c_int64(x.stride(0)), C.c_int64(x.shape[0]), C.c_int64(x.shape[1]), C.c_float(eps), _ptr(out),
+                                _stream()), "seedx_row_stats")
     return out
 
 

@@ -74,16 +74,78 @@ class _ParamRegistry:
 
     def __init__(self):
         self.slots = {}
+        self.folded = []          # _FoldedLinear objects: their consistency is checked once an update is complete
 
-    def add(self, key, dest, fn):
-        self.slots[key] = (dest, fn)
+    def add(self, key, dest, fn, hook=None):
+        """hook(value) runs after the copy (derived tensors of a folded layer)"""
+        self.slots[key] = (dest, fn, hook)
 
     def update(self, key, value):
-        dest, fn = self.slots[key]
+        dest, fn, hook = self.slots[key]
         new = fn(value)
         if new.shape != dest.shape:
             raise SeedxError(f"{key}: shape {tuple(value.shape)} does not match the loaded model")
         dest.copy_(new)
+        if hook is not None:
+            hook(value)
+
+    def finish(self):
+        for f in self.folded:
+            f.check()
+
+
+class _FoldedLinear:
+    """A linear layer that follows a LayerNorm, stored with the normalisation folded in (seedx_gemm_args.ln_stats):
+         LN(x) . W^T + b  =  rstd * (x . (W*gamma)^T - mean * colsum) + (W . beta + b)
+    w = fp16(W * gamma) [N, K] (rows possibly interleaved / concatenated from several checkpoint tensors), colsum[n] = sum_k float(w[n, k]) —
+    taken from the ROUNDED weights so that a constant row cancels exactly —, bias = W . beta + b in fp32.  gamma / beta stay referenced so that a
+    later partial checkpoint (to_k / to_v only, adapter_modules.py:20-33) can re-fold the rows it replaces."""
+
+    def __init__(self, parts, gamma, beta, dev, bias=None, pack=None):
+        """parts: list of raw [n_i, K] weights concatenated along rows; pack: optional row permutation applied after concatenation"""
+        self.gamma, self.beta, self.dev, self.pack = gamma, beta, dev, (pack or (lambda t: t))
+        w = self.pack(torch.cat([p_.float() for p_ in parts], dim=0))
+        self.N, self.K = w.shape
+        self.w = torch.empty((self.N, self.K), device=dev, dtype=torch.float16)
+        self.colsum = torch.empty((self.N,), device=dev, dtype=torch.float32)
+        self.raw_bias = None if bias is None else _f(self.pack(bias), dev)
+        self.bias = torch.empty((self.N,), device=dev, dtype=torch.float32)
+        self.stale_rows = None                     # set when gamma / beta changed: rows still folded with the old values
+        self._set(slice(0, self.N), w)
+
+    def _set(self, rows, w_raw):
+        w_raw = w_raw.to(self.dev, torch.float32)
+        wf = (w_raw * self.gamma[None, :]).to(torch.float16)
+        self.w[rows].copy_(wf)
+        self.colsum[rows].copy_(wf.float().sum(dim=1))
+        b = w_raw @ self.beta
+        self.bias[rows].copy_(b if self.raw_bias is None else b + self.raw_bias[rows])
+        if self.stale_rows is not None:
+            self.stale_rows[rows] = False
+
+    def set_rows(self, rows, w_raw):
+        """replace a row range by a raw (un-folded, un-packed) checkpoint tensor; only valid for un-permuted layouts"""
+        self._set(rows, w_raw)
+
+    def set_all(self, w_raw):
+        self._set(slice(0, self.N), self.pack(w_raw.float()))
+
+    def set_bias(self, b_raw):
+        new = _f(self.pack(b_raw), self.dev)
+        self.bias.add_(new - self.raw_bias)
+        self.raw_bias.copy_(new)
+
+    def norm_changed(self):
+        self.stale_rows = torch.ones((self.N,), dtype=torch.bool)
+
+    def check(self):
+        if self.stale_rows is not None:
+            if bool(self.stale_rows.any()):
+                raise SeedxError("a checkpoint that replaces a LayerNorm folded into the following projection must also carry that projection's weights")
+            self.stale_rows = None
+
+    def ln(self, stats):
+        return (stats, self.colsum)
 
 
 def _interleave_rows(w):
@@ -169,34 +231,37 @@ class _Transformer:
         for k in range(depth):
             b = f"{p}.transformer_blocks.{k}"
             g = lambda s: sd[f"{b}.{s}"]  # noqa: E731
-            w_ff = g("ff.net.0.proj.weight")
-            b_ff = g("ff.net.0.proj.bias")
-            # GEGLU: interleave [hidden_j, gate_j] rows so the gate sits beside its value in one accumulator tile
-            w_il, b_il = _interleave_rows(w_ff), _interleave_rows(b_ff)
+            n1 = (_f(g("norm1.weight"), dev), _f(g("norm1.bias"), dev))
+            n2 = (_f(g("norm2.weight"), dev), _f(g("norm2.bias"), dev))
+            n3 = (_f(g("norm3.weight"), dev), _f(g("norm3.bias"), dev))
+            # the three projections that read a LayerNorm output carry it folded in (no normalised copy of the stream is ever written):
+            # fused QKV (norm1), cross-attention q (norm2), GEGLU projection with [hidden_j, gate_j] interleaved rows (norm3)
+            qkv = _FoldedLinear([g("attn1.to_q.weight"), g("attn1.to_k.weight"), g("attn1.to_v.weight")], n1[0], n1[1], dev)
+            q2 = _FoldedLinear([g("attn2.to_q.weight")], n2[0], n2[1], dev)
+            ff1 = _FoldedLinear([g("ff.net.0.proj.weight")], n3[0], n3[1], dev, bias=g("ff.net.0.proj.bias"), pack=_interleave_rows)
             self.blocks.append(dict(
-                n1=(_f(g("norm1.weight"), dev), _f(g("norm1.bias"), dev)),
-                n2=(_f(g("norm2.weight"), dev), _f(g("norm2.bias"), dev)),
-                n3=(_f(g("norm3.weight"), dev), _f(g("norm3.bias"), dev)),
-                w_qkv=_h(torch.cat([g("attn1.to_q.weight"), g("attn1.to_k.weight"), g("attn1.to_v.weight")], dim=0), dev),
+                n1=n1, n2=n2, n3=n3, qkv=qkv, q2=q2, ff1=ff1,
                 w_o1=_h(g("attn1.to_out.0.weight"), dev), b_o1=_f(g("attn1.to_out.0.bias"), dev),
-                w_q2=_h(g("attn2.to_q.weight"), dev),
                 w_kv2=_h(torch.cat([g("attn2.to_k.weight"), g("attn2.to_v.weight")], dim=0), dev),
                 w_o2=_h(g("attn2.to_out.0.weight"), dev), b_o2=_f(g("attn2.to_out.0.bias"), dev),
-                w_ff1=_h(w_il, dev), b_ff1=_f(b_il, dev),
                 w_ff2=_h(g("ff.net.2.weight"), dev), b_ff2=_f(g("ff.net.2.bias"), dev)))
             if reg is not None:
                 blk = self.blocks[-1]
                 c = blk["w_o1"].shape[0]
-                for i, nm in enumerate(("n1", "n2", "n3")):
-                    reg.add(f"{b}.norm{i + 1}.weight", blk[nm][0], ff), reg.add(f"{b}.norm{i + 1}.bias", blk[nm][1], ff)
+                reg.folded += [qkv, q2, ff1]
+                for i, (nm, fl) in enumerate((("n1", qkv), ("n2", q2), ("n3", ff1))):
+                    reg.add(f"{b}.norm{i + 1}.weight", blk[nm][0], ff, hook=lambda v, fl=fl: fl.norm_changed())
+                    reg.add(f"{b}.norm{i + 1}.bias", blk[nm][1], ff, hook=lambda v, fl=fl: fl.norm_changed())
+                keep = lambda dest: (lambda t: dest)        # the hook writes the folded rows; the registry's own copy is then a no-op  # noqa: E731
                 for i, nm in enumerate(("to_q", "to_k", "to_v")):
-                    reg.add(f"{b}.attn1.{nm}.weight", blk["w_qkv"][i * c:(i + 1) * c], hh)
-                reg.add(f"{b}.attn2.to_q.weight", blk["w_q2"], hh)
+                    rows = slice(i * c, (i + 1) * c)
+                    reg.add(f"{b}.attn1.{nm}.weight", qkv.w[rows], keep(qkv.w[rows]), hook=lambda v, rows=rows, fl=qkv: fl.set_rows(rows, v))
+                reg.add(f"{b}.attn2.to_q.weight", q2.w, keep(q2.w), hook=lambda v, fl=q2: fl.set_all(v))
                 reg.add(f"{b}.attn2.to_k.weight", blk["w_kv2"][:c], hh), reg.add(f"{b}.attn2.to_v.weight", blk["w_kv2"][c:], hh)
                 for a_, wn, bn in (("attn1", "w_o1", "b_o1"), ("attn2", "w_o2", "b_o2")):
                     reg.add(f"{b}.{a_}.to_out.0.weight", blk[wn], hh), reg.add(f"{b}.{a_}.to_out.0.bias", blk[bn], ff)
-                reg.add(f"{b}.ff.net.0.proj.weight", blk["w_ff1"], lambda t: _h(_interleave_rows(t), dev))
-                reg.add(f"{b}.ff.net.0.proj.bias", blk["b_ff1"], lambda t: _f(_interleave_rows(t), dev))
+                reg.add(f"{b}.ff.net.0.proj.weight", ff1.w, keep(ff1.w), hook=lambda v, fl=ff1: fl.set_all(v))
+                reg.add(f"{b}.ff.net.0.proj.bias", ff1.raw_bias, keep(ff1.raw_bias), hook=lambda v, fl=ff1: fl.set_bias(v))
                 reg.add(f"{b}.ff.net.2.weight", blk["w_ff2"], hh), reg.add(f"{b}.ff.net.2.bias", blk["b_ff2"], ff)
 
     def context_kv(self, ctx16):
@@ -210,7 +275,9 @@ class _Transformer:
         scale = d ** -0.5
         hn = ops.groupnorm_nhwc(x, self.norm[0], self.norm[1], 1e-6, silu=False, groups=groups, stats_ws=ws)
         hs = ops.gemm(hn.view(M, c), self.w_in, bias=self.b_in, out_dtype=self.stream_dtype)
-        nbuf = torch.empty((M, c), device=x.device, dtype=torch.float16)
+        if hs.dtype != torch.float16:
+            raise SeedxError("the folded LayerNorm path reads the residual stream as the fp16 GEMM operand: _Transformer.stream_dtype must be float16")
+        stats = torch.empty((M, 2), device=x.device, dtype=torch.float32)
         qkv = torch.empty((M, 3 * c), device=x.device, dtype=torch.float16)
         obuf = torch.empty((M, c), device=x.device, dtype=torch.float16)
         qbuf = torch.empty((M, c), device=x.device, dtype=torch.float16)
@@ -220,17 +287,18 @@ class _Transformer:
         ov = obuf.view(n, S, H, d).permute(0, 2, 1, 3)
         q2 = qbuf.view(n, S, H, d).permute(0, 2, 1, 3)
         for blk, kvb in zip(self.blocks, kv):
-            ops.layernorm(hs, blk["n1"][0], blk["n1"][1], 1e-5, out=nbuf)
-            ops.gemm(nbuf, blk["w_qkv"], out=qkv)
+            # norm1 -> fused QKV: only the row statistics are computed; the normalisation happens in the projection's epilogue
+            ops.row_stats(hs, 1e-5, out=stats)
+            ops.gemm(hs, blk["qkv"].w, out=qkv, bias=blk["qkv"].bias, ln=blk["qkv"].ln(stats))
             ops.attention(q1, k1, v1, ov, scale=scale)
             ops.gemm(obuf, blk["w_o1"], out=hs, bias=blk["b_o1"], residual=hs)
-            ops.layernorm(hs, blk["n2"][0], blk["n2"][1], 1e-5, out=nbuf)
-            ops.gemm(nbuf, blk["w_q2"], out=qbuf)
+            ops.row_stats(hs, 1e-5, out=stats)
+            ops.gemm(hs, blk["q2"].w, out=qbuf, bias=blk["q2"].bias, ln=blk["q2"].ln(stats))
             kv5 = kvb.view(n, n_ctx, 2, H, d)
             ops.attention(q2, kv5[:, :, 0].permute(0, 2, 1, 3), kv5[:, :, 1].permute(0, 2, 1, 3), ov, scale=scale)
             ops.gemm(obuf, blk["w_o2"], out=hs, bias=blk["b_o2"], residual=hs)
-            ops.layernorm(hs, blk["n3"][0], blk["n3"][1], 1e-5, out=nbuf)
-            ops.gemm(nbuf, blk["w_ff1"], out=fbuf, bias=blk["b_ff1"], act=ops.ACT_GELU, gated=True)
+            ops.row_stats(hs, 1e-5, out=stats)
+            ops.gemm(hs, blk["ff1"].w, out=fbuf, bias=blk["ff1"].bias, act=ops.ACT_GELU, gated=True, ln=blk["ff1"].ln(stats))
             ops.gemm(fbuf, blk["w_ff2"], out=hs, bias=blk["b_ff2"], residual=hs)
         h16 = hs if hs.dtype == torch.float16 else ops.cast(hs, torch.float16)
         return ops.gemm(h16, self.w_out, bias=self.b_out, residual=x.view(M, c)).view(n, h, w, c)
@@ -301,7 +369,10 @@ class UNet2DConditionModel:
                 if v.shape[1] > 8:
                     raise SeedxError("conv_in with more than 8 input channels is not supported")
                 self.cfg["in_channels"] = v.shape[1]
-            self._reg.update(k, v)
+        # LayerNorm parameters first: the projections folded with them are re-folded with the new values as their own keys arrive
+        for k in sorted((k for k in sd if k in self._reg.slots), key=lambda k: (0 if ".norm" in k else 1)):
+            self._reg.update(k, sd[k])
+        self._reg.finish()
         return unexpected
 
     def load_state_dict(self, sd, strict=False):
@@ -461,10 +532,10 @@ class _VaeAttention:
         probs = torch.empty((S, S), device=x.device, dtype=torch.float16)
         scale = c ** -0.5
         for i in range(n):
-            vt = ops.gemm(self.wv, hn[i], bias_m=self.bv)                       # V^T [c, S]: K-major operand of P.V
-            ops.gemm(q[i], k[i], out=scores, alpha=scale)
+            vt = ops.gemm(self.wv, hn[i], bias_m=self.bv, dynamic_b=True)       # V^T [c, S]: K-major operand of P.V
+            ops.gemm(q[i], k[i], out=scores, alpha=scale, dynamic_b=True)
             ops.softmax_rows(scores, 1.0, out=probs)
-            ops.gemm(probs, vt, out=out[i])
+            ops.gemm(probs, vt, out=out[i], dynamic_b=True)
         xr = x.view(n * S, c)
         bo = self.bo if alpha == 1.0 else (self.bo * alpha)
         return ops.gemm(out.view(n * S, c), self.wo, bias=bo, residual=xr, alpha=alpha).view(n, h, w, c)

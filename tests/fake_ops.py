@@ -44,11 +44,14 @@ def patchify(x, patch, kpad):
 
 
 def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, residual=None, res_row_mod=0, act=ACT_NONE, gated=False, alpha=1.0,
-         out_dtype=torch.float16, **kw):
+         out_dtype=torch.float16, ln=None, dynamic_b=False, **kw):
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 2 and not any(v is not None and v is not False and v != 0 for v in kw.values())
     if residual is not None and res_row_mod:                     # residual row = output row % res_row_mod (position tables)
         residual = residual.repeat(a.shape[0] // res_row_mod, 1)
     acc = alpha * (a.float() @ w.float().t())
+    if ln is not None:                                           # folded LayerNorm: rstd * (acc - mean * colsum)
+        st, cs = ln
+        acc = st[:, 1:2] * (acc - st[:, 0:1] * cs[None, :])
     if bias is not None:
         acc = acc + bias
     if bias_m is not None:                                       # one bias per output ROW (transposed products)
@@ -68,6 +71,15 @@ def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, 
         out = torch.empty(acc.shape, dtype=out_dtype)
     out.copy_(acc.to(out.dtype))
     return out
+
+
+def row_stats(x, eps, out=None):
+    xf = x.float()
+    st = torch.stack([xf.mean(-1), torch.rsqrt(xf.var(-1, unbiased=False) + eps)], dim=1)
+    if out is not None:
+        out.copy_(st)
+        return out
+    return st
 
 
 def layernorm(x, gamma, beta, eps, out=None, *, out_dtype=torch.float16, rms=False, add=None, out2=None):

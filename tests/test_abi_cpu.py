@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 30
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
-    assert _lib.lib().seedx_abi_version() == 1
+    assert _lib.lib().seedx_abi_version() == 2
     assert _lib.launch_count() == 0          # nothing has been launched: importing / loading does not touch a device
 
 

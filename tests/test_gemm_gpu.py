@@ -157,3 +157,27 @@ def test_gemm_unet_hot_shapes(M, N, K, kind):
         assert rel(r, want) < 2e-3
     else:
         assert rel(ops.gemm(a, w, bias=bias), acc) < 2e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(8192, 3840, 1280), (4096, 640, 640), (300, 1280, 1280), (1024, 10240, 1280)])
+@pytest.mark.parametrize("mean_shift", [0.0, 3.0])
+def test_gemm_folded_layernorm(M, N, K, mean_shift, cluster_mode):
+    """LayerNorm folded into the projection (seedx_gemm_args.ln_stats): rows of x are the A operand un-normalised, B = W * gamma, the epilogue
+    applies rstd * (acc - mean * colsum) + (W . beta + b).  Reference = fp32 F.layer_norm followed by the linear layer; rows with a mean several
+    sigma away from zero check the cancellation in acc - mean * colsum."""
+    from seedx_b200 import ops
+    x = (mk((M, K), 51) * (1.0 + mk((M, 1), 52).abs()) + mean_shift * mk((M, 1), 53)).half()
+    w = mk((N, K), 54, K ** -0.5)
+    gamma, beta, b = 1.0 + 0.2 * mk((K,), 55), 0.2 * mk((K,), 56), mk((N,), 57)
+    ref = F.layer_norm(x.float(), (K,), gamma, beta, 1e-5) @ w.t() + b
+    wf = (w * gamma[None, :]).half()
+    colsum = wf.float().sum(1).contiguous()
+    bias = (w @ beta + b).contiguous()
+    st = ops.row_stats(x, 1e-5)
+    xf = x.float()
+    assert rel(st[:, 0], xf.mean(1)) < 1e-5 and rel(st[:, 1], torch.rsqrt(xf.var(1, unbiased=False) + 1e-5)) < 1e-5
+    o = ops.gemm(x, wf, bias=bias, ln=(st, colsum), out_dtype=torch.float32)
+    assert rel(o, ref) < 1e-3          # W * gamma is rounded to fp16 once (the reference rounds the normalised activations instead)
+    if N % 2 == 0 and N >= 640:
+        og = ops.gemm(x, wf, bias=bias, ln=(st, colsum), act=ops.ACT_GELU, gated=True)
+        assert rel(og, ref[:, 0::2] * F.gelu(ref[:, 1::2])) < 3e-3

@@ -26,7 +26,10 @@ def mk(shape, seed, scale=1.0):
     (2, 10, 4096, 4096, 64, False),    # UNet self-attention 64x64
     (8, 20, 1024, 1024, 64, False),    # UNet self-attention 32x32 at batch: enough items for the two-tile kernel
     (5, 16, 1024, 1024, 104, False),   # ViT MHSA, 5 views: two-tile kernel, padded head dim
-    (2, 20, 1024, 64, 64, False),      # UNet cross-attention
+    (2, 20, 1024, 64, 64, False),      # UNet cross-attention: the 64 context tokens are one 64-key tcgen05 tile
+    (8, 10, 4096, 64, 64, False),      # ... at the 64x64 level, bench batch
+    (3, 5, 640, 48, 64, False),        # 64-key tile with 16 masked keys, ragged query tiles
+    (2, 4, 256, 64, 40, False),        # head dim padded to 64 by TMA zero fill
     (2, 16, 64, 128, 64, False),       # perceiver
     (2, 16, 1, 65, 64, False),         # AttentionPool2d (single query)
     (1, 3, 77, 33, 72, False),
@@ -48,6 +51,8 @@ def test_attention(B, H, Sq, Sk, D, causal, impl):
     lib().seedx_attention_set_impl(0)
     ref = F.scaled_dot_product_attention(qf, k.float().permute(0, 2, 1, 3), v.float().permute(0, 2, 1, 3), is_causal=causal, scale=scale)
     assert rel(o.permute(0, 2, 1, 3), ref) < 2e-3
+    if impl != "mma_sync" and Sq >= 128 and Sk <= 64 and Sk >= 16 and D <= 64 and not causal:
+        assert used == 2, "the 64-key tcgen05 tile should have handled this cross-attention shape, got %d" % used
     if impl != "mma_sync" and Sq >= 128 and Sk >= 96 and D <= 128:
         assert used in (2, 3), "a tcgen05 kernel should have handled this shape, got %d" % used
         if impl == "tcgen05_one_tile":

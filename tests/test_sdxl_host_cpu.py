@@ -46,7 +46,7 @@ def test_partial_adapter_checkpoint_updates_the_unet_in_place(patched):
     base = synth.unet_state_dict(cfg)
     m = sdxl_mod.UNet2DConditionModel(cfg, device="cpu")
     m.load_state_dict({k: v.clone() for k, v in base.items()})
-    ptrs = {k: d.data_ptr() for k, (d, _) in m._reg.slots.items()}
+    ptrs = {k: v[0].data_ptr() for k, v in m._reg.slots.items()}
     assert set(m._reg.slots) == set(base)                             # every checkpoint key has a packed destination
     part = {k: synth.randn("ft:" + k, v.shape, v.shape[-1] ** -0.5) for k, v in base.items() if k.endswith(("to_k.weight", "to_v.weight"))}
     assert len(part) >= 8
@@ -55,7 +55,7 @@ def test_partial_adapter_checkpoint_updates_the_unet_in_place(patched):
     ad.unet, ad.resampler = m, None
     ad.load_state_dict({**{"unet." + k: v for k, v in part.items()}, "unet.not_a_parameter": torch.zeros(1)})
     assert m.cfg["in_channels"] == 8
-    assert ptrs == {k: d.data_ptr() for k, (d, _) in m._reg.slots.items()}
+    assert ptrs == {k: v[0].data_ptr() for k, v in m._reg.slots.items()}
     merged = {**base, **part}
     cfg8 = dict(cfg, in_channels=8)
     B, hw = 1, 16
@@ -71,6 +71,15 @@ def test_partial_adapter_checkpoint_updates_the_unet_in_place(patched):
     assert unexpected == ["bogus"] and len(missing) == len(base) - 1
     with pytest.raises(sdxl_mod.SeedxError):
         m.load_state_dict({"conv_out.weight": torch.zeros(5, 7, 3, 3)})
+    # LayerNorms are folded into the projections that read them: a checkpoint that changes one must bring those projections along
+    blk = "down_blocks.1.attentions.0.transformer_blocks.0."
+    g2 = {blk + "norm1.weight": synth.randn("ft:g", base[blk + "norm1.weight"].shape, 0.2, 1.0), blk + "norm1.bias": synth.randn("ft:b", base[blk + "norm1.bias"].shape, 0.2)}
+    with pytest.raises(sdxl_mod.SeedxError):
+        m.load_state_dict(dict(g2))
+    qkv = {blk + f"attn1.{n}.weight": merged[blk + f"attn1.{n}.weight"] for n in ("to_q", "to_k", "to_v")}
+    m.load_state_dict({**g2, **qkv})
+    merged.update(g2)
+    assert rel(m(x, 301.0, ctx, added_cond_kwargs=dict(text_embeds=te, time_ids=tid)), osd.unet_forward(merged, cfg8, x, 301.0, ctx, te, tid)) < 5e-3
 
 
 def test_vae_host_wiring_vs_oracle(patched):
