@@ -90,6 +90,16 @@ typedef struct seedx_gemm_args {
   /* B is produced by the kernel launched just before this one on the same stream (activation x activation products).  Default 0: B holds
    * weights, whose first tiles are requested before the programmatic-dependent-launch wait. */
   int32_t b_dynamic;
+  /* ln_parts > 0: ln_stats is NOT (mean, rstd) but ln_parts x [M] fp32 pairs (sum, sum of squares) as written through row_part by the GEMM
+   * that produced A (K = 32 * ln_parts columns); mean / rstd are then formed in this epilogue with ln_eps. */
+  int32_t ln_parts;
+  float ln_eps;
+  /* Statistics of the stored fp16 output for the normalisation that reads it next, emitted by the epilogue (no extra pass over the tensor):
+   *   row_part fp32 [N/32][M][2]: per row, (sum, sum of squares) over each 32-column chunk  -> LayerNorm folded into the next GEMM (ln_parts)
+   *   col_part fp32 [M/32][N][2]: per column, (sum, sum of squares) over each 32-row slab   -> seedx_groupnorm_nhwc_from_partials
+   * Requirements: fp16 output, 16-byte aligned rows, no gating, batch 1, M % 32 == 0, N % 32 == 0.  NULL = off. */
+  float* row_part;
+  float* col_part;
 } seedx_gemm_args;
 
 int seedx_gemm_f16(const seedx_gemm_args* args, void* stream);
@@ -153,6 +163,12 @@ int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, int64_t c2,
                          const float* gamma, const float* beta, float eps, int silu_act, void* out, void* raw_out,
                          void* stats_ws, void* stream);
 int64_t seedx_groupnorm_ws_bytes(int64_t n, int groups);
+/* Same normalisation, with the statistics taken from the column partials the producing GEMM / conv epilogues wrote (col_part of
+ * seedx_gemm_args: fp32 [n*hw/32][c][2], hw % 32 == 0) instead of a pass over the tensor: a finalize kernel adds the partials of each
+ * (image, group) in a fixed order (bit-reproducible), then the same apply pass runs.  part2 belongs to x2 (NULL when x2 is NULL). */
+int seedx_groupnorm_nhwc_from_partials(const void* x1, int64_t c1, const float* part1, const void* x2, int64_t c2, const float* part2, int64_t n,
+                                       int64_t hw, int groups, const float* gamma, const float* beta, float eps, int silu_act, void* out,
+                                       void* raw_out, void* stats_ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Small HBM-bound data-movement kernels

@@ -34,6 +34,7 @@ class GemmArgs(C.Structure):
         ("conv_n", C.c_int64), ("conv_h", C.c_int64), ("conv_w", C.c_int64), ("conv_c", C.c_int64),
         ("tile_n", C.c_int32),
         ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("b_dynamic", C.c_int32),
+        ("ln_parts", C.c_int32), ("ln_eps", C.c_float), ("row_part", C.c_void_p), ("col_part", C.c_void_p),
     ]
 
 

@@ -38,6 +38,11 @@ struct GemmParams {
   const float2* ln_stats;                 // [M] (mean, rstd) or NULL
   const float* ln_colsum;                 // [N] sum_k B[n][k]
   int b_static;                           // B does not depend on the preceding kernel (weights): its first tiles are requested before the PDL wait
+  int ln_parts;                           // > 0: ln_stats holds ln_parts x [M] (sum, sum of squares) partials written by the producer of A (row_part)
+  float ln_eps, ln_inv_cols;
+  // statistics of the STORED output, emitted by the epilogue for the normalisation that reads it next (fp16 output, TMA epilogue only):
+  float2* row_part;                       // [N/32][M]  per row:    (sum, sumsq) over the 32 columns of a chunk      -> LayerNorm of the next GEMM
+  float2* col_part;                       // [M/32][N]  per column: (sum, sumsq) over the 32 rows of a warp's slab   -> GroupNorm (fixed-order finalize)
   // conv
   int conv, taps_w, c_chunks, conv_w, conv_h, tile_w, tile_h, tiles_per_img, tiles_w, pad, imgs_per_tile;
 };
@@ -287,7 +292,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float bm = (p.bias_m != nullptr && row_ok) ? p.bias_m[row] : 0.f;
       float ln_rstd = 1.f, ln_nmr = 0.f;       // folded LayerNorm: x = rstd * acc + (-mean * rstd) * colsum[n]
       if (p.ln_stats != nullptr && row_ok) {
-        const float2 mr = __ldg(p.ln_stats + row);
+        float2 mr;
+        if (p.ln_parts > 0) {      // partial sums of the row, one per 32-column chunk of the producing GEMM, added in chunk order
+          float s1 = 0.f, s2 = 0.f;
+          for (int k = 0; k < p.ln_parts; ++k) {
+            const float2 q = __ldcg(p.ln_stats + (long long)k * p.M + row);
+            s1 += q.x, s2 += q.y;
+          }
+          const float mean = s1 * p.ln_inv_cols;
+          mr = make_float2(mean, rsqrtf(fmaxf(s2 * p.ln_inv_cols - mean * mean, 0.f) + p.ln_eps));
+        } else {
+          mr = __ldg(p.ln_stats + row);
+        }
         ln_rstd = mr.y, ln_nmr = -mr.x * mr.y;
       }
       const float* bg = (p.bias_g != nullptr && row_ok) ? p.bias_g + (long long)(row / p.bias_g_rows) * p.N : nullptr;
@@ -457,6 +473,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (lane == 0) {
             tma_store_3d(&tmD, stg_out + (uint32_t)ob * tile_bytes, ocol0, row_base, b);
             bulk_commit();
+          }
+          if (p.row_part != nullptr && row_ok) {                      // this thread's row over the 32 columns of the chunk
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) s1 += x[i], s2 = fmaf(x[i], x[i], s2);
+            p.row_part[(long long)(col0 >> 5) * p.M + row] = make_float2(s1, s2);
+          }
+          if (p.col_part != nullptr) {
+            // lane = column: walk the 32 staged rows (the fp16 values the consumer will read) in row order.  RB = 64 here (fp16, not gated).
+            const uint32_t tb = stg_out + (uint32_t)ob * tile_bytes + (uint32_t)((lane & 7) * 2);
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t a = tb + (uint32_t)(r * 64) + ((((uint32_t)lane >> 3) ^ (((uint32_t)r >> 1) & 3u)) << 4);
+              unsigned short hv;
+              asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(hv) : "r"(a));
+              const float v = __half2float(__ushort_as_half(hv));
+              s1 += v, s2 = fmaf(v, v, s2);
+            }
+            if (col0 + lane < col_end) p.col_part[(long long)(row_base >> 5) * p.N + col0 + lane] = make_float2(s1, s2);
           }
           continue;
         }
@@ -752,6 +788,15 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
                   "seedx_gemm_f16: folded LayerNorm needs a plain un-batched GEMM, N %% 4 == 0 and aligned statistics");
   }
   p.ln_stats = (const float2*)a->ln_stats, p.ln_colsum = a->ln_colsum;
+  p.ln_parts = a->ln_parts, p.ln_eps = a->ln_eps, p.ln_inv_cols = a->ln_parts > 0 ? 1.0f / (32.0f * (float)a->ln_parts) : 0.f;
+  SEEDX_REQUIRE(a->ln_parts >= 0 && (a->ln_parts == 0 || (a->ln_stats && 32LL * a->ln_parts == a->K)),
+                "seedx_gemm_f16: ln_parts=%d must cover K=%lld columns in 32-column chunks", a->ln_parts, (long long)a->K);
+  if (a->row_part || a->col_part) {
+    SEEDX_REQUIRE(tma_epi && !a->gated && a->out_dtype == SEEDX_F16 && a->batch == 1 && a->N % 32 == 0 && a->M % 32 == 0,
+                  "seedx_gemm_f16: output statistics need the TMA epilogue (16-byte aligned fp16 output), no gating, batch 1, M and N multiples of 32");
+    SEEDX_REQUIRE(((uintptr_t)a->row_part % 8 == 0) && ((uintptr_t)a->col_part % 8 == 0), "seedx_gemm_f16: statistics buffers must be 8-byte aligned");
+  }
+  p.row_part = (float2*)a->row_part, p.col_part = (float2*)a->col_part;
   p.b_static = a->b_dynamic ? 0 : 1;
   p.bias_n = a->bias_n, p.bias_m = a->bias_m, p.bias_g = a->bias_g;
   p.bias_g_rows = a->bias_g ? (int)a->bias_g_rows : 1;

@@ -385,6 +385,41 @@ gn_stats_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict_
   }
 }
 
+// Statistics from the column partials the producing GEMM / conv epilogue wrote (seedx_gemm_args.col_part: per 32-row slab and channel,
+// (sum, sum of squares) of the stored fp16 values).  One CTA per (group, image): thread t adds the (slab, channel) pairs t, t + 256, ... of its
+// group in that order (fp64), then a fixed shuffle / shared-memory tree: bit-reproducible like gn_stats_kernel, but it reads 1/8 of the bytes
+// of the tensor instead of all of them and needs no atomics or tickets.
+__global__ void __launch_bounds__(256)
+gn_finalize_kernel(const float2* __restrict__ part1, int c1, const float2* __restrict__ part2, int c2, int slabs_per_img, int groups, int hw,
+                   float eps, float2* __restrict__ stats) {
+  pdl_wait();
+  pdl_trigger();
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int C = c1 + c2, cpg = C / groups;
+  const int total = slabs_per_img * cpg;
+  double s1 = 0.0, s2 = 0.0;
+  for (int idx = threadIdx.x; idx < total; idx += 256) {
+    const int slab = idx / cpg, ch = g * cpg + idx % cpg;
+    const long long srow = (long long)n * slabs_per_img + slab;
+    const float2 q = ch < c1 ? __ldcg(part1 + srow * c1 + ch) : __ldcg(part2 + srow * c2 + (ch - c1));
+    s1 += (double)q.x, s2 += (double)q.y;
+  }
+  for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o), s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  __shared__ double sh[2][8];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[0][w] = s1, sh[1][w] = s2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < 8; ++k) a += sh[0][k], b += sh[1][k];
+    const double cnt = (double)hw * (double)cpg;
+    const double m = a / cnt;
+    double var = b / cnt - m * m;
+    if (var < 0.0) var = 0.0;
+    stats[(long long)n * groups + g] = make_float2((float)m, (float)(1.0 / sqrt(var + (double)eps)));
+  }
+}
+
 __global__ void __launch_bounds__(320)
 gn_apply_kernel(const __half* __restrict__ x1, int c1, const __half* __restrict__ x2, int c2, int hw, int groups,
                 const float2* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -551,6 +586,43 @@ extern "C" int64_t seedx_groupnorm_ws_bytes(int64_t n, int groups) {
   return n * groups * 2 * (int64_t)sizeof(double) + n * nblk * groups * 2 * (int64_t)sizeof(float) + n * (int64_t)sizeof(unsigned);
 }
 
+static int gn_launch_apply(const void* x1, int64_t c1, const void* x2, int64_t c2, int64_t n, int64_t hw, int groups, const float2* stats,
+                           const float* gamma, const float* beta, int silu_act, void* out, void* raw_out, cudaStream_t st) {
+  const int64_t C = c1 + c2, vpp = C / 8;
+  // apply: ~8 CTAs per SM in flight, at least 16 pixels per block; block = whole pixels (lanes * vpp threads) when a pixel fits
+  int64_t ppb = (hw * n + 148 * 8 - 1) / (148 * 8);
+  if (ppb < 16) ppb = 16;
+  if (ppb > hw) ppb = hw;
+  dim3 g2((unsigned)((hw + ppb - 1) / ppb), (unsigned)n);
+  const size_t smem = (size_t)C * 2 * sizeof(float);
+  const int a_lanes = vpp <= 320 ? (int)(320 / vpp) : 0;
+  const int a_threads = a_lanes > 0 ? (int)(a_lanes * vpp) : 256;
+  launch_k(gn_apply_kernel, g2, a_threads, smem, st, (const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw, groups, stats,
+           gamma, beta, silu_act, (__half*)out, (__half*)raw_out, (int)ppb, a_lanes);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "groupnorm apply launch");
+}
+
+extern "C" int seedx_groupnorm_nhwc_from_partials(const void* x1, int64_t c1, const float* part1, const void* x2, int64_t c2, const float* part2,
+                                                  int64_t n, int64_t hw, int groups, const float* gamma, const float* beta, float eps, int silu_act,
+                                                  void* out, void* raw_out, void* stats_ws, void* stream) {
+  SEEDX_REQUIRE(x1 && out && stats_ws && part1, "seedx_groupnorm_nhwc_from_partials: null pointer");
+  if (!x2) c2 = 0;
+  SEEDX_REQUIRE(!x2 || part2, "seedx_groupnorm_nhwc_from_partials: x2 needs its partials");
+  const int64_t C = c1 + c2;
+  SEEDX_REQUIRE(c1 % 8 == 0 && c2 % 8 == 0 && groups > 0 && groups <= 128 && C % groups == 0, "seedx_groupnorm_nhwc_from_partials: bad channel counts");
+  SEEDX_REQUIRE(n > 0 && n <= 65535 && hw > 0 && hw % 32 == 0, "seedx_groupnorm_nhwc_from_partials: hw=%lld must be a multiple of 32 (slab = 32 rows)",
+                (long long)hw);
+  cudaStream_t st = (cudaStream_t)stream;
+  float2* stats = (float2*)stats_ws;
+  dim3 grid((unsigned)groups, (unsigned)n);
+  launch_k(gn_finalize_kernel, grid, 256, 0, st, (const float2*)part1, (int)c1, (const float2*)part2, (int)c2, (int)(hw / 32), groups, (int)hw, eps,
+           stats);
+  count_launch();
+  SEEDX_CUDA(cudaGetLastError());
+  return gn_launch_apply(x1, c1, x2, c2, n, hw, groups, stats, gamma, beta, silu_act, out, raw_out, st);
+}
+
 extern "C" int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, int64_t c2, int64_t n, int64_t hw, int groups,
                                     const float* gamma, const float* beta, float eps, int silu_act, void* out, void* raw_out,
                                     void* stats_ws, void* stream) {
@@ -578,16 +650,6 @@ extern "C" int seedx_groupnorm_nhwc(const void* x1, int64_t c1, const void* x2, 
            groups, (int)spb, stats, partials, tickets, tpp, eps);
   count_launch();
   SEEDX_CUDA(cudaGetLastError());
-  // apply: ~8 CTAs per SM in flight, at least 16 pixels per block; block = whole pixels (lanes * vpp threads) when a pixel fits
-  int64_t ppb = (hw * n + 148 * 8 - 1) / (148 * 8);
-  if (ppb < 16) ppb = 16;
-  if (ppb > hw) ppb = hw;
-  dim3 g2((unsigned)((hw + ppb - 1) / ppb), (unsigned)n);
-  const size_t smem = (size_t)C * 2 * sizeof(float);
-  const int a_lanes = vpp <= 320 ? (int)(320 / vpp) : 0;
-  const int a_threads = a_lanes > 0 ? (int)(a_lanes * vpp) : 256;
-  launch_k(gn_apply_kernel, g2, a_threads, smem, st, (const __half*)x1, (int)c1, (const __half*)x2, (int)c2, (int)hw, groups, (const float2*)stats,
-           gamma, beta, silu_act, (__half*)out, (__half*)raw_out, (int)ppb, a_lanes);
-  count_launch();
+  if (int e = gn_launch_apply(x1, c1, x2, c2, n, hw, groups, (const float2*)stats, gamma, beta, silu_act, out, raw_out, st)) return e;
   return check_cuda(cudaGetLastError(), "groupnorm kernels launch");
 }

@@ -34,11 +34,14 @@ def _require_cuda(*ts):
 
 
 def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, residual=None, res_row_mod=0,
-         act=ACT_NONE, gated=False, alpha=1.0, out_dtype=torch.float16, tile_n=0, ln=None, dynamic_b=False):
+         act=ACT_NONE, gated=False, alpha=1.0, out_dtype=torch.float16, tile_n=0, ln=None, dynamic_b=False, row_part=None, col_part=None):
     """out[b,m,n] = epi(alpha * a[b,m,:] . w[(b,)n,:]).
 
     a: fp16 [M,K] or [B,M,K] (last dim contiguous); w: fp16 [N,K] or [B,N,K]; returns/updates out [.., M, N_out].
-    ln = (row_stats fp32 [M,2], colsum fp32 [N]): LayerNorm of `a` folded into the epilogue (w = gamma-scaled weights, bias = W.beta + b).
+    ln = (row_stats fp32 [M,2], colsum fp32 [N]): LayerNorm of `a` folded into the epilogue (w = gamma-scaled weights, bias = W.beta + b);
+         (row partials fp32 [K/32, M, 2], colsum, eps): the same with the statistics formed from the partial sums the producer of `a` emitted.
+    row_part / col_part: fp32 outputs [N/32, M, 2] / [M/32, N, 2] receiving partial (sum, sum of squares) of the stored output per row chunk /
+         per 32-row slab and column, for the LayerNorm / GroupNorm that reads this output next (see stats_buffers()).
     dynamic_b: w is an activation written by the kernel launched just before (default: weights, prefetched before the PDL wait).
     """
     _require_cuda(a, w, out, bias, residual)
@@ -77,12 +80,27 @@ def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, 
     g.act, g.gated, g.out_dtype = act, int(gated), _dt(out)
     g.tile_n = tile_n
     if ln is not None:
-        st, cs = ln
-        assert st.dtype == torch.float32 and st.is_contiguous() and st.numel() == 2 * M and cs.dtype == torch.float32 and cs.is_contiguous() and cs.numel() == N
+        st, cs = ln[0], ln[1]
+        assert st.dtype == torch.float32 and st.is_contiguous() and cs.dtype == torch.float32 and cs.is_contiguous() and cs.numel() == N
+        if len(ln) == 3:
+            assert st.numel() == 2 * M * (K // 32) and K % 32 == 0
+            g.ln_parts, g.ln_eps = K // 32, float(ln[2])
+        else:
+            assert st.numel() == 2 * M
         g.ln_stats, g.ln_colsum = st.data_ptr(), cs.data_ptr()
+    _set_parts(g, row_part, col_part, M, n_out)
     g.b_dynamic = int(dynamic_b)
     check(lib().seedx_gemm_f16(C.byref(g), _stream()), "seedx_gemm_f16")
     return out
+
+
+def _set_parts(g, row_part, col_part, M, N):
+    if row_part is not None:
+        assert row_part.dtype == torch.float32 and row_part.is_contiguous() and row_part.numel() == 2 * M * (N // 32) and N % 32 == 0
+        g.row_part = row_part.data_ptr()
+    if col_part is not None:
+        assert col_part.dtype == torch.float32 and col_part.is_contiguous() and col_part.numel() == 2 * N * (M // 32) and M % 32 == 0
+        g.col_part = col_part.data_ptr()
 
 
 def row_stats(x, eps, out=None):
@@ -97,7 +115,7 @@ def row_stats(x, eps, out=None):
 
 
 def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None, act=ACT_NONE,
-                out_dtype=torch.float16, tile_n=0, alpha=1.0):
+                out_dtype=torch.float16, tile_n=0, alpha=1.0, col_part=None):
     """Stride-1 'same' convolution as an implicit GEMM.  x: fp16 NHWC [N,H,W,C]; w: fp16 [Cout, taps*taps*roundup(C,64)]
     (k = (kh*taps+kw)*Cpad + c); out: NHWC [N,H,W,Cout].  bias_g: fp32 [N, Cout] added per image."""
     _require_cuda(x, w, out, bias, residual)
@@ -128,6 +146,7 @@ def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None
     g.conv_taps_h = g.conv_taps_w = taps
     g.conv_n, g.conv_h, g.conv_w, g.conv_c = n, h, wd, c
     g.tile_n = tile_n
+    _set_parts(g, None, col_part, n * h * wd, cout)
     check(lib().seedx_gemm_f16(C.byref(g), _stream()), "seedx_gemm_f16(conv)")
     return out
 
@@ -193,8 +212,10 @@ def groupnorm_ws(n, groups, device):
     return torch.empty(((nbytes + 7) // 8,), device=device, dtype=torch.float64)
 
 
-def groupnorm_nhwc(x1, gamma, beta, eps, *, x2=None, silu=False, groups=32, out=None, raw_out=None, stats_ws=None):
-    """GroupNorm(+SiLU) over NHWC fp16 [N,H,W,C1] (optionally channel-concatenated with x2 [N,H,W,C2])."""
+def groupnorm_nhwc(x1, gamma, beta, eps, *, x2=None, silu=False, groups=32, out=None, raw_out=None, stats_ws=None, part1=None, part2=None):
+    """GroupNorm(+SiLU) over NHWC fp16 [N,H,W,C1] (optionally channel-concatenated with x2 [N,H,W,C2]).
+    part1 (and part2 when x2 is given): the col_part statistics the kernels that produced x1 / x2 emitted — the statistics pass over the tensor
+    is then replaced by a finalize over the partials."""
     _require_cuda(x1, x2, out)
     assert x1.dtype == torch.float16 and x1.is_contiguous()
     n, h, w, c1 = x1.shape
@@ -207,6 +228,13 @@ def groupnorm_nhwc(x1, gamma, beta, eps, *, x2=None, silu=False, groups=32, out=
     if stats_ws is None:
         stats_ws = groupnorm_ws(n, groups, x1.device)
     assert stats_ws.numel() * stats_ws.element_size() >= lib().seedx_groupnorm_ws_bytes(C.c_int64(n), C.c_int(groups))
+    if part1 is not None and (x2 is None or part2 is not None) and (h * w) % 32 == 0:
+        assert part1.dtype == torch.float32 and part1.numel() == 2 * c1 * (n * h * w // 32)
+        assert part2 is None or (part2.dtype == torch.float32 and part2.numel() == 2 * c2 * (n * h * w // 32))
+        check(lib().seedx_groupnorm_nhwc_from_partials(_ptr(x1), C.c_int64(c1), _ptr(part1), _ptr(x2), C.c_int64(c2), _ptr(part2), C.c_int64(n),
+                                                       C.c_int64(h * w), C.c_int(groups), _ptr(gamma), _ptr(beta), C.c_float(eps), C.c_int(int(silu)),
+                                                       _ptr(out), _ptr(raw_out), _ptr(stats_ws), _stream()), "seedx_groupnorm_nhwc_from_partials")
+        return out
     check(lib().seedx_groupnorm_nhwc(_ptr(x1), C.c_int64(c1), _ptr(x2), C.c_int64(c2), C.c_int64(n), C.c_int64(h * w), C.c_int(groups),
                                      _ptr(gamma), _ptr(beta), C.c_float(eps), C.c_int(int(silu)), _ptr(out), _ptr(raw_out), _ptr(stats_ws),
                                      _stream()), "seedx_groupnorm_nhwc")

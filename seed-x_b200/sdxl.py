@@ -45,6 +45,29 @@ def _f(t, dev):
     return t.float().to(dev).contiguous()
 
 
+# Statistics for the next normalisation come out of the producing kernel's epilogue (seedx_gemm_args.col_part / row_part) instead of a pass over
+# the tensor; SEEDX_EPI_STATS=0 restores the separate statistics kernels (A/B switch, same results up to summation order).
+EPI_STATS = os.environ.get("SEEDX_EPI_STATS", "1") != "0"
+
+
+def _new_col_part(n, h, w, c, dev):
+    """buffer for the column partials of an NHWC fp16 map [n,h,w,c] that a GroupNorm will read, or None when the shape is not eligible"""
+    if not EPI_STATS or (h * w) % 32 or c % 32:
+        return None
+    return torch.empty((n * h * w // 32, c, 2), device=dev, dtype=torch.float32)
+
+
+def _tag(t, part):
+    """attach the partials to the tensor OBJECT that travels to the consumer (a reused storage address can never inherit stale statistics)"""
+    if part is not None:
+        t.seedx_col_part = part
+    return t
+
+
+def _part(t):
+    return getattr(t, "seedx_col_part", None) if t is not None else None
+
+
 def pack_conv(w, dev, cin_pad_to=None):
     """[Cout, Cin, k, k] -> fp16 [Cout, k*k*Cpad], k index = (kh*k + kw)*Cpad + c, Cpad = roundup(Cin, 64)."""
     cout, cin, k, _ = w.shape
@@ -198,18 +221,22 @@ class _Resnet:
             raw = torch.empty((n, h, w, x.shape[3] + skip.shape[3]), device=x.device, dtype=torch.float16)
         b1, b2, bsc = (self.b1, self.b2, self.bsc) if alpha == 1.0 else self._scaled(alpha)
         eps = self.eps * alpha * alpha
-        a = ops.groupnorm_nhwc(x, self.n1[0], self.n1[1], eps, x2=skip, silu=True, groups=groups, raw_out=raw, stats_ws=ws)
+        a = ops.groupnorm_nhwc(x, self.n1[0], self.n1[1], eps, x2=skip, silu=True, groups=groups, raw_out=raw, stats_ws=ws,
+                               part1=_part(x), part2=_part(skip))
         tb = ops.gemm(semb, self.wt, bias=self.bt, out_dtype=torch.float32) if self.wt is not None else None
         if tb is not None and alpha != 1.0:
             raise SeedxError("scaled-stream ResnetBlock2D with a time embedding is not used by any model")
-        a = ops.conv2d_nhwc(a, self.w1, bias=b1, bias_g=tb, alpha=alpha)
-        a = ops.groupnorm_nhwc(a, self.n2[0], self.n2[1], eps, silu=True, groups=groups, stats_ws=ws)
+        cout = self.w1.shape[0]
+        p1 = _new_col_part(n, h, w, cout, x.device)            # norm2 statistics: emitted by conv1's epilogue
+        a = ops.conv2d_nhwc(a, self.w1, bias=b1, bias_g=tb, alpha=alpha, col_part=p1)
+        a = ops.groupnorm_nhwc(a, self.n2[0], self.n2[1], eps, silu=True, groups=groups, stats_ws=ws, part1=p1)
         xin = raw if raw is not None else x
         if self.wsc is not None:
             sc = ops.gemm(xin.view(n * h * w, xin.shape[3]), self.wsc, bias=bsc).view(n, h, w, -1)     # linear in the scaled input
         else:
             sc = xin
-        return ops.conv2d_nhwc(a, self.w2, bias=b2, residual=sc, alpha=alpha)
+        p2 = _new_col_part(n, h, w, cout, x.device)            # statistics of the block output for whichever GroupNorm reads it next
+        return _tag(ops.conv2d_nhwc(a, self.w2, bias=b2, residual=sc, alpha=alpha, col_part=p2), p2)
 
 
 class _Transformer:
@@ -273,11 +300,20 @@ class _Transformer:
         S, M, H = h * w, n * h * w, self.heads
         d = c // H
         scale = d ** -0.5
-        hn = ops.groupnorm_nhwc(x, self.norm[0], self.norm[1], 1e-6, silu=False, groups=groups, stats_ws=ws)
-        hs = ops.gemm(hn.view(M, c), self.w_in, bias=self.b_in, out_dtype=self.stream_dtype)
-        if hs.dtype != torch.float16:
+        hn = ops.groupnorm_nhwc(x, self.norm[0], self.norm[1], 1e-6, silu=False, groups=groups, stats_ws=ws, part1=_part(x))
+        if self.stream_dtype != torch.float16:
             raise SeedxError("the folded LayerNorm path reads the residual stream as the fp16 GEMM operand: _Transformer.stream_dtype must be float16")
-        stats = torch.empty((M, 2), device=x.device, dtype=torch.float32)
+        # LayerNorm statistics of the residual stream: row partials written by the epilogue of every GEMM that stores the stream (32-column chunks,
+        # added up in the consumer's epilogue); shapes that cannot use them fall back to the row-statistics kernel
+        rp = torch.empty((c // 32, M, 2), device=x.device, dtype=torch.float32) if (EPI_STATS and M % 32 == 0 and c % 32 == 0) else None
+        stats = None if rp is not None else torch.empty((M, 2), device=x.device, dtype=torch.float32)
+
+        def ln_of(fl):
+            if rp is not None:
+                return (rp, fl.colsum, 1e-5)
+            ops.row_stats(hs, 1e-5, out=stats)
+            return (stats, fl.colsum)
+        hs = ops.gemm(hn.view(M, c), self.w_in, bias=self.b_in, out_dtype=torch.float16, row_part=rp)
         qkv = torch.empty((M, 3 * c), device=x.device, dtype=torch.float16)
         obuf = torch.empty((M, c), device=x.device, dtype=torch.float16)
         qbuf = torch.empty((M, c), device=x.device, dtype=torch.float16)
@@ -287,21 +323,18 @@ class _Transformer:
         ov = obuf.view(n, S, H, d).permute(0, 2, 1, 3)
         q2 = qbuf.view(n, S, H, d).permute(0, 2, 1, 3)
         for blk, kvb in zip(self.blocks, kv):
-            # norm1 -> fused QKV: only the row statistics are computed; the normalisation happens in the projection's epilogue
-            ops.row_stats(hs, 1e-5, out=stats)
-            ops.gemm(hs, blk["qkv"].w, out=qkv, bias=blk["qkv"].bias, ln=blk["qkv"].ln(stats))
+            # norm1 -> fused QKV, norm2 -> cross-attention q, norm3 -> GEGLU: the normalisation happens in the projection's epilogue
+            ops.gemm(hs, blk["qkv"].w, out=qkv, bias=blk["qkv"].bias, ln=ln_of(blk["qkv"]))
             ops.attention(q1, k1, v1, ov, scale=scale)
-            ops.gemm(obuf, blk["w_o1"], out=hs, bias=blk["b_o1"], residual=hs)
-            ops.row_stats(hs, 1e-5, out=stats)
-            ops.gemm(hs, blk["q2"].w, out=qbuf, bias=blk["q2"].bias, ln=blk["q2"].ln(stats))
+            ops.gemm(obuf, blk["w_o1"], out=hs, bias=blk["b_o1"], residual=hs, row_part=rp)
+            ops.gemm(hs, blk["q2"].w, out=qbuf, bias=blk["q2"].bias, ln=ln_of(blk["q2"]))
             kv5 = kvb.view(n, n_ctx, 2, H, d)
             ops.attention(q2, kv5[:, :, 0].permute(0, 2, 1, 3), kv5[:, :, 1].permute(0, 2, 1, 3), ov, scale=scale)
-            ops.gemm(obuf, blk["w_o2"], out=hs, bias=blk["b_o2"], residual=hs)
-            ops.row_stats(hs, 1e-5, out=stats)
-            ops.gemm(hs, blk["ff1"].w, out=fbuf, bias=blk["ff1"].bias, act=ops.ACT_GELU, gated=True, ln=blk["ff1"].ln(stats))
-            ops.gemm(fbuf, blk["w_ff2"], out=hs, bias=blk["b_ff2"], residual=hs)
-        h16 = hs if hs.dtype == torch.float16 else ops.cast(hs, torch.float16)
-        return ops.gemm(h16, self.w_out, bias=self.b_out, residual=x.view(M, c)).view(n, h, w, c)
+            ops.gemm(obuf, blk["w_o2"], out=hs, bias=blk["b_o2"], residual=hs, row_part=rp)
+            ops.gemm(hs, blk["ff1"].w, out=fbuf, bias=blk["ff1"].bias, act=ops.ACT_GELU, gated=True, ln=ln_of(blk["ff1"]))
+            ops.gemm(fbuf, blk["w_ff2"], out=hs, bias=blk["b_ff2"], residual=hs, row_part=rp)
+        po = _new_col_part(n, h, w, c, x.device)
+        return _tag(ops.gemm(hs, self.w_out, bias=self.b_out, residual=x.view(M, c), col_part=po).view(n, h, w, c), po)
 
 
 # diffusers name of the block above: src/inference/eval_img2edit_seed_x_edit.py:8 imports it (and never instantiates it)
@@ -313,7 +346,8 @@ def _conv_s2(x, w, b, pad_before):
     n, h, wd, c = x.shape
     ho, wo = h // 2, wd // 2
     a = ops.im2col_nhwc(x, 3, 2, pad_before, ho, wo)
-    return ops.gemm(a, w, bias=b).view(n, ho, wo, -1)
+    part = _new_col_part(n, ho, wo, w.shape[0], x.device)
+    return _tag(ops.gemm(a, w, bias=b, col_part=part).view(n, ho, wo, -1), part)
 
 
 def pack_conv_dense(w, dev):
@@ -473,7 +507,8 @@ class UNet2DConditionModel:
         emb = ops.gemm(e1, self.t2[0], bias=self.t2[1], residual=cond["aug"], out_dtype=torch.float32)
         semb = ops.unary_f16(emb, act=ops.ACT_SILU)
 
-        h = ops.conv2d_nhwc(x_in, self.conv_in[0], bias=self.conv_in[1])
+        pin = _new_col_part(Be, x_in.shape[1], x_in.shape[2], self.conv_in[0].shape[0], self.device)
+        h = _tag(ops.conv2d_nhwc(x_in, self.conv_in[0], bias=self.conv_in[1], col_part=pin), pin)
         skips = [h]
         for i, blk in enumerate(self.down):
             for j, res in enumerate(blk["res"]):
@@ -493,8 +528,10 @@ class UNet2DConditionModel:
                 if blk["att"]:
                     h = blk["att"][j](h, cond["up"][i][j], T, G, ws)
             if blk["us"] is not None:
-                h = ops.conv2d_nhwc(ops.upsample2x_nhwc(h), blk["us"][0], bias=blk["us"][1])
-        a = ops.groupnorm_nhwc(h, self.norm_out[0], self.norm_out[1], 1e-5, silu=True, groups=G, stats_ws=ws)
+                up = ops.upsample2x_nhwc(h)
+                pu = _new_col_part(up.shape[0], up.shape[1], up.shape[2], blk["us"][0].shape[0], self.device)
+                h = _tag(ops.conv2d_nhwc(up, blk["us"][0], bias=blk["us"][1], col_part=pu), pu)
+        a = ops.groupnorm_nhwc(h, self.norm_out[0], self.norm_out[1], 1e-5, silu=True, groups=G, stats_ws=ws, part1=_part(h))
         return ops.conv2d_nhwc(a, self.conv_out[0], bias=self.conv_out[1], out_dtype=torch.float32, tile_n=64)
 
     def __call__(self, sample, timestep, encoder_hidden_states, added_cond_kwargs=None, **kw):
@@ -524,7 +561,7 @@ class _VaeAttention:
         alpha: scale of the residual stream x (see _Resnet.__call__); q/k/v come from the scale-invariant GroupNorm output."""
         n, h, w, c = x.shape
         S = h * w
-        hn = ops.groupnorm_nhwc(x, self.norm[0], self.norm[1], 1e-6 * alpha * alpha, silu=False, groups=groups, stats_ws=ws).view(n, S, c)
+        hn = ops.groupnorm_nhwc(x, self.norm[0], self.norm[1], 1e-6 * alpha * alpha, silu=False, groups=groups, stats_ws=ws, part1=_part(x)).view(n, S, c)
         q = ops.gemm(hn.view(n * S, c), self.wq, bias=self.bq).view(n, S, c)
         k = ops.gemm(hn.view(n * S, c), self.wk, bias=self.bk).view(n, S, c)
         out = torch.empty((n, S, c), device=x.device, dtype=torch.float16)
@@ -538,7 +575,8 @@ class _VaeAttention:
             ops.gemm(probs, vt, out=out[i], dynamic_b=True)
         xr = x.view(n * S, c)
         bo = self.bo if alpha == 1.0 else (self.bo * alpha)
-        return ops.gemm(out.view(n * S, c), self.wo, bias=bo, residual=xr, alpha=alpha).view(n, h, w, c)
+        po = _new_col_part(n, h, w, c, x.device)
+        return _tag(ops.gemm(out.view(n * S, c), self.wo, bias=bo, residual=xr, alpha=alpha, col_part=po).view(n, h, w, c), po)
 
 
 class AutoencoderKL:
@@ -657,7 +695,8 @@ class AutoencoderKL:
         ws = ops.groupnorm_ws(B, G, self.device)
         z = ops.nchw_to_nhwc_f16(latents.to(self.device).float().contiguous(), 8, scale=scale)
         x = ops.gemm(z.view(B * h * w, 8), self.post_quant[0], bias=self.post_quant[1]).view(B, h, w, -1)
-        x = ops.conv2d_nhwc(x, self.d_conv_in[0], bias=sb(self.d_conv_in[1]), alpha=al)
+        pc = _new_col_part(B, h, w, self.d_conv_in[0].shape[0], self.device)
+        x = _tag(ops.conv2d_nhwc(x, self.d_conv_in[0], bias=sb(self.d_conv_in[1]), alpha=al, col_part=pc), pc)
         x = self.d_mid[0](x, None, None, G, ws, al)
         x = self.d_mid[1](x, G, ws, al)
         x = self.d_mid[2](x, None, None, G, ws, al)
@@ -665,8 +704,10 @@ class AutoencoderKL:
             for r in res:
                 x = r(x, None, None, G, ws, al)
             if us is not None:
-                x = ops.conv2d_nhwc(ops.upsample2x_nhwc(x), us[0], bias=sb(us[1]))     # linear in the scaled stream
-        a = ops.groupnorm_nhwc(x, self.d_norm_out[0], self.d_norm_out[1], 1e-6 * al * al, silu=True, groups=G, stats_ws=ws)
+                up = ops.upsample2x_nhwc(x)
+                pu = _new_col_part(up.shape[0], up.shape[1], up.shape[2], us[0].shape[0], self.device)
+                x = _tag(ops.conv2d_nhwc(up, us[0], bias=sb(us[1]), col_part=pu), pu)     # linear in the scaled stream
+        a = ops.groupnorm_nhwc(x, self.d_norm_out[0], self.d_norm_out[1], 1e-6 * al * al, silu=True, groups=G, stats_ws=ws, part1=_part(x))
         return ops.conv2d_nhwc(a, self.d_conv_out[0], bias=self.d_conv_out[1], tile_n=64, out_dtype=torch.float32)
 
     def decode(self, latents, scale=1.0):
@@ -684,7 +725,8 @@ class AutoencoderKL:
         sb = (lambda b: b) if al == 1.0 else (lambda b: b * al)
         ws = ops.groupnorm_ws(B, G, self.device)
         x = ops.nchw_to_nhwc_f16(image.to(self.device).float().contiguous(), 8)
-        x = ops.conv2d_nhwc(x, self.e_conv_in[0], bias=sb(self.e_conv_in[1]), alpha=al)
+        pc = _new_col_part(B, x.shape[1], x.shape[2], self.e_conv_in[0].shape[0], self.device)
+        x = _tag(ops.conv2d_nhwc(x, self.e_conv_in[0], bias=sb(self.e_conv_in[1]), alpha=al, col_part=pc), pc)
         for res, ds in self.e_down:
             for r in res:
                 x = r(x, None, None, G, ws, al)
@@ -693,7 +735,7 @@ class AutoencoderKL:
         x = self.e_mid[0](x, None, None, G, ws, al)
         x = self.e_mid[1](x, G, ws, al)
         x = self.e_mid[2](x, None, None, G, ws, al)
-        a = ops.groupnorm_nhwc(x, self.e_norm_out[0], self.e_norm_out[1], 1e-6 * al * al, silu=True, groups=G, stats_ws=ws)
+        a = ops.groupnorm_nhwc(x, self.e_norm_out[0], self.e_norm_out[1], 1e-6 * al * al, silu=True, groups=G, stats_ws=ws, part1=_part(x))
         m = ops.conv2d_nhwc(a, self.e_conv_out[0], bias=self.e_conv_out[1], tile_n=64)
         n, h, w, c = m.shape
         mo = ops.gemm(m.view(n * h * w, c), self.quant[0], bias=self.quant[1], out_dtype=torch.float32).view(n, h, w, -1)

@@ -44,13 +44,17 @@ def patchify(x, patch, kpad):
 
 
 def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, residual=None, res_row_mod=0, act=ACT_NONE, gated=False, alpha=1.0,
-         out_dtype=torch.float16, ln=None, dynamic_b=False, **kw):
+         out_dtype=torch.float16, ln=None, dynamic_b=False, row_part=None, col_part=None, **kw):
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 2 and not any(v is not None and v is not False and v != 0 for v in kw.values())
     if residual is not None and res_row_mod:                     # residual row = output row % res_row_mod (position tables)
         residual = residual.repeat(a.shape[0] // res_row_mod, 1)
     acc = alpha * (a.float() @ w.float().t())
     if ln is not None:                                           # folded LayerNorm: rstd * (acc - mean * colsum)
-        st, cs = ln
+        st, cs = ln[0], ln[1]
+        if len(ln) == 3:                                         # statistics from the producer's row partials [K/32, M, 2]
+            tot = st.view(-1, a.shape[0], 2).sum(0)
+            mean = tot[:, 0] / a.shape[1]
+            st = torch.stack([mean, torch.rsqrt((tot[:, 1] / a.shape[1] - mean * mean).clamp_min(0) + ln[2])], dim=1)
         acc = st[:, 1:2] * (acc - st[:, 0:1] * cs[None, :])
     if bias is not None:
         acc = acc + bias
@@ -70,7 +74,19 @@ def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, 
     if out is None:
         out = torch.empty(acc.shape, dtype=out_dtype)
     out.copy_(acc.to(out.dtype))
+    _emit_parts(out, acc, row_part, col_part)
     return out
+
+
+def _emit_parts(out, acc, row_part, col_part):
+    """epilogue statistics of seedx_gemm_f16: row partials from the fp32 values, column partials from the stored fp16 values"""
+    M, N = acc.shape
+    if row_part is not None:
+        v = acc.float().view(M, N // 32, 32)
+        row_part.view(N // 32, M, 2).copy_(torch.stack([v.sum(-1), (v * v).sum(-1)], dim=-1).permute(1, 0, 2))
+    if col_part is not None:
+        v = out.reshape(M, N).float().view(M // 32, 32, N)
+        col_part.view(M // 32, N, 2).copy_(torch.stack([v.sum(1), (v * v).sum(1)], dim=-1))
 
 
 def row_stats(x, eps, out=None):
@@ -254,7 +270,7 @@ def add_bcast_f16(a, b, out=None):
 
 
 # ---- stage 3 (NHWC fp16 feature maps) ---------------------------------------------------------------------------------------------------
-def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None, act=ACT_NONE, out_dtype=torch.float16, tile_n=0, alpha=1.0):
+def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None, act=ACT_NONE, out_dtype=torch.float16, tile_n=0, alpha=1.0, col_part=None):
     """stride-1 'same' conv; w packed [Cout, taps*taps*Cpad] with k = (kh*taps + kw)*Cpad + c, Cpad = roundup(Cin, 64); bias_g fp32 [N, Cout] per image"""
     n, h, wd, c = x.shape
     cout = w.shape[0]
@@ -273,6 +289,7 @@ def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None
     if out is None:
         out = torch.empty((n, h, wd, cout), dtype=out_dtype)
     out.copy_(y.to(out.dtype))
+    _emit_parts(out.view(-1, cout), y.reshape(-1, cout), None, col_part)
     return out
 
 
@@ -280,11 +297,24 @@ def groupnorm_ws(n, groups, device):
     return torch.empty((1,), dtype=torch.float64)
 
 
-def groupnorm_nhwc(x1, gamma, beta, eps, *, x2=None, silu=False, groups=32, out=None, raw_out=None, stats_ws=None):
+def groupnorm_nhwc(x1, gamma, beta, eps, *, x2=None, silu=False, groups=32, out=None, raw_out=None, stats_ws=None, part1=None, part2=None):
     x = torch.cat([x1, x2], dim=3) if x2 is not None else x1
     if raw_out is not None:
         raw_out.copy_(x)
-    y = F.group_norm(x.float().permute(0, 3, 1, 2), groups, gamma, beta, eps)
+    n, h, w, C = x.shape
+    if part1 is not None and (x2 is None or part2 is not None) and (h * w) % 32 == 0:
+        # statistics from the producers' column partials (seedx_groupnorm_nhwc_from_partials), not from the tensor
+        parts = torch.cat([part1.view(-1, x1.shape[3], 2)] + ([part2.view(-1, x2.shape[3], 2)] if x2 is not None else []), dim=1)   # [n*hw/32, C, 2]
+        tot = parts.view(n, h * w // 32, groups, C // groups, 2).double().sum(dim=(1, 3))                                                # [n, groups, 2]
+        cnt = h * w * (C // groups)
+        mean = tot[..., 0] / cnt
+        rstd = torch.rsqrt((tot[..., 1] / cnt - mean * mean).clamp_min(0) + eps)
+        cpg = C // groups
+        xf = x.float().view(n, h * w, groups, cpg)
+        y = ((xf - mean[:, None, :, None].float()) * rstd[:, None, :, None].float()).view(n, h, w, C) * gamma + beta
+        y = y.permute(0, 3, 1, 2)
+    else:
+        y = F.group_norm(x.float().permute(0, 3, 1, 2), groups, gamma, beta, eps)
     if silu:
         y = F.silu(y)
     y = y.permute(0, 2, 3, 1).to(torch.float16)

@@ -181,3 +181,33 @@ def test_gemm_folded_layernorm(M, N, K, mean_shift, cluster_mode):
     if N % 2 == 0 and N >= 640:
         og = ops.gemm(x, wf, bias=bias, ln=(st, colsum), act=ops.ACT_GELU, gated=True)
         assert rel(og, ref[:, 0::2] * F.gelu(ref[:, 1::2])) < 3e-3
+
+
+@pytest.mark.parametrize("M,N,K,res", [(8192, 1280, 1280, True), (4096, 640, 2560, True), (1024, 320, 64, False), (256, 96, 128, True)])
+def test_gemm_epilogue_statistics(M, N, K, res, cluster_mode):
+    """row_part / col_part (seedx_gemm_args): (sum, sum of squares) of the stored output per row over each 32-column chunk and per column over each
+    32-row slab, then the consumers: a GEMM with the LayerNorm folded in that forms mean / rstd from the row partials, GroupNorm from the column partials"""
+    from seedx_b200 import ops
+    a = mk((M, K), 61).half()
+    w = mk((N, K), 62, K ** -0.5).half()
+    bias = mk((N,), 63)
+    r = mk((M, N), 64).half() if res else None
+    want = a.float() @ w.float().t() + bias + (r.float() if res else 0)
+    rp = torch.empty((N // 32, M, 2), device="cuda")
+    cp = torch.empty((M // 32, N, 2), device="cuda")
+    out = r.clone() if res else None
+    out = ops.gemm(a, w, out=out, bias=bias, residual=out if res else None, row_part=rp, col_part=cp)
+    assert rel(out, want) < 2e-3
+    o32 = out.float()
+    v = want.view(M, N // 32, 32)
+    assert rel(rp[..., 0].t(), v.sum(-1)) < 2e-3 and rel(rp[..., 1].t(), (v * v).sum(-1)) < 2e-3
+    c = o32.view(M // 32, 32, N)              # column partials are taken from the stored fp16 values: exact up to the summation order
+    assert rel(cp[..., 0], c.sum(1)) < 1e-5 and rel(cp[..., 1], (c * c).sum(1)) < 1e-5
+    if N % 64 == 0:
+        # consumer 1: LayerNorm(out) -> linear, statistics from the row partials
+        w2 = mk((256, N), 65, N ** -0.5)
+        gamma, beta = 1.0 + 0.2 * mk((N,), 66), 0.2 * mk((N,), 67)
+        ref = F.layer_norm(o32, (N,), gamma, beta, 1e-5) @ w2.t()
+        wf = (w2 * gamma[None, :]).half()
+        o2 = ops.gemm(out, wf, bias=(w2 @ beta).contiguous(), ln=(rp, wf.float().sum(1).contiguous(), 1e-5), out_dtype=torch.float32)
+        assert rel(o2, ref) < 1.5e-3

@@ -108,6 +108,33 @@ def test_groupnorm(n, h, w, c1, c2, silu):
         assert torch.equal(raw, xc)
 
 
+@pytest.mark.parametrize("n,h,w,c1,c2", [(2, 32, 32, 320, 0), (2, 16, 16, 1280, 640), (1, 64, 64, 640, 320), (3, 8, 8, 128, 0), (8, 32, 32, 1280, 1280)])
+def test_groupnorm_from_epilogue_partials(n, h, w, c1, c2):
+    """GroupNorm whose statistics come from the column partials emitted by the producing conv / GEMM epilogues (no pass over the tensor): the 3x3 conv
+    that produces x1 (and a 1x1 GEMM that produces the skip x2) write col_part; the finalize over the partials is bit-reproducible and the result
+    matches torch GroupNorm(+SiLU) of the stored fp16 tensors, including groups that straddle the x1 | x2 boundary (C/32 = 60 channels per group)"""
+    from seedx_b200 import ops
+    xin = mk((n, h, w, 64), 21).half()
+    w1 = mk((c1, 9 * 64), 22, (9 * 64) ** -0.5).half()
+    p1 = torch.empty((n * h * w // 32, c1, 2), device="cuda")
+    x1 = ops.conv2d_nhwc(xin, w1, bias=mk((c1,), 23), col_part=p1)
+    x2 = p2 = None
+    if c2:
+        w2 = mk((c2, 64), 24, 0.2).half()
+        p2 = torch.empty((n * h * w // 32, c2, 2), device="cuda")
+        x2 = ops.gemm(xin.view(-1, 64), w2, bias=mk((c2,), 25) - 0.5, col_part=p2).view(n, h, w, c2)
+    C = c1 + c2
+    g, b = mk((C,), 3) + 1.0, mk((C,), 4)
+    xc = torch.cat([x1, x2], dim=3) if c2 else x1
+    ref = F.silu(F.group_norm(xc.float().permute(0, 3, 1, 2), 32, g, b, 1e-5)).permute(0, 2, 3, 1)
+    out = ops.groupnorm_nhwc(x1, g, b, 1e-5, x2=x2, silu=True, part1=p1, part2=p2).clone()
+    assert rel(out, ref) < 2e-3
+    plain = ops.groupnorm_nhwc(x1, g, b, 1e-5, x2=x2, silu=True)          # statistics pass over the tensor
+    assert rel(out, plain) < 1e-3
+    for _ in range(2):
+        assert torch.equal(ops.groupnorm_nhwc(x1, g, b, 1e-5, x2=x2, silu=True, part1=p1, part2=p2), out)
+
+
 def test_patchify_cast_pool():
     from seedx_b200 import ops
     x = mk((2, 3, 56, 42), 1)
