@@ -108,6 +108,12 @@ int seedx_gemm_f16(const seedx_gemm_args* args, void* stream);
 void seedx_gemm_set_cluster(int mode);
 /* developer aid: device buffer of 8 uint64 per CTA that receives %globaltimer phase stamps of the following GEMM launches (NULL = off) */
 void seedx_gemm_set_debug(void* device_buffer);
+/* Stream-K schedule for launches whose last wave of whole tiles would leave SMs idle (e.g. M = 8192, N = 1280: 192 pair-tiles on 74 CTA pairs =
+ * 2.6 waves): every cluster takes an equal share of the (tile, k-block) iterations; partial accumulators of split tiles go through a workspace.
+ * seedx_gemm_set_workspace hands the library that workspace (>= 32 MB recommended, 256-byte aligned, first 16 KB zero-filled by the caller, owned
+ * by the caller, used by one stream at a time); without it, or with mode 0, every launch is data-parallel.  mode: 0 off, 1 auto (default), 2 always. */
+int seedx_gemm_set_workspace(void* device_buffer, int64_t bytes);
+void seedx_gemm_set_stream_k(int mode);
 /* A/B switch for the epilogue: 1 (default) = output/residual tiles staged in shared memory and moved by TMA, 0 = direct row-per-thread stores */
 void seedx_gemm_set_tma_epilogue(int on);
 

@@ -41,6 +41,12 @@ struct GemmParams {
   int ln_parts;                           // > 0: ln_stats holds ln_parts x [M] (sum, sum of squares) partials written by the producer of A (row_part)
   float ln_eps, ln_inv_cols;
   // statistics of the STORED output, emitted by the epilogue for the normalisation that reads it next (fp16 output, TMA epilogue only):
+  // stream-K schedule (host: seedx_gemm_set_workspace): every cluster takes an equal share of the linearised (tile, k-block) iterations; a
+  // cluster that starts inside a tile writes its raw fp32 partial accumulator to sk_scratch[cluster], the cluster that holds the tile's first
+  // k-block adds those partials in cluster order before its normal epilogue (fixed order: bit-reproducible)
+  int stream_k;
+  float* sk_scratch;                      // [clusters][CL][128][BN] fp32
+  unsigned* sk_flags;                     // [clusters][CL][EPI_WARPS], 0 between launches
   float2* row_part;                       // [N/32][M]  per row:    (sum, sumsq) over the 32 columns of a chunk      -> LayerNorm of the next GEMM
   float2* col_part;                       // [M/32][N]  per column: (sum, sumsq) over the 32 rows of a warp's slab   -> GroupNorm (fixed-order finalize)
   // conv
@@ -86,6 +92,35 @@ SEEDX_DEVINL float apply_act(float x, int act) {
   if (act == SEEDX_ACT_GELU_ERF) return gelu_erf_fast(x);
   if (act == SEEDX_ACT_SILU) return silu(x);
   return x;
+}
+
+// Work list of one cluster: segments (tile, k-blocks [kb0, kb1)).  Data-parallel: whole tiles first, first + step, ...  Stream-K: the
+// iterations [it, it1) of the linearised (tile, k-block) space, cut at tile boundaries.
+struct SegState {
+  long long it, it1;
+  int t_next;
+};
+SEEDX_DEVINL SegState seg_init(const GemmParams& p, int cluster, int n_clusters, int num_tiles) {
+  SegState s;
+  s.t_next = cluster;
+  const long long total = (long long)num_tiles * p.k_blocks;
+  s.it = p.stream_k ? (long long)cluster * total / n_clusters : 0;
+  s.it1 = p.stream_k ? (long long)(cluster + 1) * total / n_clusters : 0;
+  return s;
+}
+SEEDX_DEVINL bool seg_next(const GemmParams& p, SegState& s, int n_clusters, int num_tiles, int& t, int& kb0, int& kb1) {
+  if (p.stream_k) {
+    if (s.it >= s.it1) return false;
+    t = (int)(s.it / p.k_blocks);
+    kb0 = (int)(s.it - (long long)t * p.k_blocks);
+    const long long left = s.it1 - s.it;
+    kb1 = (left < (long long)(p.k_blocks - kb0)) ? kb0 + (int)left : p.k_blocks;
+    s.it += kb1 - kb0;
+    return true;
+  }
+  if (s.t_next >= num_tiles) return false;
+  t = s.t_next, s.t_next += n_clusters, kb0 = 0, kb1 = p.k_blocks;
+  return true;
 }
 
 // CL = CTAs per MMA (1, or 2 = a CTA pair on one 256 x BN tile, tcgen05 cta_group::2).  In pair mode each CTA stages its own 128 rows
@@ -153,18 +188,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // Weights never depend on the kernel before this one: the B halves of the first stages of this CTA's first tile are requested BEFORE the
   // dependency wait (their bytes are already counted on the `full` barriers; the A halves follow after the wait).
   int b_pre = 0;
-  if (p.b_static && tile0 < num_tiles) b_pre = p.k_blocks < STAGES ? p.k_blocks : STAGES;
-  if (warp == 0 && lane == 0 && b_pre > 0) {
-    const int b = tile0 / tiles_per_batch;
-    const int n_blk = (tile0 - b * tiles_per_batch) / m_groups;
-    for (int kb = 0; kb < b_pre; ++kb) {
-      const uint32_t sb = smem_base + kb * Cfg::STAGE_BYTES + A_STAGE_BYTES;
-      if (CL == 1) {
-        mbar_expect_tx(full_bar(kb), Cfg::STAGE_BYTES);
-        tma_load_3d(sb, &tmB, full_bar(kb), kb * BK, n_blk * BN, p.b_batched ? b : 0);
-      } else {
-        if (crank == 0) mbar_expect_tx(full_bar(kb), CL * Cfg::STAGE_BYTES);
-        tma_load_3d_2sm(sb, &tmB, mapa_cluster(full_bar(kb), 0), kb * BK, n_blk * BN + crank * (BN / CL), p.b_batched ? b : 0);
+  {
+    SegState s0 = seg_init(p, tile0, tile_step, num_tiles);
+    int t, kb0, kb1;
+    if (p.b_static && seg_next(p, s0, tile_step, num_tiles, t, kb0, kb1)) {
+      b_pre = (kb1 - kb0) < STAGES ? (kb1 - kb0) : STAGES;
+      if (warp == 0 && lane == 0) {
+        const int b = t / tiles_per_batch;
+        const int n_blk = (t - b * tiles_per_batch) / m_groups;
+        for (int i = 0; i < b_pre; ++i) {
+          const uint32_t sb = smem_base + i * Cfg::STAGE_BYTES + A_STAGE_BYTES;
+          if (CL == 1) {
+            mbar_expect_tx(full_bar(i), Cfg::STAGE_BYTES);
+            tma_load_3d(sb, &tmB, full_bar(i), (kb0 + i) * BK, n_blk * BN, p.b_batched ? b : 0);
+          } else {
+            if (crank == 0) mbar_expect_tx(full_bar(i), CL * Cfg::STAGE_BYTES);
+            tma_load_3d_2sm(sb, &tmB, mapa_cluster(full_bar(i), 0), (kb0 + i) * BK, n_blk * BN + crank * (BN / CL), p.b_batched ? b : 0);
+          }
+        }
       }
     }
   }
@@ -177,7 +218,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = tile0; t < num_tiles; t += tile_step) {
+      SegState ss = seg_init(p, tile0, tile_step, num_tiles);
+      int t, kb0, kb1;
+      bool first_seg = true;
+      while (seg_next(p, ss, tile_step, num_tiles, t, kb0, kb1)) {
         const int b = t / tiles_per_batch;
         const int r = t - b * tiles_per_batch;
         const int n_blk = r / m_groups;
@@ -194,11 +238,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             w0 = (rem - th_i * p.tiles_w) * p.tile_w;
           }
         }
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + A_STAGE_BYTES;
-          const bool b_done = (t == tile0) && (kb < b_pre);   // this stage's barrier is armed and its B half is in flight already
+          const bool b_done = first_seg && (kb - kb0 < b_pre);   // this stage's barrier is armed and its B half is in flight already
           if (CL == 1) {
             if (!b_done) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
             if (p.conv) {
@@ -231,6 +275,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             phase ^= 1u;
           }
         }
+        first_seg = false;
       }
     }
   } else if (warp == 1) {
@@ -241,13 +286,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = tile0; t < num_tiles; t += tile_step) {
+      SegState ss = seg_init(p, tile0, tile_step, num_tiles);
+      int t, kb0, kb1;
+      bool first_seg = true;
+      while (seg_next(p, ss, tile_step, num_tiles, t, kb0, kb1)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < p.k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
-          if (t == tile0 && kb == 0) GEMM_STAMP(3);
+          if (first_seg && kb == kb0) GEMM_STAMP(3);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t adesc = umma_desc_k_sw128(sa);
@@ -255,8 +303,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             // advance 16 fp16 = 32 B inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            if (CL == 1) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-            else umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            if (CL == 1) umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0);
+            else umma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, ((kb - kb0) | k) != 0);
           }
           if (CL == 1) umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
           else umma_commit_2sm(empty_bar(stage));      // ... in both CTAs
@@ -269,6 +317,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else umma_commit_2sm(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
+        first_seg = false;
       }
     }
   } else {
@@ -278,7 +327,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t epi_res_phase = 0;   // parity bits of this warp's two residual barriers
-    for (int t = tile0; t < num_tiles; t += tile_step) {
+    SegState ss = seg_init(p, tile0, tile_step, num_tiles);
+    int t, kb0, kb1;
+    bool first_seg = true;
+    while (seg_next(p, ss, tile_step, num_tiles, t, kb0, kb1)) {
       const int b = t / tiles_per_batch;
       const int r = t - b * tiles_per_batch;
       const int n_blk = r / m_groups;
@@ -329,15 +381,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_load_3d(stg_res + (uint32_t)rb * tile_bytes, &tmR, res_bar(ew, rb), out_col(k), p.res_row_mod ? (row_base % p.res_row_mod) : row_base,
                     p.r_batched ? b : 0);
       };
+      // ---- stream-K roles of this segment
+      const bool sk_partial = kb0 > 0;                          // the tile's first k-blocks belong to an earlier cluster: hand my raw sums over
+      const bool sk_owner = (kb0 == 0) && (kb1 < p.k_blocks);   // later clusters hold the rest of this tile: add their partials, then finish
+      const int my_cluster = tile0;
+      const size_t sk_tile_elems = (size_t)BM * BN;
+      if (sk_partial) {
+        mbar_wait_relaxed(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        float* dst = p.sk_scratch + ((size_t)my_cluster * CL + crank) * sk_tile_elems + (size_t)(lane_grp * 32 + lane) * BN;
+#pragma unroll 1
+        for (int c = chunk0; c < BN; c += 64) {
+          if (n0 + c >= col_end) break;
+          __syncwarp();
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *(uint4*)(dst + c + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        __threadfence();                                        // my stores are visible device-wide before the flag
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p.sk_flags + ((size_t)my_cluster * CL + crank) * EPI_WARPS + ew), "r"(1u) : "memory");
+          if (CL == 1) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+        first_seg = false;
+        continue;
+      }
+      int sk_last = my_cluster;                                 // contributors = clusters my_cluster+1 .. sk_last
+      if (sk_owner) {
+        const long long total = (long long)num_tiles * p.k_blocks;
+        const long long tile_end = (long long)(t + 1) * p.k_blocks;
+        while (sk_last + 1 < tile_step && (long long)(sk_last + 1) * total / tile_step < tile_end) ++sk_last;
+      }
       if (tma_res && lane == 0)
         for (int k = 0; k < nres && k < n_chunks; ++k) issue_res(k);  // in flight while the main loop of this tile is still running
       int kchunk = 0;
       mbar_wait_relaxed(tfull_bar(acc), acc_phase);   // accumulator of this tile complete
       if (warp == 2 && lane == 0) {
-        if (t == tile0) GEMM_STAMP(4);
+        if (first_seg) GEMM_STAMP(4);
         GEMM_STAMP(5);                                 // overwritten every tile: the last tile's value survives
       }
       tc_fence_after();
+      if (sk_owner) {                                  // the contributors wrote their partials at the START of their work: normally long done
+        for (int cc = my_cluster + 1; cc <= sk_last; ++cc) {
+          const unsigned* f = p.sk_flags + ((size_t)cc * CL + crank) * EPI_WARPS + ew;
+          unsigned ready = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(ready) : "l"(f) : "memory");
+            if (!ready) __nanosleep(64);
+          } while (!ready);
+        }
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int c = chunk0; c < BN; c += 64) {
         if (n0 + c >= col_end) break;  // warp-uniform
@@ -345,6 +446,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t v[32];
         tmem_ld32(taddr + (uint32_t)c, v);
         tmem_ld_wait();
+        if (sk_owner) {            // partial sums of the later k-blocks, added in cluster order (fixed order: reproducible)
+          for (int cc = my_cluster + 1; cc <= sk_last; ++cc) {
+            const float* src = p.sk_scratch + ((size_t)cc * CL + crank) * sk_tile_elems + (size_t)(lane_grp * 32 + lane) * BN + c;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 q = __ldcg((const float4*)(src + i));
+              v[i] = __float_as_uint(__uint_as_float(v[i]) + q.x), v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + q.y);
+              v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + q.z), v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + q.w);
+            }
+          }
+        }
         float x[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) * p.alpha + bm;
@@ -573,9 +685,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (lane == 0) {
         if (CL == 1) mbar_arrive(tempty_bar(acc));
         else mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));  // the leader's MMA thread owns the accumulator hand-shake
+        if (sk_owner)                                                // flags back to 0: one writer and one reader each, nobody else looks at them
+          for (int cc = my_cluster + 1; cc <= sk_last; ++cc) p.sk_flags[((size_t)cc * CL + crank) * EPI_WARPS + ew] = 0u;
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+      first_seg = false;
     }
     if (p.tma_epi && lane == 0) bulk_wait_read<0>();  // shared memory stays alive until the last TMA store has read it
     if (warp == 2 && lane == 0) GEMM_STAMP(6);
@@ -597,6 +712,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 void count_launch();
 
+// stream-K fix-up workspace (seedx_gemm_set_workspace): flags first (zeroed by the caller), partial tiles behind them
+static int g_gemm_stream_k = 1;       // 0 = off, 1 = auto, 2 = whenever legal (tests)
+static float* g_sk_scratch = nullptr;
+static size_t g_sk_scratch_bytes = 0;
+static unsigned* g_sk_flags = nullptr;
+constexpr size_t SK_FLAG_BYTES = 16384;
+
 template <int BN, int CL>
 static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p_in,
                           cudaStream_t st) {
@@ -617,6 +739,22 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   const int groups = ((p.m_blocks + CL - 1) / CL) * p.n_blocks * p.batch;
   const int max_clusters = num_sms() / CL;
   const int grid = (groups < max_clusters ? groups : max_clusters) * CL;
+  // Stream-K when the last wave of whole tiles would leave SMs idle: every cluster gets total/clusters k-iterations instead of whole tiles.
+  // Needs the fix-up workspace, at least 4 iterations per cluster (no empty cluster, a partial is worth its round trip) and a tile that
+  // fits a scratch slot.
+  p.stream_k = 0;
+  {
+    const int clusters = grid / CL;
+    const long long total = (long long)groups * p.k_blocks;
+    const int rem = groups % clusters;
+    const bool idle_tail = rem != 0 && (double)(clusters - rem) / clusters / ((groups + clusters - 1) / clusters) > 0.04;   // > 4 % of the launch idle
+    const size_t need = (size_t)clusters * CL * BM * BN * sizeof(float);
+    if (g_gemm_stream_k != 0 && g_sk_scratch != nullptr && need <= g_sk_scratch_bytes && total >= 4LL * clusters && groups > clusters &&
+        (idle_tail || g_gemm_stream_k == 2)) {
+      p.stream_k = 1;
+      p.sk_scratch = g_sk_scratch, p.sk_flags = g_sk_flags;
+    }
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -682,6 +820,19 @@ using namespace seedx;
 extern "C" void seedx_gemm_set_debug(void* device_buffer) { seedx::g_gemm_dbg = (unsigned long long*)device_buffer; }
 extern "C" void seedx_gemm_set_cluster(int mode) { seedx::g_gemm_cluster = mode; }
 extern "C" void seedx_gemm_set_tma_epilogue(int on) { seedx::g_gemm_tma_epi = on; }
+extern "C" void seedx_gemm_set_stream_k(int mode) { seedx::g_gemm_stream_k = mode; }
+extern "C" int seedx_gemm_set_workspace(void* ptr, int64_t bytes) {
+  if (ptr == nullptr) {
+    seedx::g_sk_scratch = nullptr, seedx::g_sk_flags = nullptr, seedx::g_sk_scratch_bytes = 0;
+    return 0;
+  }
+  SEEDX_REQUIRE(((uintptr_t)ptr % 256 == 0) && bytes > (int64_t)seedx::SK_FLAG_BYTES, "seedx_gemm_set_workspace: need a 256-byte aligned buffer larger than %d bytes",
+                (int)seedx::SK_FLAG_BYTES);
+  seedx::g_sk_flags = (unsigned*)ptr;
+  seedx::g_sk_scratch = (float*)((char*)ptr + seedx::SK_FLAG_BYTES);
+  seedx::g_sk_scratch_bytes = (size_t)bytes - seedx::SK_FLAG_BYTES;
+  return 0;
+}
 
 extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
   SEEDX_REQUIRE(a != nullptr, "seedx_gemm_f16: null args");
