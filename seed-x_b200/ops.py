@@ -33,6 +33,21 @@ def _require_cuda(*ts):
             raise _lib.SeedxError("seedx ops need CUDA tensors: there is no CPU fallback path")
 
 
+_workspace = {}
+
+
+def _ensure_workspace(device):
+    """stream-K fix-up workspace of seedx_gemm_f16 (include/seedx.h: seedx_gemm_set_workspace), one per process: 16 KB of flags (zero) + room for
+    one fp32 partial tile per cluster (148 x 128 x 256 x 4 B = 19.4 MB).  Allocated on the first GEMM — before any CUDA-graph capture, which
+    always follows an eager warm-up pass."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _workspace:
+        buf = torch.zeros((24 * 1024 * 1024 + 16384,), device=device, dtype=torch.uint8)
+        check(lib().seedx_gemm_set_workspace(C.c_void_p(buf.data_ptr()), C.c_int64(buf.numel())), "seedx_gemm_set_workspace")
+        _workspace[key] = buf
+    return _workspace[key]
+
+
 def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, residual=None, res_row_mod=0,
          act=ACT_NONE, gated=False, alpha=1.0, out_dtype=torch.float16, tile_n=0, ln=None, dynamic_b=False, row_part=None, col_part=None):
     """out[b,m,n] = epi(alpha * a[b,m,:] . w[(b,)n,:]).
@@ -45,6 +60,7 @@ def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, 
     dynamic_b: w is an activation written by the kernel launched just before (default: weights, prefetched before the PDL wait).
     """
     _require_cuda(a, w, out, bias, residual)
+    _ensure_workspace(a.device)
     assert a.dtype == torch.float16 and w.dtype == torch.float16
     assert a.stride(-1) == 1 and w.stride(-1) == 1
     batched = a.dim() == 3
@@ -119,6 +135,7 @@ def conv2d_nhwc(x, w, out=None, *, taps=3, bias=None, bias_g=None, residual=None
     """Stride-1 'same' convolution as an implicit GEMM.  x: fp16 NHWC [N,H,W,C]; w: fp16 [Cout, taps*taps*roundup(C,64)]
     (k = (kh*taps+kw)*Cpad + c); out: NHWC [N,H,W,Cout].  bias_g: fp32 [N, Cout] added per image."""
     _require_cuda(x, w, out, bias, residual)
+    _ensure_workspace(x.device)
     assert x.dtype == torch.float16 and x.is_contiguous() and w.is_contiguous()
     n, h, wd, c = x.shape
     cout, K = w.shape

@@ -211,3 +211,52 @@ def test_gemm_epilogue_statistics(M, N, K, res, cluster_mode):
         wf = (w2 * gamma[None, :]).half()
         o2 = ops.gemm(out, wf, bias=(w2 @ beta).contiguous(), ln=(rp, wf.float().sum(1).contiguous(), 1e-5), out_dtype=torch.float32)
         assert rel(o2, ref) < 1.5e-3
+
+
+@pytest.fixture(params=["data_parallel", "stream_k"])
+def stream_k_mode(request):
+    """run a test with the stream-K schedule forced off and forced on wherever it is legal"""
+    from seedx_b200._lib import lib
+    lib().seedx_gemm_set_stream_k(0 if request.param == "data_parallel" else 2)
+    yield request.param
+    lib().seedx_gemm_set_stream_k(1)
+
+
+@pytest.mark.parametrize("M,N,K,tile_n", [(8192, 1280, 1280, 0), (8192, 1280, 5120, 224), (8192, 1280, 320, 256), (32768, 640, 640, 0), (4096, 3072, 1024, 160),
+                                          (2500, 1000, 4096, 128), (19000, 520, 192, 64), (8192, 10240, 1280, 0)])
+def test_gemm_stream_k(M, N, K, tile_n, stream_k_mode, cluster_mode):
+    """stream-K: clusters take equal shares of the (tile, k-block) iterations; tiles cut between clusters are completed through the fp32 partial
+    workspace in a fixed order.  Same results as the data-parallel schedule to fp32 summation order, bit-identical from run to run, with every
+    epilogue kind (bias, gating, in-place residual through the TMA epilogue, fp32 output)."""
+    from seedx_b200 import ops
+    a = mk((M, K), 71).half()
+    w = mk((N, K), 72, K ** -0.5).half()
+    bias = mk((N,), 73)
+    acc = a.float() @ w.float().t() + bias
+    o32 = ops.gemm(a, w, bias=bias, out_dtype=torch.float32, tile_n=tile_n)
+    assert rel(o32, acc) < 1e-5
+    assert torch.equal(o32, ops.gemm(a, w, bias=bias, out_dtype=torch.float32, tile_n=tile_n))
+    r = mk((M, N), 74).half()
+    want = acc + r.float()
+    ops.gemm(a, w, out=r, bias=bias, residual=r, tile_n=tile_n)
+    assert rel(r, want) < 2e-3
+    if N % 2 == 0:
+        o = ops.gemm(a, w, bias=bias, act=ops.ACT_GELU, gated=True, tile_n=tile_n)
+        assert rel(o, acc[:, 0::2] * F.gelu(acc[:, 1::2])) < 2e-3
+
+
+@pytest.mark.parametrize("n,h,w,c,cout", [(8, 32, 32, 1280, 1280), (2, 64, 64, 640, 640), (3, 32, 32, 320, 640)])
+def test_conv_stream_k(n, h, w, c, cout, stream_k_mode):
+    from seedx_b200 import ops
+    x = mk((n, c, h, w), 81).half()
+    wt = mk((cout, c, 3, 3), 82, (c * 9) ** -0.5).half()
+    bias, temb = mk((cout,), 83), mk((n, cout), 84)
+    ref = (F.conv2d(x.float(), wt.float(), bias=bias, padding=1) + temb[:, :, None, None]).permute(0, 2, 3, 1).contiguous()
+    wp = wt.permute(0, 2, 3, 1).reshape(cout, 9 * c).contiguous()
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    res = mk((n, h, w, cout), 85).half()
+    part = torch.empty((n * h * w // 32, cout, 2), device="cuda")
+    o = ops.conv2d_nhwc(xn, wp, taps=3, bias=bias, bias_g=temb, residual=res, col_part=part)
+    assert rel(o, ref + res.float()) < 2e-3
+    c32 = o.float().view(-1, 32, cout)
+    assert rel(part[..., 0], c32.sum(1)) < 1e-5
