@@ -54,6 +54,8 @@ def lib():
         _lib.seedx_abi_version.restype = C.c_int
         if "SEEDX_GEMM_CLUSTER" in os.environ:      # experiment switch: 0 = single-CTA tiles, 1 = auto, 2 = CTA pairs whenever legal
             _lib.seedx_gemm_set_cluster(int(os.environ["SEEDX_GEMM_CLUSTER"]))
+        if "SEEDX_GEMM_STREAM_K" in os.environ:      # 0 = data-parallel tiles only, 1 = auto (default), 2 = stream-K wherever legal
+            _lib.seedx_gemm_set_stream_k(int(os.environ["SEEDX_GEMM_STREAM_K"]))
         if "SEEDX_GEMM_TMA_EPI" in os.environ:
             _lib.seedx_gemm_set_tma_epilogue(int(os.environ["SEEDX_GEMM_TMA_EPI"]))
     return _lib

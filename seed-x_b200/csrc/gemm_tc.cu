@@ -803,7 +803,9 @@ static int choose_tile_n(int m_tiles, int N, int k_blocks, bool heavy_epilogue, 
     if (only32 && bn % 32 != 0) continue;  // the TMA epilogue stores whole 32-column chunks
     const int n_blocks = (N + bn - 1) / bn;
     const long long tiles = (long long)m_tiles * n_blocks;
-    const long long waves = (tiles + sms - 1) / sms;
+    // stream-K (workspace present): a launch of more than one wave costs its fractional number of waves plus the partial-tile round trip
+    const bool sk = g_gemm_stream_k != 0 && g_sk_scratch != nullptr && tiles > sms && (long long)tiles * k_blocks >= 4LL * sms;
+    const double waves = sk ? (double)tiles / sms + 0.12 : (double)((tiles + sms - 1) / sms);
     const double mma_k16 = fmax(bn / 2.0, (4096.0 + 32.0 * bn) / 91.0);
     const double mma = k_blocks * 4.0 * mma_k16;
     const double epi = bn * (heavy_epilogue ? 14.0 : 8.0) + 300.0;

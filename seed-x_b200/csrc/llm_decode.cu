@@ -206,35 +206,56 @@ decode_attn_kernel(const float* __restrict__ qkv_all, const int* __restrict__ st
   float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int t0 = 0; t0 <= pos; t0 += DA_GROUPS) {  // warp-uniform trip count: the half-warp shuffles need all 32 lanes
-    const int t = t0 + grp;
-    const bool valid = t <= pos;
-    uint4 kq = make_uint4(0, 0, 0, 0), vq = make_uint4(0, 0, 0, 0);
-    if (valid) {   // one half-warp = one token: 16 lanes x 16 bytes = the head's 256 contiguous bytes of the row (two full 128 B lines)
-      const long long r = kv_row(pt, page_shift, t) * D + h * HD + gl_lane * 8;
-      kq = *(const uint4*)(kcache + r);
-      vq = *(const uint4*)(vcache + r);
-    }
-    const __half2* kh = (const __half2*)&kq;
-    float s = 0.f;
+  // Each half-warp owns tokens grp, grp + 16, ...; DA_UNROLL of them are requested before the first is consumed, so a CTA keeps
+  // 16 x DA_UNROLL x 512 B of K/V reads in flight instead of one dependent 32-byte pair per half-warp (the walk over ~300 cached tokens was
+  // load-latency bound: 11 % of the token step for < 4 % of its bytes).
+  constexpr int DA_UNROLL = 4;
+  for (int t0 = 0; t0 <= pos; t0 += DA_GROUPS * DA_UNROLL) {  // warp-uniform trip count: the half-warp shuffles need all 32 lanes
+    uint4 kq[DA_UNROLL], vq[DA_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(kh[j]);
-      s += f.x * q[2 * j] + f.y * q[2 * j + 1];
+    for (int u = 0; u < DA_UNROLL; ++u) {
+      const int t = t0 + u * DA_GROUPS + grp;
+      kq[u] = make_uint4(0, 0, 0, 0), vq[u] = make_uint4(0, 0, 0, 0);
+      if (t <= pos) {   // one half-warp = one token: 16 lanes x 16 bytes = the head's 256 contiguous bytes of the row (two full 128 B lines)
+        const long long r = kv_row(pt, page_shift, t) * D + h * HD + gl_lane * 8;
+        kq[u] = *(const uint4*)(kcache + r);
+        vq[u] = *(const uint4*)(vcache + r);
+      }
     }
+    float sc[DA_UNROLL];
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);  // within the 16-lane group
-    if (valid) {
-      const float nm = fmaxf(m, s);
-      const float corr = __expf(m - nm);
-      const float p = __expf(s - nm);
-      l = l * corr + p;
-      const __half2* vh = (const __half2*)&vq;
+    for (int u = 0; u < DA_UNROLL; ++u) {
+      const __half2* kh = (const __half2*)&kq[u];
+      float s = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(vh[j]);
-        acc[2 * j] = acc[2 * j] * corr + p * f.x;
-        acc[2 * j + 1] = acc[2 * j + 1] * corr + p * f.y;
+        const float2 f = __half22float2(kh[j]);
+        s += f.x * q[2 * j] + f.y * q[2 * j + 1];
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);  // within the 16-lane group
+      sc[u] = (t0 + u * DA_GROUPS + grp <= pos) ? s : -INFINITY;
+    }
+    // one rescale for the DA_UNROLL tokens (same arithmetic as token-by-token up to the order of the exponentials' reference maximum)
+    float nm = m;
+#pragma unroll
+    for (int u = 0; u < DA_UNROLL; ++u) nm = fmaxf(nm, sc[u]);
+    if (nm > -INFINITY) {
+      const float corr = __expf(m - nm);
+      l *= corr;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= corr;
+#pragma unroll
+      for (int u = 0; u < DA_UNROLL; ++u) {
+        const float p = __expf(sc[u] - nm);      // exp(-inf) = 0 for the slots past the end
+        l += p;
+        const __half2* vh = (const __half2*)&vq[u];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(vh[j]);
+          acc[2 * j] = fmaf(p, f.x, acc[2 * j]);
+          acc[2 * j + 1] = fmaf(p, f.y, acc[2 * j + 1]);
+        }
       }
       m = nm;
     }
