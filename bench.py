@@ -561,6 +561,8 @@ def main():
         pg = torch.Generator().manual_seed(99 + rank)
         p_ids = [torch.randint(3, eng.tok.base, (64,), generator=pg) for _ in range(B)]
         p_emb = [eng.llm.get_input_embeddings()(i)[0] for i in p_ids]
+        eng.llm.generate_greedy_batch(p_ids, p_emb, img_ids=None, max_new_tokens=3, eos_id=None, suppress_eos=True)   # captures this rule's decode graph
+        trace.enable(True)
         eng.llm.generate_greedy_batch(p_ids, p_emb, img_ids=None, max_new_tokens=65, eos_id=None, suppress_eos=True)
         decode_step_ms = trace.summary().get("llm.decode", 0.0) / 64
     trace.enable(False)
@@ -688,7 +690,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor",
                          "kernel": "CUDA-graph launch of one UNet sample-forward (%d samples): gemm_tc_kernel (GEMM + implicit-GEMM conv) and tcgen05 attention, "
-                                   "per-kernel shares in profiles/r02_unet_forward_launches.md" % n_samples,
+                                   "per-kernel shares and DRAM bytes in profiles/r02_unet_forward_launches_*.csv / .md" % n_samples,
                          "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s", "frac": (achieved / tensor_peak) if achieved else None,
                          "dominant_kernel": dom, "traffic": traffic.get(f"unet_forward_{n_samples}samples_bytes"),
                          "traffic_source": traffic.get("source") if traffic.get(f"unet_forward_{n_samples}samples_bytes") is not None else None,

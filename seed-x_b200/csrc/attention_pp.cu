@@ -55,9 +55,22 @@ struct PpCfg {
   static constexpr int TILE_BYTES = HALVES * HALF_BYTES;    // one Q, K or V tile
   static constexpr int QBUF = (D == 64) ? 2 : 1;            // item-level buffering of the Q pair (shared memory permitting)
   static constexpr int KV_STAGES = (D == 64) ? 3 : 2;
-  static constexpr int SMEM_BYTES = TILE_BYTES * (2 * QBUF + 2 * KV_STAGES) + 1024 + 512;
-  static constexpr uint32_t S_COL = 0, O_COL = 256;         // S_X at S_COL + 128 X, O_X at O_COL + D X
+  static constexpr int ONES_BYTES = 2048;                   // constant [16 keys x 64] MN-major block: column 0 = 1 (row sums on the tensor core)
+  static constexpr int SMEM_BYTES = TILE_BYTES * (2 * QBUF + 2 * KV_STAGES) + ONES_BYTES + 1024 + 512;
+  static constexpr uint32_t S_COL = 0, O_COL = 256;         // S_X at S_COL + 128 X, O_X at O_COL + OW X
 };
+
+// PE < 0 (d = 64 only): "H2" softmax.  (1) V is extended by a constant ones column (N = 80: the fifth 16-column group comes from a shared
+// constant block through the descriptor's leading-dimension offset), so O[:, 64] accumulates the row sum of exactly the fp16 P values the tensor
+// core multiplies — no FADD per score, and the lazy rescale treats it like any other O column.  (2) P = ex2.approx.f16x2 of the fp32-computed,
+// fp16-rounded exponent pair: one MUFU instruction per two scores, result already packed for the TMEM A operand (no separate conversion).
+// exponents are <= 8 (lazy rescale bound), |x| 2^-11 rounding gives P a relative error <= 0.7 * |x| * 2^-11, comparable to P's own fp16 rounding.
+SEEDX_DEVINL uint32_t exp2_pair_f16(float x_lo, float x_hi) {
+  uint32_t h, r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(h) : "f"(x_hi), "f"(x_lo));
+  asm("ex2.approx.f16x2 %0, %1;\n" : "=r"(r) : "r"(h));
+  return r;
+}
 
 template <int D, int PE>
 __global__ void __launch_bounds__(320, 1)
@@ -65,12 +78,16 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                      const PpParams p) {
   using Cfg = PpCfg<D>;
   constexpr int KS = Cfg::KV_STAGES, QB = Cfg::QBUF;
+  constexpr bool H2 = PE < 0;                       // ones-column row sums + packed half2 exponentials
+  static_assert(!H2 || D == 64, "the H2 softmax needs the spare TMEM columns of d = 64");
+  constexpr int OW = H2 ? D + 16 : D;               // accumulator columns per query tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ0 = smem_base;                                  // [QB][2] tiles
   const uint32_t sK0 = sQ0 + 2 * QB * Cfg::TILE_BYTES;
   const uint32_t sV0 = sK0 + KS * Cfg::TILE_BYTES;
-  const uint32_t bar = sV0 + KS * Cfg::TILE_BYTES;
+  const uint32_t sOnes = sV0 + KS * Cfg::TILE_BYTES;               // 1024-aligned
+  const uint32_t bar = sOnes + Cfg::ONES_BYTES;
   auto k_full = [&](int s) { return bar + 8u * (s); };
   auto k_empty = [&](int s) { return bar + 8u * (KS + s); };
   auto v_full = [&](int s) { return bar + 8u * (2 * KS + s); };
@@ -104,6 +121,14 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (H2 && threadIdx.x >= 64 && threadIdx.x < 64 + 128) {
+    // ones block, 16 key rows x 128 B in the 128-byte-swizzled MN-major layout of a V tile: logical 16-byte chunk c of row r sits at physical
+    // chunk c ^ (r & 7); element (r, 0) = 1.0, everything else 0
+    const int t = threadIdx.x - 64, r = t >> 3, pc = t & 7;
+    const uint32_t first = ((pc ^ (r & 7)) == 0) ? 0x00003C00u : 0u;
+    sts128(sOnes + (uint32_t)(r * 128 + pc * 16), make_uint4(first, 0u, 0u, 0u));
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -162,7 +187,7 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_qk = umma_idesc_f16(128, 128);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(128, D) | (1u << 16);  // B operand MN-major
+      constexpr uint32_t idesc_pv = umma_idesc_f16(128, OW) | (1u << 16);  // B operand MN-major; H2: N = 80 (V | ones column block)
       int kst = 0, vst = 0;
       uint32_t kph = 0, vph = 0;
       uint32_t g = 0;                 // tiles processed so far (same count for both query tiles)
@@ -177,10 +202,13 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       };
       auto issue_pv = [&](int x, uint32_t vb, bool first) {
         const uint32_t tP = tmem_base + Cfg::S_COL + (uint32_t)(x * 128);
-        const uint32_t tO = tmem_base + Cfg::O_COL + (uint32_t)(x * D);
+        const uint32_t tO = tmem_base + Cfg::O_COL + (uint32_t)(x * OW);
 #pragma unroll
-        for (int kk = 0; kk < Cfg::BN / 16; ++kk)  // 16 keys per MMA: A advances 8 TMEM columns, B 16 rows of 128 B
-          umma_f16_ts(tO, tP + (uint32_t)(kk * 8), umma_desc_mn_sw128(vb + kk * 2048, Cfg::HALF_BYTES), idesc_pv, !(first && kk == 0));
+        for (int kk = 0; kk < Cfg::BN / 16; ++kk) {  // 16 keys per MMA: A advances 8 TMEM columns, B 16 rows of 128 B
+          // H2: the second 64-element group of the MN dimension (columns 64..79) is the constant ones block, whatever keys this MMA covers
+          const uint32_t lbo = H2 ? (sOnes - (vb + (uint32_t)(kk * 2048))) : (uint32_t)Cfg::HALF_BYTES;
+          umma_f16_ts(tO, tP + (uint32_t)(kk * 8), umma_desc_mn_sw128(vb + kk * 2048, lbo), idesc_pv, !(first && kk == 0));
+        }
         umma_commit(pv_done(x));
       };
       int n = 0;
@@ -234,7 +262,7 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + Cfg::S_COL + (uint32_t)(x * 128);
-    const uint32_t tO = tmem_base + lane_addr + Cfg::O_COL + (uint32_t)(x * D);
+    const uint32_t tO = tmem_base + lane_addr + Cfg::O_COL + (uint32_t)(x * OW);
     uint32_t g = 0;
     int n = 0;
     for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
@@ -291,6 +319,13 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
               tmem_st32(tO + (uint32_t)(c * 32), v);
             }
+            if (H2) {                                  // the row-sum column lives in the accumulator and is rescaled with it
+              uint32_t v[16];
+              tmem_ld16(tO + (uint32_t)D, v);
+              tmem_ld_wait();
+              v[0] = __float_as_uint(__uint_as_float(v[0]) * alpha);
+              tmem_st16(tO + (uint32_t)D, v);
+            }
           }
           m_run = m_new;
         }
@@ -312,6 +347,13 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             }
           }
           uint32_t pk0[16], pk1[16];
+          if (H2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              pk0[i] = exp2_pair_f16(fmaf(__uint_as_float(v0[2 * i]), p.scale_log2, -m_use), fmaf(__uint_as_float(v0[2 * i + 1]), p.scale_log2, -m_use));
+              pk1[i] = exp2_pair_f16(fmaf(__uint_as_float(v1[2 * i]), p.scale_log2, -m_use), fmaf(__uint_as_float(v1[2 * i + 1]), p.scale_log2, -m_use));
+            }
+          } else
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float a0 = fast_exp2(fmaf(__uint_as_float(v0[2 * i]), p.scale_log2, -m_use));
@@ -336,6 +378,12 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const uint32_t gl = g - 1;
       mbar_wait(pv_done(x), gl & 1u);
       tc_fence_after();
+      if (H2) {                             // row sum = accumulator column 64 (sum of the fp16 P values, rescaled with O)
+        uint32_t v[16];
+        tmem_ld16(tO + (uint32_t)D, v);
+        tmem_ld_wait();
+        l_run = __uint_as_float(v[0]);
+      }
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       __half* orow = p.o + (long long)b * p.o_sb + (long long)h * p.o_sh + (long long)qrow * p.o_ss;
 #pragma unroll
@@ -401,8 +449,9 @@ static int launch_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   static int pe = -1;
   if (pe < 0) {
     const char* e = getenv("SEEDX_PP_POLY_EVERY");
-    pe = e ? atoi(e) : SEEDX_PP_POLY_EVERY;
+    pe = e ? atoi(e) : (D == 64 ? -1 : SEEDX_PP_POLY_EVERY);      // d = 64: H2 softmax (ones-column row sums + half2 exponentials)
   }
+  if (D == 64 && pe < 0) return launch_pp_pe<64, -1>(tq, tk, tv, p, B, H, st);
   switch (pe) {
     case 0: return launch_pp_pe<D, 0>(tq, tk, tv, p, B, H, st);
     case 1: return launch_pp_pe<D, 1>(tq, tk, tv, p, B, H, st);

@@ -134,7 +134,7 @@ def test_conv_nhwc_unet_hot_shapes(n, h, w, c, cout):
     o = ops.conv2d_nhwc(xn, wp, taps=3, bias=bias, bias_g=temb, residual=res, out_dtype=torch.float16)
     assert rel(o, ref + res.float()) < 2e-3
     o32 = ops.conv2d_nhwc(xn, wp, taps=3, bias=bias, bias_g=temb, out_dtype=torch.float32)
-    assert rel(o32, ref) < 1e-5
+    assert rel(o32, ref) < 3e-5          # fp32 accumulation over up to 23 040 products: the summation order alone moves this to ~1e-5
 
 
 @pytest.mark.parametrize("M,N,K,kind", [(8192, 10240, 1280, "geglu"), (32768, 5120, 640, "geglu"), (8192, 1280, 5120, "residual"),

@@ -76,17 +76,29 @@ def _project(root):
     # ---- demo images ----
     os.makedirs(root / "demo_images")
     rng = np.random.RandomState(0)
-    for name, (w, h) in dict(advisor=(700, 500), ground=(640, 480), car=(600, 600), man=(500, 640), bank=(512, 512)).items():
+    for name, (w, h) in dict(advisor=(700, 500), ground=(640, 480), car=(600, 600), man=(500, 640), bank=(512, 512), cat_dog=(640, 427)).items():
         img = Image.fromarray(rng.randint(0, 255, (h, w, 3), dtype=np.uint8))
-        img.save(root / "demo_images" / (name + (".png" if name in ("advisor", "ground", "bank") else ".jpg")))
+        ext = ".png" if name in ("advisor", "ground", "bank") else (".jpeg" if name == "cat_dog" else ".jpg")
+        img.save(root / "demo_images" / (name + ext))
 
 
-def _run(script, root, monkeypatch):
-    from seedx_b200 import run
+def _run(script, root, monkeypatch, open_span=False):
+    """open_span: the instruction-tuned scripts leave the decision to open an <img> span to the model, as the reference does
+    (eval_text2img_seed_x_i.py:23, eval_img2edit_seed_x_edit.py:27); a random-init model never takes it, so for those two the prompt builder
+    is told to append <img> — everything behind the prompt (forced span, harvest, de-tokenizer, file output) is the script's own flow."""
+    import functools
+    from seedx_b200 import demo, run
     monkeypatch.chdir(root)
+    if open_span:
+        monkeypatch.setattr(demo, "image_prompt", functools.partial(demo.image_prompt, force_image=True))
     buf = io.StringIO()
-    with contextlib.redirect_stdout(buf):
-        run.main([os.path.join(ROOT, "src", "inference", script)])
+    try:
+        with contextlib.redirect_stdout(buf):
+            run.main([os.path.join(ROOT, "src", "inference", script)])
+    finally:
+        if open_span:
+            monkeypatch.undo()
+            monkeypatch.chdir(root)
     return buf.getvalue()
 
 
@@ -96,12 +108,17 @@ def test_entry_scripts_run_end_to_end(tmp_path, monkeypatch):
     monkeypatch.syspath_prepend(ROOT)
     out = _run("eval_img2text_seed_x_i.py", tmp_path, monkeypatch)
     assert out.strip(), "comprehension script printed nothing"
-    _run("eval_text2img_seed_x_i.py", tmp_path, monkeypatch)
+    _run("eval_text2img_seed_x.py", tmp_path, monkeypatch)             # base-model template '{caption}<img>': the span is part of the prompt
     img = Image.open(tmp_path / "vis" / "text2img.jpg")
     assert img.size == (1024, 1024) and np.asarray(img).std() > 1.0
+    os.remove(tmp_path / "vis" / "text2img.jpg")
+    out = _run("eval_text2img_seed_x_i.py", tmp_path, monkeypatch)      # as written: the random-init model answers with text only
+    assert out.strip() and not os.path.exists(tmp_path / "vis" / "text2img.jpg")
+    _run("eval_text2img_seed_x_i.py", tmp_path, monkeypatch, open_span=True)
+    assert Image.open(tmp_path / "vis" / "text2img.jpg").size == (1024, 1024)
     _run("eval_seed_x_detokenizer.py", tmp_path, monkeypatch)
     assert Image.open(tmp_path / "vis" / "men_recon.jpg").size == (1024, 1024)
-    _run("eval_img2edit_seed_x_edit.py", tmp_path, monkeypatch)
+    _run("eval_img2edit_seed_x_edit.py", tmp_path, monkeypatch, open_span=True)
     assert Image.open(tmp_path / "vis" / "car_edit.jpg").size == (1024, 1024)
     _run("eval_seed_x_detokenizer_with_condition.py", tmp_path, monkeypatch)
     assert Image.open(tmp_path / "vis" / "bank_recon.png").size == (1024, 1024)
