@@ -245,7 +245,8 @@ int seedx_scatter_rows(const void* src, int src_dtype, const int32_t* src_idx, c
                        void* stream);
 /* hidden[b][state[b][0] - state[b][3] - 1, :] = x[b]  (last_hidden_states harvest, seed_x.py:196-197) */
 int seedx_store_hidden(const float* x, const int32_t* state, int batch, int64_t max_rows, int64_t dim, float* hidden, void* stream);
-/* AutoImageTokenGenerationProcessor (generation.py:19-31) + argmax + append to seq/state per sequence, no host sync */
+/* AutoImageTokenGenerationProcessor (generation.py:19-31) + argmax + append to seq/state per sequence, no host sync.  A sequence whose state[b][1]
+ * is non-zero (EOS produced, or retired by the host in continuous batching) is parked: nothing is appended and its length stops growing. */
 int seedx_logits_argmax(float* logits, int64_t vocab, const int32_t* img_ids, int n_img_ids, int32_t* seq, int32_t* state, int batch, int eos_id,
                         int suppress_eos, int64_t max_len, void* stream);
 

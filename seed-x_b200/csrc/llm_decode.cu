@@ -401,7 +401,9 @@ logits_argmax_kernel(float* __restrict__ logits_all, int V, const int* __restric
     __syncthreads();
     next = sidx[0];
   }
-  if (threadIdx.x == 0 && len < max_len) {
+  // a slot whose state[1] is non-zero is parked: it has produced its EOS (the host truncates there anyway) or the host has retired the request
+  // (continuous batching: a free slot waits for the next admission) — its sequence, KV length and harvest row stop moving
+  if (threadIdx.x == 0 && len < max_len && state[1] == 0) {
     seq[len] = next;
     state[0] = len + 1;
     state[2] += 1;

@@ -215,7 +215,7 @@ def logits_argmax(logits, img_ids, seq, state, eos_id, suppress_eos):
             if suppress_eos and eos_id is not None and 0 <= eos_id < logits.shape[1]:
                 logits[b, eos_id] = float("-inf")
             nxt = int(torch.argmax(logits[b]))
-        if n < seq.shape[1]:
+        if n < seq.shape[1] and int(state[b, 1]) == 0:              # parked slots (EOS produced / retired by the host) stop moving
             seq[b, n] = nxt
             state[b, 0] = n + 1
             state[b, 2] += 1

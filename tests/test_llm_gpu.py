@@ -418,3 +418,32 @@ def test_agent_generate_matches_the_reference_generate_golden():
     e = rel(out["img_gen_feat"], g["img_gen_feat"])
     print(f"agent vs the reference's own generate: img_gen_feat rel = {e:.3e}")
     assert e < TOL
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_continuous_batching_gpu(graph):
+    """ContinuousBatcher on the device: staggered arrivals on 4 slots — requests are admitted between replays of ONE captured decode
+    graph — give, request by request, the ids of the reference's own greedy loop (golden) and of isolated generate_greedy runs; a retired slot is
+    parked by state[.][1] and re-used; the forced image span of an admitted request rides through its prefill (jump-forward)."""
+    from seedx_b200.serving import ContinuousBatcher
+    g = torch.load(os.path.join(GOLD, "llama_tiny.pt"))
+    m, cfg = _llm()
+    sd = synth.llama_state_dict(cfg)
+    tok = synth.SynthTokenizer(vocab=cfg["vocab"])
+    img_ids = tok.encode("".join(["<img>"] + ["<img_{:05d}>".format(i) for i in range(64)] + ["</img>"]))
+    emb_of = lambda ids: sd["model.embed_tokens.weight"][torch.tensor(ids)].float()  # noqa: E731
+    base = list(g["ids"])
+    ids_b = base + [tok.encode("<img>")[0]]
+    reqs = [(base, g["embeds"], 16), (ids_b, emb_of(ids_b), 72), (base[:9], emb_of(base[:9]), 20), (base[3:15], emb_of(base[3:15]), 9), (base[:6], emb_of(base[:6]), 33),
+            (ids_b[4:], emb_of(ids_b[4:]), 70)]
+    want = [m.generate_greedy(i, e.cuda(), img_ids=img_ids, max_new_tokens=n) for i, e, n in reqs]
+    assert want[0].sequences[0][len(base):].tolist() == g["text_gen_ids"] and want[1].sequences[0][len(ids_b):].tolist() == g["img_gen_ids"]
+    cb = ContinuousBatcher(m, slots=4, img_ids=img_ids, eos_id=None, use_graph=graph)
+    got = cb.run(arrivals={0: [reqs[0], reqs[1]], 2: [reqs[2]], 3: [reqs[3], reqs[4]], 25: [reqs[5]]})
+    assert sorted(got) == list(range(len(reqs)))
+    for rid, w in enumerate(want):
+        assert torch.equal(got[rid].sequences, w.sequences), rid
+        assert rel(got[rid].last_hidden_states, w.last_hidden_states) < 1e-3, rid
+    assert cb.idle() and cb.steps < sum(w.n_generated for w in want) // 2
+    if graph:
+        assert cb.graph is not None

@@ -241,3 +241,38 @@ def test_agent_generate_matches_the_reference_generate(monkeypatch, host):
                          max_new_tokens=70, num_img_gen_tokens=64)
     assert out["text"] == g["text"] and out["has_img_output"] and out["num_gen_imgs"] == 1
     assert rel(out["img_gen_feat"], g["img_gen_feat"]) < TOL
+
+
+def test_continuous_batching_equals_isolated_runs(host, monkeypatch):
+    """seedx_b200.serving.ContinuousBatcher on the CPU double: five requests (two of them ending inside a forced image span, one hitting EOS early,
+    ragged budgets) arrive staggered on two sequence slots; every request's ids and harvested hidden rows equal those of the same request run alone
+    through generate_greedy, pages go back to the pool, and more requests than slots queue instead of failing."""
+    from seedx_b200 import serving
+    monkeypatch.setattr(serving, "ops", fake_ops)
+    g, tok, sd = host["g"], host["tok"], host["sd"]
+    emb_of = lambda ids: sd["model.embed_tokens.weight"][torch.tensor(ids)].float()  # noqa: E731
+    base = list(g["ids"])
+    reqs = [(base, g["embeds"], 12), (host["ids_b"], host["emb_b"], 70), (base[:9], g["embeds"][:9], 20), (base[:5] + [tok.encode("<img>")[0]], None, 30),
+            (base[2:14], None, 7)]
+    reqs = [(i, e if e is not None else emb_of(i), n) for i, e, n in reqs]
+    solo = host["make"](max_len=256, kv_page_size=16)
+    # an EOS that really occurs: the id request 2 generates third becomes the EOS id for everybody
+    probe = solo.generate_greedy(reqs[2][0], reqs[2][1], img_ids=host["img_ids"], max_new_tokens=20, use_graph=False)
+    eos = int(probe.sequences[0][len(reqs[2][0]) + 2])
+    want = [solo.generate_greedy(i, e, img_ids=host["img_ids"], max_new_tokens=n, eos_id=eos, use_graph=False) for i, e, n in reqs]
+    assert want[2].n_generated == 3                                            # stopped at (and including) the EOS
+    m = host["make"](max_len=256, kv_page_size=16, kv_pages=40)
+    cb = serving.ContinuousBatcher(m, slots=2, img_ids=host["img_ids"], eos_id=eos, use_graph=False)
+    free0 = m.kv_alloc.n_free() if hasattr(m.kv_alloc, "n_free") else None
+    got = cb.run(arrivals={0: [reqs[0]], 1: [reqs[1], reqs[2]], 4: [reqs[3]], 30: [reqs[4]]})
+    assert sorted(got) == [0, 1, 2, 3, 4]
+    for rid, w in enumerate(want):
+        o = got[rid]
+        assert o.n_generated == w.n_generated, rid
+        assert torch.equal(o.sequences, w.sequences), rid
+        assert o.last_hidden_states.shape == w.last_hidden_states.shape and (w.last_hidden_states.numel() == 0 or rel(o.last_hidden_states, w.last_hidden_states) < TOL), rid   # torch CPU matmuls of 1 vs 2 rows differ in summation order
+    assert cb.idle() and all(r is None for r in cb.live)
+    # lock-step would need max(steps) per wave of 2; continuous admission overlaps the long image span of request 1 with requests 2 and 3
+    assert cb.steps < sum(w.n_generated for w in want)
+    with pytest.raises(serving.SeedxError):
+        cb.submit(base, g["embeds"], 10 ** 6)
