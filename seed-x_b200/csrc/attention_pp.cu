@@ -449,7 +449,9 @@ static int launch_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
   static int pe = -1;
   if (pe < 0) {
     const char* e = getenv("SEEDX_PP_POLY_EVERY");
-    pe = e ? atoi(e) : (D == 64 ? -1 : SEEDX_PP_POLY_EVERY);      // d = 64: H2 softmax (ones-column row sums + half2 exponentials)
+    // -1 selects the H2 softmax (d = 64 only).  Measured on B200 (8 x 10 heads x 4096^2, d = 64): H2 571 TF/s vs 624 TF/s for the 1/8 polynomial
+    // split — the N = 80 PV MMAs and the cvt + ex2.f16x2 pair cost more than the FADDs and MUFU slots they free — so it stays an experiment.
+    pe = e ? atoi(e) : SEEDX_PP_POLY_EVERY;
   }
   if (D == 64 && pe < 0) return launch_pp_pe<64, -1>(tq, tk, tv, p, B, H, st);
   switch (pe) {

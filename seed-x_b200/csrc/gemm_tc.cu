@@ -385,11 +385,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool sk_partial = kb0 > 0;                          // the tile's first k-blocks belong to an earlier cluster: hand my raw sums over
       const bool sk_owner = (kb0 == 0) && (kb1 < p.k_blocks);   // later clusters hold the rest of this tile: add their partials, then finish
       const int my_cluster = tile0;
-      const size_t sk_tile_elems = (size_t)BM * BN;
+      constexpr int BNP = (BN + 31) & ~31;                      // scratch row stride: the last 32-column chunk of a tile may reach past BN
+      const size_t sk_tile_elems = (size_t)BM * BNP;
       if (sk_partial) {
         mbar_wait_relaxed(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        float* dst = p.sk_scratch + ((size_t)my_cluster * CL + crank) * sk_tile_elems + (size_t)(lane_grp * 32 + lane) * BN;
+        float* dst = p.sk_scratch + ((size_t)my_cluster * CL + crank) * sk_tile_elems + (size_t)(lane_grp * 32 + lane) * BNP;
 #pragma unroll 1
         for (int c = chunk0; c < BN; c += 64) {
           if (n0 + c >= col_end) break;
@@ -448,7 +449,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
         if (sk_owner) {            // partial sums of the later k-blocks, added in cluster order (fixed order: reproducible)
           for (int cc = my_cluster + 1; cc <= sk_last; ++cc) {
-            const float* src = p.sk_scratch + ((size_t)cc * CL + crank) * sk_tile_elems + (size_t)(lane_grp * 32 + lane) * BN + c;
+            const float* src = p.sk_scratch + ((size_t)cc * CL + crank) * sk_tile_elems + (size_t)(lane_grp * 32 + lane) * BNP + c;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               const float4 q = __ldcg((const float4*)(src + i));
@@ -592,7 +593,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < 32; ++i) s1 += x[i], s2 = fmaf(x[i], x[i], s2);
             p.row_part[(long long)(col0 >> 5) * p.M + row] = make_float2(s1, s2);
           }
-          if (p.col_part != nullptr) {
+          if (p.col_part != nullptr && row_base < p.M) {    // (M % 32 == 0: a slab is either wholly inside the matrix or wholly outside)
             // lane = column: walk the 32 staged rows (the fp16 values the consumer will read) in row order.  RB = 64 here (fp16, not gated).
             const uint32_t tb = stg_out + (uint32_t)ob * tile_bytes + (uint32_t)((lane & 7) * 2);
             float s1 = 0.f, s2 = 0.f;
@@ -748,7 +749,7 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     const long long total = (long long)groups * p.k_blocks;
     const int rem = groups % clusters;
     const bool idle_tail = rem != 0 && (double)(clusters - rem) / clusters / ((groups + clusters - 1) / clusters) > 0.04;   // > 4 % of the launch idle
-    const size_t need = (size_t)clusters * CL * BM * BN * sizeof(float);
+    const size_t need = (size_t)clusters * CL * BM * ((BN + 31) & ~31) * sizeof(float);
     if (g_gemm_stream_k != 0 && g_sk_scratch != nullptr && need <= g_sk_scratch_bytes && total >= 4LL * clusters && groups > clusters &&
         (idle_tail || g_gemm_stream_k == 2)) {
       p.stream_k = 1;
