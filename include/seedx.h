@@ -156,6 +156,9 @@ int seedx_layernorm(const void* x, int x_dtype, int64_t ldx, const float* gamma,
 /* per-row LayerNorm statistics of an fp16 matrix: stats[r] = (mean, 1/sqrt(var + eps)) over cols columns, fp32, two-pass on the cached row.
  * Feeds the folded-LayerNorm epilogue of seedx_gemm_f16 (ln_stats): the normalised activations are never written to memory. */
 int seedx_row_stats(const void* x, int x_dtype, int64_t ldx, int64_t rows, int64_t cols, float eps, float* stats, void* stream);
+/* the same statistics from the row partials a producing GEMM emitted through seedx_gemm_args.row_part (fp32 [nparts][rows][2], cols = 32 * nparts):
+ * nparts * 8 bytes are read per row instead of the row */
+int seedx_row_stats_from_partials(const float* parts, int nparts, int64_t rows, int64_t cols, float eps, float* stats, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GroupNorm (+ optional SiLU) on NHWC fp16 images; the input may be the channel-concatenation [x1 | x2] (UNet skip

@@ -11,6 +11,7 @@
 //
 // Reference call sites replaced: see include/seedx.h (seedx_gemm_f16).
 #include <math.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "../../include/seedx.h"
@@ -63,6 +64,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int EPI_OUT_BYTES = 4096;                      // per epilogue warp: output tiles (2 x <=2 KB, or 1 x 4 KB)
 constexpr int EPI_RES_BYTES = 8192;                      // per epilogue warp: residual tiles, ideally every chunk of a 256-wide tile in flight
 constexpr int MAX_STAGES = 8;
+constexpr int VEC_BYTES = 2048;                          // per-tile column vectors of the epilogue (bias_n, LayerNorm column sums), 2 x 256 fp32
 
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
@@ -73,10 +75,10 @@ struct TileCfg {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   // pipeline depth for a given amount of epilogue staging (runtime: depends on whether a residual is streamed through shared memory)
   static int stages_for(int epi_bytes) {
-    const int fit = (SMEM_LIMIT - 1024 - 512 - epi_bytes) / STAGE_BYTES;
+    const int fit = (SMEM_LIMIT - 1024 - 512 - VEC_BYTES - epi_bytes) / STAGE_BYTES;
     return fit > MAX_STAGES ? MAX_STAGES : fit;
   }
-  static int smem_for(int stages, int epi_bytes) { return stages * STAGE_BYTES + epi_bytes + 1024 /*align slack*/ + 512 /*barriers*/; }
+  static int smem_for(int stages, int epi_bytes) { return stages * STAGE_BYTES + epi_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + VEC_BYTES; }
   // two accumulator stages; the last 32-column epilogue chunk of a stage may over-read up to 16 columns -> keep them allocated
   static constexpr int TMEM_COLS = pow2_cols(2 * BN + 16);
 };
@@ -147,6 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
   auto res_bar = [&](int w, int i) { return bar_base + 8u * (2 * STAGES + 6 + 4 * w + i); };  // residual tile landed (per epilogue warp, <= 4 buffers)
+  const uint32_t vec_base = bar_base + 512u;       // [bias_n tile | colsum tile], 256 fp32 each: staged once per tile, read as broadcast 128-bit loads
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -390,7 +393,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (sk_partial) {
         mbar_wait_relaxed(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        float* dst = p.sk_scratch + ((size_t)my_cluster * CL + crank) * sk_tile_elems + (size_t)(lane_grp * 32 + lane) * BNP;
+        // layout of a slot: [BNP / 4 column quads][128 rows][4 floats]: the 32 lanes (= rows) of a store cover 512 contiguous bytes
+        float* dst = p.sk_scratch + ((size_t)my_cluster * CL + crank) * sk_tile_elems + (size_t)(lane_grp * 32 + lane) * 4;
 #pragma unroll 1
         for (int c = chunk0; c < BN; c += 64) {
           if (n0 + c >= col_end) break;
@@ -399,7 +403,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld32(taddr + (uint32_t)c, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) *(uint4*)(dst + c + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          for (int i = 0; i < 32; i += 4) *(uint4*)(dst + (size_t)((c + i) >> 2) * (BM * 4)) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
         __threadfence();                                        // my stores are visible device-wide before the flag
         tc_fence_before();
@@ -422,6 +426,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (tma_res && lane == 0)
         for (int k = 0; k < nres && k < n_chunks; ++k) issue_res(k);  // in flight while the main loop of this tile is still running
+      // column vectors of this tile -> shared memory (while the main loop is still running): the chunk loop then reads them with broadcast
+      // 128-bit shared loads instead of 16 dependent L1/L2 round trips per chunk, which is what the short-K epilogues were waiting on
+      const bool use_vec = p.bias_n != nullptr || p.ln_stats != nullptr;
+      if (use_vec) {
+        asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");      // every epilogue warp has finished reading the previous tile's vectors
+        for (int i = ew * 32 + lane; i < BN; i += EPI_WARPS * 32) {
+          const bool in = n0 + i < col_end;
+          const float bv = (p.bias_n != nullptr && in) ? __ldg(p.bias_n + n0 + i) : 0.f;
+          const float cv = (p.ln_stats != nullptr && in) ? __ldg(p.ln_colsum + n0 + i) : 0.f;
+          asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(vec_base + 4u * (uint32_t)i), "f"(bv) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(vec_base + 1024u + 4u * (uint32_t)i), "f"(cv) : "memory");
+        }
+        asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");
+      }
       int kchunk = 0;
       mbar_wait_relaxed(tfull_bar(acc), acc_phase);   // accumulator of this tile complete
       if (warp == 2 && lane == 0) {
@@ -449,46 +467,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tmem_ld_wait();
         if (sk_owner) {            // partial sums of the later k-blocks, added in cluster order (fixed order: reproducible)
           for (int cc = my_cluster + 1; cc <= sk_last; ++cc) {
-            const float* src = p.sk_scratch + ((size_t)cc * CL + crank) * sk_tile_elems + (size_t)(lane_grp * 32 + lane) * BNP + c;
+            const float* src = p.sk_scratch + ((size_t)cc * CL + crank) * sk_tile_elems + (size_t)(lane_grp * 32 + lane) * 4;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 q = __ldcg((const float4*)(src + i));
+              const float4 q = __ldcg((const float4*)(src + (size_t)((c + i) >> 2) * (BM * 4)));
               v[i] = __float_as_uint(__uint_as_float(v[i]) + q.x), v[i + 1] = __float_as_uint(__uint_as_float(v[i + 1]) + q.y);
               v[i + 2] = __float_as_uint(__uint_as_float(v[i + 2]) + q.z), v[i + 3] = __float_as_uint(__uint_as_float(v[i + 3]) + q.w);
             }
           }
         }
         float x[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]) * p.alpha + bm;
         const int col0 = n0 + c;
-        const bool chunk_full = col0 + 32 <= col_end;
         if (p.ln_stats != nullptr) {
-          if (chunk_full) {
+          // folded LayerNorm (alpha = 1, no bias_m: host check): x = rstd * acc + (bias - rstd * mean * colsum) -> two FFMAs per value
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 q = __ldg((const float4*)(p.ln_colsum + col0 + i));
-              x[i] = fmaf(x[i], ln_rstd, ln_nmr * q.x), x[i + 1] = fmaf(x[i + 1], ln_rstd, ln_nmr * q.y);
-              x[i + 2] = fmaf(x[i + 2], ln_rstd, ln_nmr * q.z), x[i + 3] = fmaf(x[i + 3], ln_rstd, ln_nmr * q.w);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < col_end) x[i] = fmaf(x[i], ln_rstd, ln_nmr * __ldg(p.ln_colsum + col0 + i));
+          for (int i = 0; i < 32; i += 4) {
+            const uint4 qb = lds128(vec_base + 4u * (uint32_t)(c + i)), qc = lds128(vec_base + 1024u + 4u * (uint32_t)(c + i));
+            x[i] = fmaf(__uint_as_float(v[i]), ln_rstd, fmaf(ln_nmr, __uint_as_float(qc.x), __uint_as_float(qb.x)));
+            x[i + 1] = fmaf(__uint_as_float(v[i + 1]), ln_rstd, fmaf(ln_nmr, __uint_as_float(qc.y), __uint_as_float(qb.y)));
+            x[i + 2] = fmaf(__uint_as_float(v[i + 2]), ln_rstd, fmaf(ln_nmr, __uint_as_float(qc.z), __uint_as_float(qb.z)));
+            x[i + 3] = fmaf(__uint_as_float(v[i + 3]), ln_rstd, fmaf(ln_nmr, __uint_as_float(qc.w), __uint_as_float(qb.w)));
           }
-        }
-        if (p.bias_n != nullptr) {
-          if (chunk_full && p.bias_vec) {
+        } else if (p.bias_n != nullptr) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 q = __ldg((const float4*)(p.bias_n + col0 + i));
-              x[i] += q.x, x[i + 1] += q.y, x[i + 2] += q.z, x[i + 3] += q.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (col0 + i < col_end) x[i] += __ldg(p.bias_n + col0 + i);
+          for (int i = 0; i < 32; i += 4) {
+            const uint4 qb = lds128(vec_base + 4u * (uint32_t)(c + i));
+            x[i] = fmaf(__uint_as_float(v[i]), p.alpha, __uint_as_float(qb.x) + bm), x[i + 1] = fmaf(__uint_as_float(v[i + 1]), p.alpha, __uint_as_float(qb.y) + bm);
+            x[i + 2] = fmaf(__uint_as_float(v[i + 2]), p.alpha, __uint_as_float(qb.z) + bm), x[i + 3] = fmaf(__uint_as_float(v[i + 3]), p.alpha, __uint_as_float(qb.w) + bm);
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = fmaf(__uint_as_float(v[i]), p.alpha, bm);
         }
         if (bg != nullptr) {
 #pragma unroll
@@ -715,6 +724,7 @@ void count_launch();
 
 // stream-K fix-up workspace (seedx_gemm_set_workspace): flags first (zeroed by the caller), partial tiles behind them
 static int g_gemm_stream_k = 1;       // 0 = off, 1 = auto, 2 = whenever legal (tests)
+static int g_sk_min_kblocks = 96;     // auto mode: shortest K (in 64-element blocks) that is split
 static float* g_sk_scratch = nullptr;
 static size_t g_sk_scratch_bytes = 0;
 static unsigned* g_sk_flags = nullptr;
@@ -750,8 +760,11 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     const int rem = groups % clusters;
     const bool idle_tail = rem != 0 && (double)(clusters - rem) / clusters / ((groups + clusters - 1) / clusters) > 0.04;   // > 4 % of the launch idle
     const size_t need = (size_t)clusters * CL * BM * ((BN + 31) & ~31) * sizeof(float);
+    // measured on B200 (profiles/r02_unet_forward_launches_*): the fix-up round trip pays off from ~100 k-blocks per tile (the 3x3 convs with
+    // C >= 1280, K = 11 520: -10 ... -17 %), not for the K = 1280 ... 5120 transformer GEMMs, whose whole launch is 30 - 100 us
+    const bool long_k = p.k_blocks >= g_sk_min_kblocks;
     if (g_gemm_stream_k != 0 && g_sk_scratch != nullptr && need <= g_sk_scratch_bytes && total >= 4LL * clusters && groups > clusters &&
-        (idle_tail || g_gemm_stream_k == 2)) {
+        ((idle_tail && long_k) || g_gemm_stream_k == 2)) {
       p.stream_k = 1;
       p.sk_scratch = g_sk_scratch, p.sk_flags = g_sk_flags;
     }
@@ -805,7 +818,8 @@ static int choose_tile_n(int m_tiles, int N, int k_blocks, bool heavy_epilogue, 
     const int n_blocks = (N + bn - 1) / bn;
     const long long tiles = (long long)m_tiles * n_blocks;
     // stream-K (workspace present): a launch of more than one wave costs its fractional number of waves plus the partial-tile round trip
-    const bool sk = g_gemm_stream_k != 0 && g_sk_scratch != nullptr && tiles > sms && (long long)tiles * k_blocks >= 4LL * sms;
+    const bool sk = g_gemm_stream_k != 0 && g_sk_scratch != nullptr && tiles > sms && (long long)tiles * k_blocks >= 4LL * sms &&
+                    (k_blocks >= g_sk_min_kblocks || g_gemm_stream_k == 2);
     const double waves = sk ? (double)tiles / sms + 0.12 : (double)((tiles + sms - 1) / sms);
     const double mma_k16 = fmax(bn / 2.0, (4096.0 + 32.0 * bn) / 91.0);
     const double mma = k_blocks * 4.0 * mma_k16;
@@ -823,7 +837,10 @@ using namespace seedx;
 extern "C" void seedx_gemm_set_debug(void* device_buffer) { seedx::g_gemm_dbg = (unsigned long long*)device_buffer; }
 extern "C" void seedx_gemm_set_cluster(int mode) { seedx::g_gemm_cluster = mode; }
 extern "C" void seedx_gemm_set_tma_epilogue(int on) { seedx::g_gemm_tma_epi = on; }
-extern "C" void seedx_gemm_set_stream_k(int mode) { seedx::g_gemm_stream_k = mode; }
+extern "C" void seedx_gemm_set_stream_k(int mode) {
+  seedx::g_gemm_stream_k = mode;
+  if (const char* e = getenv("SEEDX_SK_MIN_KBLOCKS")) seedx::g_sk_min_kblocks = atoi(e);
+}
 extern "C" int seedx_gemm_set_workspace(void* ptr, int64_t bytes) {
   if (ptr == nullptr) {
     seedx::g_sk_scratch = nullptr, seedx::g_sk_flags = nullptr, seedx::g_sk_scratch_bytes = 0;
@@ -940,6 +957,7 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
     SEEDX_REQUIRE(a->ln_stats && a->ln_colsum, "seedx_gemm_f16: ln_stats and ln_colsum go together");
     SEEDX_REQUIRE(a->batch == 1 && !conv && ((uintptr_t)a->ln_colsum % 16 == 0) && ((uintptr_t)a->ln_stats % 8 == 0) && a->N % 4 == 0,
                   "seedx_gemm_f16: folded LayerNorm needs a plain un-batched GEMM, N %% 4 == 0 and aligned statistics");
+    SEEDX_REQUIRE(a->alpha == 1.0f && a->bias_m == nullptr, "seedx_gemm_f16: folded LayerNorm takes alpha = 1 and no per-row bias");
   }
   p.ln_stats = (const float2*)a->ln_stats, p.ln_colsum = a->ln_colsum;
   p.ln_parts = a->ln_parts, p.ln_eps = a->ln_eps, p.ln_inv_cols = a->ln_parts > 0 ? 1.0f / (32.0f * (float)a->ln_parts) : 0.f;

@@ -253,6 +253,23 @@ row_stats_kernel(const __half* __restrict__ x, long long ldx, long long rows, in
   }
 }
 
+// (mean, rstd) per row from the row partials a producing GEMM epilogue wrote (seedx_gemm_args.row_part: [parts][rows] (sum, sum of squares) over
+// 32-column chunks): one thread per row, chunk order, coalesced 8-byte loads — parts * 8 bytes per row instead of the row itself.
+__global__ void __launch_bounds__(256)
+row_finalize_kernel(const float2* __restrict__ parts, int nparts, long long rows, float inv_cols, float eps, float2* __restrict__ stats) {
+  pdl_wait();
+  pdl_trigger();
+  const long long row = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (row >= rows) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int k = 0; k < nparts; ++k) {
+    const float2 q = __ldcg(parts + (long long)k * rows + row);
+    s1 += q.x, s2 += q.y;
+  }
+  const float mean = s1 * inv_cols;
+  stats[row] = make_float2(mean, rsqrtf(fmaxf(s2 * inv_cols - mean * mean, 0.f) + eps));
+}
+
 // scalar fallback (cols not a multiple of 4 or unaligned rows): one CTA per row
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(LN_THREADS)
@@ -569,6 +586,14 @@ extern "C" int seedx_row_stats(const void* x, int x_dtype, int64_t ldx, int64_t 
   else e = launch_k(row_stats_kernel<8>, grid, LN_THREADS, 0, st, (const __half*)x, (long long)ldx, (long long)rows, (int)cols, eps, (float2*)stats);
   count_launch();
   return check_cuda(e != cudaSuccess ? e : cudaGetLastError(), "row_stats_kernel launch");
+}
+
+extern "C" int seedx_row_stats_from_partials(const float* parts, int nparts, int64_t rows, int64_t cols, float eps, float* stats, void* stream) {
+  SEEDX_REQUIRE(parts && stats && nparts > 0 && rows > 0 && cols == 32LL * nparts, "seedx_row_stats_from_partials: cols must be 32 * nparts");
+  launch_k(row_finalize_kernel, (unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream, (const float2*)parts, nparts, (long long)rows,
+           1.0f / (float)cols, eps, (float2*)stats);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "row_finalize_kernel launch");
 }
 
 // CTAs per image of the statistics pass: ~4 waves of CTAs over the batch, >= 32 pixels each

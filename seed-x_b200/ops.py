@@ -110,6 +110,18 @@ def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, 
     return out
 
 
+def row_finalize(row_part, eps, out=None):
+    """(mean, rstd) per row from the row partials [cols/32, rows, 2] a producing GEMM emitted (gemm(..., row_part=...)) -> fp32 [rows, 2]"""
+    _require_cuda(row_part, out)
+    assert row_part.dtype == torch.float32 and row_part.is_contiguous() and row_part.dim() == 3 and row_part.shape[2] == 2
+    nparts, rows = row_part.shape[0], row_part.shape[1]
+    if out is None:
+        out = torch.empty((rows, 2), device=row_part.device, dtype=torch.float32)
+    check(lib().seedx_row_stats_from_partials(_ptr(row_part), C.c_int(nparts), C.c_int64(rows), C.c_int64(32 * nparts), C.c_float(eps), _ptr(out), _stream()),
+          "seedx_row_stats_from_partials")
+    return out
+
+
 def _set_parts(g, row_part, col_part, M, N):
     if row_part is not None:
         assert row_part.dtype == torch.float32 and row_part.is_contiguous() and row_part.numel() == 2 * M * (N // 32) and N % 32 == 0

@@ -303,15 +303,17 @@ class _Transformer:
         hn = ops.groupnorm_nhwc(x, self.norm[0], self.norm[1], 1e-6, silu=False, groups=groups, stats_ws=ws, part1=_part(x))
         if self.stream_dtype != torch.float16:
             raise SeedxError("the folded LayerNorm path reads the residual stream as the fp16 GEMM operand: _Transformer.stream_dtype must be float16")
-        # LayerNorm statistics of the residual stream: row partials written by the epilogue of every GEMM that stores the stream (32-column chunks,
-        # added up in the consumer's epilogue); shapes that cannot use them fall back to the row-statistics kernel
+        # LayerNorm statistics of the residual stream: row partials written by the epilogue of every GEMM that stores the stream (one (sum, sumsq)
+        # pair per 32-column chunk), reduced to (mean, rstd) per row by a finalize kernel that reads c/32 * 8 bytes per row instead of the row;
+        # shapes that cannot use them fall back to the row-statistics kernel over the stream itself
         rp = torch.empty((c // 32, M, 2), device=x.device, dtype=torch.float32) if (EPI_STATS and M % 32 == 0 and c % 32 == 0) else None
-        stats = None if rp is not None else torch.empty((M, 2), device=x.device, dtype=torch.float32)
+        stats = torch.empty((M, 2), device=x.device, dtype=torch.float32)
 
         def ln_of(fl):
             if rp is not None:
-                return (rp, fl.colsum, 1e-5)
-            ops.row_stats(hs, 1e-5, out=stats)
+                ops.row_finalize(rp, 1e-5, out=stats)
+            else:
+                ops.row_stats(hs, 1e-5, out=stats)
             return (stats, fl.colsum)
         hs = ops.gemm(hn.view(M, c), self.w_in, bias=self.b_in, out_dtype=torch.float16, row_part=rp)
         qkv = torch.empty((M, 3 * c), device=x.device, dtype=torch.float16)

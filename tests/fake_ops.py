@@ -89,6 +89,17 @@ def _emit_parts(out, acc, row_part, col_part):
         col_part.view(M // 32, N, 2).copy_(torch.stack([v.sum(1), (v * v).sum(1)], dim=-1))
 
 
+def row_finalize(row_part, eps, out=None):
+    tot = row_part.sum(0)
+    cols = 32 * row_part.shape[0]
+    mean = tot[:, 0] / cols
+    st = torch.stack([mean, torch.rsqrt((tot[:, 1] / cols - mean * mean).clamp_min(0) + eps)], dim=1)
+    if out is not None:
+        out.copy_(st)
+        return out
+    return st
+
+
 def row_stats(x, eps, out=None):
     xf = x.float()
     st = torch.stack([xf.mean(-1), torch.rsqrt(xf.var(-1, unbiased=False) + eps)], dim=1)

@@ -201,6 +201,8 @@ def test_gemm_epilogue_statistics(M, N, K, res, cluster_mode):
     o32 = out.float()
     v = want.view(M, N // 32, 32)
     assert rel(rp[..., 0].t(), v.sum(-1)) < 2e-3 and rel(rp[..., 1].t(), (v * v).sum(-1)) < 2e-3
+    fin = ops.row_finalize(rp, 1e-5)           # (mean, rstd) from the partials = the statistics of the stored rows
+    assert rel(fin[:, 0], o32.mean(1)) < 2e-3 and rel(fin[:, 1], torch.rsqrt(o32.var(1, unbiased=False) + 1e-5)) < 2e-3
     c = o32.view(M // 32, 32, N)              # column partials are taken from the stored fp16 values: exact up to the summation order
     assert rel(cp[..., 0], c.sum(1)) < 1e-5 and rel(cp[..., 1], (c * c).sum(1)) < 1e-5
     if N % 64 == 0:
