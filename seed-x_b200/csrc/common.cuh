@@ -341,19 +341,19 @@ SEEDX_DEVINL float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
 }
-// ~14 FP32 ops + 2 MUFU (rcp, ex2) per value: the GEGLU epilogue of the UNet feed-forward GEMMs is issue-bound on this function
+// exact (erf) GELU in 9 FP32 issue slots + 1 MUFU per value — the GEGLU epilogue of the UNet feed-forward GEMMs is issue-bound on this function
+// (round 1 used Abramowitz-Stegun 7.1.26: 15 FP32 + 2 MUFU).  erf(t) = 1 - 2^(-q(t)) for t >= 0 with q a degree-5 polynomial without constant
+// term, fitted to -log2(erfc(t)) on [0, 4.3] (max |error| of erf 8.6e-7, monotone beyond: 2^-q underflows to 0 = erf saturates at 1), so
+//   gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) = max(x, 0) - 0.5 |x| 2^(-q(|x| / sqrt 2)).
 SEEDX_DEVINL float gelu_erf_fast(float x) {
-  const float ax = fabsf(x);
-  const float z = ax * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float w = ax * 0.84932180028801904272f;          // sqrt(log2(e) / 2): exp(-z^2) = 2^(-w^2)
-  const float erf_abs = fmaf(-poly, fast_exp2(-w * w), 1.0f);
-  return fmaf(0.5f * ax, erf_abs, 0.5f * x);             // 0.5 x (1 + sign(x) erf|z|)
+  const float t = fabsf(x) * 0.70710678118654752440f;
+  float q = fmaf(t, 0.0030152f, -0.02984835f);
+  q = fmaf(q, t, 0.14897545f);
+  q = fmaf(q, t, 0.9183691f);
+  q = fmaf(q, t, 1.627908f);
+  q *= t;
+  const float e = fast_exp2(-q);
+  return fmaf(-0.5f * fabsf(x), e, fmaxf(x, 0.f));
 }
 SEEDX_DEVINL float silu(float x) { return x * rcp_approx(1.0f + fast_exp2(-1.4426950408889634f * x)); }
 

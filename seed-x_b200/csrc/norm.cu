@@ -259,15 +259,26 @@ __global__ void __launch_bounds__(256)
 row_finalize_kernel(const float2* __restrict__ parts, int nparts, long long rows, float inv_cols, float eps, float2* __restrict__ stats) {
   pdl_wait();
   pdl_trigger();
-  const long long row = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (row >= rows) return;
+  // 64 rows per CTA, 4 threads per row (thread = row + 64 * sub): sub s adds the chunks k = s, s + 4, ... in order with all its loads in flight,
+  // the four sub-sums are combined in a fixed order -> deterministic, 4x the CTAs and a quarter of the dependent-load chain of one thread per row
+  __shared__ float2 sh[4][64];
+  const int r = threadIdx.x & 63, sub = threadIdx.x >> 6;
+  const long long row = (long long)blockIdx.x * 64 + r;
   float s1 = 0.f, s2 = 0.f;
-  for (int k = 0; k < nparts; ++k) {
-    const float2 q = __ldcg(parts + (long long)k * rows + row);
-    s1 += q.x, s2 += q.y;
+  if (row < rows) {
+#pragma unroll 4
+    for (int k = sub; k < nparts; k += 4) {
+      const float2 q = __ldcg(parts + (long long)k * rows + row);
+      s1 += q.x, s2 += q.y;
+    }
   }
-  const float mean = s1 * inv_cols;
-  stats[row] = make_float2(mean, rsqrtf(fmaxf(s2 * inv_cols - mean * mean, 0.f) + eps));
+  sh[sub][r] = make_float2(s1, s2);
+  __syncthreads();
+  if (sub == 0 && row < rows) {
+    const float a = (sh[0][r].x + sh[1][r].x) + (sh[2][r].x + sh[3][r].x), b = (sh[0][r].y + sh[1][r].y) + (sh[2][r].y + sh[3][r].y);
+    const float mean = a * inv_cols;
+    stats[row] = make_float2(mean, rsqrtf(fmaxf(b * inv_cols - mean * mean, 0.f) + eps));
+  }
 }
 
 // scalar fallback (cols not a multiple of 4 or unaligned rows): one CTA per row
@@ -414,13 +425,17 @@ gn_finalize_kernel(const float2* __restrict__ part1, int c1, const float2* __res
   const int g = blockIdx.x, n = blockIdx.y;
   const int C = c1 + c2, cpg = C / groups;
   const int total = slabs_per_img * cpg;
-  double s1 = 0.0, s2 = 0.0;
+  // a thread adds its (slab, channel) pairs in index order in fp32 (each is already a sum over 32 rows; a thread sees total / 256 of them),
+  // the cross-thread tree runs in fp64
+  float f1 = 0.f, f2 = 0.f;
+#pragma unroll 4
   for (int idx = threadIdx.x; idx < total; idx += 256) {
     const int slab = idx / cpg, ch = g * cpg + idx % cpg;
     const long long srow = (long long)n * slabs_per_img + slab;
     const float2 q = ch < c1 ? __ldcg(part1 + srow * c1 + ch) : __ldcg(part2 + srow * c2 + (ch - c1));
-    s1 += (double)q.x, s2 += (double)q.y;
+    f1 += q.x, f2 += q.y;
   }
+  double s1 = (double)f1, s2 = (double)f2;
   for (int o = 16; o > 0; o >>= 1) s1 += __shfl_xor_sync(0xffffffffu, s1, o), s2 += __shfl_xor_sync(0xffffffffu, s2, o);
   __shared__ double sh[2][8];
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -590,7 +605,7 @@ extern "C" int seedx_row_stats(const void* x, int x_dtype, int64_t ldx, int64_t 
 
 extern "C" int seedx_row_stats_from_partials(const float* parts, int nparts, int64_t rows, int64_t cols, float eps, float* stats, void* stream) {
   SEEDX_REQUIRE(parts && stats && nparts > 0 && rows > 0 && cols == 32LL * nparts, "seedx_row_stats_from_partials: cols must be 32 * nparts");
-  launch_k(row_finalize_kernel, (unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream, (const float2*)parts, nparts, (long long)rows,
+  launch_k(row_finalize_kernel, (unsigned)((rows + 63) / 64), 256, 0, (cudaStream_t)stream, (const float2*)parts, nparts, (long long)rows,
            1.0f / (float)cols, eps, (float2*)stats);
   count_launch();
   return check_cuda(cudaGetLastError(), "row_finalize_kernel launch");
