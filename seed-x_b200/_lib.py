@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libseedx.so")
+LIB_PATH = os.environ.get("SEEDX_LIB") or os.path.join(_HERE, "lib", "libseedx.so")     # SEEDX_LIB: A/B builds of the kernel library (tools/)
 
 F16, F32 = 1, 2
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2

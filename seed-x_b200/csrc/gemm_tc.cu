@@ -194,6 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   {
     SegState s0 = seg_init(p, tile0, tile_step, num_tiles);
     int t, kb0, kb1;
+#ifndef SEEDX_GEMM_NO_BPRE
     if (p.b_static && seg_next(p, s0, tile_step, num_tiles, t, kb0, kb1)) {
       b_pre = (kb1 - kb0) < STAGES ? (kb1 - kb0) : STAGES;
       if (warp == 0 && lane == 0) {
@@ -211,6 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+#endif
   }
   pdl_wait();
   pdl_trigger();
@@ -428,7 +430,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int k = 0; k < nres && k < n_chunks; ++k) issue_res(k);  // in flight while the main loop of this tile is still running
       // column vectors of this tile -> shared memory (while the main loop is still running): the chunk loop then reads them with broadcast
       // 128-bit shared loads instead of 16 dependent L1/L2 round trips per chunk, which is what the short-K epilogues were waiting on
+#ifdef SEEDX_GEMM_NO_VEC
+      const bool use_vec = false;
+#else
       const bool use_vec = p.bias_n != nullptr || p.ln_stats != nullptr;
+#endif
       if (use_vec) {
         asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");      // every epilogue warp has finished reading the previous tile's vectors
         for (int i = ew * 32 + lane; i < BN; i += EPI_WARPS * 32) {
@@ -478,7 +484,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         float x[32];
         const int col0 = n0 + c;
-        if (p.ln_stats != nullptr) {
+#ifdef SEEDX_GEMM_NO_VEC
+        {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = fmaf(__uint_as_float(v[i]), p.alpha, bm);
+          if (p.bias_n != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (col0 + i + 4 <= col_end) {
+                const float4 q = __ldg((const float4*)(p.bias_n + col0 + i));
+                x[i] += q.x, x[i + 1] += q.y, x[i + 2] += q.z, x[i + 3] += q.w;
+              }
+            }
+          }
+        }
+        constexpr bool kVec = false;
+#else
+        constexpr bool kVec = true;
+#endif
+        if (kVec && p.ln_stats != nullptr) {
           // folded LayerNorm (alpha = 1, no bias_m: host check): x = rstd * acc + (bias - rstd * mean * colsum) -> two FFMAs per value
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
@@ -488,14 +512,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             x[i + 2] = fmaf(__uint_as_float(v[i + 2]), ln_rstd, fmaf(ln_nmr, __uint_as_float(qc.z), __uint_as_float(qb.z)));
             x[i + 3] = fmaf(__uint_as_float(v[i + 3]), ln_rstd, fmaf(ln_nmr, __uint_as_float(qc.w), __uint_as_float(qb.w)));
           }
-        } else if (p.bias_n != nullptr) {
+        } else if (kVec && p.bias_n != nullptr) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const uint4 qb = lds128(vec_base + 4u * (uint32_t)(c + i));
             x[i] = fmaf(__uint_as_float(v[i]), p.alpha, __uint_as_float(qb.x) + bm), x[i + 1] = fmaf(__uint_as_float(v[i + 1]), p.alpha, __uint_as_float(qb.y) + bm);
             x[i + 2] = fmaf(__uint_as_float(v[i + 2]), p.alpha, __uint_as_float(qb.z) + bm), x[i + 3] = fmaf(__uint_as_float(v[i + 3]), p.alpha, __uint_as_float(qb.w) + bm);
           }
-        } else {
+        } else if (kVec) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = fmaf(__uint_as_float(v[i]), p.alpha, bm);
         }

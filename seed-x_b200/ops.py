@@ -42,6 +42,9 @@ def _ensure_workspace(device):
     always follows an eager warm-up pass."""
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     if key not in _workspace:
+        if not hasattr(lib(), "seedx_gemm_set_workspace"):       # an older build of the library loaded through SEEDX_LIB (tools/ab_gemm.py)
+            _workspace[key] = None
+            return None
         buf = torch.zeros((24 * 1024 * 1024 + 16384,), device=device, dtype=torch.uint8)
         check(lib().seedx_gemm_set_workspace(C.c_void_p(buf.data_ptr()), C.c_int64(buf.numel())), "seedx_gemm_set_workspace")
         _workspace[key] = buf
