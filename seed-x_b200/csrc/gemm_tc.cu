@@ -64,7 +64,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int EPI_OUT_BYTES = 4096;                      // per epilogue warp: output tiles (2 x <=2 KB, or 1 x 4 KB)
 constexpr int EPI_RES_BYTES = 8192;                      // per epilogue warp: residual tiles, ideally every chunk of a 256-wide tile in flight
 constexpr int MAX_STAGES = 8;
-constexpr int VEC_BYTES = 2048;                          // per-tile column vectors of the epilogue (bias_n, LayerNorm column sums), 2 x 256 fp32
+constexpr int VEC_BYTES = 1024;                          // one per-tile column vector of the epilogue (bias_n | LayerNorm column sums), 256 fp32
 
 constexpr int pow2_cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
@@ -74,11 +74,14 @@ struct TileCfg {
   static constexpr int B_STAGE_BYTES = (BN / CL) * BK * 2;   // a CTA of a pair stages only its half of the B tile
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   // pipeline depth for a given amount of epilogue staging (runtime: depends on whether a residual is streamed through shared memory)
-  static int stages_for(int epi_bytes) {
-    const int fit = (SMEM_LIMIT - 1024 - 512 - VEC_BYTES - epi_bytes) / STAGE_BYTES;
+  // `tail_bytes` = barriers (512) + the per-tile epilogue vectors (1 KB per vector in use).  The dynamic shared memory is declared 1024-byte
+  // aligned (the 128-byte-swizzled tiles need it), so no alignment slack is budgeted: every kilobyte decides whether one more pipeline stage fits
+  // (a 2 KB vector region that cost the 256-wide residual tiles their fourth stage made every short-K GEMM ~10 % slower).
+  static int stages_for(int epi_bytes, int tail_bytes) {
+    const int fit = (SMEM_LIMIT - tail_bytes - epi_bytes) / STAGE_BYTES;
     return fit > MAX_STAGES ? MAX_STAGES : fit;
   }
-  static int smem_for(int stages, int epi_bytes) { return stages * STAGE_BYTES + epi_bytes + 1024 /*align slack*/ + 512 /*barriers*/ + VEC_BYTES; }
+  static int smem_for(int stages, int epi_bytes, int tail_bytes) { return stages * STAGE_BYTES + epi_bytes + tail_bytes; }
   // two accumulator stages; the last 32-column epilogue chunk of a stage may over-read up to 16 columns -> keep them allocated
   static constexpr int TMEM_COLS = pow2_cols(2 * BN + 16);
 };
@@ -138,8 +141,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using Cfg = TileCfg<BN, CL>;
   const int STAGES = p.stages;
   if (threadIdx.x == 0) GEMM_STAMP(0);
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0u) __trap();                          // the launch budgets no alignment slack (TileCfg::smem_for)
   const uint32_t epi_base = smem_base + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned
   const uint32_t bar_base = epi_base + (uint32_t)(EPI_WARPS * p.epi_warp_bytes);
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
@@ -442,7 +446,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float bv = (p.bias_n != nullptr && in) ? __ldg(p.bias_n + n0 + i) : 0.f;
           const float cv = (p.ln_stats != nullptr && in) ? __ldg(p.ln_colsum + n0 + i) : 0.f;
           asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(vec_base + 4u * (uint32_t)i), "f"(bv) : "memory");
-          asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(vec_base + 1024u + 4u * (uint32_t)i), "f"(cv) : "memory");
+          if (p.ln_stats != nullptr) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(vec_base + 1024u + 4u * (uint32_t)i), "f"(cv) : "memory");
         }
         asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");
       }
@@ -765,12 +769,13 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   }
   GemmParams p = p_in;
   const int epi_bytes = EPI_WARPS * p.epi_warp_bytes;
-  p.stages = Cfg::stages_for(epi_bytes);
+  const int tail_bytes = 512 + (p.bias_n != nullptr || p.ln_stats != nullptr ? VEC_BYTES : 0) + (p.ln_stats != nullptr ? VEC_BYTES : 0);
+  p.stages = Cfg::stages_for(epi_bytes, tail_bytes);
   if (p.stages < 2) {
     set_error("seedx_gemm_f16: tile %dx%d does not fit in shared memory with %d B of epilogue staging", BM * CL, BN, epi_bytes);
     return 5;
   }
-  const int smem_bytes = Cfg::smem_for(p.stages, epi_bytes);
+  const int smem_bytes = Cfg::smem_for(p.stages, epi_bytes, tail_bytes);
   const int groups = ((p.m_blocks + CL - 1) / CL) * p.n_blocks * p.batch;
   const int max_clusters = num_sms() / CL;
   const int grid = (groups < max_clusters ? groups : max_clusters) * CL;
