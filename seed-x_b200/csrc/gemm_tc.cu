@@ -101,20 +101,24 @@ SEEDX_DEVINL float apply_act(float x, int act) {
 
 // Work list of one cluster: segments (tile, k-blocks [kb0, kb1)).  Data-parallel: whole tiles first, first + step, ...  Stream-K: the
 // iterations [it, it1) of the linearised (tile, k-block) space, cut at tile boundaries.
+// SK is a compile-time property of the kernel: with the schedule as a run-time flag the data-parallel launches (the large majority) ran ~10 %
+// slower than round 1's kernel — measured with tools/ab_gemm2.py — although none of the stream-K code executed.
 struct SegState {
   long long it, it1;
   int t_next;
 };
+template <bool SK>
 SEEDX_DEVINL SegState seg_init(const GemmParams& p, int cluster, int n_clusters, int num_tiles) {
   SegState s;
   s.t_next = cluster;
   const long long total = (long long)num_tiles * p.k_blocks;
-  s.it = p.stream_k ? (long long)cluster * total / n_clusters : 0;
-  s.it1 = p.stream_k ? (long long)(cluster + 1) * total / n_clusters : 0;
+  s.it = SK ? (long long)cluster * total / n_clusters : 0;
+  s.it1 = SK ? (long long)(cluster + 1) * total / n_clusters : 0;
   return s;
 }
+template <bool SK>
 SEEDX_DEVINL bool seg_next(const GemmParams& p, SegState& s, int n_clusters, int num_tiles, int& t, int& kb0, int& kb1) {
-  if (p.stream_k) {
+  if (SK) {
     if (s.it >= s.it1) return false;
     t = (int)(s.it / p.k_blocks);
     kb0 = (int)(s.it - (long long)t * p.k_blocks);
@@ -134,7 +138,7 @@ SEEDX_DEVINL bool seg_next(const GemmParams& p, SegState& s, int n_clusters, int
 // drop by a third, which is what bounds the single-CTA kernel (measured: TMA multicast of B does NOT help, cta_group::2 does).
 // All TMA transaction bytes of the pair complete on the leader's `full` barrier; the leader's commits arrive on both CTAs' `empty`
 // and `tmem_full` barriers; both CTAs' epilogue warps arrive on the leader's `tmem_empty` barrier.
-template <int BN, int CL>
+template <int BN, int CL, bool SK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
@@ -196,10 +200,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // dependency wait (their bytes are already counted on the `full` barriers; the A halves follow after the wait).
   int b_pre = 0;
   {
-    SegState s0 = seg_init(p, tile0, tile_step, num_tiles);
+    SegState s0 = seg_init<SK>(p, tile0, tile_step, num_tiles);
     int t, kb0, kb1;
 #ifndef SEEDX_GEMM_NO_BPRE
-    if (p.b_static && seg_next(p, s0, tile_step, num_tiles, t, kb0, kb1)) {
+    if (p.b_static && seg_next<SK>(p, s0, tile_step, num_tiles, t, kb0, kb1)) {
       b_pre = (kb1 - kb0) < STAGES ? (kb1 - kb0) : STAGES;
       if (warp == 0 && lane == 0) {
         const int b = t / tiles_per_batch;
@@ -227,10 +231,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      SegState ss = seg_init(p, tile0, tile_step, num_tiles);
+      SegState ss = seg_init<SK>(p, tile0, tile_step, num_tiles);
       int t, kb0, kb1;
       bool first_seg = true;
-      while (seg_next(p, ss, tile_step, num_tiles, t, kb0, kb1)) {
+      while (seg_next<SK>(p, ss, tile_step, num_tiles, t, kb0, kb1)) {
         const int b = t / tiles_per_batch;
         const int r = t - b * tiles_per_batch;
         const int n_blk = r / m_groups;
@@ -295,10 +299,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      SegState ss = seg_init(p, tile0, tile_step, num_tiles);
+      SegState ss = seg_init<SK>(p, tile0, tile_step, num_tiles);
       int t, kb0, kb1;
       bool first_seg = true;
-      while (seg_next(p, ss, tile_step, num_tiles, t, kb0, kb1)) {
+      while (seg_next<SK>(p, ss, tile_step, num_tiles, t, kb0, kb1)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -336,10 +340,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t epi_res_phase = 0;   // parity bits of this warp's two residual barriers
-    SegState ss = seg_init(p, tile0, tile_step, num_tiles);
+    SegState ss = seg_init<SK>(p, tile0, tile_step, num_tiles);
     int t, kb0, kb1;
     bool first_seg = true;
-    while (seg_next(p, ss, tile_step, num_tiles, t, kb0, kb1)) {
+    while (seg_next<SK>(p, ss, tile_step, num_tiles, t, kb0, kb1)) {
       const int b = t / tiles_per_batch;
       const int r = t - b * tiles_per_batch;
       const int n_blk = r / m_groups;
@@ -391,8 +395,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     p.r_batched ? b : 0);
       };
       // ---- stream-K roles of this segment
-      const bool sk_partial = kb0 > 0;                          // the tile's first k-blocks belong to an earlier cluster: hand my raw sums over
-      const bool sk_owner = (kb0 == 0) && (kb1 < p.k_blocks);   // later clusters hold the rest of this tile: add their partials, then finish
+      const bool sk_partial = SK && kb0 > 0;                          // the tile's first k-blocks belong to an earlier cluster: hand my raw sums over
+      const bool sk_owner = SK && (kb0 == 0) && (kb1 < p.k_blocks);   // later clusters hold the rest of this tile: add their partials, then finish
       const int my_cluster = tile0;
       constexpr int BNP = (BN + 31) & ~31;                      // scratch row stride: the last 32-column chunk of a tile may reach past BN
       const size_t sk_tile_elems = (size_t)BM * BNP;
@@ -762,9 +766,12 @@ template <int BN, int CL>
 static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tr, const GemmParams& p_in,
                           cudaStream_t st) {
   using Cfg = TileCfg<BN, CL>;
+  // stream-K kernels exist for CTA pairs with 32-column-multiple tiles of at least 128 columns (where the schedule is ever chosen)
+  constexpr bool kHasSK = (CL == 2) && (BN % 32 == 0) && (BN >= 128);
   static bool attr_done = false;
   if (!attr_done) {
-    SEEDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    SEEDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    if (kHasSK) SEEDX_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, CL, kHasSK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_done = true;
   }
   GemmParams p = p_in;
@@ -792,7 +799,7 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     // measured on B200 (profiles/r02_unet_forward_launches_*): the fix-up round trip pays off from ~100 k-blocks per tile (the 3x3 convs with
     // C >= 1280, K = 11 520: -10 ... -17 %), not for the K = 1280 ... 5120 transformer GEMMs, whose whole launch is 30 - 100 us
     const bool long_k = p.k_blocks >= g_sk_min_kblocks;
-    if (g_gemm_stream_k != 0 && g_sk_scratch != nullptr && need <= g_sk_scratch_bytes && total >= 4LL * clusters && groups > clusters &&
+    if (kHasSK && g_gemm_stream_k != 0 && g_sk_scratch != nullptr && need <= g_sk_scratch_bytes && total >= 4LL * clusters && groups > clusters &&
         ((idle_tail && long_k) || g_gemm_stream_k == 2)) {
       p.stream_k = 1;
       p.sk_scratch = g_sk_scratch, p.sk_flags = g_sk_flags;
@@ -810,7 +817,8 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  const cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL>, ta, tb, td, tr, p);
+  const cudaError_t e = (kHasSK && p.stream_k) ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL, kHasSK>, ta, tb, td, tr, p)
+                                               : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, CL, false>, ta, tb, td, tr, p);
   count_launch();
   return check_cuda(e != cudaSuccess ? e : cudaGetLastError(), "gemm_tc_kernel launch");
 }
@@ -847,7 +855,7 @@ static int choose_tile_n(int m_tiles, int N, int k_blocks, bool heavy_epilogue, 
     const int n_blocks = (N + bn - 1) / bn;
     const long long tiles = (long long)m_tiles * n_blocks;
     // stream-K (workspace present): a launch of more than one wave costs its fractional number of waves plus the partial-tile round trip
-    const bool sk = g_gemm_stream_k != 0 && g_sk_scratch != nullptr && tiles > sms && (long long)tiles * k_blocks >= 4LL * sms &&
+    const bool sk = (bn % 32 == 0 && bn >= 128) && g_gemm_stream_k != 0 && g_sk_scratch != nullptr && tiles > sms && (long long)tiles * k_blocks >= 4LL * sms &&
                     (k_blocks >= g_sk_min_kblocks || g_gemm_stream_k == 2);
     const double waves = sk ? (double)tiles / sms + 0.12 : (double)((tiles + sms - 1) / sms);
     const double mma_k16 = fmax(bn / 2.0, (4096.0 + 32.0 * bn) / 91.0);
