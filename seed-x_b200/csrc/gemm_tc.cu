@@ -340,6 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t epi_res_phase = 0;   // parity bits of this warp's two residual barriers
+    int vec_nblk = -1;            // column block whose bias / column-sum vectors sit in shared memory
     SegState ss = seg_init<SK>(p, tile0, tile_step, num_tiles);
     int t, kb0, kb1;
     bool first_seg = true;
@@ -441,9 +442,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef SEEDX_GEMM_NO_VEC
       const bool use_vec = false;
 #else
-      const bool use_vec = p.bias_n != nullptr || p.ln_stats != nullptr;
+      const bool use_vec = (p.bias_n != nullptr || p.ln_stats != nullptr) && n_blk != vec_nblk;   // consecutive tiles of a CTA mostly differ in m only
 #endif
       if (use_vec) {
+        vec_nblk = n_blk;
         asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");      // every epilogue warp has finished reading the previous tile's vectors
         for (int i = ew * 32 + lane; i < BN; i += EPI_WARPS * 32) {
           const bool in = n0 + i < col_end;
