@@ -52,7 +52,9 @@ EPI_STATS = os.environ.get("SEEDX_EPI_STATS", "1") != "0"
 
 def _new_col_part(n, h, w, c, dev):
     """buffer for the column partials of an NHWC fp16 map [n,h,w,c] that a GroupNorm will read, or None when the shape is not eligible"""
-    if not EPI_STATS or (h * w) % 32 or c % 32:
+    # maps of more than 256 x 256 pixels (the upper levels of the VAE) keep the statistics pass: their partials would be > 100 MB per tensor and the
+    # per-(image, group) finalize, one CTA each, has too little parallelism to read them quickly (measured: 86 us vs 100 us for the pass, with slower convs)
+    if not EPI_STATS or (h * w) % 32 or c % 32 or h * w > 65536:
         return None
     return torch.empty((n * h * w // 32, c, 2), device=dev, dtype=torch.float32)
 
