@@ -372,7 +372,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         ln_rstd = mr.y, ln_nmr = -mr.x * mr.y;
       }
-      const float* bg = (p.bias_g != nullptr && row_ok) ? p.bias_g + (long long)(row / p.bias_g_rows) * p.N : nullptr;
+      // per-row-group bias (time embedding of a ResnetBlock2D): when the 128 rows of this CTA's tile lie in one group (bias_g_rows % 128 == 0) it is
+      // folded into the staged bias vector; otherwise every value fetches its own element
+      const bool bg_vec = p.bias_g != nullptr && (p.bias_g_rows % BM) == 0;
+      const int bg_grp = p.bias_g != nullptr ? (m_blk * BM) / p.bias_g_rows : 0;
+      const float* bg = (p.bias_g != nullptr && row_ok && !bg_vec) ? p.bias_g + (long long)(row / p.bias_g_rows) * p.N : nullptr;
       const int rrow = p.res_row_mod ? (row % p.res_row_mod) : row;
 
       const int col_end = min(p.N, n0 + BN);   // columns of this tile that exist
@@ -442,14 +446,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef SEEDX_GEMM_NO_VEC
       const bool use_vec = false;
 #else
-      const bool use_vec = (p.bias_n != nullptr || p.ln_stats != nullptr) && n_blk != vec_nblk;   // consecutive tiles of a CTA mostly differ in m only
+      const int vec_key = n_blk + (bg_vec ? (bg_grp + 1) * 65536 : 0);
+      const bool use_vec = (p.bias_n != nullptr || p.ln_stats != nullptr || bg_vec) && vec_key != vec_nblk;   // consecutive tiles of a CTA mostly differ in m only
 #endif
       if (use_vec) {
-        vec_nblk = n_blk;
+        vec_nblk = vec_key;
         asm volatile("bar.sync 1, %0;\n" ::"n"(EPI_WARPS * 32) : "memory");      // every epilogue warp has finished reading the previous tile's vectors
         for (int i = ew * 32 + lane; i < BN; i += EPI_WARPS * 32) {
           const bool in = n0 + i < col_end;
-          const float bv = (p.bias_n != nullptr && in) ? __ldg(p.bias_n + n0 + i) : 0.f;
+          float bv = (p.bias_n != nullptr && in) ? __ldg(p.bias_n + n0 + i) : 0.f;
+          if (bg_vec && in && m_blk * BM < p.M) bv += __ldg(p.bias_g + (long long)bg_grp * p.N + n0 + i);
           const float cv = (p.ln_stats != nullptr && in) ? __ldg(p.ln_colsum + n0 + i) : 0.f;
           asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(vec_base + 4u * (uint32_t)i), "f"(bv) : "memory");
           if (p.ln_stats != nullptr) asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(vec_base + 1024u + 4u * (uint32_t)i), "f"(cv) : "memory");
@@ -522,7 +528,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             x[i + 2] = fmaf(__uint_as_float(v[i + 2]), ln_rstd, fmaf(ln_nmr, __uint_as_float(qc.z), __uint_as_float(qb.z)));
             x[i + 3] = fmaf(__uint_as_float(v[i + 3]), ln_rstd, fmaf(ln_nmr, __uint_as_float(qc.w), __uint_as_float(qb.w)));
           }
-        } else if (kVec && p.bias_n != nullptr) {
+        } else if (kVec && (p.bias_n != nullptr || bg_vec)) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const uint4 qb = lds128(vec_base + 4u * (uint32_t)(c + i));
@@ -758,7 +764,7 @@ void count_launch();
 
 // stream-K fix-up workspace (seedx_gemm_set_workspace): flags first (zeroed by the caller), partial tiles behind them
 static int g_gemm_stream_k = 1;       // 0 = off, 1 = auto, 2 = whenever legal (tests)
-static int g_sk_min_kblocks = 96;     // auto mode: shortest K (in 64-element blocks) that is split
+static int g_sk_min_kblocks = 80;     // auto mode: shortest K (in 64-element blocks) that is split (K >= 5120)
 static float* g_sk_scratch = nullptr;
 static size_t g_sk_scratch_bytes = 0;
 static unsigned* g_sk_flags = nullptr;
@@ -778,7 +784,7 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   }
   GemmParams p = p_in;
   const int epi_bytes = EPI_WARPS * p.epi_warp_bytes;
-  const int tail_bytes = 512 + (p.bias_n != nullptr || p.ln_stats != nullptr ? VEC_BYTES : 0) + (p.ln_stats != nullptr ? VEC_BYTES : 0);
+  const int tail_bytes = 512 + (p.bias_n != nullptr || p.ln_stats != nullptr || p.bias_g != nullptr ? VEC_BYTES : 0) + (p.ln_stats != nullptr ? VEC_BYTES : 0);
   p.stages = Cfg::stages_for(epi_bytes, tail_bytes);
   if (p.stages < 2) {
     set_error("seedx_gemm_f16: tile %dx%d does not fit in shared memory with %d B of epilogue staging", BM * CL, BN, epi_bytes);
