@@ -100,6 +100,12 @@ typedef struct seedx_gemm_args {
    * Requirements: fp16 output, 16-byte aligned rows, no gating, batch 1, M % 32 == 0, N % 32 == 0.  NULL = off. */
   float* row_part;
   float* col_part;
+  /* With row_part: the epilogue warp that delivers the last partial of a 32-row slab reduces the slab's partials (chunk order) to (mean, rstd) and
+   * stores them in row_stats_out fp32 [M][2] with eps row_eps — what seedx_row_stats_from_partials computes, without the extra launch.
+   * row_tickets: uint32 [M/32], zero before the launch; the kernel leaves them zero. */
+  float* row_stats_out;
+  uint32_t* row_tickets;
+  float row_eps;
 } seedx_gemm_args;
 
 int seedx_gemm_f16(const seedx_gemm_args* args, void* stream);

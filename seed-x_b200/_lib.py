@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("tile_n", C.c_int32),
         ("ln_stats", C.c_void_p), ("ln_colsum", C.c_void_p), ("b_dynamic", C.c_int32),
         ("ln_parts", C.c_int32), ("ln_eps", C.c_float), ("row_part", C.c_void_p), ("col_part", C.c_void_p),
+        ("row_stats_out", C.c_void_p), ("row_tickets", C.c_void_p), ("row_eps", C.c_float),
     ]
 
 

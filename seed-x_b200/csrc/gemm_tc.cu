@@ -50,6 +50,11 @@ struct GemmParams {
   unsigned* sk_flags;                     // [clusters][CL][EPI_WARPS], 0 between launches
   float2* row_part;                       // [N/32][M]  per row:    (sum, sumsq) over the 32 columns of a chunk      -> LayerNorm of the next GEMM
   float2* col_part;                       // [M/32][N]  per column: (sum, sumsq) over the 32 rows of a warp's slab   -> GroupNorm (fixed-order finalize)
+  // optional: the warp that delivers the LAST partial of a 32-row slab (ticket per slab, self-resetting) turns the slab's row partials into
+  // (mean, rstd) right here, in chunk order (deterministic whoever comes last): no separate finalize launch for the consumer's folded LayerNorm
+  float2* row_stats_out;                  // [M] (mean, rstd)
+  unsigned* row_tickets;                  // [M/32], zero before the launch, zero again after it
+  float row_eps;
   // conv
   int conv, taps_w, c_chunks, conv_w, conv_h, tile_w, tile_h, tiles_per_img, tiles_w, pad, imgs_per_tile;
 };
@@ -732,6 +737,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
+      if (p.row_stats_out != nullptr && row_base < p.M) {
+        // my partials of this slab are written: take a ticket.  A slab receives 2 * n_blocks deliveries (the even- and the odd-chunk warp of its lane
+        // quarter, once per column block); the last one reduces the slab.
+        __threadfence();
+        __syncwarp();
+        unsigned last = 0;
+        if (lane == 0) last = (atomicAdd(p.row_tickets + (row_base >> 5), 1u) == (unsigned)(2 * p.n_blocks - 1)) ? 1u : 0u;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          __threadfence();
+          if (row_ok) {
+            const int parts = p.N >> 5;
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+            for (int k = 0; k < parts; ++k) {
+              const float2 q = __ldcg(p.row_part + (long long)k * p.M + row);
+              s1 += q.x, s2 += q.y;
+            }
+            const float inv = 1.0f / (float)p.N;
+            const float mean = s1 * inv;
+            p.row_stats_out[row] = make_float2(mean, rsqrtf(fmaxf(s2 * inv - mean * mean, 0.f) + p.row_eps));
+          }
+          if (lane == 0) p.row_tickets[row_base >> 5] = 0u;
+        }
+      }
       if (lane == 0) {
         if (CL == 1) mbar_arrive(tempty_bar(acc));
         else mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));  // the leader's MMA thread owns the accumulator hand-shake
@@ -1014,6 +1044,11 @@ extern "C" int seedx_gemm_f16(const seedx_gemm_args* a, void* stream) {
     SEEDX_REQUIRE(((uintptr_t)a->row_part % 8 == 0) && ((uintptr_t)a->col_part % 8 == 0), "seedx_gemm_f16: statistics buffers must be 8-byte aligned");
   }
   p.row_part = (float2*)a->row_part, p.col_part = (float2*)a->col_part;
+  if (a->row_stats_out || a->row_tickets) {
+    SEEDX_REQUIRE(a->row_part && a->row_stats_out && a->row_tickets && ((uintptr_t)a->row_stats_out % 8 == 0),
+                  "seedx_gemm_f16: row_stats_out needs row_part and row_tickets (M/32 zeroed counters)");
+  }
+  p.row_stats_out = (float2*)a->row_stats_out, p.row_tickets = a->row_tickets, p.row_eps = a->row_eps;
   p.b_static = a->b_dynamic ? 0 : 1;
   p.bias_n = a->bias_n, p.bias_m = a->bias_m, p.bias_g = a->bias_g;
   p.bias_g_rows = a->bias_g ? (int)a->bias_g_rows : 1;

@@ -52,12 +52,14 @@ def _ensure_workspace(device):
 
 
 def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, residual=None, res_row_mod=0,
-         act=ACT_NONE, gated=False, alpha=1.0, out_dtype=torch.float16, tile_n=0, ln=None, dynamic_b=False, row_part=None, col_part=None):
+         act=ACT_NONE, gated=False, alpha=1.0, out_dtype=torch.float16, tile_n=0, ln=None, dynamic_b=False, row_part=None, col_part=None,
+         row_stats=None):
     """out[b,m,n] = epi(alpha * a[b,m,:] . w[(b,)n,:]).
 
     a: fp16 [M,K] or [B,M,K] (last dim contiguous); w: fp16 [N,K] or [B,N,K]; returns/updates out [.., M, N_out].
     ln = (row_stats fp32 [M,2], colsum fp32 [N]): LayerNorm of `a` folded into the epilogue (w = gamma-scaled weights, bias = W.beta + b);
          (row partials fp32 [K/32, M, 2], colsum, eps): the same with the statistics formed from the partial sums the producer of `a` emitted.
+    row_stats = (stats fp32 [M,2], tickets int32 [M/32] zeroed, eps): with row_part, (mean, rstd) per row of the output written by this launch itself.
     row_part / col_part: fp32 outputs [N/32, M, 2] / [M/32, N, 2] receiving partial (sum, sum of squares) of the stored output per row chunk /
          per 32-row slab and column, for the LayerNorm / GroupNorm that reads this output next (see stats_buffers()).
     dynamic_b: w is an activation written by the kernel launched just before (default: weights, prefetched before the PDL wait).
@@ -108,6 +110,10 @@ def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, 
             assert st.numel() == 2 * M
         g.ln_stats, g.ln_colsum = st.data_ptr(), cs.data_ptr()
     _set_parts(g, row_part, col_part, M, n_out)
+    if row_stats is not None:          # (stats fp32 [M, 2], tickets int32 [M/32] (zero), eps): the last epilogue warp of a 32-row slab finalizes it
+        st, tk, eps = row_stats
+        assert row_part is not None and st.dtype == torch.float32 and st.numel() == 2 * M and tk.dtype == torch.int32 and tk.numel() >= M // 32
+        g.row_stats_out, g.row_tickets, g.row_eps = st.data_ptr(), tk.data_ptr(), float(eps)
     g.b_dynamic = int(dynamic_b)
     check(lib().seedx_gemm_f16(C.byref(g), _stream()), "seedx_gemm_f16")
     return out

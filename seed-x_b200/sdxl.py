@@ -310,14 +310,14 @@ class _Transformer:
         # shapes that cannot use them fall back to the row-statistics kernel over the stream itself
         rp = torch.empty((c // 32, M, 2), device=x.device, dtype=torch.float32) if (EPI_STATS and M % 32 == 0 and c % 32 == 0) else None
         stats = torch.empty((M, 2), device=x.device, dtype=torch.float32)
+        # the epilogue warp that delivers a 32-row slab's last partial also reduces the slab to (mean, rstd): no statistics launch at all
+        rs = (stats, torch.zeros((M // 32,), device=x.device, dtype=torch.int32), 1e-5) if rp is not None else None
 
         def ln_of(fl):
-            if rp is not None:
-                ops.row_finalize(rp, 1e-5, out=stats)
-            else:
+            if rp is None:
                 ops.row_stats(hs, 1e-5, out=stats)
             return (stats, fl.colsum)
-        hs = ops.gemm(hn.view(M, c), self.w_in, bias=self.b_in, out_dtype=torch.float16, row_part=rp)
+        hs = ops.gemm(hn.view(M, c), self.w_in, bias=self.b_in, out_dtype=torch.float16, row_part=rp, row_stats=rs)
         qkv = torch.empty((M, 3 * c), device=x.device, dtype=torch.float16)
         obuf = torch.empty((M, c), device=x.device, dtype=torch.float16)
         qbuf = torch.empty((M, c), device=x.device, dtype=torch.float16)
@@ -330,13 +330,13 @@ class _Transformer:
             # norm1 -> fused QKV, norm2 -> cross-attention q, norm3 -> GEGLU: the normalisation happens in the projection's epilogue
             ops.gemm(hs, blk["qkv"].w, out=qkv, bias=blk["qkv"].bias, ln=ln_of(blk["qkv"]))
             ops.attention(q1, k1, v1, ov, scale=scale)
-            ops.gemm(obuf, blk["w_o1"], out=hs, bias=blk["b_o1"], residual=hs, row_part=rp)
+            ops.gemm(obuf, blk["w_o1"], out=hs, bias=blk["b_o1"], residual=hs, row_part=rp, row_stats=rs)
             ops.gemm(hs, blk["q2"].w, out=qbuf, bias=blk["q2"].bias, ln=ln_of(blk["q2"]))
             kv5 = kvb.view(n, n_ctx, 2, H, d)
             ops.attention(q2, kv5[:, :, 0].permute(0, 2, 1, 3), kv5[:, :, 1].permute(0, 2, 1, 3), ov, scale=scale)
-            ops.gemm(obuf, blk["w_o2"], out=hs, bias=blk["b_o2"], residual=hs, row_part=rp)
+            ops.gemm(obuf, blk["w_o2"], out=hs, bias=blk["b_o2"], residual=hs, row_part=rp, row_stats=rs)
             ops.gemm(hs, blk["ff1"].w, out=fbuf, bias=blk["ff1"].bias, act=ops.ACT_GELU, gated=True, ln=ln_of(blk["ff1"]))
-            ops.gemm(fbuf, blk["w_ff2"], out=hs, bias=blk["b_ff2"], residual=hs, row_part=rp)
+            ops.gemm(fbuf, blk["w_ff2"], out=hs, bias=blk["b_ff2"], residual=hs, row_part=rp, row_stats=rs)
         po = _new_col_part(n, h, w, c, x.device)
         return _tag(ops.gemm(hs, self.w_out, bias=self.b_out, residual=x.view(M, c), col_part=po).view(n, h, w, c), po)
 

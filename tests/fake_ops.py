@@ -44,7 +44,7 @@ def patchify(x, patch, kpad):
 
 
 def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, residual=None, res_row_mod=0, act=ACT_NONE, gated=False, alpha=1.0,
-         out_dtype=torch.float16, ln=None, dynamic_b=False, row_part=None, col_part=None, **kw):
+         out_dtype=torch.float16, ln=None, dynamic_b=False, row_part=None, col_part=None, row_stats=None, **kw):
     assert a.dtype == torch.float16 and w.dtype == torch.float16 and a.dim() == 2 and not any(v is not None and v is not False and v != 0 for v in kw.values())
     if residual is not None and res_row_mod:                     # residual row = output row % res_row_mod (position tables)
         residual = residual.repeat(a.shape[0] // res_row_mod, 1)
@@ -75,6 +75,9 @@ def gemm(a, w, out=None, *, bias=None, bias_m=None, bias_g=None, bias_g_rows=0, 
         out = torch.empty(acc.shape, dtype=out_dtype)
     out.copy_(acc.to(out.dtype))
     _emit_parts(out, acc, row_part, col_part)
+    if row_stats is not None:
+        row_finalize(row_part.view(-1, acc.shape[0], 2), row_stats[2], out=row_stats[0])
+        assert int(row_stats[1].abs().sum()) == 0            # tickets: zero before, zero after
     return out
 
 

@@ -196,8 +196,12 @@ def test_gemm_epilogue_statistics(M, N, K, res, cluster_mode):
     rp = torch.empty((N // 32, M, 2), device="cuda")
     cp = torch.empty((M // 32, N, 2), device="cuda")
     out = r.clone() if res else None
-    out = ops.gemm(a, w, out=out, bias=bias, residual=out if res else None, row_part=rp, col_part=cp)
+    st_epi = torch.empty((M, 2), device="cuda")
+    tickets = torch.zeros((M // 32,), device="cuda", dtype=torch.int32)
+    out = ops.gemm(a, w, out=out, bias=bias, residual=out if res else None, row_part=rp, col_part=cp, row_stats=(st_epi, tickets, 1e-5))
     assert rel(out, want) < 2e-3
+    assert int(tickets.abs().sum()) == 0                                # the slab tickets reset themselves
+    assert torch.equal(st_epi, ops.row_finalize(rp, 1e-5))              # finalized in the epilogue = the finalize kernel, bit for bit (same chunk order)
     o32 = out.float()
     v = want.view(M, N // 32, 32)
     assert rel(rp[..., 0].t(), v.sum(-1)) < 2e-3 and rel(rp[..., 1].t(), (v * v).sum(-1)) < 2e-3
