@@ -48,6 +48,7 @@ def _f(t, dev):
 # Statistics for the next normalisation come out of the producing kernel's epilogue (seedx_gemm_args.col_part / row_part) instead of a pass over
 # the tensor; SEEDX_EPI_STATS=0 restores the separate statistics kernels (A/B switch, same results up to summation order).
 EPI_STATS = os.environ.get("SEEDX_EPI_STATS", "1") != "0"
+ROW_TICKETS = os.environ.get("SEEDX_ROW_TICKETS", "1") != "0"     # 0: LayerNorm statistics by the row-finalize kernel instead of inside the producing GEMM
 
 
 def _new_col_part(n, h, w, c, dev):
@@ -311,11 +312,13 @@ class _Transformer:
         rp = torch.empty((c // 32, M, 2), device=x.device, dtype=torch.float32) if (EPI_STATS and M % 32 == 0 and c % 32 == 0) else None
         stats = torch.empty((M, 2), device=x.device, dtype=torch.float32)
         # the epilogue warp that delivers a 32-row slab's last partial also reduces the slab to (mean, rstd): no statistics launch at all
-        rs = (stats, torch.zeros((M // 32,), device=x.device, dtype=torch.int32), 1e-5) if rp is not None else None
+        rs = (stats, torch.zeros((M // 32,), device=x.device, dtype=torch.int32), 1e-5) if (rp is not None and ROW_TICKETS) else None
 
         def ln_of(fl):
             if rp is None:
                 ops.row_stats(hs, 1e-5, out=stats)
+            elif rs is None:
+                ops.row_finalize(rp, 1e-5, out=stats)
             return (stats, fl.colsum)
         hs = ops.gemm(hn.view(M, c), self.w_in, bias=self.b_in, out_dtype=torch.float16, row_part=rp, row_stats=rs)
         qkv = torch.empty((M, 3 * c), device=x.device, dtype=torch.float16)

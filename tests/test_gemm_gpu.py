@@ -201,7 +201,11 @@ def test_gemm_epilogue_statistics(M, N, K, res, cluster_mode):
     out = ops.gemm(a, w, out=out, bias=bias, residual=out if res else None, row_part=rp, col_part=cp, row_stats=(st_epi, tickets, 1e-5))
     assert rel(out, want) < 2e-3
     assert int(tickets.abs().sum()) == 0                                # the slab tickets reset themselves
-    assert torch.equal(st_epi, ops.row_finalize(rp, 1e-5))              # finalized in the epilogue = the finalize kernel, bit for bit (same chunk order)
+    assert rel(st_epi, ops.row_finalize(rp, 1e-5)) < 1e-5              # finalized in the epilogue (chunk order) = the finalize kernel (4 interleaved sub-sums)
+    st2 = torch.empty_like(st_epi)
+    ops.gemm(a, w, out=(r.clone() if res else None), bias=bias, residual=None, row_part=rp, row_stats=(st2, tickets, 1e-5)) if not res else None
+    if not res:
+        assert torch.equal(st2, st_epi)                                 # run-to-run bit-reproducible whichever warp comes last
     o32 = out.float()
     v = want.view(M, N // 32, 32)
     assert rel(rp[..., 0].t(), v.sum(-1)) < 2e-3 and rel(rp[..., 1].t(), (v * v).sum(-1)) < 2e-3
