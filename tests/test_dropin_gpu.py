@@ -43,6 +43,10 @@ def _write_pretrained(root):
     return vit_cfg, lc, ucfg, vcfg, rcfg
 
 
+def sd_dir_of(pre):
+    return pre / "stable-diffusion-xl-base-1.0"
+
+
 def test_yaml_factories_and_loaders(tmp_path):
     compat.install()
     import hydra
@@ -71,6 +75,38 @@ def test_yaml_factories_and_loaders(tmp_path):
     transform = hydra.utils.instantiate(load("processer/qwen_448_transform.yaml"))
     discrete = hydra.utils.instantiate(load("discrete_model/discrete_identity.yaml")).to("cuda").eval()
     adapter.init_pipe(vae=vae, scheduler=sched, visual_encoder=vit, image_transform=transform, discrete_model=discrete, dtype=torch.float16, device="cuda")
+
+    # ---- numeric check of every loader: what was read from disk computes what the oracle computes from the same checkpoint tensors
+    from oracle import llm as ollm
+    from oracle import resampler_xl as orx
+    from oracle import sdxl as osd
+    from oracle import vit as ovit
+    rel = lambda a, b: ((a.float().cpu() - b.float().cpu()).norm() / b.float().cpu().norm()).item()  # noqa: E731
+    x_img = synth.image("dropin_img", 1, 224)
+    e_vit = rel(vit(x_img.cuda()), ovit.vit_forward(torch.load(pre / "QwenViT" / "qwen_vit_G.pt"), x_img, 2))
+    from safetensors.torch import load_file
+    lsd = {k: v.float() for k, v in load_file(str(pre / "seed_x_i" / "llm" / "model.safetensors")).items()}
+    ids = [1, 17, 254, 99, 512, 33, 8, 640]
+    emb = lsd["model.embed_tokens.weight"][torch.tensor(ids)]
+    ref_logits, _, _ = ollm.llama_forward(lsd, lc, emb, 0, None)
+    logits, _ = llm.logits_all(llm.prefill(emb.cuda()))
+    e_llm = rel(logits, ref_logits)
+    usd = {k: v.float() for k, v in load_file(str(sd_dir_of(pre) / "unet" / "diffusion_pytorch_model.safetensors")).items()}
+    xs, ctx, te = synth.randn("dropin_x", (1, 4, 16, 16)), synth.randn("dropin_ctx", (1, 16, 256)), synth.randn("dropin_te", (1, 160))
+    tid = torch.tensor([[256.0, 256.0, 0.0, 0.0, 256.0, 256.0]])
+    e_unet = rel(unet(xs.cuda(), 301.0, ctx.cuda(), added_cond_kwargs=dict(text_embeds=te.cuda(), time_ids=tid.cuda())),
+                 osd.unet_forward(usd, ucfg, xs, 301.0, ctx, te, tid))
+    vsd = torch.load(sd_dir_of(pre) / "vae" / "diffusion_pytorch_model.bin")
+    z = synth.randn("dropin_z", (1, 4, 16, 16))
+    e_vae = rel(vae.decode(z.cuda()), osd.vae_decode(vsd, vcfg, z))
+    rsd = {k[len("resampler."):]: v for k, v in torch.load(pre / "seed_detokenizer" / "first_stage" / "pytorch_model.bin").items()}
+    f_in = synth.randn("dropin_feats", (1, 64, 256))
+    p_ref, pool_ref = orx.resampler_xl(rsd, rcfg, f_in)
+    p_got, pool_got = adapter.resampler(f_in.cuda().half())
+    e_rx = max(rel(p_got, p_ref), rel(pool_got, pool_ref))
+    print(f"loaders vs oracle on the checkpoint tensors: ViT {e_vit:.2e}, LLaMA logits {e_llm:.2e}, UNet eps {e_unet:.2e}, VAE {e_vae:.2e}, ResamplerXLV2 {e_rx:.2e}")
+    assert e_vit < 1e-3 and e_llm < 1e-3 and e_unet < 5e-3 and e_vae < 5e-3 and e_rx < 2e-3, (e_vit, e_llm, e_unet, e_vae, e_rx)
+    assert vae.cfg["force_upcast"] is True and vae.stream_scale == 2.0 ** -7        # config.json without the key: diffusers' default (upcast)
 
     # the flow of eval_img2edit / eval_text2img on a synthetic image
     import numpy as np

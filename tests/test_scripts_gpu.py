@@ -40,8 +40,7 @@ def _project(root):
             if "sdxl_adapter" in rel:
                 y["resampler"].update(dim=rcfg["dim"], depth=rcfg["depth"], heads=rcfg["heads"], embedding_dim=256, output1_dim=rcfg["output1_dim"],
                                       output2_dim=rcfg["output2_dim"])
-            if "tokenizer" in rel:        # no sentencepiece model offline: the synthetic id map with the reference's added tokens
-                y = {"_target_": "seedx_b200.synth.SynthTokenizer", "vocab": lc["vocab"]}
+            # the tokenizer YAML stays the reference's: transformers.LlamaTokenizer.from_pretrained on a directory built offline below
             if rel.endswith("llm_seed_x_lora.yaml"):
                 continue
             os.makedirs(root / os.path.dirname(rel), exist_ok=True)
@@ -49,6 +48,9 @@ def _project(root):
     # ---- pretrained ----
     pre = root / "pretrained"
     os.makedirs(pre / "QwenViT")
+    import real_tokenizer                      # a REAL LlamaTokenizer directory (synthetic SentencePiece vocabulary + the reference's 330 added tokens)
+    assert lc["vocab"] == 694 + len(real_tokenizer.ADDED)
+    real_tokenizer.build(str(pre / "cvlm_llama2_tokenizer_100img_and_224loc_addpatch"), base_vocab=694)
     torch.save(synth.vit_state_dict(**VIT), pre / "QwenViT" / "qwen_vit_G.pt")
     for variant in ("seed_x", "seed_x_i", "seed_x_edit"):
         os.makedirs(pre / variant / "llm"), os.makedirs(pre / variant / "agent")
