@@ -81,6 +81,13 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   constexpr bool H2 = PE < 0;                       // ones-column row sums + packed half2 exponentials
   static_assert(!H2 || D == 64, "the H2 softmax needs the spare TMEM columns of d = 64");
   constexpr int OW = H2 ? D + 16 : D;               // accumulator columns per query tile
+  // d = 64 (not H2) leaves tensor-memory columns 384..511 free: P gets its own 64 columns per query tile instead of overwriting S.  S then
+  // survives the exponential pass, which allows the ONE-PASS softmax below: unmasked tiles are exponentiated against the running reference
+  // maximum (first tile: the maximum of its first 32 scores) while the largest P of the row is tracked on the packed fp16 results; only if a
+  // row outgrew the reference by more than 2^8 is the tile redone the two-pass way from the intact scores.  Tensor memory reads at 64 B/clk per
+  // sub-partition, so reading S once instead of twice, with the next 32 columns in flight under the current chunk's exponentials, is what counts.
+  constexpr bool SEP_P = (D == 64) && !H2;
+  constexpr uint32_t P_COL = 384;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ0 = smem_base;                                  // [QB][2] tiles
@@ -201,7 +208,7 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         umma_commit(s_full(x));
       };
       auto issue_pv = [&](int x, uint32_t vb, bool first) {
-        const uint32_t tP = tmem_base + Cfg::S_COL + (uint32_t)(x * 128);
+        const uint32_t tP = SEP_P ? tmem_base + P_COL + (uint32_t)(x * 64) : tmem_base + Cfg::S_COL + (uint32_t)(x * 128);
         const uint32_t tO = tmem_base + Cfg::O_COL + (uint32_t)(x * OW);
 #pragma unroll
         for (int kk = 0; kk < Cfg::BN / 16; ++kk) {  // 16 keys per MMA: A advances 8 TMEM columns, B 16 rows of 128 B
@@ -263,6 +270,7 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t tS = tmem_base + lane_addr + Cfg::S_COL + (uint32_t)(x * 128);
     const uint32_t tO = tmem_base + lane_addr + Cfg::O_COL + (uint32_t)(x * OW);
+    const uint32_t tPw = SEP_P ? tmem_base + lane_addr + P_COL + (uint32_t)(x * 64) : tS;   // where this row's packed P goes
     uint32_t g = 0;
     int n = 0;
     for (int it = blockIdx.x; it < p.items; it += gridDim.x, ++n) {
@@ -277,6 +285,58 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tc_fence_after();
         const bool need_mask = (j * Cfg::BN + Cfg::BN > p.sk) || (p.causal && (j * Cfg::BN + Cfg::BN - 1 > m0 + x * Cfg::BM + causal_off));
         auto masked = [&](int key) { return key >= p.sk || (p.causal && key > qrow + causal_off); };
+        if (SEP_P && !need_mask) {
+          // ---- one-pass tile (see SEP_P above)
+          uint32_t va[32], vb[32];
+          tmem_ld32(tS, va);
+          tmem_ld_wait();
+          tmem_ld32(tS + 32u, vb);
+          const bool first = (m_run == -INFINITY);
+          if (first) {                                           // reference for the first tile: its first 32 scores
+            float e0 = __uint_as_float(va[0]), e1 = __uint_as_float(va[1]), e2 = __uint_as_float(va[2]), e3 = __uint_as_float(va[3]);
+#pragma unroll
+            for (int i = 4; i < 32; i += 4) {
+              e0 = fmaxf(e0, __uint_as_float(va[i])), e1 = fmaxf(e1, __uint_as_float(va[i + 1]));
+              e2 = fmaxf(e2, __uint_as_float(va[i + 2])), e3 = fmaxf(e3, __uint_as_float(va[i + 3]));
+            }
+            m_run = fmaxf(fmaxf(e0, e1), fmaxf(e2, e3)) * p.scale_log2;
+          }
+          const float m_use1 = m_run;
+          float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+          __half2 pm2 = __floats2half2_rn(0.f, 0.f);
+          auto chunk = [&](const uint32_t (&v)[32], int c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float a0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_use1));
+              const float xb0 = fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_use1);
+              const float b0 = (PE > 0 && (i % (PE > 0 ? PE : 1)) == PE - 1) ? pp_exp2_poly3(xb0) : fast_exp2(xb0);
+              rs4[i & 3] += a0 + b0;
+              const __half2 h0 = __floats2half2_rn(a0, b0);
+              pm2 = __hmax2(pm2, h0);                            // an overflowed value is +inf in fp16 and wins the maximum
+              pk[i] = *(const uint32_t*)&h0;
+            }
+            tmem_st16(tPw + (uint32_t)(c * 16), pk);
+          };
+          chunk(va, 0);
+          tmem_ld_wait();
+          tmem_ld32(tS + 64u, va);
+          chunk(vb, 1);
+          tmem_ld_wait();
+          tmem_ld32(tS + 96u, vb);
+          chunk(va, 2);
+          tmem_ld_wait();
+          chunk(vb, 3);
+          const float pm = fmaxf(__low2float(pm2), __high2float(pm2));
+          tmem_st_wait();
+          if (!__any_sync(0xffffffffu, pm > 256.0f)) {          // every row of this warp stayed within 2^8 of its reference: done
+            l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
+            tc_fence_before();
+            mbar_arrive(p_full(x));
+            continue;
+          }
+          // fall through: the P written above is overwritten below; S is intact, and l_run / O have not been touched
+        }
         // ---- pass 1: row maximum of the raw scores (the softmax scale is folded into the exp2 FFMA of pass 2)
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
@@ -366,8 +426,8 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             __half2 h0 = __floats2half2_rn(a0, b0), h1 = __floats2half2_rn(a1, b1);
             pk0[i] = *(uint32_t*)&h0, pk1[i] = *(uint32_t*)&h1;
           }
-          tmem_st16(tS + (uint32_t)(c2 * 32), pk0);
-          tmem_st16(tS + (uint32_t)(c2 * 32 + 16), pk1);
+          tmem_st16(tPw + (uint32_t)(c2 * 32), pk0);
+          tmem_st16(tPw + (uint32_t)(c2 * 32 + 16), pk1);
         }
         tmem_st_wait();
         l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));

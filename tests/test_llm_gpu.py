@@ -22,7 +22,7 @@ def mk(shape, seed, scale=1.0):
     return (torch.randn(shape, generator=g) * scale).cuda()
 
 
-@pytest.mark.parametrize("N,K", [(5120, 5120), (15360, 5120), (27648, 5120), (5120, 13824), (32330, 5120), (7, 64)])
+@pytest.mark.parametrize("N,K", [(5120, 5120), (15360, 5120), (27648, 5120), (5120, 13824), (32330, 5120), (7, 64), (9, 512), (1201, 1024)])
 def test_gemv(N, K):
     from seedx_b200 import ops
     W = mk((N, K), 1, K ** -0.5).half()

@@ -59,6 +59,26 @@ def test_attention(B, H, Sq, Sk, D, causal, impl):
             assert used == 2
 
 
+@pytest.mark.parametrize("growth", [0.0, 1.5, 6.0])
+def test_attention_one_pass_softmax_redo(growth):
+    """The two-tile kernel exponentiates tiles after the first against the RUNNING maximum (one pass) and redoes a tile from the intact scores when a row
+    outgrew that reference by more than 2^8.  Keys whose magnitude rises with their index push later tiles above the running maximum: a little
+    (lazy rescale only), and by far more than 2^8 (redo path; fp16 P would be inf without it)."""
+    from seedx_b200 import ops
+    from seedx_b200._lib import lib
+    B, H, S, D = 8, 20, 1024, 64
+    q = mk((B, S, H, D), 11).half()
+    ramp = (1.0 + growth * torch.arange(S, device="cuda").float() / S).view(1, S, 1, 1)
+    k = (mk((B, S, H, D), 12) * ramp).half()
+    v = mk((B, S, H, D), 13).half()
+    o = torch.empty((B, S, H, D), device="cuda", dtype=torch.float16)
+    ops.attention(q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3), o.permute(0, 2, 1, 3), scale=D ** -0.5)
+    assert lib().seedx_attention_last_impl() == 3
+    ref = F.scaled_dot_product_attention(q.float().permute(0, 2, 1, 3), k.float().permute(0, 2, 1, 3), v.float().permute(0, 2, 1, 3), scale=D ** -0.5)
+    assert torch.isfinite(o).all()
+    assert rel(o.permute(0, 2, 1, 3), ref) < 2e-3
+
+
 def test_attention_strided_qkv():
     """ViT layout: packed [N,S,heads,3,d] projection output read in place."""
     from seedx_b200 import ops
