@@ -240,8 +240,15 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mbar_wait(v_full(vst), vph);
           if (j == 0) mbar_wait(o_free(0), (uint32_t)((n & 1) ^ 1));   // epilogue of the previous item has drained O_A
           tc_fence_after();
+          // P in its own columns (SEP_P): S_A is free once P_A is complete, so the next QK^T goes ahead of PV on the in-order tensor pipe and
+          // the softmax of tile j+1 can start one MMA earlier
+          if (SEP_P && more) {
+            mbar_wait(k_full(kst), kph);
+            tc_fence_after();
+            issue_qk(0, sQA, sK0 + kst * Cfg::TILE_BYTES);
+          }
           issue_pv(0, sV0 + vst * Cfg::TILE_BYTES, j == 0);
-          if (more) {
+          if (!SEP_P && more) {
             mbar_wait(k_full(kst), kph);
             tc_fence_after();
             issue_qk(0, sQA, sK0 + kst * Cfg::TILE_BYTES);
@@ -250,10 +257,16 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           mbar_wait(p_full(1), g & 1u);
           if (j == 0) mbar_wait(o_free(1), (uint32_t)((n & 1) ^ 1));
           tc_fence_after();
+          if (SEP_P && more) {
+            issue_qk(1, sQB, sK0 + kst * Cfg::TILE_BYTES);
+            umma_commit(k_empty(kst));
+            if (j + 2 == n_tiles) umma_commit(q_empty(qb));   // last QK^T of this item issued: the Q pair may be overwritten
+            if (++kst == KS) kst = 0, kph ^= 1u;
+          }
           issue_pv(1, sV0 + vst * Cfg::TILE_BYTES, j == 0);
           umma_commit(v_empty(vst));
           if (++vst == KS) vst = 0, vph ^= 1u;
-          if (more) {
+          if (!SEP_P && more) {
             issue_qk(1, sQB, sK0 + kst * Cfg::TILE_BYTES);
             umma_commit(k_empty(kst));
             if (j + 2 == n_tiles) umma_commit(q_empty(qb));   // last QK^T of this item issued: the Q pair may be overwritten
@@ -315,6 +328,10 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               const __half2 h0 = __floats2half2_rn(a0, b0);
               pm2 = __hmax2(pm2, h0);                            // an overflowed value is +inf in fp16 and wins the maximum
               pk[i] = *(const uint32_t*)&h0;
+            }
+            if (c == 0 && j > 0) {                               // P_X(j-1) must have been consumed: QK^T(j) is issued AHEAD of PV(j-1), so the
+              mbar_wait(pv_done(x), (g - 1) & 1u);               // arrival of S(j) no longer implies it (complete by now: PV takes ~256 clk)
+              tc_fence_after();
             }
             tmem_st16(tPw + (uint32_t)(c * 16), pk);
           };
@@ -390,6 +407,10 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           m_run = m_new;
         }
         const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+        if (SEP_P && j > 0) {                                    // as in the one-pass path: P_X(j-1) consumed before P_X(j) is written
+          mbar_wait(pv_done(x), (g - 1) & 1u);
+          tc_fence_after();
+        }
         // ---- pass 2: P = exp2(scale * S - m) as fp16 pairs.  Chunk c re-reads score columns [32c, 32c+32) and writes packed columns
         // [16c, 16c+16): a chunk's P never lands on columns a later chunk still has to read.
         float rs4[4] = {0.f, 0.f, 0.f, 0.f};
