@@ -105,7 +105,8 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   auto p_full = [&](int x) { return bar + 8u * (4 * KS + 6 + x); };
   auto pv_done = [&](int x) { return bar + 8u * (4 * KS + 8 + x); };
   auto o_free = [&](int x) { return bar + 8u * (4 * KS + 10 + x); };
-  const uint32_t tmem_slot = bar + 8u * (4 * KS + 12);
+  auto s_free = [&](int x) { return bar + 8u * (4 * KS + 12 + x); };   // SEP_P: the softmax has read S_X, the next QK^T may overwrite it
+  const uint32_t tmem_slot = bar + 8u * (4 * KS + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -124,6 +125,7 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       mbar_init(p_full(s), 128);
       mbar_init(pv_done(s), 1);
       mbar_init(o_free(s), 128);
+      mbar_init(s_free(s), 128);
     }
     mbar_fence_init();
   }
@@ -236,17 +238,18 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const bool more = j + 1 < n_tiles;
           // ---- query tile A
-          mbar_wait(p_full(0), g & 1u);
-          mbar_wait(v_full(vst), vph);
-          if (j == 0) mbar_wait(o_free(0), (uint32_t)((n & 1) ^ 1));   // epilogue of the previous item has drained O_A
-          tc_fence_after();
-          // P in its own columns (SEP_P): S_A is free once P_A is complete, so the next QK^T goes ahead of PV on the in-order tensor pipe and
-          // the softmax of tile j+1 can start one MMA earlier
+          // P in its own columns (SEP_P): S_A is free as soon as the softmax has LOADED it (s_free, about three quarters into the tile's
+          // exponentials), so the next QK^T goes ahead of PV on the in-order tensor pipe and S_A(j+1) is ready when the softmax comes back for it
           if (SEP_P && more) {
+            mbar_wait(s_free(0), g & 1u);
             mbar_wait(k_full(kst), kph);
             tc_fence_after();
             issue_qk(0, sQA, sK0 + kst * Cfg::TILE_BYTES);
           }
+          mbar_wait(p_full(0), g & 1u);
+          mbar_wait(v_full(vst), vph);
+          if (j == 0) mbar_wait(o_free(0), (uint32_t)((n & 1) ^ 1));   // epilogue of the previous item has drained O_A
+          tc_fence_after();
           issue_pv(0, sV0 + vst * Cfg::TILE_BYTES, j == 0);
           if (!SEP_P && more) {
             mbar_wait(k_full(kst), kph);
@@ -254,15 +257,17 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             issue_qk(0, sQA, sK0 + kst * Cfg::TILE_BYTES);
           }
           // ---- query tile B
-          mbar_wait(p_full(1), g & 1u);
-          if (j == 0) mbar_wait(o_free(1), (uint32_t)((n & 1) ^ 1));
-          tc_fence_after();
           if (SEP_P && more) {
+            mbar_wait(s_free(1), g & 1u);
+            tc_fence_after();
             issue_qk(1, sQB, sK0 + kst * Cfg::TILE_BYTES);
             umma_commit(k_empty(kst));
             if (j + 2 == n_tiles) umma_commit(q_empty(qb));   // last QK^T of this item issued: the Q pair may be overwritten
             if (++kst == KS) kst = 0, kph ^= 1u;
           }
+          mbar_wait(p_full(1), g & 1u);
+          if (j == 0) mbar_wait(o_free(1), (uint32_t)((n & 1) ^ 1));
+          tc_fence_after();
           issue_pv(1, sV0 + vst * Cfg::TILE_BYTES, j == 0);
           umma_commit(v_empty(vst));
           if (++vst == KS) vst = 0, vph ^= 1u;
@@ -317,8 +322,7 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const float m_use1 = m_run;
           float rs4[4] = {0.f, 0.f, 0.f, 0.f};
           __half2 pm2 = __floats2half2_rn(0.f, 0.f);
-          auto chunk = [&](const uint32_t (&v)[32], int c) {
-            uint32_t pk[16];
+          auto comp = [&](const uint32_t (&v)[32], uint32_t (&pk)[16]) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const float a0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_use1));
@@ -329,30 +333,46 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
               pm2 = __hmax2(pm2, h0);                            // an overflowed value is +inf in fp16 and wins the maximum
               pk[i] = *(const uint32_t*)&h0;
             }
-            if (c == 0 && j > 0) {                               // P_X(j-1) must have been consumed: QK^T(j) is issued AHEAD of PV(j-1), so the
-              mbar_wait(pv_done(x), (g - 1) & 1u);               // arrival of S(j) no longer implies it (complete by now: PV takes ~256 clk)
-              tc_fence_after();
-            }
-            tmem_st16(tPw + (uint32_t)(c * 16), pk);
           };
-          chunk(va, 0);
+          uint32_t pka[16], pkb[16];
+          comp(va, pka);
           tmem_ld_wait();
           tmem_ld32(tS + 64u, va);
-          chunk(vb, 1);
+          comp(vb, pkb);
+          if (j > 0) {                                           // P_X(j-1) must have been consumed: QK^T(j) is issued AHEAD of PV(j-1), so the arrival
+            mbar_wait(pv_done(x), (g - 1) & 1u);                 // of S(j) no longer implies it.  The first store is held back to the second chunk:
+            tc_fence_after();                                    // PV(j-1) (~256 clk after QK^T(j)) has normally retired by then
+          }
+          tmem_st16(tPw, pka);
+          tmem_st16(tPw + 16u, pkb);
           tmem_ld_wait();
           tmem_ld32(tS + 96u, vb);
-          chunk(va, 2);
+          comp(va, pka);
+          tmem_st16(tPw + 32u, pka);
           tmem_ld_wait();
-          chunk(vb, 3);
+          // S is in registers now.  Whether the tile stayed within 2^8 of its reference is known before the last chunk is exponentiated:
+          // the largest P of chunks 0..2 and the largest raw score of chunk 3.  If so, S_X is released to the next QK^T right here.
+          float e0 = __uint_as_float(vb[0]), e1 = __uint_as_float(vb[1]), e2 = __uint_as_float(vb[2]), e3 = __uint_as_float(vb[3]);
+#pragma unroll
+          for (int i = 4; i < 32; i += 4) {
+            e0 = fmaxf(e0, __uint_as_float(vb[i])), e1 = fmaxf(e1, __uint_as_float(vb[i + 1]));
+            e2 = fmaxf(e2, __uint_as_float(vb[i + 2])), e3 = fmaxf(e3, __uint_as_float(vb[i + 3]));
+          }
           const float pm = fmaxf(__low2float(pm2), __high2float(pm2));
-          tmem_st_wait();
-          if (!__any_sync(0xffffffffu, pm > 256.0f)) {          // every row of this warp stayed within 2^8 of its reference: done
+          const bool ovf = !(pm <= 256.0f) || fmaf(fmaxf(fmaxf(e0, e1), fmaxf(e2, e3)), p.scale_log2, -m_use1) > 8.0f;
+          if (!__any_sync(0xffffffffu, ovf)) {                   // every row of this warp stays within 2^8 of its reference
+            tc_fence_before();
+            mbar_arrive(s_free(x));
+            comp(vb, pkb);
+            tmem_st16(tPw + 48u, pkb);
+            tmem_st_wait();
             l_run += (rs4[0] + rs4[1]) + (rs4[2] + rs4[3]);
             tc_fence_before();
             mbar_arrive(p_full(x));
             continue;
           }
-          // fall through: the P written above is overwritten below; S is intact, and l_run / O have not been touched
+          tmem_st_wait();
+          // fall through: the P written above is overwritten below; S is intact (not released), and l_run / O have not been touched
         }
         // ---- pass 1: row maximum of the raw scores (the softmax scale is folded into the exp2 FFMA of pass 2)
         float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -453,6 +473,7 @@ flash_attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         tmem_st_wait();
         l_run = l_run * alpha + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
         tc_fence_before();
+        if (SEP_P) mbar_arrive(s_free(x));
         mbar_arrive(p_full(x));
       }
       // ---- epilogue: normalise and store this row (D contiguous fp16)
@@ -532,7 +553,9 @@ static int launch_pp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtenso
     const char* e = getenv("SEEDX_PP_POLY_EVERY");
     // -1 selects the H2 softmax (d = 64 only).  Measured on B200 (8 x 10 heads x 4096^2, d = 64): H2 571 TF/s vs 624 TF/s for the 1/8 polynomial
     // split — the N = 80 PV MMAs and the cvt + ex2.f16x2 pair cost more than the FADDs and MUFU slots they free — so it stays an experiment.
-    pe = e ? atoi(e) : SEEDX_PP_POLY_EVERY;
+    // d = 64 with the one-pass softmax and the early release of S: the softmax no longer waits for the tensor pipe and its instruction count
+    // decides — MUFU only 493 us, 1/8 polynomial 514 us, 1/4 554 us (8 x 10 x 4096^2); d = 128 keeps the 1/8 split
+    pe = e ? atoi(e) : (D == 64 ? 0 : SEEDX_PP_POLY_EVERY);
   }
   if (D == 64 && pe < 0) return launch_pp_pe<64, -1>(tq, tk, tv, p, B, H, st);
   switch (pe) {

@@ -49,6 +49,8 @@ kc = torch.randn(Bq, 1024, H * d, device=dev).half(); vc = torch.randn_like(kc)
 qkv10 = torch.randn(Bq, 3 * H * d, device=dev); st = torch.tensor([[T, 0, 0, 1]] * Bq, dtype=torch.int32, device=dev)
 inv = (1.0 / (10000.0 ** (torch.arange(0, d, 2, dtype=torch.float32) / d))).to(dev); o10 = torch.empty(Bq, H * d, device=dev)
 jobs.append(lambda: ops.decode_attention(qkv10, st, inv, kc, vc, o10, H, d))
+if os.environ.get("JOBS"):                       # e.g. JOBS=0,1: only the two self-attention launches
+    jobs = [jobs[int(i)] for i in os.environ["JOBS"].split(",")]
 for _ in range(2):
     for j in jobs:
         j()
