@@ -27,8 +27,8 @@ for N in (5120, 10240, 20480, 40960, 81920, 163840):
     us = e0.elapsed_time(e1) / 5 / calls * 1e3
     mb = N * K * 2 / 1e6
     res.append((mb, us))
-    print(f"N={N:7d}: {mb:8.1f} MB  {us:8.1f} us  {mb/us/1e3*1e3/1e3:6.2f} TB/s", flush=True)
+    print(f"N={N:7d}: {mb:8.1f} MB  {us:8.1f} us  {mb/us:6.2f} TB/s", flush=True)
     del Ws
 (m0, t0), (m1, t1) = res[-3], res[-1]
 bw = (m1 - m0) / (t1 - t0)
-print(f"slope between the two largest: {bw/1e3*1e3/1e3:.2f} TB/s; constant a = {t1 - m1 / bw:.1f} us")
+print(f"slope between N=40960 and N=163840: {bw:.2f} TB/s (MB/us); constant a = {t1 - m1 / bw:.1f} us per launch")
