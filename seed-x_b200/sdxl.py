@@ -298,6 +298,15 @@ class _Transformer:
         """cross-attention K/V of every block for a step-invariant context [B*T, ctx_dim] (hoisted out of the sampler loop)."""
         return [ops.gemm(ctx16, blk["w_kv2"]) for blk in self.blocks]
 
+    def _row_tickets(self, slabs, device):
+        """persistent ticket counters of the in-epilogue row finalize: the kernel that takes a slab's last ticket resets it, so one zeroed buffer
+        per block and slab count serves every call of this block (no fill kernel per transformer in the forward)"""
+        key = (str(device), slabs)
+        tk = self.__dict__.setdefault("_tickets", {})
+        if key not in tk:
+            tk[key] = torch.zeros((slabs,), device=device, dtype=torch.int32)
+        return tk[key]
+
     def __call__(self, x, kv, n_ctx, groups, ws):
         n, h, w, c = x.shape
         S, M, H = h * w, n * h * w, self.heads
@@ -312,7 +321,7 @@ class _Transformer:
         rp = torch.empty((c // 32, M, 2), device=x.device, dtype=torch.float32) if (EPI_STATS and M % 32 == 0 and c % 32 == 0) else None
         stats = torch.empty((M, 2), device=x.device, dtype=torch.float32)
         # the epilogue warp that delivers a 32-row slab's last partial also reduces the slab to (mean, rstd): no statistics launch at all
-        rs = (stats, torch.zeros((M // 32,), device=x.device, dtype=torch.int32), 1e-5) if (rp is not None and ROW_TICKETS) else None
+        rs = (stats, self._row_tickets(M // 32, x.device), 1e-5) if (rp is not None and ROW_TICKETS) else None
 
         def ln_of(fl):
             if rp is None:
