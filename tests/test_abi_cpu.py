@@ -106,3 +106,21 @@ def test_scheduler_known_answers():
     assert a.timesteps == [float(t) for t in range(981, 0, -20)] and len(a.sigmas) == 51 and a.sigmas[-1] == 0.0
     assert all(x > y for x, y in zip(a.sigmas, a.sigmas[1:]))
     assert abs(a.init_noise_sigma - (a.sigmas[0] ** 2 + 1) ** 0.5) < 1e-12 and abs(a.sigmas[0] - s._sig[981]) < 1e-12
+
+
+def test_integration_md_ctypes_stub_mirrors_the_gemm_struct():
+    """INTEGRATION.md shows the ctypes binding a reference maintainer would add; the library reads the whole seedx_gemm_args, so the stub must carry
+    every field at the offset of the real binding (which the tests above pin against include/seedx.h)."""
+    import ctypes as C
+    import re
+    from seedx_b200._lib import GemmArgs as Real
+    src = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class GemmArgs\(C.Structure\):.*?\n(    _fields_ = \[.*?\]\n)", src, re.S)
+    assert m, "INTEGRATION.md no longer shows the GemmArgs stub"
+    ns = {"C": C}
+    exec("class GemmArgs(C.Structure):\n" + m.group(1), ns)
+    stub = ns["GemmArgs"]
+    assert C.sizeof(stub) == C.sizeof(Real)
+    assert [n for n, _ in stub._fields_] == [n for n, _ in Real._fields_]
+    for n, _ in stub._fields_:
+        assert getattr(stub, n).offset == getattr(Real, n).offset, n
