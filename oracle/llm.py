@@ -8,7 +8,8 @@ Restates
   /root/reference/src/models/mllm/seed_x.py:130-223 (ContinuousLVLM.generate),
   /root/reference/src/models/mllm/peft_models.py:62-82 + PEFT 0.4.0 (vendored: /root/reference/proj/peft) LoRA forward, lora.py:808-832,
   transformers==4.30.2 GenerationMixin.greedy_search as used at seed_x.py:184-189 (THIRD-PARTY, absent:
-  the loop semantics are "parity unpinned" — the installed transformers 5.5 cannot drive the reference model).
+  the installed transformers 5.5.0 cannot drive the reference's xformers model class, but tests/test_hf_generate_pin_cpu.py pins this loop and
+  the forward below against HF's own LlamaForCausalLM.generate called the way seed_x.py:184-189 calls it: ids, EOS stop, harvested hidden rows).
 PINNED: forward logits / hidden states / KV and the logits processor against golden vectors produced by the reference
 modules themselves (tests/golden/llama_tiny.pt, make_golden.py); the greedy loop against the same loop run around the
 reference forward + the reference's own processor class; the LoRA / vocabulary-growth path against the reference's
